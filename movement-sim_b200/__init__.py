@@ -1,0 +1,409 @@
+"""movement_sim_b200 — Python host binding of libmsim_cuda.so (the C ABI in include/msim.h).
+
+This is plumbing for tests and bench.py: every compute call goes straight through the C ABI into the
+hand-written sm_100a kernels under csrc/.  There is no CPU fallback and no other backend: if the
+shared library is missing, importing this module raises; if no B200-class GPU is present, creating a
+Simulation raises MsimError(MSIM_ERR_CUDA).
+
+The directory is called ``movement-sim_b200`` (not a Python identifier); ``import movement_sim_b200``
+works through the one-line shim module at the repository root.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmsim_cuda.so")
+
+# ---- data model (byte-identical to include/msim.h) ------------------------------------------------
+ENTITY_DTYPE = np.dtype(
+    [
+        ("color", "<f4", (4,)),
+        ("rand_state", "<u4", (4,)),
+        ("pos", "<f4", (2,)),
+        ("target", "<f4", (2,)),
+        ("direction", "<f4", (2,)),
+        ("road_index", "<u4"),
+        ("initialized", "<u4"),
+    ]
+)
+ROAD_DTYPE = np.dtype(
+    [
+        ("start_pos", "<f4", (2,)),
+        ("start_index", "<u4"),
+        ("start_count", "<u4"),
+        ("end_pos", "<f4", (2,)),
+        ("end_index", "<u4"),
+        ("end_count", "<u4"),
+    ]
+)
+QUADTREE_NODE_DTYPE = np.dtype(
+    [
+        ("acquire_lock", "<i4"),
+        ("write_lock", "<i4"),
+        ("reader_lock", "<i4"),
+        ("offset_x", "<f4"),
+        ("offset_y", "<f4"),
+        ("width", "<f4"),
+        ("height", "<f4"),
+        ("content_type", "<u4"),
+        ("entity_count", "<u4"),
+        ("first", "<u4"),
+        ("prev_node_index", "<u4"),
+        ("next_tl", "<u4"),
+        ("next_tr", "<u4"),
+        ("next_bl", "<u4"),
+        ("next_br", "<u4"),
+        ("padding", "<u4"),
+    ]
+)
+assert ENTITY_DTYPE.itemsize == 64 and ROAD_DTYPE.itemsize == 32 and QUADTREE_NODE_DTYPE.itemsize == 64
+
+MSIM_ABI_VERSION = 1
+(MSIM_OK, MSIM_ERR_INVALID, MSIM_ERR_CUDA, MSIM_ERR_OOM, MSIM_ERR_UNSUPPORTED, MSIM_ERR_IO, MSIM_ERR_PARSE,
+ MSIM_ERR_CAPACITY, MSIM_ERR_INTERNAL) = range(9)
+FLAG_NO_COLLISIONS = 1 << 0
+FLAG_NO_PAIR_COUNT = 1 << 1
+FLAG_NO_QUADTREE = 1 << 2
+
+# every symbol include/msim.h declares (tests/test_abi.py checks the library exports exactly these)
+ABI_SYMBOLS = [
+    "msim_create", "msim_destroy", "msim_last_error", "msim_status_string", "msim_upload_entities",
+    "msim_dispatch", "msim_enqueue_move", "msim_enqueue_collide", "msim_enqueue_ticks", "msim_sync",
+    "msim_set_stream", "msim_read_entities", "msim_read_positions", "msim_read_collision_flags",
+    "msim_read_quadtree_nodes", "msim_read_debug", "msim_get_stats", "msim_get_device_view",
+    "msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid",
+    "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
+    "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
+    "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
+]
+
+
+class MsimError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"msim status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class PushConsts(C.Structure):
+    _pack_ = 1
+    _fields_ = [
+        ("world_size_x", C.c_float),
+        ("world_size_y", C.c_float),
+        ("node_count", C.c_uint32),
+        ("max_depth", C.c_uint32),
+        ("entity_node_cap", C.c_uint32),
+        ("collision_radius", C.c_float),
+        ("tick", C.c_uint32),
+    ]
+
+
+assert C.sizeof(PushConsts) == 28
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("device", C.c_int32),
+        ("flags", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("world_w", C.c_float),
+        ("world_h", C.c_float),
+        ("collision_radius", C.c_float),
+        ("quadtree_max_depth", C.c_uint32),
+        ("quadtree_node_cap", C.c_uint32),
+        ("reserved1", C.c_uint32),
+        ("roads", C.c_void_p),
+        ("road_count", C.c_uint64),
+        ("connections", C.c_void_p),
+        ("connection_count", C.c_uint64),
+        ("entities", C.c_void_p),
+        ("entity_count", C.c_uint64),
+        ("entity_capacity", C.c_uint64),
+        ("cuda_stream", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("entity_count", C.c_uint64),
+        ("move_passes", C.c_uint64),
+        ("collide_passes", C.c_uint64),
+        ("last_pair_count", C.c_uint64),
+        ("total_pair_count", C.c_uint64),
+        ("last_flagged_count", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("grid_cells_x", C.c_uint32),
+        ("grid_cells_y", C.c_uint32),
+        ("key_bits", C.c_uint32),
+        ("sort_passes", C.c_uint32),
+        ("cell_size", C.c_float),
+        ("reserved", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class DeviceView(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("target", C.c_void_p), ("road", C.c_void_p), ("rng", C.c_void_p), ("count", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libmsim_cuda.so; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()). "
+            "movement_sim_b200 has no CPU or alternative backend."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+    sigs = {
+        "msim_create": (i32, [C.POINTER(_Config), C.POINTER(vp)]),
+        "msim_destroy": (None, [vp]),
+        "msim_last_error": (C.c_char_p, [vp]),
+        "msim_status_string": (C.c_char_p, [i32]),
+        "msim_upload_entities": (i32, [vp, vp, u64]),
+        "msim_dispatch": (i32, [vp, C.POINTER(PushConsts)]),
+        "msim_enqueue_move": (i32, [vp]),
+        "msim_enqueue_collide": (i32, [vp]),
+        "msim_enqueue_ticks": (i32, [vp, u32, i32]),
+        "msim_sync": (i32, [vp]),
+        "msim_set_stream": (i32, [vp, vp]),
+        "msim_read_entities": (i32, [vp, vp, u64]),
+        "msim_read_positions": (i32, [vp, vp, u64]),
+        "msim_read_collision_flags": (i32, [vp, vp, u64]),
+        "msim_read_quadtree_nodes": (i32, [vp, vp, u64, C.POINTER(u64)]),
+        "msim_read_debug": (i32, [vp, vp]),
+        "msim_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "msim_get_device_view": (i32, [vp, C.POINTER(DeviceView)]),
+        "msim_map_load_json": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "msim_map_save_json": (i32, [vp, C.c_char_p]),
+        "msim_map_generate_city": (i32, [f32, f32, f32, f32, f32, u64, C.POINTER(vp)]),
+        "msim_map_generate_grid": (i32, [u32, u32, f32, C.POINTER(vp)]),
+        "msim_map_free": (None, [vp]),
+        "msim_map_width": (f32, [vp]),
+        "msim_map_height": (f32, [vp]),
+        "msim_map_road_count": (u64, [vp]),
+        "msim_map_connection_count": (u64, [vp]),
+        "msim_map_roads": (vp, [vp]),
+        "msim_map_connections": (vp, [vp]),
+        "msim_map_last_error": (C.c_char_p, []),
+        "msim_entities_init": (i32, [vp, u64, u64, u64, vp, vp]),
+        "msim_calc_node_count": (u64, [u32]),
+        "msim_abi_version": (u32, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+# ---- map -------------------------------------------------------------------------------------
+class Map:
+    """Road graph: `roads` (ROAD_DTYPE) + flat `connections` (uint32) + world size.
+    Mirrors sim::Map (/root/reference/src/sim/Map.hpp:27-47) minus the render-only roadPieces."""
+
+    def __init__(self, width: float, height: float, roads: np.ndarray, connections: np.ndarray):
+        self.width = float(np.float32(width))
+        self.height = float(np.float32(height))
+        self.roads = np.ascontiguousarray(roads, dtype=ROAD_DTYPE)
+        self.connections = np.ascontiguousarray(connections, dtype=np.uint32)
+
+    @classmethod
+    def _take(cls, handle) -> "Map":
+        L = lib()
+        try:
+            nr, nc = L.msim_map_road_count(handle), L.msim_map_connection_count(handle)
+            roads = np.empty(nr, dtype=ROAD_DTYPE)
+            conns = np.empty(nc, dtype=np.uint32)
+            if nr:
+                C.memmove(roads.ctypes.data, L.msim_map_roads(handle), nr * 32)
+            if nc:
+                C.memmove(conns.ctypes.data, L.msim_map_connections(handle), nc * 4)
+            return cls(L.msim_map_width(handle), L.msim_map_height(handle), roads, conns)
+        finally:
+            L.msim_map_free(handle)
+
+    @classmethod
+    def load_json(cls, path: str) -> "Map":
+        """Map::load_from_file (/root/reference/src/sim/Map.cpp:28-150)."""
+        L = lib()
+        h = C.c_void_p()
+        rc = L.msim_map_load_json(os.fsencode(path), C.byref(h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        return cls._take(h)
+
+    @classmethod
+    def city(cls, world_w: float = 29007.4609, world_h: float = 16463.7656, spacing: float = 35.0, jitter: float = 0.3,
+             drop_prob: float = 0.12, seed: int = 2022) -> "Map":
+        """Seeded stand-in for the missing munich.json (world size from
+        /root/reference/shader_validation/src/main.cpp:155)."""
+        L = lib()
+        h = C.c_void_p()
+        rc = L.msim_map_generate_city(world_w, world_h, spacing, jitter, drop_prob, seed, C.byref(h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        return cls._take(h)
+
+    @classmethod
+    def grid(cls, nx: int, ny: int, spacing: float = 20.0) -> "Map":
+        L = lib()
+        h = C.c_void_p()
+        rc = L.msim_map_generate_grid(nx, ny, spacing, C.byref(h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        return cls._take(h)
+
+    def init_entities(self, count: int, seed: int = 42, box=None) -> np.ndarray:
+        """Simulator::add_entities (/root/reference/src/sim/Simulator.cpp:114-129), seeded."""
+        L = lib()
+        out = np.zeros(count, dtype=ENTITY_DTYPE)
+        boxp = None
+        if box is not None:
+            box = np.ascontiguousarray(box, dtype=np.float32)
+            assert box.shape == (4,)
+            boxp = box.ctypes.data
+        rc = L.msim_entities_init(self.roads.ctypes.data, self.roads.shape[0], count, seed, boxp, out.ctypes.data)
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        return out
+
+
+def calc_node_count(depth: int) -> int:
+    return int(lib().msim_calc_node_count(depth))
+
+
+# ---- simulation handle -----------------------------------------------------------------------
+class Simulation:
+    """One msim_handle: the resident entity population of one GPU."""
+
+    def __init__(self, m: Map, entities: np.ndarray, radius: float = 10.0, device: int = 0, flags: int = 0,
+                 stream: int | None = None, capacity: int = 0, quadtree_depth: int = 8, quadtree_cap: int = 10):
+        L = lib()
+        ents = np.ascontiguousarray(entities, dtype=ENTITY_DTYPE)
+        self.map = m
+        self.radius = float(np.float32(radius))
+        self._cfg = _Config(
+            MSIM_ABI_VERSION, device, flags, 0, m.width, m.height, self.radius, quadtree_depth, quadtree_cap, 0,
+            m.roads.ctypes.data, m.roads.shape[0], m.connections.ctypes.data if m.connections.size else None, m.connections.shape[0],
+            ents.ctypes.data if ents.size else None, ents.shape[0], capacity, stream,
+        )
+        self._h = C.c_void_p()
+        rc = L.msim_create(C.byref(self._cfg), C.byref(self._h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_last_error(None).decode())
+        self.count = ents.shape[0]
+        self.quadtree_depth, self.quadtree_cap = quadtree_depth, quadtree_cap
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().msim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != MSIM_OK:
+            raise MsimError(rc, lib().msim_last_error(self._h).decode())
+
+    # -- dispatch
+    def push_consts(self, tick: int) -> PushConsts:
+        """The reference's push constants (/root/reference/src/sim/Simulator.cpp:94-101)."""
+        return PushConsts(self.map.width, self.map.height, calc_node_count(self.quadtree_depth), self.quadtree_depth,
+                          self.quadtree_cap, self.radius, tick)
+
+    def dispatch(self, tick: int):
+        pc = self.push_consts(tick)
+        self._check(lib().msim_dispatch(self._h, C.byref(pc)))
+
+    def enqueue_move(self):
+        self._check(lib().msim_enqueue_move(self._h))
+
+    def enqueue_collide(self):
+        self._check(lib().msim_enqueue_collide(self._h))
+
+    def enqueue_ticks(self, sim_ticks: int, collisions: bool):
+        self._check(lib().msim_enqueue_ticks(self._h, sim_ticks, 1 if collisions else 0))
+
+    def sync(self):
+        self._check(lib().msim_sync(self._h))
+
+    def set_stream(self, stream: int | None):
+        self._check(lib().msim_set_stream(self._h, stream))
+
+    # -- transfers
+    def upload(self, entities: np.ndarray):
+        ents = np.ascontiguousarray(entities, dtype=ENTITY_DTYPE)
+        self._check(lib().msim_upload_entities(self._h, ents.ctypes.data, ents.shape[0]))
+        self.count = ents.shape[0]
+
+    def upload_ptr(self, ptr: int, count: int):
+        self._check(lib().msim_upload_entities(self._h, ptr, count))
+        self.count = count
+
+    def read_entities(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.count, dtype=ENTITY_DTYPE)
+        assert out.dtype == ENTITY_DTYPE and out.flags.c_contiguous
+        self._check(lib().msim_read_entities(self._h, out.ctypes.data, out.shape[0]))
+        return out
+
+    def read_entities_ptr(self, ptr: int, count: int):
+        self._check(lib().msim_read_entities(self._h, ptr, count))
+
+    def read_positions(self) -> np.ndarray:
+        out = np.empty((self.count, 2), dtype=np.float32)
+        self._check(lib().msim_read_positions(self._h, out.ctypes.data, self.count))
+        return out
+
+    def read_collision_flags(self) -> np.ndarray:
+        out = np.empty(self.count, dtype=np.uint8)
+        self._check(lib().msim_read_collision_flags(self._h, out.ctypes.data, self.count))
+        return out
+
+    def read_quadtree_nodes(self) -> np.ndarray:
+        cap = calc_node_count(self.quadtree_depth)
+        out = np.zeros(cap, dtype=QUADTREE_NODE_DTYPE)
+        n = C.c_uint64()
+        self._check(lib().msim_read_quadtree_nodes(self._h, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value]
+
+    def read_debug(self) -> np.ndarray:
+        out = np.zeros(10, dtype=np.uint32)
+        self._check(lib().msim_read_debug(self._h, out.ctypes.data))
+        return out
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(lib().msim_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def device_view(self) -> DeviceView:
+        v = DeviceView()
+        self._check(lib().msim_get_device_view(self._h, C.byref(v)))
+        return v

@@ -1,0 +1,590 @@
+// api.cu — the C ABI of libmsim_cuda.so (include/msim.h): handle lifetime, HBM allocation, the
+// dispatch state machine of the reference's host driver, and the AoS<->SoA boundary copies.
+//
+// Reference behaviour mirrored here (/root/reference/src/sim/Simulator.cpp):
+//   :52-103   buffer creation + push constants      -> msim_create
+//   :191-192  one-off upload                        -> msim_create / msim_upload_entities
+//   :220-235  two blocking dispatches per sim tick  -> msim_dispatch (tick parity, shader :860-879)
+//   :248-273  readbacks                             -> msim_read_*
+// No CPU fallback exists: without a usable sm_100 device every compute entry point fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "msim_internal.h"
+
+using namespace msim;
+
+namespace {
+thread_local std::string g_create_error;
+
+constexpr uint64_t MAX_ENTITIES_PER_HANDLE = 1ull << 30;  // look-back words carry 30-bit counts
+constexpr uint32_t MAX_GRID_CELLS = 1u << 27;
+constexpr uint32_t STAGE_ENTITIES = 1u << 20;  // 64 MiB AoS staging chunk
+}  // namespace
+
+struct msim_handle {
+    int device{0};
+    int sm_count{148};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+    uint32_t flags{0};
+
+    uint32_t n{0};
+    uint32_t cap{0};  // padded to a multiple of 64 entities
+    float world_w{0}, world_h{0}, radius{0};
+    uint32_t qt_depth{8}, qt_cap{10};
+
+    // resident state
+    float2* pos[2]{nullptr, nullptr};
+    int cur{0};
+    float2* target{nullptr};
+    uint32_t* road{nullptr};
+    uint4* rng{nullptr};
+    float4* color0{nullptr};
+    float2* dir0{nullptr};
+    uint32_t* arrived{nullptr};
+    msim_road* roads{nullptr};
+    uint32_t* conn{nullptr};
+    uint64_t road_count{0}, conn_count{0};
+
+    // neighbour structure
+    uint32_t* keys{nullptr};
+    uint64_t* sort_a{nullptr};
+    uint64_t* sort_b{nullptr};
+    uint64_t* sorted{nullptr};
+    float2* sorted_pos{nullptr};
+    uint2* cell_range{nullptr};
+    uint32_t cell_capacity{0};
+    uint8_t* flag_sorted{nullptr};
+    uint8_t* flag_entity{nullptr};
+    void* sort_mem{nullptr};
+    SortWorkspace ws{};
+    GridParams grid{};
+    int key_bits{1};
+
+    Counters* counters{nullptr};
+    unsigned int* scratch{nullptr};  // [0] uninitialised count, [1] max road index
+    msim_entity* stage{nullptr};
+
+    bool uninitialised{false};
+    bool has_moved{false};
+    bool keys_valid{false};
+    bool collided{false};
+    bool flags_scattered{false};
+    uint64_t move_passes{0}, collide_passes{0}, launches{0}, initialised_total{0};
+    uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0};
+
+    std::string error;
+};
+
+namespace {
+
+int fail(msim_handle* h, int code, const std::string& msg) {
+    if (h) h->error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define MSIM_CUDA(h, call)                                                                                         \
+    do {                                                                                                           \
+        cudaError_t err__ = (call);                                                                                \
+        if (err__ != cudaSuccess) {                                                                                \
+            return fail((h), err__ == cudaErrorMemoryAllocation ? MSIM_ERR_OOM : MSIM_ERR_CUDA,                    \
+                        std::string(#call) + ": " + cudaGetErrorString(err__));                                    \
+        }                                                                                                          \
+    } while (0)
+
+// smallest binary32 T with sqrtf(T) >= r; then (d2 < T) <=> (sqrtf(d2) < r) because sqrtf is monotone
+// and correctly rounded on both host and device.
+float exact_hit_threshold(float r) {
+    if (!(r > 0.0f)) return 0.0f;
+    float t = static_cast<float>(static_cast<double>(r) * static_cast<double>(r));
+    while (t > 0.0f && std::sqrt(t) >= r) t = std::nextafter(t, 0.0f);
+    while (std::sqrt(t) < r) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
+// Cell edge slightly above the radius: two points closer than r must land in adjacent cells even
+// after the rounding of pos * inv_cell (error <= cells_per_axis * 2^-24 cell units).
+void configure_grid(msim_handle* h) {
+    GridParams g{};
+    g.radius = h->radius;
+    g.hit_threshold = exact_hit_threshold(h->radius);
+    double r = h->radius > 0.0f ? static_cast<double>(h->radius) : 1.0;
+    double w = h->world_w > 0.0f ? h->world_w : 1.0, hh = h->world_h > 0.0f ? h->world_h : 1.0;
+    double cell = r;
+    for (int iter = 0; iter < 64; iter++) {
+        const double axis = std::max(w, hh) / cell + 2.0;
+        const double eps = std::max(1.0 / 1024.0, axis / 2097152.0);  // >= 4x the rounding bound
+        const double c = cell * (1.0 + eps);
+        const double ncx = std::floor(w / c) + 1.0, ncy = std::floor(hh / c) + 1.0;
+        if (ncx * ncy <= static_cast<double>(MAX_GRID_CELLS)) {
+            g.inv_cell = static_cast<float>(1.0 / c);
+            // inv_cell rounded to float may exceed 1/c by half an ulp: fold that into the margin check
+            g.ncx = static_cast<int>(ncx);
+            g.ncy = static_cast<int>(ncy);
+            break;
+        }
+        cell *= 2.0;
+    }
+    if (g.ncx < 1) g.ncx = 1;
+    if (g.ncy < 1) g.ncy = 1;
+    g.ncells = static_cast<uint32_t>(g.ncx) * static_cast<uint32_t>(g.ncy);
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < g.ncells) bits++;
+    h->key_bits = bits;
+    h->grid = g;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count ? count * sizeof(T) : sizeof(T));
+}
+
+void free_all(msim_handle* h) {
+    cudaSetDevice(h->device);
+    cudaFree(h->pos[0]); cudaFree(h->pos[1]); cudaFree(h->target); cudaFree(h->road); cudaFree(h->rng);
+    cudaFree(h->color0); cudaFree(h->dir0); cudaFree(h->arrived); cudaFree(h->roads); cudaFree(h->conn);
+    cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
+    cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
+    cudaFree(h->scratch); cudaFree(h->stage);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+int ensure_cells(msim_handle* h) {
+    if (h->grid.ncells <= h->cell_capacity) return MSIM_OK;
+    cudaFree(h->cell_range);
+    h->cell_range = nullptr;
+    h->cell_capacity = 0;
+    MSIM_CUDA(h, dev_alloc(&h->cell_range, h->grid.ncells));
+    h->cell_capacity = h->grid.ncells;
+    return MSIM_OK;
+}
+
+int alloc_collision_buffers(msim_handle* h) {
+    if (h->keys) return MSIM_OK;
+    MSIM_CUDA(h, dev_alloc(&h->keys, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->sort_a, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->sort_b, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->sorted_pos, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->flag_sorted, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->flag_entity, h->cap));
+    MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
+    const size_t ws_bytes = sort_workspace_bytes(h->cap);
+    MSIM_CUDA(h, cudaMalloc(&h->sort_mem, ws_bytes));
+    sort_workspace_bind(h->ws, h->sort_mem, h->cap);
+    h->ws.error_flag = &h->counters->error_flag;
+    return ensure_cells(h);
+}
+
+int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
+    if (count > h->cap) return fail(h, MSIM_ERR_CAPACITY, "msim_upload_entities: count exceeds entity_capacity");
+    if (count && !src) return fail(h, MSIM_ERR_INVALID, "msim_upload_entities: null source");
+    MSIM_CUDA(h, cudaMemsetAsync(h->scratch, 0, 2 * sizeof(unsigned int), h->stream));
+    for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
+        const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
+        MSIM_CUDA(h, cudaMemcpyAsync(h->stage, src + off, static_cast<size_t>(chunk) * sizeof(msim_entity), cudaMemcpyHostToDevice, h->stream));
+        h->launches += launch_unpack(h->stream, static_cast<uint32_t>(off), chunk, h->stage, h->pos[0], h->target, h->road, h->rng, h->color0,
+                                     h->dir0, nullptr, h->scratch);
+    }
+    h->launches += launch_max_road(h->stream, static_cast<uint32_t>(count), h->road, h->scratch + 1);
+    unsigned int host_scratch[2] = {0, 0};
+    MSIM_CUDA(h, cudaMemcpyAsync(host_scratch, h->scratch, sizeof(host_scratch), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    MSIM_CUDA(h, cudaGetLastError());
+    h->n = static_cast<uint32_t>(count);
+    h->cur = 0;
+    h->has_moved = false;
+    h->keys_valid = false;
+    h->collided = false;
+    h->flags_scattered = false;
+    if (h->flag_entity) MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
+    if (count && host_scratch[1] >= h->road_count) {
+        h->n = 0;
+        return fail(h, MSIM_ERR_INVALID, "entity road_index out of range (max " + std::to_string(host_scratch[1]) + ", roads " + std::to_string(h->road_count) + ")");
+    }
+    if (host_scratch[0] != 0 && host_scratch[0] != count) {
+        h->n = 0;
+        return fail(h, MSIM_ERR_UNSUPPORTED, "mixed initialized flags: the reference uploads every entity with initialized = 0 (Simulator.cpp:121-127); all-0 or all-1 is supported");
+    }
+    h->uninitialised = host_scratch[0] != 0;
+    return MSIM_OK;
+}
+
+int check_device_errors(msim_handle* h) {
+    Counters c{};
+    MSIM_CUDA(h, cudaMemcpyAsync(&c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    MSIM_CUDA(h, cudaGetLastError());
+    h->last_pairs = c.pairs_last;
+    h->total_pairs = c.pairs_total;
+    h->last_flagged = c.flagged_last;
+    if (c.error_flag) return fail(h, MSIM_ERR_INTERNAL, "radix sort look-back watchdog tripped");
+    return MSIM_OK;
+}
+
+// first dispatch after an upload of uninitialised entities: the shader's init branch only
+// (random_move.comp:863-867) — every entity is registered with the neighbour structure, nothing moves.
+bool consume_init_dispatch(msim_handle* h) {
+    if (!h->uninitialised) return false;
+    h->uninitialised = false;
+    h->initialised_total += h->n;
+    return true;
+}
+
+int enqueue_move(msim_handle* h) {
+    if (consume_init_dispatch(h)) return MSIM_OK;
+    const bool emit = !(h->flags & MSIM_FLAG_NO_COLLISIONS);
+    if (emit) {
+        const int rc = alloc_collision_buffers(h);
+        if (rc != MSIM_OK) return rc;
+    }
+    h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->road, h->rng, h->arrived,
+                               h->roads, h->conn, h->conn_count, emit ? h->keys : nullptr, h->grid, nullptr, h->counters);
+    h->cur ^= 1;
+    h->has_moved = true;
+    h->keys_valid = emit;
+    h->move_passes++;
+    return MSIM_OK;
+}
+
+int enqueue_collide(msim_handle* h) {
+    if (h->flags & MSIM_FLAG_NO_COLLISIONS) return fail(h, MSIM_ERR_INVALID, "collision dispatch on a handle created with MSIM_FLAG_NO_COLLISIONS");
+    if (consume_init_dispatch(h)) return MSIM_OK;
+    int rc = alloc_collision_buffers(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->keys_valid) {
+        h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid);
+        h->keys_valid = true;
+    }
+    h->launches += launch_sort(h->stream, h->n, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted);
+    h->launches += launch_build_cells(h->stream, h->n, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid);
+    h->launches += launch_query(h->stream, h->n, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid,
+                                !(h->flags & MSIM_FLAG_NO_PAIR_COUNT), h->counters);
+    h->collided = true;
+    h->flags_scattered = false;
+    h->collide_passes++;
+    return MSIM_OK;
+}
+
+int bind(msim_handle* h) {
+    if (!h) return MSIM_ERR_INVALID;
+    MSIM_CUDA(h, cudaSetDevice(h->device));
+    return MSIM_OK;
+}
+
+int materialise_flags(msim_handle* h) {
+    if (h->collided && !h->flags_scattered) {
+        h->launches += launch_scatter_flags(h->stream, h->n, h->sorted, h->flag_sorted, h->flag_entity);
+        h->flags_scattered = true;
+    }
+    return MSIM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* msim_status_string(int status) {
+    switch (status) {
+        case MSIM_OK: return "ok";
+        case MSIM_ERR_INVALID: return "invalid argument";
+        case MSIM_ERR_CUDA: return "CUDA error";
+        case MSIM_ERR_OOM: return "out of memory";
+        case MSIM_ERR_UNSUPPORTED: return "unsupported";
+        case MSIM_ERR_IO: return "I/O error";
+        case MSIM_ERR_PARSE: return "parse error";
+        case MSIM_ERR_CAPACITY: return "capacity exceeded";
+        case MSIM_ERR_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+
+const char* msim_last_error(const msim_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int msim_create(const msim_config* cfg, msim_handle** out) {
+    if (!out) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: out is null");
+    *out = nullptr;
+    if (!cfg) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: cfg is null");
+    if (cfg->abi_version != MSIM_ABI_VERSION) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: abi_version mismatch");
+    if (!cfg->roads || cfg->road_count == 0) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: the map has no roads");
+    if (cfg->road_count > 0xffffffffull) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: more than 2^32 roads");
+    if (cfg->connection_count && !cfg->connections) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: connections is null");
+    if (cfg->entity_count && !cfg->entities) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: entities is null");
+    const uint64_t capacity = cfg->entity_capacity ? cfg->entity_capacity : cfg->entity_count;
+    if (capacity < cfg->entity_count) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: entity_capacity < entity_count");
+    if (capacity > MAX_ENTITIES_PER_HANDLE) return fail(nullptr, MSIM_ERR_UNSUPPORTED, "msim_create: more than 2^30 entities per handle");
+    if (!(cfg->world_w >= 0.0f) || !(cfg->world_h >= 0.0f)) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: bad world size");
+    for (uint64_t i = 0; i < cfg->connection_count; i++) {
+        if (cfg->connections[i] >= cfg->road_count)
+            return fail(nullptr, MSIM_ERR_INVALID, "msim_create: connections[" + std::to_string(i) + "] = " + std::to_string(cfg->connections[i]) + " is not a road index");
+    }
+
+    int device_count = 0;
+    cudaError_t err = cudaGetDeviceCount(&device_count);
+    if (err != cudaSuccess || device_count == 0)
+        return fail(nullptr, MSIM_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(err) + " (libmsim_cuda has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= device_count) return fail(nullptr, MSIM_ERR_INVALID, "msim_create: device ordinal out of range");
+    cudaDeviceProp prop{};
+    err = cudaGetDeviceProperties(&prop, cfg->device);
+    if (err != cudaSuccess) return fail(nullptr, MSIM_ERR_CUDA, cudaGetErrorString(err));
+    if (prop.major != 10) return fail(nullptr, MSIM_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only");
+
+    msim_handle* h = new (std::nothrow) msim_handle();
+    if (!h) return fail(nullptr, MSIM_ERR_OOM, "out of host memory");
+    h->device = cfg->device;
+    h->sm_count = prop.multiProcessorCount;
+    h->flags = cfg->flags;
+    h->world_w = cfg->world_w;
+    h->world_h = cfg->world_h;
+    h->radius = cfg->collision_radius;
+    h->qt_depth = cfg->quadtree_max_depth ? cfg->quadtree_max_depth : 8;
+    h->qt_cap = cfg->quadtree_node_cap ? cfg->quadtree_node_cap : 10;
+    h->road_count = cfg->road_count;
+    h->conn_count = cfg->connection_count;
+    h->cap = static_cast<uint32_t>((capacity + 63ull) & ~63ull);
+    if (h->cap == 0) h->cap = 64;
+
+    auto body = [&]() -> int {
+        MSIM_CUDA(h, cudaSetDevice(h->device));
+        if (cfg->cuda_stream) {
+            h->stream = static_cast<cudaStream_t>(cfg->cuda_stream);
+        } else {
+            MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            h->own_stream = true;
+        }
+        MSIM_CUDA(h, dev_alloc(&h->pos[0], h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->pos[1], h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->target, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->road, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->rng, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->color0, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->dir0, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->arrived, h->cap / 32 + 2));
+        MSIM_CUDA(h, dev_alloc(&h->roads, h->road_count));
+        MSIM_CUDA(h, dev_alloc(&h->conn, h->conn_count));
+        MSIM_CUDA(h, dev_alloc(&h->counters, 1));
+        MSIM_CUDA(h, dev_alloc(&h->scratch, 4));
+        MSIM_CUDA(h, dev_alloc(&h->stage, std::min<uint64_t>(STAGE_ENTITIES, h->cap)));
+        MSIM_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(Counters), h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->pos[0], 0, sizeof(float2) * h->cap, h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->pos[1], 0, sizeof(float2) * h->cap, h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->target, 0, sizeof(float2) * h->cap, h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->arrived, 0, sizeof(uint32_t) * (h->cap / 32 + 2), h->stream));
+        MSIM_CUDA(h, cudaMemcpyAsync(h->roads, cfg->roads, sizeof(msim_road) * h->road_count, cudaMemcpyHostToDevice, h->stream));
+        if (h->conn_count)
+            MSIM_CUDA(h, cudaMemcpyAsync(h->conn, cfg->connections, sizeof(uint32_t) * h->conn_count, cudaMemcpyHostToDevice, h->stream));
+        configure_grid(h);
+        return upload(h, cfg->entities, cfg->entity_count);
+    };
+    const int rc = body();
+    if (rc != MSIM_OK) {
+        g_create_error = h->error;
+        free_all(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return MSIM_OK;
+}
+
+void msim_destroy(msim_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+}
+
+int msim_upload_entities(msim_handle* h, const msim_entity* src, uint64_t count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    return upload(h, src, count);
+}
+
+int msim_set_stream(msim_handle* h, void* cuda_stream) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) {
+        cudaStreamDestroy(h->stream);
+        h->own_stream = false;
+    }
+    if (cuda_stream) {
+        h->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return MSIM_OK;
+}
+
+int msim_enqueue_move(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    return enqueue_move(h);
+}
+
+int msim_enqueue_collide(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    return enqueue_collide(h);
+}
+
+int msim_enqueue_ticks(msim_handle* h, uint32_t sim_ticks, int with_collisions) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    for (uint32_t t = 0; t < sim_ticks; t++) {
+        rc = enqueue_move(h);
+        if (rc != MSIM_OK) return rc;
+        if (with_collisions) {
+            rc = enqueue_collide(h);
+            if (rc != MSIM_OK) return rc;
+        }
+    }
+    return MSIM_OK;
+}
+
+int msim_sync(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    return check_device_errors(h);
+}
+
+int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!pc) return fail(h, MSIM_ERR_INVALID, "msim_dispatch: push constants are null");
+    if (pc->world_size_x != h->world_w || pc->world_size_y != h->world_h || pc->collision_radius != h->radius) {
+        // push constants are per-dispatch state in the reference: follow them
+        MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->world_w = pc->world_size_x;
+        h->world_h = pc->world_size_y;
+        h->radius = pc->collision_radius;
+        configure_grid(h);
+        h->keys_valid = false;
+        if (h->keys) {
+            rc = ensure_cells(h);
+            if (rc != MSIM_OK) return rc;
+        }
+    }
+    rc = (pc->tick % 2u == 0u) ? enqueue_move(h) : enqueue_collide(h);
+    if (rc != MSIM_OK) return rc;
+    return check_device_errors(h);
+}
+
+int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
+    if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
+    materialise_flags(h);
+    PackArgs a{};
+    a.pos_cur = h->pos[h->cur];
+    a.pos_prev = h->pos[h->cur ^ 1];
+    a.target = h->target;
+    a.road = h->road;
+    a.rng = h->rng;
+    a.color0 = h->color0;
+    a.dir0 = h->dir0;
+    a.arrived = h->arrived;
+    a.flag_entity = h->collided ? h->flag_entity : nullptr;
+    a.init_mask = nullptr;
+    a.initialized_all = h->uninitialised ? 0u : 1u;
+    a.has_moved = h->has_moved ? 1u : 0u;
+    for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
+        const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
+        h->launches += launch_pack(h->stream, static_cast<uint32_t>(off), chunk, a, h->stage);
+        MSIM_CUDA(h, cudaMemcpyAsync(dst + off, h->stage, static_cast<size_t>(chunk) * sizeof(msim_entity), cudaMemcpyDeviceToHost, h->stream));
+    }
+    return check_device_errors(h);
+}
+
+int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: count exceeds the resident entity count");
+    if (count && !dst_xy) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: dst is null");
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst_xy, h->pos[h->cur], count * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+    return check_device_errors(h);
+}
+
+int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_collision_flags: count exceeds the resident entity count");
+    if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_collision_flags: dst is null");
+    if (!h->collided) {
+        std::memset(dst, 0, count);
+        return MSIM_OK;
+    }
+    materialise_flags(h);
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, h->flag_entity, count, cudaMemcpyDeviceToHost, h->stream));
+    rc = check_device_errors(h);
+    for (uint64_t i = 0; i < count; i++) dst[i] = dst[i] == 2 ? 1 : 0;
+    return rc;
+}
+
+int msim_read_quadtree_nodes(msim_handle* h, msim_quadtree_node* dst, uint64_t cap, uint64_t* count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!dst || cap == 0 || !count) return fail(h, MSIM_ERR_INVALID, "msim_read_quadtree_nodes: bad arguments");
+    // Root only for now (gpu_quad_tree::init_node_zero, GpuQuadTree.cpp:6-10): a single ENTITY leaf
+    // spanning the world.  The display tree built from the sorted cell keys is SURVEY §8f row 1.
+    std::memset(dst, 0, sizeof(msim_quadtree_node));
+    dst[0].width = h->world_w;
+    dst[0].height = h->world_h;
+    dst[0].content_type = 2;
+    dst[0].entity_count = h->uninitialised ? 0 : h->n;
+    *count = 1;
+    return MSIM_OK;
+}
+
+int msim_read_debug(msim_handle* h, uint32_t dst[10]) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!dst) return fail(h, MSIM_ERR_INVALID, "msim_read_debug: dst is null");
+    rc = check_device_errors(h);
+    std::memset(dst, 0, 10 * sizeof(uint32_t));
+    dst[0] = static_cast<uint32_t>(h->initialised_total);
+    dst[1] = static_cast<uint32_t>(h->total_pairs);
+    return rc;
+}
+
+int msim_get_stats(msim_handle* h, msim_stats* out) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!out) return fail(h, MSIM_ERR_INVALID, "msim_get_stats: out is null");
+    rc = check_device_errors(h);
+    std::memset(out, 0, sizeof(*out));
+    out->entity_count = h->n;
+    out->move_passes = h->move_passes;
+    out->collide_passes = h->collide_passes;
+    out->last_pair_count = h->last_pairs;
+    out->total_pair_count = h->total_pairs;
+    out->last_flagged_count = h->last_flagged;
+    out->kernel_launches = h->launches;
+    out->grid_cells_x = static_cast<uint32_t>(h->grid.ncx);
+    out->grid_cells_y = static_cast<uint32_t>(h->grid.ncy);
+    out->key_bits = static_cast<uint32_t>(h->key_bits);
+    out->sort_passes = static_cast<uint32_t>((h->key_bits + RADIX_BITS - 1) / RADIX_BITS);
+    out->cell_size = h->grid.inv_cell > 0.0f ? 1.0f / h->grid.inv_cell : 0.0f;
+    return rc;
+}
+
+int msim_get_device_view(msim_handle* h, msim_device_view* out) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!out) return fail(h, MSIM_ERR_INVALID, "msim_get_device_view: out is null");
+    out->pos = h->pos[h->cur];
+    out->target = h->target;
+    out->road = h->road;
+    out->rng = h->rng;
+    out->count = h->n;
+    return MSIM_OK;
+}
+
+}  // extern "C"

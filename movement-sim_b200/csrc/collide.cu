@@ -1,0 +1,140 @@
+// collide.cu — the odd-tick dispatch: who has a neighbour within the collision radius?
+//
+// Observable contract taken from the reference shader (/root/reference/src/sim/shader/random_move.comp):
+//   :875-877  every entity turns green (0,1,0,1), then
+//   :545-547  both members of every in-range pair turn blue (0,0,1,1);
+//   :551-562  in_range(a,b,r): |dx|<=r, |dy|<=r and sqrt(dx*dx+dy*dy) < r  (strict).
+// The reference finds the pairs by walking a lock-protected quadtree (:564-719).  Here the pairs are
+// found on a uniform cell grid (edge slightly above r) built from the radix-sorted cell keys:
+//   build_cells : gathers positions into cell order and records, per cell, {first, ~end} of its run
+//   query       : one thread per sorted entity scans the 3 cell rows around it; the three cells of a
+//                 row are adjacent keys, hence ONE contiguous run of the sorted position array
+// The colour is kept as a 1-byte flag per sorted slot and expanded to RGBA at readback (pack.cu).
+// The predicate is evaluated without sqrt: hit_threshold is the exact binary32 bound T with
+// (d2 < T) <=> (sqrtf(d2) < r), computed on the host (api.cu), so flags match the oracle bit for bit.
+#include "msim_internal.h"
+
+namespace msim {
+namespace {
+
+__global__ void __launch_bounds__(256)
+build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const float2* __restrict__ pos,
+                   float2* __restrict__ sorted_pos, uint2* __restrict__ cell_range) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool in = j < n;
+    unsigned long long kv = in ? __ldcs(sorted + j) : ~0ull;
+    const uint32_t key = static_cast<uint32_t>(kv >> 32);
+    uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+    if (!in) return;
+    if (lane == 0) prev_key = (j == 0) ? 0xffffffffu : static_cast<uint32_t>(sorted[j - 1] >> 32);
+    const uint32_t idx = static_cast<uint32_t>(kv);
+    sorted_pos[j] = pos[idx];  // 8-byte gather, coalesced store
+    if (j == 0 || key != prev_key) {
+        cell_range[key].x = j;                       // first slot of this cell
+        if (j != 0) cell_range[prev_key].y = ~j;     // one past the last slot of the previous cell
+    }
+    if (j == n - 1) cell_range[key].y = ~n;
+}
+
+// squared distance with individually rounded operations, as the oracle computes it
+__device__ __forceinline__ float dist2(float2 a, float2 b) {
+    const float dx = __fsub_rn(a.x, b.x);
+    const float dy = __fsub_rn(a.y, b.y);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+template <bool COUNT_PAIRS>
+__global__ void __launch_bounds__(256)
+query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __restrict__ cell_range,
+             uint8_t* __restrict__ flag_sorted, GridParams grid, Counters* __restrict__ counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t pairs = 0;
+    bool hit = false;
+    if (j < n) {
+        const float2 p = sorted_pos[j];
+        int cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
+        int cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
+        cx = min(max(cx, 0), grid.ncx - 1);
+        cy = min(max(cy, 0), grid.ncy - 1);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, grid.ncx - 1);
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, grid.ncy - 1);
+        for (int yy = y0; yy <= y1 && (COUNT_PAIRS || !hit); yy++) {
+            const uint2* row = cell_range + static_cast<size_t>(yy) * grid.ncx;
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            for (int xx = x0; xx <= x1; xx++) {
+                const uint2 r = __ldg(row + xx);  // empty cell = {0xffffffff, ~0xffffffff = 0}: neutral for min/max
+                lo = min(lo, r.x);
+                hi = max(hi, ~r.y);
+            }
+            for (uint32_t k = lo; k < hi; k++) {
+                if (k == j) continue;
+                const float2 q = __ldg(sorted_pos + k);
+                if (dist2(q, p) < grid.hit_threshold) {
+                    hit = true;
+                    if (COUNT_PAIRS) pairs += (k < j) ? 1u : 0u;  // each unordered pair once
+                    else break;
+                }
+            }
+        }
+        flag_sorted[j] = hit ? 1 : 0;
+    }
+    // per-warp reduction, one atomic per warp per counter
+    const uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit));
+    if (COUNT_PAIRS) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) pairs += __shfl_down_sync(0xffffffffu, pairs, d);
+    }
+    if (lane == 0) {
+        if (hits) atomicAdd(&counters->flagged_last, static_cast<unsigned long long>(hits));
+        if (COUNT_PAIRS && pairs) atomicAdd(&counters->pairs_last, static_cast<unsigned long long>(pairs));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_flags_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const uint8_t* __restrict__ flag_sorted,
+                     uint8_t* __restrict__ flag_entity) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t idx = static_cast<uint32_t>(__ldcs(sorted + j));
+    flag_entity[idx] = flag_sorted[j] + 1;  // 1 = green, 2 = blue (0 = "no collision pass yet")
+}
+
+__global__ void begin_pass_kernel(Counters* c) {
+    c->pairs_last = 0;
+    c->flagged_last = 0;
+}
+__global__ void end_pass_kernel(Counters* c) { c->pairs_total += c->pairs_last; }
+
+}  // namespace
+
+int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint2* cell_range,
+                       const GridParams& grid) {
+    cudaMemsetAsync(cell_range, 0xff, static_cast<size_t>(grid.ncells) * sizeof(uint2), s);
+    if (n == 0) return 0;
+    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, cell_range);
+    return 1;
+}
+
+int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted, const GridParams& grid,
+                 bool count_pairs, Counters* counters) {
+    begin_pass_kernel<<<1, 1, 0, s>>>(counters);
+    int launches = 1;
+    if (n != 0) {
+        const uint32_t blocks = (n + 255u) / 256u;
+        if (count_pairs) query_kernel<true><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
+        else query_kernel<false><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
+        launches++;
+    }
+    end_pass_kernel<<<1, 1, 0, s>>>(counters);
+    return launches + 1;
+}
+
+int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity) {
+    if (n == 0) return 0;
+    scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), flag_sorted, flag_entity);
+    return 1;
+}
+
+}  // namespace msim

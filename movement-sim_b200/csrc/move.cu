@@ -1,0 +1,196 @@
+// move.cu — the even-tick dispatch: advance every entity along the road graph.
+//
+// Semantics follow the reference shader /root/reference/src/sim/shader/random_move.comp:
+//   :725-746  xorshift128 / next_float / next(state,min,max)
+//   :778-828  new_target       :830-839  update_direction       :841-852  move
+//   :869-873  main(), even tick
+// with IEEE binary32 round-to-nearest arithmetic and NO fused multiply-add (every product and sum is
+// an explicit __fmul_rn/__fadd_rn; sqrt and divide are the correctly rounded __fsqrt_rn/__fdiv_rn),
+// which is what the CPU oracle (oracle/msim_oracle.c) computes — positions come out bit-identical.
+//
+// B200 mapping: HBM-bound streaming kernel.  Per entity-update it must read pos (8 B) and target
+// (8 B) and write pos (8 B) = 24 B; road/rng/target are written only for the ~1/25 entities that
+// reach their waypoint.  Two entities share one 128-bit load/store (float4 = 2 x float2); each
+// thread keeps MOVE_ITEMS such pairs in flight; streaming (.cs) hints keep the one-touch entity
+// state from displacing the road/connection tables in L2, which are read through the read-only
+// path (__ldg).  `direction` is never stored: it is a pure function of (previous pos, target, arrival bit)
+// and is rebuilt at readback (pack.cu), so the per-tick traffic stays at the 24 B minimum.
+#include "msim_internal.h"
+
+namespace msim {
+namespace {
+
+constexpr int MOVE_THREADS = 256;
+constexpr int MOVE_ITEMS = 2;  // float4 pairs per thread -> 4 entities per thread per iteration
+constexpr float SPEED = 1.4f;  // random_move.comp:750
+
+__device__ __forceinline__ float as_f(uint32_t u) { return __uint_as_float(u); }
+
+// random_move.comp:725-736
+__device__ __forceinline__ uint32_t xorshift128(uint4& s) {
+    uint32_t t = s.w;
+    const uint32_t x = s.x;
+    s.w = s.z;
+    s.z = s.y;
+    s.y = x;
+    t ^= t << 11;
+    t ^= t >> 8;
+    s.x = t ^ x ^ (x >> 19);
+    return s.x;
+}
+
+// random_move.comp:738-746: uint(ceil(float(min) + (next_float(state) * float(max - min + 1)))) - 1
+__device__ __forceinline__ uint32_t next_range(uint4& s, uint32_t lo, uint32_t hi) {
+    const float f = __fmul_rn(__uint2float_rn(xorshift128(s)), 2.3283064365386962890625e-10f);  // * 2^-32, exact
+    const float prod = __fmul_rn(f, __uint2float_rn(hi - lo + 1u));
+    const float sum = __fadd_rn(__uint2float_rn(lo), prod);
+    return __float2uint_ru(sum) - 1u;  // ceil, then the conversion is exact
+}
+
+// connections[] with the canonical out-of-bounds rule: past-the-end reads yield road 0
+__device__ __forceinline__ uint32_t read_connection(const uint32_t* __restrict__ conn, uint64_t count, uint64_t idx) {
+    return idx < count ? __ldg(conn + idx) : 0u;
+}
+
+// random_move.comp:778-828.  `tgt` is the waypoint just reached; returns the new waypoint.
+__device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* __restrict__ road, uint4* __restrict__ rng,
+                                             const uint4* __restrict__ roads, const uint32_t* __restrict__ conn,
+                                             uint64_t conn_count) {
+    const uint32_t cur = road[e];
+    const uint4 a = __ldg(roads + 2ull * cur);      // start: pos.x pos.y connectedIndex connectedCount
+    const uint4 b = __ldg(roads + 2ull * cur + 1);  // end
+    const bool at_start = (tgt.x == as_f(a.x)) && (tgt.y == as_f(a.y));
+    const uint4 here = at_start ? a : b;
+    const uint4 far = at_start ? b : a;
+    if (here.w <= 1u) {  // dead end: turn around, road unchanged (:786-789, :794-797)
+        return make_float2(as_f(far.x), as_f(far.y));
+    }
+    uint32_t next_road;
+    if (here.w == 2u) {  // :802-804
+        next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + 1ull);
+    } else {  // :805-810
+        uint4 s = rng[e];
+        const uint32_t off = next_range(s, 1u, here.w);
+        rng[e] = s;
+        next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + off);
+    }
+    const uint4 ns = __ldg(roads + 2ull * next_road);
+    const uint4 ne = __ldg(roads + 2ull * next_road + 1);  // same 32-byte sector as ns
+    road[e] = next_road;                                  // :820
+    const bool from_start = (as_f(ns.x) == tgt.x) && (as_f(ns.y) == tgt.y);  // :814-819
+    return from_start ? make_float2(as_f(ne.x), as_f(ne.y)) : make_float2(as_f(ns.x), as_f(ns.y));
+}
+
+// update_direction(index, pos) + move(index) (:830-852).  Returns the new position; sets `arrived`
+// and rewrites `t` when the waypoint was reached.
+__device__ __forceinline__ float2 step_entity(uint32_t e, float2 p, float2& t, bool& arrived, uint32_t* __restrict__ road,
+                                              uint4* __restrict__ rng, const uint4* __restrict__ roads,
+                                              const uint32_t* __restrict__ conn, uint64_t conn_count) {
+    const float dx = __fsub_rn(t.x, p.x);
+    const float dy = __fsub_rn(t.y, p.y);
+    // length(target - pos) == distance(pos, target) bit for bit: the squares are sign-blind
+    const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    if (len > SPEED) {
+        const float dirx = __fmul_rn(__fdiv_rn(dx, len), SPEED);
+        const float diry = __fmul_rn(__fdiv_rn(dy, len), SPEED);
+        arrived = false;
+        return make_float2(__fadd_rn(p.x, dirx), __fadd_rn(p.y, diry));
+    }
+    arrived = true;
+    const float2 reached = t;
+    t = new_target(e, reached, road, rng, roads, conn, conn_count);
+    return reached;
+}
+
+template <bool EMIT_KEYS>
+__global__ void __launch_bounds__(MOVE_THREADS)
+move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, float4* __restrict__ target,
+            uint32_t* __restrict__ road, uint4* __restrict__ rng, uint32_t* __restrict__ arrived_mask,
+            const uint4* __restrict__ roads, const uint32_t* __restrict__ conn, uint64_t conn_count,
+            uint2* __restrict__ keys, GridParams grid) {
+    const uint32_t pairs = (n + 1u) >> 1;
+    const uint32_t pairs_pad = (pairs + 31u) & ~31u;  // arrays are padded, whole warps stay converged
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t PER_BLOCK = MOVE_THREADS * MOVE_ITEMS;
+
+    for (uint32_t base = blockIdx.x * PER_BLOCK; base < pairs_pad; base += gridDim.x * PER_BLOCK) {
+        float4 P[MOVE_ITEMS], T[MOVE_ITEMS];
+        bool live[MOVE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < MOVE_ITEMS; k++) {
+            const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
+            live[k] = pi < pairs_pad;
+            if (live[k]) {
+                P[k] = __ldcs(pos_in + pi);
+                T[k] = __ldcs(target + pi);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MOVE_ITEMS; k++) {
+            if (!live[k]) continue;  // warp-uniform
+            const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
+            const uint32_t e0 = pi * 2u, e1 = e0 + 1u;
+            float2 t0 = make_float2(T[k].x, T[k].y), t1 = make_float2(T[k].z, T[k].w);
+            float2 q0 = make_float2(P[k].x, P[k].y), q1 = make_float2(P[k].z, P[k].w);
+            bool arr0 = false, arr1 = false;
+            if (e0 < n) q0 = step_entity(e0, q0, t0, arr0, road, rng, roads, conn, conn_count);
+            if (e1 < n) q1 = step_entity(e1, q1, t1, arr1, road, rng, roads, conn, conn_count);
+            __stcs(pos_out + pi, make_float4(q0.x, q0.y, q1.x, q1.y));
+            if (arr0 || arr1) target[pi] = make_float4(t0.x, t0.y, t1.x, t1.y);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, arr0);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, arr1);
+            if (lane == 0) {
+                const uint32_t w = (pi >> 5) * 2u;
+                *reinterpret_cast<uint2*>(arrived_mask + w) = make_uint2(m0, m1);
+            }
+            if (EMIT_KEYS) {
+                keys[pi] = make_uint2(cell_key_of(q0, grid), cell_key_of(q1, grid));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ keys, GridParams grid) {
+    const uint32_t pairs_pad = (((n + 1u) >> 1) + 31u) & ~31u;
+    for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < pairs_pad; pi += gridDim.x * blockDim.x) {
+        const float4 p = __ldcs(pos + pi);
+        keys[pi] = make_uint2(cell_key_of(make_float2(p.x, p.y), grid), cell_key_of(make_float2(p.z, p.w), grid));
+    }
+}
+
+}  // namespace
+
+int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, float2* target, uint32_t* road,
+                uint4* rng, uint32_t* arrived, const msim_road* roads, const uint32_t* connections, uint64_t connection_count,
+                uint32_t* keys, const GridParams& grid, uint8_t* /*init_mask*/, Counters* /*counters*/) {
+    if (n == 0) return 0;
+    const uint32_t pairs = (n + 1u) >> 1;
+    const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
+    uint32_t blocks = (pairs + per_block - 1) / per_block;
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;  // 8 x 256 threads = 2048 threads per SM
+    if (blocks > resident) blocks = resident;  // grid-stride: a whole number of CTAs per SM
+    const float4* pin = reinterpret_cast<const float4*>(pos_in);
+    float4* pout = reinterpret_cast<float4*>(pos_out);
+    float4* tgt = reinterpret_cast<float4*>(target);
+    const uint4* rd = reinterpret_cast<const uint4*>(roads);
+    if (keys) {
+        move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, road, rng, arrived, rd, connections, connection_count,
+                                                          reinterpret_cast<uint2*>(keys), grid);
+    } else {
+        move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, road, rng, arrived, rd, connections, connection_count,
+                                                           nullptr, grid);
+    }
+    return 1;
+}
+
+int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid) {
+    if (n == 0) return 0;
+    const uint32_t pairs = (n + 1u) >> 1;
+    uint32_t blocks = (pairs + 255u) / 256u;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    keygen_kernel<<<blocks, 256, 0, s>>>(n, reinterpret_cast<const float4*>(pos), reinterpret_cast<uint2*>(keys), grid);
+    return 1;
+}
+
+}  // namespace msim

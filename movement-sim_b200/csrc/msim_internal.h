@@ -1,0 +1,124 @@
+// msim_internal.h — internal declarations shared by the CUDA translation units of libmsim_cuda.so.
+//
+// HBM layout (structure of arrays, one element per entity, capacity `cap`):
+//   pos[2]   float2   ping-pong position buffers (move reads pos[cur], writes pos[cur^1])
+//   target   float2   current waypoint
+//   road     u32      current road index              (touched only on arrival)
+//   rng      uint4    xorshift128 state (x,y,z,w)     (touched only on arrival at a junction of >2 roads)
+//   color0   float4   colour as uploaded              (cold: readback only)
+//   dir0     float2   direction as uploaded           (cold: readback before the first move pass)
+//   arrived  u32 bitmask, written by the move pass; lets readback reconstruct `direction` exactly
+//            without storing 8 B per entity per tick (see pack.cu)
+// Neighbour structure, rebuilt every collision pass:
+//   keys     u32      cell key (row-major) emitted by the move pass or by keygen
+//   sort_a/b u64      (key << 32 | entity index) pairs, ping-pong for the LSD radix passes
+//   sorted_pos float2 positions in cell order
+//   cell_range uint2  per cell {first, ~end} into the sorted order (0xFF-filled = empty)
+//   flag_sorted u8    collision flag per sorted slot (scattered back lazily at readback)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msim.h"
+
+namespace msim {
+
+// ---- neighbour grid geometry -----------------------------------------------------------------
+struct GridParams {
+    float inv_cell;      // 1 / cell edge
+    float hit_threshold; // d2 < hit_threshold  <=>  sqrtf(d2) < radius  (exact, see api.cu)
+    float radius;
+    int ncx, ncy;        // cells per axis
+    uint32_t ncells;
+};
+
+// ---- radix sort constants --------------------------------------------------------------------
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
+constexpr int MAX_SORT_PASSES = 4;
+
+struct SortWorkspace {
+    uint32_t* hist;          // [MAX_SORT_PASSES][RADIX] global digit histograms
+    uint32_t* tile_counter;  // [MAX_SORT_PASSES] dynamic tile ids
+    uint32_t* tile_state;    // [MAX_SORT_PASSES][tiles][RADIX] decoupled look-back words
+    uint32_t* error_flag;    // set by the look-back watchdog
+    void* zero_base;         // start of the region that must be zeroed before every sort
+    size_t zero_bytes;
+    uint32_t tiles_cap;
+};
+
+// ---- device counters -------------------------------------------------------------------------
+struct Counters {
+    unsigned long long pairs_last;
+    unsigned long long pairs_total;
+    unsigned long long flagged_last;
+    unsigned long long initialised_total;
+    unsigned int error_flag;
+    unsigned int pad;
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) ------------------------
+// move.cu
+int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, float2* target,
+                uint32_t* road, uint4* rng, uint32_t* arrived, const msim_road* roads, const uint32_t* connections,
+                uint64_t connection_count, uint32_t* keys /* nullable */, const GridParams& grid,
+                uint8_t* init_mask /* nullable */, Counters* counters);
+int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid);
+
+// sort.cu
+size_t sort_workspace_bytes(uint32_t capacity);
+void sort_workspace_bind(SortWorkspace& ws, void* base, uint32_t capacity);
+// sorts (key, index) by key; result lands in *result (either buf_a or buf_b)
+int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits,
+                const SortWorkspace& ws, uint64_t** result);
+
+// collide.cu
+int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos,
+                       uint2* cell_range, const GridParams& grid);
+int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted,
+                 const GridParams& grid, bool count_pairs, Counters* counters);
+int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity);
+
+// pack.cu
+struct PackArgs {
+    const float2* pos_cur;
+    const float2* pos_prev;
+    const float2* target;
+    const uint32_t* road;
+    const uint4* rng;
+    const float4* color0;
+    const float2* dir0;
+    const uint32_t* arrived;
+    const uint8_t* flag_entity;  // nullable: no collision pass since upload -> colour as uploaded
+    const uint8_t* init_mask;    // nullable
+    uint32_t initialized_all;    // value of `initialized` when init_mask == nullptr
+    uint32_t has_moved;          // 0: direction = dir0
+};
+int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst);
+int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target,
+                  uint32_t* road, uint4* rng, float4* color0, float2* dir0, uint8_t* init_mask, unsigned int* uninit_count);
+int launch_max_road(cudaStream_t s, uint32_t n, const uint32_t* road, unsigned int* out_max);
+
+// ---- device helpers shared by several translation units ---------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t cell_key_of(float2 p, const GridParams& g) {
+    // single multiply per axis (no FMA involved), floor, clamp: monotone in each coordinate
+    int cx = __float2int_rd(__fmul_rn(p.x, g.inv_cell));
+    int cy = __float2int_rd(__fmul_rn(p.y, g.inv_cell));
+    cx = min(max(cx, 0), g.ncx - 1);
+    cy = min(max(cy, 0), g.ncy - 1);
+    return static_cast<uint32_t>(cy) * static_cast<uint32_t>(g.ncx) + static_cast<uint32_t>(cx);
+}
+
+// bit position of entity e inside the `arrived` mask written by the move kernel: entities are
+// processed as float4 pairs (2*lane, 2*lane+1) of a 64-entity warp chunk; each parity has its own word.
+__device__ __forceinline__ uint32_t arrived_word(uint32_t e) { return (e >> 6) * 2u + (e & 1u); }
+__device__ __forceinline__ uint32_t arrived_bit(uint32_t e) { return (e & 63u) >> 1; }
+#endif
+
+}  // namespace msim

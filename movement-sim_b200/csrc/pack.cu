@@ -1,0 +1,107 @@
+// pack.cu — the boundary transposes between the reference's 64-byte AoS entity
+// (/root/reference/src/sim/Entity.hpp:33-46, shader EntityDescriptor random_move.comp:5-13) and the
+// resident structure-of-arrays state.
+//
+//   unpack : OpTensorSyncDevice side (Simulator.cpp:191-192) — AoS chunk in device staging -> SoA
+//   pack   : OpTensorSyncLocal side  (Simulator.cpp:250,262) — SoA -> AoS chunk, re-creating the two
+//            fields the hot path never stores:
+//              direction  = update_direction() of the last move pass (random_move.comp:830-839):
+//                           from the previous position for walkers, from the reached waypoint
+//                           towards the new one for entities that arrived (:848-850);
+//              colour     = as uploaded until the first collision pass, then green / blue
+//                           (:876, :546-547) from the 1-byte collision flag.
+#include "msim_internal.h"
+
+namespace msim {
+namespace {
+
+constexpr float SPEED = 1.4f;
+
+__device__ __forceinline__ float2 direction_from(float2 from, float2 target) {
+    const float dx = __fsub_rn(target.x, from.x);
+    const float dy = __fsub_rn(target.y, from.y);
+    const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    if (len == 0.0f) return make_float2(0.0f, 0.0f);
+    return make_float2(__fmul_rn(__fdiv_rn(dx, len), SPEED), __fmul_rn(__fdiv_rn(dy, len), SPEED));
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(uint32_t first, uint32_t count, PackArgs a, float4* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t e = first + i;
+    const float2 p = a.pos_cur[e];
+    const float2 t = a.target[e];
+    float2 dir;
+    if (a.has_moved) {
+        const bool arrived = (a.arrived[arrived_word(e)] >> arrived_bit(e)) & 1u;
+        dir = direction_from(arrived ? p : a.pos_prev[e], t);
+    } else {
+        dir = a.dir0[e];
+    }
+    float4 color;
+    const uint8_t flag = a.flag_entity ? a.flag_entity[e] : 0;
+    if (flag == 0) color = a.color0[e];
+    else color = (flag == 2) ? make_float4(0.f, 0.f, 1.f, 1.f) : make_float4(0.f, 1.f, 0.f, 1.f);
+    const uint4 s = a.rng[e];
+    float4* out = dst + static_cast<size_t>(i) * 4;
+    out[0] = color;
+    out[1] = make_float4(__uint_as_float(s.x), __uint_as_float(s.y), __uint_as_float(s.z), __uint_as_float(s.w));
+    out[2] = make_float4(p.x, p.y, t.x, t.y);
+    out[3] = make_float4(dir.x, dir.y, __uint_as_float(a.road[e]), __uint_as_float(a.initialized_all));
+}
+
+__global__ void __launch_bounds__(256)
+unpack_kernel(uint32_t first, uint32_t count, const float4* __restrict__ src, float2* __restrict__ pos, float2* __restrict__ target,
+              uint32_t* __restrict__ road, uint4* __restrict__ rng, float4* __restrict__ color0, float2* __restrict__ dir0,
+              unsigned int* __restrict__ uninit_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool uninit = false;
+    if (i < count) {
+        const uint32_t e = first + i;
+        const float4* in = src + static_cast<size_t>(i) * 4;
+        const float4 c = in[0], s = in[1], pt = in[2], dr = in[3];
+        color0[e] = c;
+        rng[e] = make_uint4(__float_as_uint(s.x), __float_as_uint(s.y), __float_as_uint(s.z), __float_as_uint(s.w));
+        pos[e] = make_float2(pt.x, pt.y);
+        target[e] = make_float2(pt.z, pt.w);
+        dir0[e] = make_float2(dr.x, dr.y);
+        road[e] = __float_as_uint(dr.z);
+        uninit = __float_as_uint(dr.w) == 0u;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, uninit);
+    if ((threadIdx.x & 31u) == 0 && m) atomicAdd(uninit_count, static_cast<unsigned int>(__popc(m)));
+}
+
+__global__ void __launch_bounds__(256) max_road_kernel(uint32_t n, const uint32_t* __restrict__ road, unsigned int* __restrict__ out_max) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, road[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31u) == 0) atomicMax(out_max, m);
+}
+
+}  // namespace
+
+int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst) {
+    if (count == 0) return 0;
+    pack_kernel<<<(count + 255u) / 256u, 256, 0, s>>>(first, count, a, reinterpret_cast<float4*>(dst));
+    return 1;
+}
+
+int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target, uint32_t* road,
+                  uint4* rng, float4* color0, float2* dir0, uint8_t* /*init_mask*/, unsigned int* uninit_count) {
+    if (count == 0) return 0;
+    unpack_kernel<<<(count + 255u) / 256u, 256, 0, s>>>(first, count, reinterpret_cast<const float4*>(src), pos, target, road, rng, color0, dir0,
+                                                        uninit_count);
+    return 1;
+}
+
+int launch_max_road(cudaStream_t s, uint32_t n, const uint32_t* road, unsigned int* out_max) {
+    if (n == 0) return 0;
+    uint32_t blocks = (n + 255u) / 256u;
+    if (blocks > 1184u) blocks = 1184u;
+    max_road_kernel<<<blocks, 256, 0, s>>>(n, road, out_max);
+    return 1;
+}
+
+}  // namespace msim

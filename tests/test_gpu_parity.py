@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bar: bit-exact on every field (road index, RNG state, target, position, direction, colour
+flag, pair count).  The stated tolerance for float positions is therefore 0 ULP.
+
+Configs follow BASELINE.json: config 1 (test_map, 10 k entities, seed 42, 1000 move passes, collisions
+off) in full; the Munich-style city at sizes the oracle finishes in seconds; full sizes through
+size-independent properties in test_gpu_scale.py."""
+import numpy as np
+import pytest
+
+from conftest import assert_entities_equal, oracle_dispatch, oracle_map, to_oracle_entities
+
+pytestmark = pytest.mark.gpu
+
+
+def run_oracle(O, ents, omap, radius, ticks):
+    """ticks = list of dispatch tick numbers, as Simulator::sim_tick issues them (2,3,4,5,...)."""
+    e = to_oracle_entities(O, ents)
+    pairs = []
+    for t in ticks:
+        p = oracle_dispatch(O, e, omap, radius, t)
+        if t % 2 == 1:
+            pairs.append(p)
+    return e, pairs
+
+
+def test_config1_test_map_10k_1000_moves(msim, orc, test_map):
+    """BASELINE config 1: test_map.json, 10 k entities, seed 42, 1000 move passes, collisions off."""
+    ents = test_map.init_entities(10_000, seed=42)
+    omap = oracle_map(orc, test_map)
+    want = to_oracle_entities(orc, ents)
+    orc.move_pass(want, omap)  # first dispatch: initialise only
+    with msim.Simulation(test_map, ents, flags=msim.FLAG_NO_COLLISIONS) as sim:
+        sim.dispatch(2)  # init-only dispatch (random_move.comp:863-867)
+        got = sim.read_entities()
+        assert_entities_equal(got, want, what="after init dispatch")
+        assert sim.read_debug()[0] == 10_000
+        for step in range(1000):
+            sim.dispatch(4 + 2 * step)
+            orc.move_pass(want, omap)
+            if step in (0, 1, 45, 46, 47, 499, 999):
+                assert_entities_equal(sim.read_entities(), want, what=f"move pass {step + 1}")
+        st = sim.stats()
+        assert st["move_passes"] == 1000 and st["collide_passes"] == 0
+
+
+def test_enqueue_ticks_matches_dispatch(msim, orc, test_map):
+    ents = test_map.init_entities(4097, seed=3)
+    omap = oracle_map(orc, test_map)
+    want = to_oracle_entities(orc, ents)
+    for _ in range(1 + 300):
+        orc.move_pass(want, omap)
+    with msim.Simulation(test_map, ents, flags=msim.FLAG_NO_COLLISIONS) as sim:
+        sim.dispatch(2)
+        sim.enqueue_ticks(300, False)
+        sim.sync()
+        assert_entities_equal(sim.read_entities(), want, what="300 enqueued move passes")
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 63, 64, 65, 127, 1023, 4096, 4097, 12_345])
+def test_ragged_sizes_full_ticks(msim, orc, small_city, n):
+    """Empty and ragged populations through complete sim ticks (move + collide)."""
+    ents = small_city.init_entities(n, seed=100 + n)
+    omap = oracle_map(orc, small_city)
+    ticks = list(range(2, 2 + 2 * 12))
+    want, want_pairs = run_oracle(orc, ents, omap, 10.0, ticks)
+    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+        got_pairs = []
+        for t in ticks:
+            sim.dispatch(t)
+            if t % 2 == 1:
+                got_pairs.append(sim.stats()["last_pair_count"])
+        got = sim.read_entities()
+    assert_entities_equal(got, want, what=f"n={n}")
+    assert got_pairs == want_pairs
+
+
+def test_city_100k_collisions_every_tick(msim, orc, small_city):
+    """Munich-style street graph, collisions on: every field and the pair count, tick by tick."""
+    n = 100_000
+    ents = small_city.init_entities(n, seed=42)
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+        for t in range(2, 2 + 2 * 30):
+            sim.dispatch(t)
+            p = oracle_dispatch(orc, want, omap, 10.0, t)
+            if t % 2 == 1:
+                st = sim.stats()
+                assert st["last_pair_count"] == p, f"tick {t}"
+                assert st["last_flagged_count"] == int(orc.collision_flags(want).sum()), f"tick {t}"
+            if t in (3, 4, 5, 21, 61):
+                assert_entities_equal(sim.read_entities(), want, what=f"tick {t}")
+        assert_entities_equal(sim.read_entities(), want, what="final")
+        flags = sim.read_collision_flags()
+        assert (flags == orc.collision_flags(want)).all()
+        dbg = sim.read_debug()
+        assert dbg[0] == n
+
+
+def test_flags_only_mode_matches(msim, orc, small_city):
+    n = 50_000
+    ents = small_city.init_entities(n, seed=9)
+    omap = oracle_map(orc, small_city)
+    ticks = list(range(2, 2 + 2 * 20))
+    want, _ = run_oracle(orc, ents, omap, 10.0, ticks)
+    with msim.Simulation(small_city, ents, radius=10.0, flags=msim.FLAG_NO_PAIR_COUNT) as sim:
+        for t in ticks:
+            sim.dispatch(t)
+        assert_entities_equal(sim.read_entities(), want, what="flags-only")
+
+
+@pytest.mark.parametrize("radius", [0.0, 0.5, 3.0, 10.0, 37.5, 250.0])
+def test_point_clouds_vs_brute_force(msim, orc, small_city, radius):
+    """Collision predicate on arbitrary (off-road) positions, including exact-distance edge cases."""
+    rng = np.random.default_rng(int(radius * 10) + 1)
+    n = 6000
+    ents = small_city.init_entities(n, seed=5)
+    ents["initialized"] = 1
+    xy = (rng.random((n, 2)) * np.array([small_city.width, small_city.height])).astype(np.float32)
+    # exact-radius pairs and duplicates: strict '<' must hold
+    xy[1] = xy[0] + np.array([radius, 0], dtype=np.float32)
+    xy[3] = xy[2]
+    xy[5] = xy[4] + np.array([0, np.nextafter(np.float32(radius), np.float32(0))], dtype=np.float32)
+    xy[6] = [0, 0]
+    xy[7] = [small_city.width, small_city.height]
+    ents["pos"] = xy
+    ents["target"] = xy  # nobody moves anywhere sensible; only the collision pass is exercised
+    want = to_oracle_entities(orc, ents)
+    want_pairs = orc.collide_pass_brute(want, radius)
+    with msim.Simulation(small_city, ents, radius=radius) as sim:
+        sim.dispatch(3)
+        got = sim.read_entities()
+        st = sim.stats()
+    assert_entities_equal(got, want, fields=["color", "pos", "initialized"], what=f"r={radius}")
+    assert st["last_pair_count"] == want_pairs
+
+
+def test_stacked_entities(msim, orc, test_map):
+    """App. B10: everybody starts stacked on four points; cells must take unbounded occupancy."""
+    n = 3000
+    ents = test_map.init_entities(n, seed=1)
+    omap = oracle_map(orc, test_map)
+    ticks = [2, 3, 4, 5, 6, 7]
+    want, want_pairs = run_oracle(orc, ents, omap, 10.0, ticks)
+    with msim.Simulation(test_map, ents, radius=10.0) as sim:
+        got_pairs = []
+        for t in ticks:
+            sim.dispatch(t)
+            if t % 2 == 1:
+                got_pairs.append(sim.stats()["last_pair_count"])
+        assert_entities_equal(sim.read_entities(), want, what="stacked")
+    assert got_pairs == want_pairs
+
+
+def test_upload_readback_roundtrip_and_reupload(msim, orc, small_city):
+    ents = small_city.init_entities(5000, seed=77)
+    ents["direction"] = np.random.default_rng(0).random((5000, 2)).astype(np.float32)
+    with msim.Simulation(small_city, ents) as sim:
+        assert_entities_equal(sim.read_entities(), ents, what="untouched round trip")
+        sim.dispatch(2)
+        sim.dispatch(3)
+        sim.dispatch(4)
+        mid = sim.read_entities()
+        # re-upload the read-back state: must continue exactly like an uninterrupted run
+        sim.dispatch(5)
+        sim.dispatch(6)
+        a = sim.read_entities()
+        sim.upload(mid)
+        sim.dispatch(5)
+        sim.dispatch(6)
+        b = sim.read_entities()
+    assert_entities_equal(a, b, what="re-upload continuation")
+
+
+def test_collide_without_prior_move_and_radius_change(msim, orc, small_city):
+    ents = small_city.init_entities(20_000, seed=11)
+    ents["initialized"] = 1
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+        sim.dispatch(3)
+        p0 = oracle_dispatch(orc, want, omap, 10.0, 3)
+        assert sim.stats()["last_pair_count"] == p0
+        sim.dispatch(4)
+        oracle_dispatch(orc, want, omap, 10.0, 4)
+        sim.radius = 25.0  # push constants carry the radius per dispatch (PushConsts.hpp:17)
+        sim.dispatch(5)
+        p1 = oracle_dispatch(orc, want, omap, 25.0, 5)
+        assert sim.stats()["last_pair_count"] == p1
+        assert_entities_equal(sim.read_entities(), want, what="after radius change")
+
+
+def test_invalid_inputs(msim, small_city):
+    ents = small_city.init_entities(100, seed=1)
+    bad = ents.copy()
+    bad["road_index"][5] = small_city.roads.shape[0] + 3
+    with pytest.raises(msim.MsimError) as ei:
+        msim.Simulation(small_city, bad)
+    assert ei.value.status == msim.MSIM_ERR_INVALID
+    mixed = ents.copy()
+    mixed["initialized"][::2] = 1
+    with pytest.raises(msim.MsimError) as ei:
+        msim.Simulation(small_city, mixed)
+    assert ei.value.status == msim.MSIM_ERR_UNSUPPORTED
+    with msim.Simulation(small_city, ents, flags=msim.FLAG_NO_COLLISIONS) as sim:
+        with pytest.raises(msim.MsimError):
+            sim.dispatch(3)
