@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — entity-updates/sec of the per-tick entity update on B200, with the HBM roofline of the
+dominant kernel and a CPU baseline timed in the same run.  Contract: see DESIGN.md §Measurement.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A "step" is one sim tick = one move pass + one collision pass over the whole resident population
+(Simulator::sim_tick, /root/reference/src/sim/Simulator.cpp:213-241), except for the collisions-off
+workloads where it is one move pass.  Default workload: BASELINE.json configs[2], the configuration
+its metric is quoted on ("Munich map ... 10M entities ... collisions on ... 1/2/4/8 B200").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (entities per GPU, collisions, map)
+    "munich_10m_collisions": dict(entities=10_000_000, collisions=True, map="city"),
+    "munich_1m_nocollisions": dict(entities=1_000_000, collisions=False, map="city"),
+    "test_map_10k_nocollisions": dict(entities=10_000, collisions=False, map="test_map"),
+}
+METRIC = "entity-updates/sec"
+SURVEY_BYTES = {True: 124.0, False: 24.0}  # B_coll (23-bit keys, 3 passes) / B_move
+# algorithmic HBM bytes per entity per launch of each kernel
+KERNEL_BYTES = {
+    "move": 28.0,  # pos R8 + target R8 + pos W8 + cell key W4 (24.0 when collisions are off)
+    "keygen": 12.0,
+    "histogram": 4.0,
+    "sort_pass0": 12.0,  # key R4 + pair W8
+    "sort_pass1": 16.0,
+    "sort_pass2": 16.0,
+    "sort_pass3": 16.0,
+    "build_cells": 24.0,  # pair R8 + pos gather R8 + sorted pos W8
+    "query": 9.0,  # sorted pos R8 + flag W1 (neighbour reads are cache hits)
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload: str):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload, {})
+    return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the GPU is under the bench load."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid: str | None):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+        if uuid:
+            cmd += ["-i", uuid]
+        try:
+            self.proc = subprocess.Popen(cmd, stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        # "under load": samples in the upper half of the power range seen
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": 0}
+        thr = (max(power) + min(power)) / 2 if max(power) > min(power) + 50 else min(power)
+        loaded = [c for c, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(loaded), "power_w_max": max(power)}
+
+
+def build_workload(M, name: str, entities_override: int | None, seed: int = 42):
+    w = dict(WORKLOADS[name])
+    if entities_override:
+        w["entities"] = entities_override
+    if w["map"] == "city":
+        m = M.Map.city()  # 29007.4609 x 16463.7656 m Munich stand-in, seed 2022
+        w["map_desc"] = f"synthetic Munich stand-in {m.width:.1f}x{m.height:.1f} m, {m.roads.shape[0]} roads (munich.json absent from the reference checkout)"
+    else:
+        m = M.Map.load_json(os.path.join(ROOT, "tests", "golden", "test_map.json"))
+        w["map_desc"] = "test_map.json (4 roads)"
+    return w, m
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU: the reference's own CPU path (oracle/_ref quadtree) + the oracle port
+# --------------------------------------------------------------------------------------------------
+def cpu_step(O, e, omap, radius, threads, collisions, use_ref):
+    """One sim tick on the host.  Movement always comes from the oracle port (the reference's CPU
+    harness has no road-graph movement, shader_validation/src/main.cpp:923-957); the neighbour
+    structure is the reference's own quadtree when oracle/_ref is available: rebuilt by
+    quad_tree_insert (single-threaded: its multi-threaded insert and its incremental
+    quad_tree_update trip the harness's own lock assertions) and queried by
+    quad_tree_check_collisions on all host threads."""
+    O.move_pass(e, omap, threads=threads)
+    if not collisions:
+        return
+    if use_ref:
+        q = O.RefQuadTree(omap.world_w, omap.world_h, radius, 10)
+        q.insert(e["pos"], 1)
+        q.collide(threads)
+    else:
+        O.collide_pass(e, omap.world_w, omap.world_h, radius, threads=threads)
+
+
+def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, use_ref, threads):
+    e = np.ascontiguousarray(ents_aos).view(O.ENTITY_DTYPE).copy()
+    e["initialized"] = 1
+    for _ in range(warmup):
+        cpu_step(O, e, omap, radius, threads, collisions, use_ref)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(O, e, omap, radius, threads, collisions, use_ref)
+    dt = time.perf_counter() - t0
+    return e.shape[0] * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import movement_sim_b200 as M
+    from oracle import oracle as O
+
+    w, m = build_workload(M, args.workload, args.entities)
+    threads = os.cpu_count() or 1
+    use_ref = O.ref_available() and w["collisions"]
+    sample = min(w["entities"], args.ref_sample, int(O.ref().ref_capacity()) if use_ref else 1 << 62)
+    omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
+    ents = m.init_entities(sample, seed=42)
+    e = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()
+    O.move_pass(e, omap, threads=threads)  # init dispatch
+    for _ in range(args.preroll):
+        O.move_pass(e, omap, threads=threads)
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    warmup = max(1, min(args.warmup, 2))
+    value, sec = time_cpu(O, e, omap, 10.0, w["collisions"], steps, warmup, use_ref, threads)
+    kind = "reference" if use_ref else "port"
+    sample_desc = (f"{sample} of {w['entities']} entities of the same workload, {steps} sim ticks after {args.preroll} pre-roll move passes; "
+                   + ("movement = oracle port on all threads, neighbour structure = reference quadtree (oracle/_ref): insert on 1 thread, collision walk on all threads"
+                      if use_ref else "oracle port (move + cell-grid collisions) on all threads"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
+        "data": "synthetic", "config": {"workload": args.workload, "entities_sampled": sample, "collisions": w["collisions"], "map": w["map_desc"]},
+        "cpu_baseline": {"value": value, "unit": "entity-updates/s", "cores": threads, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": value, "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import movement_sim_b200 as M
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    M.lib()  # fail loudly without the CUDA library
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from movement_sim_b200 import sharding  # noqa: F401  (multi-GPU path)
+
+        return sharding.bench_main(args, M, rank, world, local_rank)
+
+    w, m = build_workload(M, args.workload, args.entities)
+    n = w["entities"]
+    collisions = w["collisions"]
+    peak, peak_src = load_peaks()
+    stream = torch.cuda.Stream()
+    ents = m.init_entities(n, seed=42)
+    flags = 0 if collisions else M.FLAG_NO_COLLISIONS
+    sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=flags, stream=stream.cuda_stream)
+    sim.dispatch(2)  # the reference's first dispatch: initialise only
+    sim.enqueue_ticks(args.preroll, False)  # disperse the population along the roads (untimed)
+    sim.enqueue_ticks(1, collisions)
+    sim.sync()
+
+    props = torch.cuda.get_device_properties(local_rank)
+    uuid = getattr(props, "uuid", None)
+    sampler = ClockSampler(f"GPU-{uuid}" if uuid and not str(uuid).startswith("GPU-") else (str(uuid) if uuid else None))
+
+    small = n * (40 if collisions else 24) < 200e6  # hot state would sit in the 126 MB L2
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if small else None
+
+    def timed_steps(k):
+        """k steps; returns device ms (CUDA events on the launching stream)."""
+        if flush_buf is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(k):
+                sim.enqueue_ticks(1, collisions)
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+        total = 0.0
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(1)  # evict the working set from L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sim.enqueue_ticks(1, collisions)
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    timed_steps(max(3, args.warmup))
+    sim.sync()
+    launches0 = sim.stats()["kernel_launches"]
+    torch.cuda.synchronize()
+    ms = timed_steps(args.steps)
+    torch.cuda.synchronize()
+    sim.sync()
+    launches = sim.stats()["kernel_launches"] - launches0
+    value = n * args.steps / (ms * 1e-3)
+
+    # per-kernel device time over the same K steps (events around every launch; separate pass so the
+    # event records do not sit inside the throughput measurement)
+    sim.profile_begin()
+    timed_steps(args.steps)
+    kt = sim.profile_end()
+    total_kernel_ms = sum(t for _, t in kt.values())
+    traffic = load_traffic(args.workload)
+    kernels = []
+    for name, (cnt, tms) in sorted(kt.items(), key=lambda kv: -kv[1][1]):
+        bpe = KERNEL_BYTES.get(name)
+        if name == "move" and not collisions:
+            bpe = 24.0
+        entry = {"name": name, "launches": cnt, "avg_us": tms / cnt * 1e3, "share": tms / total_kernel_ms if total_kernel_ms else None}
+        if bpe:
+            gbs = bpe * n / (tms / cnt * 1e-3) / 1e9
+            entry.update({"alg_bytes_per_entity": bpe, "achieved_gbs": gbs, "frac": gbs / peak})
+        kernels.append(entry)
+    dom = next((k for k in kernels if "achieved_gbs" in k), None)
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": traffic.get(dom["name"]), "peak_source": peak_src,
+                    "alg_bytes_per_launch": dom["alg_bytes_per_entity"] * n, "avg_launch_us": dom["avg_us"], "share_of_step": dom["share"]}
+    tick_gbs = SURVEY_BYTES[collisions] * n * args.steps / (ms * 1e-3) / 1e9
+
+    # keep the GPU under the same load long enough for nvidia-smi to sample it (untimed)
+    t_end = time.time() + 1.2
+    while time.time() < t_end:
+        timed_steps(max(1, min(args.steps, 50)))
+    clocks = sampler.stop()
+
+    # ---- e2e: through the C ABI with HOST (pinned) buffers: upload AoS + sim tick + readback AoS ----
+    pinned = torch.empty(n * 64, dtype=torch.uint8, pin_memory=True)
+    ptr = pinned.data_ptr()
+    sim.read_entities_ptr(ptr, n)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    tick = 4
+
+    def e2e_step():
+        nonlocal tick
+        sim.upload_ptr(ptr, n)
+        sim.dispatch(tick)
+        if collisions:
+            sim.dispatch(tick + 1)
+        tick += 2
+        sim.read_entities_ptr(ptr, n)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    e1.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
+    e2e = {"value": n * e2e_steps / (e2e_ms * 1e-3), "unit": "entity-updates/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 64,
+           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "what": "msim_upload_entities(pinned AoS) + msim_dispatch(move)" + (" + msim_dispatch(collide)" if collisions else "") + " + msim_read_entities(pinned AoS), blocking calls"}
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        threads = os.cpu_count() or 1
+        use_ref = O.ref_available() and collisions
+        sample = min(n, args.cpu_sample, int(O.ref().ref_capacity()) if use_ref else 1 << 62)
+        host = np.frombuffer(pinned.numpy(), dtype=M.ENTITY_DTYPE)[:sample]
+        omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
+        v, sec = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, use_ref, threads)
+        v_port, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, False, threads)
+        cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": "reference" if use_ref else "port",
+               "sample": f"first {sample} entities of the resident population, {args.cpu_steps} sim ticks, {sec:.3f} s per tick; "
+                         + ("movement = oracle port (all threads), neighbour structure = reference quadtree from oracle/_ref (insert 1 thread, collision walk all threads)"
+                            if use_ref else "oracle port on all threads"),
+               "port_value": v_port}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "config": {"workload": args.workload, "entities": n, "collisions": collisions, "collision_radius_m": 10.0, "map": w["map_desc"],
+                   "entity_seed": 42, "preroll_move_passes": args.preroll, "pair_count": collisions,
+                   "l2": ("flushed between timed steps (512 MiB fill)" if small else "inputs larger than L2 (no flush)"),
+                   "grid": sim.stats()},
+        "roofline": roofline,
+        "tick": {"survey_bytes_per_entity_update": SURVEY_BYTES[collisions], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / peak,
+                 "frac_of_nominal_8tbs": tick_gbs / 8000.0, "kernel_time_ms_per_step": total_kernel_ms / args.steps},
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    sim.close()
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="munich_10m_collisions")
+    ap.add_argument("--entities", type=int, default=None, help="override the per-GPU entity count")
+    ap.add_argument("--preroll", type=int, default=256, help="untimed move passes that disperse the population before timing")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=1_000_000)
+    ap.add_argument("--ref-max-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -179,6 +179,17 @@ typedef struct msim_stats {
 } msim_stats;
 int msim_get_stats(msim_handle* h, msim_stats* out);
 
+/* Per-kernel device time between msim_profile_begin and msim_profile_end, measured with CUDA events
+ * on the handle's stream around every launch (bench.py's live roofline).  Profiling adds two event
+ * records per launch, so throughput numbers are taken with profiling off. */
+typedef struct msim_kernel_time {
+    char name[24];
+    uint64_t launches;
+    double total_ms;
+} msim_kernel_time;
+int msim_profile_begin(msim_handle* h);
+int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32_t* count);
+
 /* Device pointers of the resident SoA state, for zero-copy consumers (CUDA-GL interop, torch). */
 typedef struct msim_device_view {
     void* pos;       /* float2[count], current */

@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     "msim_dispatch", "msim_enqueue_move", "msim_enqueue_collide", "msim_enqueue_ticks", "msim_sync",
     "msim_set_stream", "msim_read_entities", "msim_read_positions", "msim_read_collision_flags",
     "msim_read_quadtree_nodes", "msim_read_debug", "msim_get_stats", "msim_get_device_view",
+    "msim_profile_begin", "msim_profile_end",
     "msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid",
     "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
@@ -153,6 +154,10 @@ class DeviceView(C.Structure):
     _fields_ = [("pos", C.c_void_p), ("target", C.c_void_p), ("road", C.c_void_p), ("rng", C.c_void_p), ("count", C.c_uint64)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("total_ms", C.c_double)]
+
+
 _lib = None
 
 
@@ -187,6 +192,8 @@ def lib():
         "msim_read_debug": (i32, [vp, vp]),
         "msim_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "msim_get_device_view": (i32, [vp, C.POINTER(DeviceView)]),
+        "msim_profile_begin": (i32, [vp]),
+        "msim_profile_end": (i32, [vp, C.POINTER(KernelTime), u32, C.POINTER(u32)]),
         "msim_map_load_json": (i32, [C.c_char_p, C.POINTER(vp)]),
         "msim_map_save_json": (i32, [vp, C.c_char_p]),
         "msim_map_generate_city": (i32, [f32, f32, f32, f32, f32, u64, C.POINTER(vp)]),
@@ -402,6 +409,16 @@ class Simulation:
         st = Stats()
         self._check(lib().msim_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+    def profile_begin(self):
+        self._check(lib().msim_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{kernel name: (launches, total_ms)} since profile_begin()."""
+        buf = (KernelTime * 32)()
+        n = C.c_uint32()
+        self._check(lib().msim_profile_end(self._h, buf, 32, C.byref(n)))
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n.value)}
 
     def device_view(self) -> DeviceView:
         v = DeviceView()

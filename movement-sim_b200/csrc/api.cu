@@ -30,6 +30,9 @@ struct msim_handle {
     int sm_count{148};
     cudaStream_t stream{nullptr};
     bool own_stream{false};
+    cudaStream_t side{nullptr};  // pass B of a move runs here while the collision pass uses `stream`
+    cudaEvent_t ev_moved{nullptr}, ev_arrived{nullptr};
+    bool side_pending{false};
     uint32_t flags{0};
 
     uint32_t n{0};
@@ -72,11 +75,13 @@ struct msim_handle {
     bool uninitialised{false};
     bool has_moved{false};
     bool keys_valid{false};
+    bool hist_valid{false};
     bool collided{false};
     bool flags_scattered{false};
     uint64_t move_passes{0}, collide_passes{0}, launches{0}, initialised_total{0};
     uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0};
 
+    Profiler prof;
     std::string error;
 };
 
@@ -151,7 +156,19 @@ void free_all(msim_handle* h) {
     cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
     cudaFree(h->scratch); cudaFree(h->stage);
+    for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_moved) cudaEventDestroy(h->ev_moved);
+    if (h->ev_arrived) cudaEventDestroy(h->ev_arrived);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+// make the main stream wait for a pass B still running on the side stream
+void join_side(msim_handle* h) {
+    if (h->side_pending) {
+        cudaStreamWaitEvent(h->stream, h->ev_arrived, 0);
+        h->side_pending = false;
+    }
 }
 
 int ensure_cells(msim_handle* h) {
@@ -183,12 +200,13 @@ int alloc_collision_buffers(msim_handle* h) {
 int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     if (count > h->cap) return fail(h, MSIM_ERR_CAPACITY, "msim_upload_entities: count exceeds entity_capacity");
     if (count && !src) return fail(h, MSIM_ERR_INVALID, "msim_upload_entities: null source");
+    join_side(h);
     MSIM_CUDA(h, cudaMemsetAsync(h->scratch, 0, 2 * sizeof(unsigned int), h->stream));
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
         const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
         MSIM_CUDA(h, cudaMemcpyAsync(h->stage, src + off, static_cast<size_t>(chunk) * sizeof(msim_entity), cudaMemcpyHostToDevice, h->stream));
         h->launches += launch_unpack(h->stream, static_cast<uint32_t>(off), chunk, h->stage, h->pos[0], h->target, h->road, h->rng, h->color0,
-                                     h->dir0, nullptr, h->scratch);
+                                     h->dir0, nullptr, h->scratch, &h->prof);
     }
     h->launches += launch_max_road(h->stream, static_cast<uint32_t>(count), h->road, h->scratch + 1);
     unsigned int host_scratch[2] = {0, 0};
@@ -199,6 +217,7 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->cur = 0;
     h->has_moved = false;
     h->keys_valid = false;
+    h->hist_valid = false;
     h->collided = false;
     h->flags_scattered = false;
     if (h->flag_entity) MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
@@ -215,13 +234,14 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
 }
 
 int check_device_errors(msim_handle* h) {
+    join_side(h);
     Counters c{};
     MSIM_CUDA(h, cudaMemcpyAsync(&c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     MSIM_CUDA(h, cudaGetLastError());
-    h->last_pairs = c.pairs_last;
+    h->last_pairs = h->n ? c.pairs_last : 0;
     h->total_pairs = c.pairs_total;
-    h->last_flagged = c.flagged_last;
+    h->last_flagged = h->n ? c.flagged_last : 0;
     if (c.error_flag) return fail(h, MSIM_ERR_INTERNAL, "radix sort look-back watchdog tripped");
     return MSIM_OK;
 }
@@ -235,18 +255,34 @@ bool consume_init_dispatch(msim_handle* h) {
     return true;
 }
 
-int enqueue_move(msim_handle* h) {
+int enqueue_move(msim_handle* h, bool want_keys) {
     if (consume_init_dispatch(h)) return MSIM_OK;
-    const bool emit = !(h->flags & MSIM_FLAG_NO_COLLISIONS);
+    const bool emit = want_keys && !(h->flags & MSIM_FLAG_NO_COLLISIONS);
     if (emit) {
         const int rc = alloc_collision_buffers(h);
         if (rc != MSIM_OK) return rc;
     }
-    h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->road, h->rng, h->arrived,
-                               h->roads, h->conn, h->conn_count, emit ? h->keys : nullptr, h->grid, nullptr, h->counters);
+    const int passes = (h->key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    if (emit) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
+    join_side(h);  // the previous pass B must have rewritten the targets before they are read again
+    h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
+                               emit ? h->keys : nullptr, h->grid, emit ? h->ws.hist : nullptr,
+                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, &h->prof);
+    if (emit && h->side) {
+        // A collision pass follows and needs only the positions and keys of pass A: pass B (gathers
+        // into the road tables, latency-bound, little bandwidth) runs beside the sort on a second stream.
+        cudaEventRecord(h->ev_moved, h->stream);
+        cudaStreamWaitEvent(h->side, h->ev_moved, 0);
+        h->launches += launch_arrive(h->side, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+        cudaEventRecord(h->ev_arrived, h->side);
+        h->side_pending = true;
+    } else {
+        h->launches += launch_arrive(h->stream, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+    }
     h->cur ^= 1;
     h->has_moved = true;
     h->keys_valid = emit;
+    h->hist_valid = emit;
     h->move_passes++;
     return MSIM_OK;
 }
@@ -257,13 +293,15 @@ int enqueue_collide(msim_handle* h) {
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
     if (!h->keys_valid) {
-        h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid);
+        h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
         h->keys_valid = true;
+        h->hist_valid = false;
     }
-    h->launches += launch_sort(h->stream, h->n, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted);
-    h->launches += launch_build_cells(h->stream, h->n, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid);
+    h->launches += launch_sort(h->stream, h->n, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid, &h->prof);
+    h->hist_valid = false;  // the sort consumed the tickets and look-back words
+    h->launches += launch_build_cells(h->stream, h->n, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid, h->counters, &h->prof);
     h->launches += launch_query(h->stream, h->n, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid,
-                                !(h->flags & MSIM_FLAG_NO_PAIR_COUNT), h->counters);
+                                !(h->flags & MSIM_FLAG_NO_PAIR_COUNT), h->counters, &h->prof);
     h->collided = true;
     h->flags_scattered = false;
     h->collide_passes++;
@@ -278,7 +316,7 @@ int bind(msim_handle* h) {
 
 int materialise_flags(msim_handle* h) {
     if (h->collided && !h->flags_scattered) {
-        h->launches += launch_scatter_flags(h->stream, h->n, h->sorted, h->flag_sorted, h->flag_entity);
+        h->launches += launch_scatter_flags(h->stream, h->n, h->sorted, h->flag_sorted, h->flag_entity, &h->prof);
         h->flags_scattered = true;
     }
     return MSIM_OK;
@@ -356,6 +394,9 @@ int msim_create(const msim_config* cfg, msim_handle** out) {
             MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             h->own_stream = true;
         }
+        MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
         MSIM_CUDA(h, dev_alloc(&h->pos[0], h->cap));
         MSIM_CUDA(h, dev_alloc(&h->pos[1], h->cap));
         MSIM_CUDA(h, dev_alloc(&h->target, h->cap));
@@ -394,6 +435,7 @@ int msim_create(const msim_config* cfg, msim_handle** out) {
 void msim_destroy(msim_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->side) cudaStreamSynchronize(h->side);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_all(h);
     delete h;
@@ -408,6 +450,7 @@ int msim_upload_entities(msim_handle* h, const msim_entity* src, uint64_t count)
 int msim_set_stream(msim_handle* h, void* cuda_stream) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
+    join_side(h);
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->own_stream) {
         cudaStreamDestroy(h->stream);
@@ -425,7 +468,7 @@ int msim_set_stream(msim_handle* h, void* cuda_stream) {
 int msim_enqueue_move(msim_handle* h) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
-    return enqueue_move(h);
+    return enqueue_move(h, true);
 }
 
 int msim_enqueue_collide(msim_handle* h) {
@@ -438,7 +481,7 @@ int msim_enqueue_ticks(msim_handle* h, uint32_t sim_ticks, int with_collisions) 
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     for (uint32_t t = 0; t < sim_ticks; t++) {
-        rc = enqueue_move(h);
+        rc = enqueue_move(h, with_collisions != 0);
         if (rc != MSIM_OK) return rc;
         if (with_collisions) {
             rc = enqueue_collide(h);
@@ -466,12 +509,13 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
         h->radius = pc->collision_radius;
         configure_grid(h);
         h->keys_valid = false;
+        h->hist_valid = false;
         if (h->keys) {
             rc = ensure_cells(h);
             if (rc != MSIM_OK) return rc;
         }
     }
-    rc = (pc->tick % 2u == 0u) ? enqueue_move(h) : enqueue_collide(h);
+    rc = (pc->tick % 2u == 0u) ? enqueue_move(h, true) : enqueue_collide(h);
     if (rc != MSIM_OK) return rc;
     return check_device_errors(h);
 }
@@ -482,6 +526,7 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
     if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
     materialise_flags(h);
+    join_side(h);
     PackArgs a{};
     a.pos_cur = h->pos[h->cur];
     a.pos_prev = h->pos[h->cur ^ 1];
@@ -497,7 +542,7 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     a.has_moved = h->has_moved ? 1u : 0u;
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
         const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
-        h->launches += launch_pack(h->stream, static_cast<uint32_t>(off), chunk, a, h->stage);
+        h->launches += launch_pack(h->stream, static_cast<uint32_t>(off), chunk, a, h->stage, &h->prof);
         MSIM_CUDA(h, cudaMemcpyAsync(dst + off, h->stage, static_cast<size_t>(chunk) * sizeof(msim_entity), cudaMemcpyDeviceToHost, h->stream));
     }
     return check_device_errors(h);
@@ -575,10 +620,52 @@ int msim_get_stats(msim_handle* h, msim_stats* out) {
     return rc;
 }
 
+int msim_profile_begin(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    h->prof.enabled = true;
+    h->prof.used = 0;
+    h->prof.ids.clear();
+    return MSIM_OK;
+}
+
+int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32_t* count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!out || !count) return fail(h, MSIM_ERR_INVALID, "msim_profile_end: null argument");
+    static const char* const names[K_COUNT] = {"move", "arrive", "keygen", "histogram", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3",
+                                               "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc"};
+    h->prof.enabled = false;
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    double ms[K_COUNT] = {0};
+    uint64_t launches[K_COUNT] = {0};
+    for (size_t i = 0; i < h->prof.ids.size(); i++) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, h->prof.pool[2 * i], h->prof.pool[2 * i + 1]) == cudaSuccess) {
+            ms[h->prof.ids[i]] += t;
+            launches[h->prof.ids[i]]++;
+        }
+    }
+    uint32_t n = 0;
+    for (int k = 0; k < K_COUNT && n < cap; k++) {
+        if (!launches[k]) continue;
+        std::memset(&out[n], 0, sizeof(out[n]));
+        std::strncpy(out[n].name, names[k], sizeof(out[n].name) - 1);
+        out[n].launches = launches[k];
+        out[n].total_ms = ms[k];
+        n++;
+    }
+    *count = n;
+    h->prof.used = 0;
+    h->prof.ids.clear();
+    return MSIM_OK;
+}
+
 int msim_get_device_view(msim_handle* h, msim_device_view* out) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!out) return fail(h, MSIM_ERR_INVALID, "msim_get_device_view: out is null");
+    join_side(h);
     out->pos = h->pos[h->cur];
     out->target = h->target;
     out->road = h->road;

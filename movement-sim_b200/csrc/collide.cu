@@ -19,8 +19,12 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const float2* __restrict__ pos,
-                   float2* __restrict__ sorted_pos, uint2* __restrict__ cell_range) {
+                   float2* __restrict__ sorted_pos, uint2* __restrict__ cell_range, Counters* __restrict__ counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) {  // per-pass counters of the query that follows
+        counters->pairs_last = 0;
+        counters->flagged_last = 0;
+    }
     const uint32_t lane = threadIdx.x & 31u;
     const bool in = j < n;
     unsigned long long kv = in ? __ldcs(sorted + j) : ~0ull;
@@ -44,6 +48,53 @@ __device__ __forceinline__ float dist2(float2 a, float2 b) {
     return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
 
+// number of slots k in [a, b) with dist2(sorted_pos[k], p) < threshold; four loads in flight
+__device__ __forceinline__ uint32_t count_in_range(const float2* __restrict__ sorted_pos, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t c = 0;
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = __ldg(sorted_pos + k), q1 = __ldg(sorted_pos + k + 1), q2 = __ldg(sorted_pos + k + 2), q3 = __ldg(sorted_pos + k + 3);
+        c += (dist2(q0, p) < threshold) ? 1u : 0u;
+        c += (dist2(q1, p) < threshold) ? 1u : 0u;
+        c += (dist2(q2, p) < threshold) ? 1u : 0u;
+        c += (dist2(q3, p) < threshold) ? 1u : 0u;
+    }
+    for (; k < b; k++) c += (dist2(__ldg(sorted_pos + k), p) < threshold) ? 1u : 0u;
+    return c;
+}
+
+// true iff some slot k in [a, b) is within range; four independent loads per step, so the scan costs
+// one memory latency per four candidates instead of one per candidate
+__device__ __forceinline__ bool any_in_range(const float2* __restrict__ sorted_pos, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = __ldg(sorted_pos + k), q1 = __ldg(sorted_pos + k + 1), q2 = __ldg(sorted_pos + k + 2), q3 = __ldg(sorted_pos + k + 3);
+        const bool h = (dist2(q0, p) < threshold) | (dist2(q1, p) < threshold) | (dist2(q2, p) < threshold) | (dist2(q3, p) < threshold);
+        if (h) return true;
+    }
+    for (; k < b; k++)
+        if (dist2(__ldg(sorted_pos + k), p) < threshold) return true;
+    return false;
+}
+
+// the three cells x0..x1 of one grid row are adjacent keys = one contiguous run [lo, hi) of the sorted order
+__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, int ncx, int yy, int x0, int x1, uint32_t& lo, uint32_t& hi) {
+    const uint2* row = cell_range + static_cast<size_t>(yy) * ncx;
+    lo = 0xffffffffu;
+    hi = 0u;
+    for (int xx = x0; xx <= x1; xx++) {
+        const uint2 r = __ldg(row + xx);  // empty cell = {0xffffffff, ~0xffffffff = 0}: neutral for min/max
+        lo = min(lo, r.x);
+        hi = max(hi, ~r.y);
+    }
+    if (lo > hi) lo = hi;  // all three empty
+}
+
+// One thread per sorted slot j.  Every unordered pair is examined from its HIGHER slot only: thread j
+// counts its in-range partners among the slots below it (the whole row above, and its own row up to
+// j) — that is the exact unique-pair count and already decides the flag for almost everybody.  Only
+// when nothing was found below does it look at the slots above (rest of its row, row below), and
+// there the first hit is enough.  Half the distance tests of a full 3x3 scan, same flags, same count.
 template <bool COUNT_PAIRS>
 __global__ void __launch_bounds__(256)
 query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __restrict__ cell_range,
@@ -54,29 +105,34 @@ query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __r
     bool hit = false;
     if (j < n) {
         const float2 p = sorted_pos[j];
+        const float thr = grid.hit_threshold;
         int cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
         int cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
         cx = min(max(cx, 0), grid.ncx - 1);
         cy = min(max(cy, 0), grid.ncy - 1);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, grid.ncx - 1);
-        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, grid.ncy - 1);
-        for (int yy = y0; yy <= y1 && (COUNT_PAIRS || !hit); yy++) {
-            const uint2* row = cell_range + static_cast<size_t>(yy) * grid.ncx;
-            uint32_t lo = 0xffffffffu, hi = 0u;
-            for (int xx = x0; xx <= x1; xx++) {
-                const uint2 r = __ldg(row + xx);  // empty cell = {0xffffffff, ~0xffffffff = 0}: neutral for min/max
-                lo = min(lo, r.x);
-                hi = max(hi, ~r.y);
+        uint32_t lo, hi;
+        // own row: slots below j, then (flags-only or nothing found) slots above j
+        uint32_t own_lo, own_hi;
+        row_run(cell_range, grid.ncx, cy, x0, x1, own_lo, own_hi);
+        if (COUNT_PAIRS) {
+            if (cy > 0) {
+                row_run(cell_range, grid.ncx, cy - 1, x0, x1, lo, hi);
+                pairs += count_in_range(sorted_pos, lo, hi, p, thr);
             }
-            for (uint32_t k = lo; k < hi; k++) {
-                if (k == j) continue;
-                const float2 q = __ldg(sorted_pos + k);
-                if (dist2(q, p) < grid.hit_threshold) {
-                    hit = true;
-                    if (COUNT_PAIRS) pairs += (k < j) ? 1u : 0u;  // each unordered pair once
-                    else break;
-                }
+            pairs += count_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
+            hit = pairs != 0;
+        } else {
+            hit = any_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
+            if (!hit && cy > 0) {
+                row_run(cell_range, grid.ncx, cy - 1, x0, x1, lo, hi);
+                hit = any_in_range(sorted_pos, lo, hi, p, thr);
             }
+        }
+        if (!hit) hit = any_in_range(sorted_pos, max(j + 1, own_lo), own_hi, p, thr);
+        if (!hit && cy + 1 < grid.ncy) {
+            row_run(cell_range, grid.ncx, cy + 1, x0, x1, lo, hi);
+            hit = any_in_range(sorted_pos, lo, hi, p, thr);
         }
         flag_sorted[j] = hit ? 1 : 0;
     }
@@ -88,7 +144,10 @@ query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __r
     }
     if (lane == 0) {
         if (hits) atomicAdd(&counters->flagged_last, static_cast<unsigned long long>(hits));
-        if (COUNT_PAIRS && pairs) atomicAdd(&counters->pairs_last, static_cast<unsigned long long>(pairs));
+        if (COUNT_PAIRS && pairs) {
+            atomicAdd(&counters->pairs_last, static_cast<unsigned long long>(pairs));
+            atomicAdd(&counters->pairs_total, static_cast<unsigned long long>(pairs));
+        }
     }
 }
 
@@ -101,39 +160,36 @@ scatter_flags_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, 
     flag_entity[idx] = flag_sorted[j] + 1;  // 1 = green, 2 = blue (0 = "no collision pass yet")
 }
 
-__global__ void begin_pass_kernel(Counters* c) {
-    c->pairs_last = 0;
-    c->flagged_last = 0;
-}
-__global__ void end_pass_kernel(Counters* c) { c->pairs_total += c->pairs_last; }
-
 }  // namespace
 
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint2* cell_range,
-                       const GridParams& grid) {
+                       const GridParams& grid, Counters* counters, Profiler* prof) {
+    prof->begin(s, K_MEMSET);
     cudaMemsetAsync(cell_range, 0xff, static_cast<size_t>(grid.ncells) * sizeof(uint2), s);
+    prof->end(s);
     if (n == 0) return 0;
-    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, cell_range);
+    prof->begin(s, K_BUILD_CELLS);
+    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, cell_range, counters);
+    prof->end(s);
     return 1;
 }
 
 int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted, const GridParams& grid,
-                 bool count_pairs, Counters* counters) {
-    begin_pass_kernel<<<1, 1, 0, s>>>(counters);
-    int launches = 1;
-    if (n != 0) {
-        const uint32_t blocks = (n + 255u) / 256u;
-        if (count_pairs) query_kernel<true><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
-        else query_kernel<false><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
-        launches++;
-    }
-    end_pass_kernel<<<1, 1, 0, s>>>(counters);
-    return launches + 1;
+                 bool count_pairs, Counters* counters, Profiler* prof) {
+    if (n == 0) return 0;
+    const uint32_t blocks = (n + 255u) / 256u;
+    prof->begin(s, K_QUERY);
+    if (count_pairs) query_kernel<true><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
+    else query_kernel<false><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
+    prof->end(s);
+    return 1;
 }
 
-int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity) {
+int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
     if (n == 0) return 0;
+    prof->begin(s, K_SCATTER_FLAGS);
     scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), flag_sorted, flag_entity);
+    prof->end(s);
     return 1;
 }
 

@@ -8,13 +8,16 @@
 // an explicit __fmul_rn/__fadd_rn; sqrt and divide are the correctly rounded __fsqrt_rn/__fdiv_rn),
 // which is what the CPU oracle (oracle/msim_oracle.c) computes — positions come out bit-identical.
 //
-// B200 mapping: HBM-bound streaming kernel.  Per entity-update it must read pos (8 B) and target
-// (8 B) and write pos (8 B) = 24 B; road/rng/target are written only for the ~1/25 entities that
-// reach their waypoint.  Two entities share one 128-bit load/store (float4 = 2 x float2); each
-// thread keeps MOVE_ITEMS such pairs in flight; streaming (.cs) hints keep the one-touch entity
-// state from displacing the road/connection tables in L2, which are read through the read-only
-// path (__ldg).  `direction` is never stored: it is a pure function of (previous pos, target, arrival bit)
-// and is rebuilt at readback (pack.cu), so the per-tick traffic stays at the 24 B minimum.
+// B200 mapping: two kernels per move pass.
+//   pass A  move_kernel    HBM-bound streaming: per entity read pos (8 B) + target (8 B), write pos
+//                          (8 B) [+ cell key 4 B]; two entities per 128-bit load/store, .cs hints so
+//                          the one-touch state does not displace the road tables in L2.  Entities
+//                          that reach their waypoint are only flagged (1 bit).
+//   pass B  arrive_kernel  the ~1/25 flagged entities pick their next waypoint: dependent gathers
+//                          into the road / connection tables (read-only path) and the RNG state,
+//                          32 arrivals per warp per round, balanced with a warp scan.
+// `direction` is never stored: it is a pure function of (previous pos, target, arrival bit) and is
+// rebuilt at readback (pack.cu), so the per-tick traffic stays at the 24 B minimum.
 #include "msim_internal.h"
 
 namespace msim {
@@ -81,33 +84,33 @@ __device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* _
     return from_start ? make_float2(as_f(ne.x), as_f(ne.y)) : make_float2(as_f(ns.x), as_f(ns.y));
 }
 
-// update_direction(index, pos) + move(index) (:830-852).  Returns the new position; sets `arrived`
-// and rewrites `t` when the waypoint was reached.
-__device__ __forceinline__ float2 step_entity(uint32_t e, float2 p, float2& t, bool& arrived, uint32_t* __restrict__ road,
-                                              uint4* __restrict__ rng, const uint4* __restrict__ roads,
-                                              const uint32_t* __restrict__ conn, uint64_t conn_count) {
+// ---- pass A: pure streaming ------------------------------------------------------------------
+// update_direction(index, pos) + the walking branch of move(index) (:830-847).  Entities that reach
+// their waypoint land exactly on it (:848) and are only flagged here.
+__device__ __forceinline__ float2 walk(float2 p, float2 t, bool& arrived) {
     const float dx = __fsub_rn(t.x, p.x);
     const float dy = __fsub_rn(t.y, p.y);
     // length(target - pos) == distance(pos, target) bit for bit: the squares are sign-blind
     const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    if (len > SPEED) {
-        const float dirx = __fmul_rn(__fdiv_rn(dx, len), SPEED);
-        const float diry = __fmul_rn(__fdiv_rn(dy, len), SPEED);
-        arrived = false;
-        return make_float2(__fadd_rn(p.x, dirx), __fadd_rn(p.y, diry));
-    }
-    arrived = true;
-    const float2 reached = t;
-    t = new_target(e, reached, road, rng, roads, conn, conn_count);
-    return reached;
+    arrived = !(len > SPEED);
+    if (arrived) return t;
+    const float dirx = __fmul_rn(__fdiv_rn(dx, len), SPEED);
+    const float diry = __fmul_rn(__fdiv_rn(dy, len), SPEED);
+    return make_float2(__fadd_rn(p.x, dirx), __fadd_rn(p.y, diry));
 }
 
+// EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
+// sort's digit histograms for all passes in shared memory (flushed once per CTA), so the neighbour
+// rebuild needs no separate histogram read of the keys.
 template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(MOVE_THREADS)
-move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, float4* __restrict__ target,
-            uint32_t* __restrict__ road, uint4* __restrict__ rng, uint32_t* __restrict__ arrived_mask,
-            const uint4* __restrict__ roads, const uint32_t* __restrict__ conn, uint64_t conn_count,
-            uint2* __restrict__ keys, GridParams grid) {
+move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
+            uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes) {
+    __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
+    if (EMIT_KEYS) {
+        for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
+        __syncthreads();
+    }
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t pairs_pad = (pairs + 31u) & ~31u;  // arrays are padded, whole warps stay converged
     const uint32_t lane = threadIdx.x & 31u;
@@ -130,13 +133,11 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
             if (!live[k]) continue;  // warp-uniform
             const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
             const uint32_t e0 = pi * 2u, e1 = e0 + 1u;
-            float2 t0 = make_float2(T[k].x, T[k].y), t1 = make_float2(T[k].z, T[k].w);
-            float2 q0 = make_float2(P[k].x, P[k].y), q1 = make_float2(P[k].z, P[k].w);
             bool arr0 = false, arr1 = false;
-            if (e0 < n) q0 = step_entity(e0, q0, t0, arr0, road, rng, roads, conn, conn_count);
-            if (e1 < n) q1 = step_entity(e1, q1, t1, arr1, road, rng, roads, conn, conn_count);
+            float2 q0 = make_float2(P[k].x, P[k].y), q1 = make_float2(P[k].z, P[k].w);
+            if (e0 < n) q0 = walk(q0, make_float2(T[k].x, T[k].y), arr0);
+            if (e1 < n) q1 = walk(q1, make_float2(T[k].z, T[k].w), arr1);
             __stcs(pos_out + pi, make_float4(q0.x, q0.y, q1.x, q1.y));
-            if (arr0 || arr1) target[pi] = make_float4(t0.x, t0.y, t1.x, t1.y);
             const uint32_t m0 = __ballot_sync(0xffffffffu, arr0);
             const uint32_t m1 = __ballot_sync(0xffffffffu, arr1);
             if (lane == 0) {
@@ -144,8 +145,63 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
                 *reinterpret_cast<uint2*>(arrived_mask + w) = make_uint2(m0, m1);
             }
             if (EMIT_KEYS) {
-                keys[pi] = make_uint2(cell_key_of(q0, grid), cell_key_of(q1, grid));
+                const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);
+                keys[pi] = make_uint2(k0, k1);
+                for (int p = 0; p < hist_passes; p++) {
+                    if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+                    if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+                }
             }
+        }
+    }
+    if (EMIT_KEYS) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < hist_passes * RADIX; i += MOVE_THREADS)
+            if (s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
+    }
+}
+
+// ---- pass B: next waypoint for the entities that arrived (new_target, :778-828) ----------------
+// Doing this inside pass A serialised up to four dependent gather chains per thread and left the
+// streaming loads waiting behind them (80 % long-scoreboard stalls, profiles/r1a).  Here a warp owns
+// 32 words of the arrival bitmask (1024 entities, ~40 arrivals), ranks the set bits with a warp scan
+// and hands exactly one arrival to each lane per round: the gather chains run 32-wide and balanced.
+constexpr int ARRIVE_THREADS = 256;
+
+__global__ void __launch_bounds__(ARRIVE_THREADS)
+arrive_kernel(uint32_t n, uint32_t words, const uint32_t* __restrict__ arrived_mask, float2* __restrict__ target,
+              uint32_t* __restrict__ road, uint4* __restrict__ rng, const uint4* __restrict__ roads,
+              const uint32_t* __restrict__ conn, uint64_t conn_count) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = blockIdx.x * ARRIVE_THREADS + threadIdx.x;  // one mask word per lane
+    const uint32_t mask = (w < words) ? __ldcs(arrived_mask + w) : 0u;
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += up;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t r = base + lane;  // rank of the arrival this lane handles
+        // owner = first lane whose inclusive count exceeds r (binary search over the warp's counts)
+        uint32_t lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t probe = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31u);
+            if (probe <= r) lo += step;
+        }
+        const uint32_t owner = min(lo, 31u);
+        const uint32_t owner_mask = __shfl_sync(0xffffffffu, mask, owner);
+        const uint32_t owner_incl = __shfl_sync(0xffffffffu, incl, owner);
+        const uint32_t owner_cnt = __shfl_sync(0xffffffffu, cnt, owner);
+        if (r < total) {
+            const uint32_t nth = r - (owner_incl - owner_cnt);          // 0-based among the owner's set bits
+            const uint32_t bit = __fns(owner_mask, 0, static_cast<int>(nth) + 1);
+            const uint32_t ow = (w - lane) + owner;                     // the owner's mask word index
+            const uint32_t e = (ow >> 1) * 64u + bit * 2u + (ow & 1u);  // inverse of arrived_word/arrived_bit
+            if (e < n) target[e] = new_target(e, target[e], road, rng, roads, conn, conn_count);
         }
     }
 }
@@ -161,9 +217,8 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 
 }  // namespace
 
-int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, float2* target, uint32_t* road,
-                uint4* rng, uint32_t* arrived, const msim_road* roads, const uint32_t* connections, uint64_t connection_count,
-                uint32_t* keys, const GridParams& grid, uint8_t* /*init_mask*/, Counters* /*counters*/) {
+int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
+                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, Profiler* prof) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
@@ -172,24 +227,33 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     if (blocks > resident) blocks = resident;  // grid-stride: a whole number of CTAs per SM
     const float4* pin = reinterpret_cast<const float4*>(pos_in);
     float4* pout = reinterpret_cast<float4*>(pos_out);
-    float4* tgt = reinterpret_cast<float4*>(target);
-    const uint4* rd = reinterpret_cast<const uint4*>(roads);
-    if (keys) {
-        move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, road, rng, arrived, rd, connections, connection_count,
-                                                          reinterpret_cast<uint2*>(keys), grid);
-    } else {
-        move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, road, rng, arrived, rd, connections, connection_count,
-                                                           nullptr, grid);
-    }
+    const float4* tgt = reinterpret_cast<const float4*>(target);
+    prof->begin(s, K_MOVE);
+    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist_passes);
+    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0);
+    prof->end(s);
     return 1;
 }
 
-int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid) {
+int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof) {
+    if (n == 0) return 0;
+    const uint32_t words = ((n + 63u) >> 6) << 1;  // two mask words per 64-entity chunk
+    prof->begin(s, K_ARRIVE);
+    arrive_kernel<<<(words + ARRIVE_THREADS - 1) / ARRIVE_THREADS, ARRIVE_THREADS, 0, s>>>(
+        n, words, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
+    prof->end(s);
+    return 1;
+}
+
+int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     uint32_t blocks = (pairs + 255u) / 256u;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
+    prof->begin(s, K_KEYGEN);
     keygen_kernel<<<blocks, 256, 0, s>>>(n, reinterpret_cast<const float4*>(pos), reinterpret_cast<uint2*>(keys), grid);
+    prof->end(s);
     return 1;
 }
 

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/msim.h"
 
 namespace msim {
@@ -62,27 +64,60 @@ struct Counters {
     unsigned int pad;
 };
 
+// ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
+enum KernelId {
+    K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
+    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_COUNT
+};
+
+struct Profiler {
+    bool enabled{false};
+    std::vector<cudaEvent_t> pool;   // reusable events
+    std::vector<int> ids;            // kernel id per (start, stop) pair in use
+    size_t used{0};                  // events handed out this session
+
+    void begin(cudaStream_t s, int id) {
+        if (!enabled) return;
+        if (used + 2 > pool.size()) {
+            pool.resize(used + 2);
+            cudaEventCreate(&pool[used]);
+            cudaEventCreate(&pool[used + 1]);
+        }
+        ids.push_back(id);
+        cudaEventRecord(pool[used], s);
+    }
+    void end(cudaStream_t s) {
+        if (!enabled) return;
+        cudaEventRecord(pool[used + 1], s);
+        used += 2;
+    }
+};
+
 // ---- kernel launchers (each returns the number of kernels it launched) ------------------------
 // move.cu
-int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, float2* target,
-                uint32_t* road, uint4* rng, uint32_t* arrived, const msim_road* roads, const uint32_t* connections,
-                uint64_t connection_count, uint32_t* keys /* nullable */, const GridParams& grid,
-                uint8_t* init_mask /* nullable */, Counters* counters);
-int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid);
+// pass A (streaming) and pass B (next waypoint of the arrived entities) of one move dispatch
+int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
+                uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
+                int hist_passes, Profiler* prof);
+int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof);
+int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
 
 // sort.cu
 size_t sort_workspace_bytes(uint32_t capacity);
 void sort_workspace_bind(SortWorkspace& ws, void* base, uint32_t capacity);
 // sorts (key, index) by key; result lands in *result (either buf_a or buf_b)
 int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits,
-                const SortWorkspace& ws, uint64_t** result);
+                const SortWorkspace& ws, uint64_t** result, bool hist_ready, Profiler* prof);
+// zeroes histograms / tickets / look-back words; call before a move pass that fuses the histogram
+void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace& ws, Profiler* prof);
 
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos,
-                       uint2* cell_range, const GridParams& grid);
+                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof);
 int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted,
-                 const GridParams& grid, bool count_pairs, Counters* counters);
-int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity);
+                 const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof);
+int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu
 struct PackArgs {
@@ -99,9 +134,9 @@ struct PackArgs {
     uint32_t initialized_all;    // value of `initialized` when init_mask == nullptr
     uint32_t has_moved;          // 0: direction = dir0
 };
-int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst);
+int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst, Profiler* prof);
 int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target,
-                  uint32_t* road, uint4* rng, float4* color0, float2* dir0, uint8_t* init_mask, unsigned int* uninit_count);
+                  uint32_t* road, uint4* rng, float4* color0, float2* dir0, uint8_t* init_mask, unsigned int* uninit_count, Profiler* prof);
 int launch_max_road(cudaStream_t s, uint32_t n, const uint32_t* road, unsigned int* out_max);
 
 // ---- device helpers shared by several translation units ---------------------------------------

@@ -82,17 +82,21 @@ __global__ void __launch_bounds__(256) max_road_kernel(uint32_t n, const uint32_
 
 }  // namespace
 
-int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst) {
+int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst, Profiler* prof) {
     if (count == 0) return 0;
+    prof->begin(s, K_PACK);
     pack_kernel<<<(count + 255u) / 256u, 256, 0, s>>>(first, count, a, reinterpret_cast<float4*>(dst));
+    prof->end(s);
     return 1;
 }
 
 int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target, uint32_t* road,
-                  uint4* rng, float4* color0, float2* dir0, uint8_t* /*init_mask*/, unsigned int* uninit_count) {
+                  uint4* rng, float4* color0, float2* dir0, uint8_t* /*init_mask*/, unsigned int* uninit_count, Profiler* prof) {
     if (count == 0) return 0;
+    prof->begin(s, K_UNPACK);
     unpack_kernel<<<(count + 255u) / 256u, 256, 0, s>>>(first, count, reinterpret_cast<const float4*>(src), pos, target, road, rng, color0, dir0,
                                                         uninit_count);
+    prof->end(s);
     return 1;
 }
 

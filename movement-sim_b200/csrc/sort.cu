@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // ---- one onesweep pass ------------------------------------------------------------------------
 // FIRST: input is the bare u32 key array, the payload (entity index) is the element's position.
 template <bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const void* __restrict__ in_raw, uint64_t* __restrict__ out, uint32_t n, int shift,
+__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const void* __restrict__ in_raw, uint64_t* __restrict__ out, uint32_t n, int shift,
                                                                 const uint32_t* __restrict__ hist /* [RADIX], this pass */,
                                                                 uint32_t* __restrict__ tile_state /* [tiles][RADIX] */,
                                                                 uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ error_flag) {
@@ -107,23 +107,37 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const void* __re
         }
     }
 
-    // -- rank inside the warp, digit by digit, in element order (stable)
-    uint32_t rank[SORT_ITEMS];
+    // -- rank inside the warp, in element order (stable).  Two phases so that nothing serialises on a
+    //    register dependency: (1) all match_any votes are issued back to back; (2) per item the lowest
+    //    peer lane bumps the warp's digit counter with a shared-memory atomic (same-address atomics of
+    //    one warp retire in program order, which is element order) and broadcasts the old value.
+    uint32_t rank[SORT_ITEMS];  // holds the peer mask between the two phases
     const uint32_t lanes_below = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
+        // peers = lanes holding the same digit.  Built from one ballot per digit bit instead of
+        // match.any: MATCH.ANY throughput capped the kernel at ~20 % issue utilisation (profiles/r1a).
         const uint32_t idx = warp_base + i * 32 + lane;
-        const uint32_t digit = (idx < n) ? (static_cast<uint32_t>(kv[i] >> (32 + shift)) & (RADIX - 1)) : RADIX;  // RADIX = "not an element"
-        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t digit = static_cast<uint32_t>(kv[i] >> (32 + shift)) & (RADIX - 1);
+        uint32_t peers = __ballot_sync(0xffffffffu, idx < n);
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; b++) {
+            const bool bit = (digit >> b) & 1u;
+            const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? vote : ~vote;
+        }
+        rank[i] = peers;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        const uint32_t digit = static_cast<uint32_t>(kv[i] >> (32 + shift)) & (RADIX - 1);
+        const uint32_t peers = rank[i];
         const int leader = __ffs(peers) - 1;
         uint32_t before = 0;
-        if (static_cast<int>(lane) == leader && digit < RADIX) {
-            before = s_warp_hist[warp][digit];
-            s_warp_hist[warp][digit] = before + __popc(peers);
-        }
+        if (static_cast<int>(lane) == leader && idx < n && peers != 0u) before = atomicAdd(&s_warp_hist[warp][digit], static_cast<uint32_t>(__popc(peers)));
         before = __shfl_sync(0xffffffffu, before, leader);
         rank[i] = before + __popc(peers & lanes_below);
-        __syncwarp();
     }
     __syncthreads();
 
@@ -213,30 +227,51 @@ void sort_workspace_bind(SortWorkspace& ws, void* base, uint32_t capacity) {
     ws.tiles_cap = static_cast<uint32_t>(tiles);
 }
 
-int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits, const SortWorkspace& ws,
-                uint64_t** result) {
-    *result = buf_a;
-    if (n == 0) return 0;
+static int sort_passes_for(int key_bits) {
     int passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
     if (passes < 1) passes = 1;
     if (passes > MAX_SORT_PASSES) passes = MAX_SORT_PASSES;
+    return passes;
+}
+
+// zero the digit histograms, the tile tickets and the look-back words one sort of n keys will use
+void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace& ws, Profiler* prof) {
+    if (n == 0) return;
+    const int passes = sort_passes_for(key_bits);
     const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    // zero histograms, tickets and only the status words this launch will use
     const size_t used_words = static_cast<size_t>(MAX_SORT_PASSES) * RADIX + 64 + static_cast<size_t>(passes) * tiles * RADIX;
+    prof->begin(s, K_MEMSET);
     cudaMemsetAsync(ws.zero_base, 0, used_words * sizeof(uint32_t), s);
-    uint32_t hblocks = (n / 4 + 255) / 256;
-    if (hblocks > 148u * 8u) hblocks = 148u * 8u;
-    if (hblocks < 1) hblocks = 1;
-    histogram_kernel<<<hblocks, 256, 0, s>>>(keys, n, ws.hist, passes);
-    int launches = 1;
+    prof->end(s);
+}
+
+int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits, const SortWorkspace& ws,
+                uint64_t** result, bool hist_ready, Profiler* prof) {
+    *result = buf_a;
+    if (n == 0) return 0;
+    const int passes = sort_passes_for(key_bits);
+    const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    int launches = 0;
+    if (!hist_ready) {  // keys did not come from the move pass: histogram them here
+        sort_prepare(s, n, key_bits, ws, prof);
+        uint32_t hblocks = (n / 4 + 255) / 256;
+        if (hblocks > 148u * 8u) hblocks = 148u * 8u;
+        if (hblocks < 1) hblocks = 1;
+        prof->begin(s, K_HISTOGRAM);
+        histogram_kernel<<<hblocks, 256, 0, s>>>(keys, n, ws.hist, passes);
+        prof->end(s);
+        launches++;
+    }
     const void* in = keys;
     uint64_t* out = buf_a;
     for (int p = 0; p < passes; p++) {
         uint32_t* state = ws.tile_state + static_cast<size_t>(p) * tiles * RADIX;
+        prof->begin(s, K_SORT_PASS0 + p);
         if (p == 0)
             onesweep_kernel<true><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
         else
             onesweep_kernel<false><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
+        prof->end(s);
         launches++;
         *result = out;
         in = out;
