@@ -1,0 +1,59 @@
+/*
+ * msim_shard.h — multi-GPU extension of the C ABI.  The reference runs on one device
+ * (one kp::Manager, src/sim/Simulator.cpp:52); sharding is new work, so nothing here replaces a
+ * reference call — it extends msim.h so that N handles (one per GPU, one process per GPU) together
+ * produce exactly what one handle would.
+ *
+ * Partition: the neighbour grid's cell rows are split into contiguous bands, one per rank, the road
+ * graph is replicated.  Per sim tick and rank:
+ *     msim_enqueue_move            owned entities move (msim.h)
+ *     msim_shard_pack              leavers -> migrant records, boundary-row entities -> halo, into two
+ *                                  fixed-size DEVICE buffers (for the rank below / above)
+ *     <exchange>                   caller sends/receives the buffers (NCCL send/recv via torch.distributed)
+ *     msim_shard_integrate         arrivals join the owned set, halo + own leavers become ghosts
+ *     msim_enqueue_collide         collision pass over owned + ghosts; ghosts get no flag, count no pair
+ * The global unique-pair count is the sum of the ranks' last_pair_count (every pair is counted by the
+ * rank that owns its higher-keyed member).  With collisions off no exchange is needed at all: shard by
+ * entity range and use plain handles.
+ */
+#ifndef MSIM_SHARD_H
+#define MSIM_SHARD_H
+
+#include "msim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Size in bytes of one exchange buffer: 32-byte header + migrant_capacity x 72 + halo_capacity x 8. */
+uint64_t msim_shard_buffer_bytes(uint32_t migrant_capacity, uint32_t halo_capacity);
+
+/* Turns a handle into one shard.  gids[i] = global id of resident entity i (host array, `count` ==
+ * resident entity count).  Capacities bound what one tick may send to ONE neighbour; overflow is
+ * reported as MSIM_ERR_CAPACITY by msim_shard_integrate.  The handle's entity_capacity must leave room
+ * for arrivals and ghosts. */
+int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint32_t migrant_capacity, uint32_t halo_capacity);
+
+/* After a move pass: this rank owns cell rows [row_lo, row_hi).  send_down / send_up are DEVICE
+ * buffers of msim_shard_buffer_bytes() (NULL when there is no neighbour on that side).  Enqueue only. */
+int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up);
+
+/* After the exchange: recv_down / recv_up are the DEVICE buffers received from the rank below / above
+ * (NULL = none).  One host round trip (counts + hole list).  Returns the new owned / ghost counts. */
+int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts);
+
+/* Global ids of the owned entities, in the order msim_read_entities returns them. */
+int msim_shard_read_gids(msim_handle* h, uint32_t* dst, uint64_t count);
+
+/* Owned entities per cell row (rows == msim_stats.grid_cells_y): input of the band re-balancer. */
+int msim_shard_row_histogram(msim_handle* h, uint32_t* dst, uint32_t rows);
+
+/* Host helper, no GPU: the cell row every position falls into, computed exactly as the device does,
+ * plus the grid dimensions — lets the caller build the initial partition. */
+int msim_grid_rows(float world_w, float world_h, float radius, const float* xy, uint64_t count, uint32_t* rows_out,
+                   uint32_t* cells_x, uint32_t* cells_y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSIM_SHARD_H */

@@ -80,6 +80,9 @@ ABI_SYMBOLS = [
     "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
     "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
+    # include/msim_shard.h
+    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_integrate", "msim_shard_read_gids",
+    "msim_shard_row_histogram", "msim_grid_rows",
 ]
 
 
@@ -194,6 +197,13 @@ def lib():
         "msim_get_device_view": (i32, [vp, C.POINTER(DeviceView)]),
         "msim_profile_begin": (i32, [vp]),
         "msim_profile_end": (i32, [vp, C.POINTER(KernelTime), u32, C.POINTER(u32)]),
+        "msim_shard_buffer_bytes": (u64, [u32, u32]),
+        "msim_shard_enable": (i32, [vp, vp, u64, u32, u32]),
+        "msim_shard_pack": (i32, [vp, u32, u32, vp, vp]),
+        "msim_shard_integrate": (i32, [vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+        "msim_shard_read_gids": (i32, [vp, vp, u64]),
+        "msim_shard_row_histogram": (i32, [vp, vp, u32]),
+        "msim_grid_rows": (i32, [f32, f32, f32, vp, u64, vp, C.POINTER(u32), C.POINTER(u32)]),
         "msim_map_load_json": (i32, [C.c_char_p, C.POINTER(vp)]),
         "msim_map_save_json": (i32, [vp, C.c_char_p]),
         "msim_map_generate_city": (i32, [f32, f32, f32, f32, f32, u64, C.POINTER(vp)]),
@@ -288,6 +298,21 @@ class Map:
         if rc != MSIM_OK:
             raise MsimError(rc, L.msim_map_last_error().decode())
         return out
+
+
+def grid_rows(world_w: float, world_h: float, radius: float, xy: np.ndarray):
+    """Cell row of every position, exactly as the device computes it; returns (rows, cells_x, cells_y)."""
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+    rows = np.empty(xy.shape[0], dtype=np.uint32)
+    cx, cy = C.c_uint32(), C.c_uint32()
+    rc = lib().msim_grid_rows(world_w, world_h, radius, xy.ctypes.data, xy.shape[0], rows.ctypes.data, C.byref(cx), C.byref(cy))
+    if rc != MSIM_OK:
+        raise MsimError(rc, "msim_grid_rows")
+    return rows, cx.value, cy.value
+
+
+def shard_buffer_bytes(migrant_capacity: int, halo_capacity: int) -> int:
+    return int(lib().msim_shard_buffer_bytes(migrant_capacity, halo_capacity))
 
 
 def calc_node_count(depth: int) -> int:
@@ -409,6 +434,30 @@ class Simulation:
         st = Stats()
         self._check(lib().msim_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+    # -- multi-GPU sharding (include/msim_shard.h)
+    def shard_enable(self, gids: np.ndarray, migrant_capacity: int, halo_capacity: int):
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        self._check(lib().msim_shard_enable(self._h, gids.ctypes.data, gids.shape[0], migrant_capacity, halo_capacity))
+
+    def shard_pack(self, row_lo: int, row_hi: int, send_down_ptr: int | None, send_up_ptr: int | None):
+        self._check(lib().msim_shard_pack(self._h, row_lo, row_hi, send_down_ptr, send_up_ptr))
+
+    def shard_integrate(self, recv_down_ptr: int | None, recv_up_ptr: int | None):
+        owned, ghosts = C.c_uint64(), C.c_uint64()
+        self._check(lib().msim_shard_integrate(self._h, recv_down_ptr, recv_up_ptr, C.byref(owned), C.byref(ghosts)))
+        self.count = owned.value
+        return owned.value, ghosts.value
+
+    def shard_read_gids(self) -> np.ndarray:
+        out = np.empty(self.count, dtype=np.uint32)
+        self._check(lib().msim_shard_read_gids(self._h, out.ctypes.data, self.count))
+        return out
+
+    def shard_row_histogram(self, rows: int) -> np.ndarray:
+        out = np.zeros(rows, dtype=np.uint32)
+        self._check(lib().msim_shard_row_histogram(self._h, out.ctypes.data, rows))
+        return out
 
     def profile_begin(self):
         self._check(lib().msim_profile_begin(self._h))

@@ -7,12 +7,15 @@
 //   :220-235  two blocking dispatches per sim tick  -> msim_dispatch (tick parity, shader :860-879)
 //   :248-273  readbacks                             -> msim_read_*
 // No CPU fallback exists: without a usable sm_100 device every compute entry point fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
+#include "../../include/msim_shard.h"
 #include "msim_internal.h"
 
 using namespace msim;
@@ -81,6 +84,23 @@ struct msim_handle {
     uint64_t move_passes{0}, collide_passes{0}, launches{0}, initialised_total{0};
     uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0};
 
+    // multi-GPU sharding (msim_shard.h): band of cell rows per handle, ghosts behind the owned entities
+    bool sharded{false};
+    bool flags_stale{false};
+    uint32_t n_ghost{0};
+    uint32_t collide_total{0}, collide_owned{0};
+    uint32_t mig_cap{0}, halo_cap{0}, holes_cap{0};
+    uint32_t* gid{nullptr};
+    uint32_t* holes{nullptr};
+    float2* local_ghosts{nullptr};
+    uint32_t* shard_ctr{nullptr};
+    uint32_t* place_dst{nullptr};
+    uint2* moves{nullptr};
+    uint32_t* row_hist{nullptr};
+    uint32_t* host_stage{nullptr};  // pinned
+    void* sent_down{nullptr};
+    void* sent_up{nullptr};
+
     Profiler prof;
     std::string error;
 };
@@ -114,12 +134,12 @@ float exact_hit_threshold(float r) {
 
 // Cell edge slightly above the radius: two points closer than r must land in adjacent cells even
 // after the rounding of pos * inv_cell (error <= cells_per_axis * 2^-24 cell units).
-void configure_grid(msim_handle* h) {
-    GridParams g{};
-    g.radius = h->radius;
-    g.hit_threshold = exact_hit_threshold(h->radius);
-    double r = h->radius > 0.0f ? static_cast<double>(h->radius) : 1.0;
-    double w = h->world_w > 0.0f ? h->world_w : 1.0, hh = h->world_h > 0.0f ? h->world_h : 1.0;
+void compute_grid(float world_w, float world_h, float radius, GridParams& g, int& key_bits) {
+    g = GridParams{};
+    g.radius = radius;
+    g.hit_threshold = exact_hit_threshold(radius);
+    double r = radius > 0.0f ? static_cast<double>(radius) : 1.0;
+    double w = world_w > 0.0f ? world_w : 1.0, hh = world_h > 0.0f ? world_h : 1.0;
     double cell = r;
     for (int iter = 0; iter < 64; iter++) {
         const double axis = std::max(w, hh) / cell + 2.0;
@@ -128,7 +148,6 @@ void configure_grid(msim_handle* h) {
         const double ncx = std::floor(w / c) + 1.0, ncy = std::floor(hh / c) + 1.0;
         if (ncx * ncy <= static_cast<double>(MAX_GRID_CELLS)) {
             g.inv_cell = static_cast<float>(1.0 / c);
-            // inv_cell rounded to float may exceed 1/c by half an ulp: fold that into the margin check
             g.ncx = static_cast<int>(ncx);
             g.ncy = static_cast<int>(ncy);
             break;
@@ -140,9 +159,10 @@ void configure_grid(msim_handle* h) {
     g.ncells = static_cast<uint32_t>(g.ncx) * static_cast<uint32_t>(g.ncy);
     int bits = 1;
     while (bits < 32 && (1ull << bits) < g.ncells) bits++;
-    h->key_bits = bits;
-    h->grid = g;
+    key_bits = bits;
 }
+
+void configure_grid(msim_handle* h) { compute_grid(h->world_w, h->world_h, h->radius, h->grid, h->key_bits); }
 
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t count) {
@@ -156,6 +176,9 @@ void free_all(msim_handle* h) {
     cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
     cudaFree(h->scratch); cudaFree(h->stage);
+    cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
+    cudaFree(h->moves); cudaFree(h->row_hist);
+    if (h->host_stage) cudaFreeHost(h->host_stage);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
@@ -220,6 +243,8 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->hist_valid = false;
     h->collided = false;
     h->flags_scattered = false;
+    h->n_ghost = 0;
+    h->flags_stale = false;
     if (h->flag_entity) MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
     if (count && host_scratch[1] >= h->road_count) {
         h->n = 0;
@@ -263,10 +288,12 @@ int enqueue_move(msim_handle* h, bool want_keys) {
         if (rc != MSIM_OK) return rc;
     }
     const int passes = (h->key_bits + RADIX_BITS - 1) / RADIX_BITS;
-    if (emit) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
+    const bool fuse_hist = emit && !h->sharded;  // sharded: the key set changes in the exchange that follows
+    h->n_ghost = 0;
+    if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
-                               emit ? h->keys : nullptr, h->grid, emit ? h->ws.hist : nullptr,
+                               emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, &h->prof);
     if (emit && h->side) {
         // A collision pass follows and needs only the positions and keys of pass A: pass B (gathers
@@ -282,7 +309,7 @@ int enqueue_move(msim_handle* h, bool want_keys) {
     h->cur ^= 1;
     h->has_moved = true;
     h->keys_valid = emit;
-    h->hist_valid = emit;
+    h->hist_valid = fuse_hist;
     h->move_passes++;
     return MSIM_OK;
 }
@@ -297,11 +324,15 @@ int enqueue_collide(msim_handle* h) {
         h->keys_valid = true;
         h->hist_valid = false;
     }
-    h->launches += launch_sort(h->stream, h->n, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid, &h->prof);
+    const uint32_t total = h->n + h->n_ghost;  // ghosts (multi-GPU halo) sit behind the owned entities
+    h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid && h->n_ghost == 0, &h->prof);
     h->hist_valid = false;  // the sort consumed the tickets and look-back words
-    h->launches += launch_build_cells(h->stream, h->n, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid, h->counters, &h->prof);
-    h->launches += launch_query(h->stream, h->n, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid,
+    h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid, h->counters, &h->prof);
+    h->launches += launch_query(h->stream, total, h->n, h->sorted, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid,
                                 !(h->flags & MSIM_FLAG_NO_PAIR_COUNT), h->counters, &h->prof);
+    h->collide_total = total;
+    h->collide_owned = h->n;
+    h->flags_stale = false;
     h->collided = true;
     h->flags_scattered = false;
     h->collide_passes++;
@@ -316,7 +347,7 @@ int bind(msim_handle* h) {
 
 int materialise_flags(msim_handle* h) {
     if (h->collided && !h->flags_scattered) {
-        h->launches += launch_scatter_flags(h->stream, h->n, h->sorted, h->flag_sorted, h->flag_entity, &h->prof);
+        h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted, h->flag_sorted, h->flag_entity, &h->prof);
         h->flags_scattered = true;
     }
     return MSIM_OK;
@@ -525,6 +556,7 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     if (rc != MSIM_OK) return rc;
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
     if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
+    if (h->flags_stale) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_integrate and the collision pass");
     materialise_flags(h);
     join_side(h);
     PackArgs a{};
@@ -671,6 +703,198 @@ int msim_get_device_view(msim_handle* h, msim_device_view* out) {
     out->road = h->road;
     out->rng = h->rng;
     out->count = h->n;
+    return MSIM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU sharding (include/msim_shard.h)
+// ------------------------------------------------------------------------------------------------
+namespace {
+ShardArrays shard_arrays(msim_handle* h) {
+    ShardArrays a{};
+    a.pos_cur = h->pos[h->cur];
+    a.pos_prev = h->pos[h->cur ^ 1];
+    a.target = h->target;
+    a.road = h->road;
+    a.rng = h->rng;
+    a.color0 = h->color0;
+    a.gid = h->gid;
+    a.keys = h->keys;
+    a.arrived = h->arrived;
+    return a;
+}
+
+int ensure_keys(msim_handle* h) {
+    int rc = alloc_collision_buffers(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->keys_valid) {
+        h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
+        h->keys_valid = true;
+        h->hist_valid = false;
+    }
+    return MSIM_OK;
+}
+}  // namespace
+
+uint64_t msim_shard_buffer_bytes(uint32_t migrant_capacity, uint32_t halo_capacity) {
+    return sizeof(ShardHeader) + static_cast<uint64_t>(migrant_capacity) * MIGRANT_BYTES + static_cast<uint64_t>(halo_capacity) * sizeof(float2);
+}
+
+int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint32_t migrant_capacity, uint32_t halo_capacity) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (count != h->n) return fail(h, MSIM_ERR_INVALID, "msim_shard_enable: count differs from the resident entity count");
+    if (count && !gids) return fail(h, MSIM_ERR_INVALID, "msim_shard_enable: gids is null");
+    if (migrant_capacity == 0 || halo_capacity == 0) return fail(h, MSIM_ERR_INVALID, "msim_shard_enable: zero capacity");
+    if (h->flags & MSIM_FLAG_NO_COLLISIONS) return fail(h, MSIM_ERR_INVALID, "msim_shard_enable: collisions-off handles shard by entity range and need no exchange");
+    if (h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_enable: already enabled");
+    rc = alloc_collision_buffers(h);
+    if (rc != MSIM_OK) return rc;
+    h->mig_cap = migrant_capacity;
+    h->halo_cap = halo_capacity;
+    h->holes_cap = 2u * migrant_capacity;
+    MSIM_CUDA(h, dev_alloc(&h->gid, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->holes, h->holes_cap));
+    MSIM_CUDA(h, dev_alloc(&h->local_ghosts, h->holes_cap));
+    MSIM_CUDA(h, dev_alloc(&h->shard_ctr, SHARD_CTR_COUNT));
+    MSIM_CUDA(h, dev_alloc(&h->place_dst, h->holes_cap));
+    MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
+    MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(h->gid, gids, count * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->sharded = true;
+    return MSIM_OK;
+}
+
+int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_pack: call msim_shard_enable first");
+    if (row_lo >= row_hi || row_hi > static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_pack: bad row range");
+    join_side(h);  // the records carry target / road / rng, which pass B of the move may still be writing
+    rc = ensure_keys(h);
+    if (rc != MSIM_OK) return rc;
+    h->n_ghost = 0;
+    h->launches += launch_shard_pack(h->stream, shard_arrays(h), h->n, h->grid.ncx, row_lo, row_hi, send_down, send_up, h->mig_cap, h->halo_cap,
+                                     h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof);
+    h->sent_down = send_down;
+    h->sent_up = send_up;
+    return MSIM_OK;
+}
+
+int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_integrate: call msim_shard_enable first");
+    // one host round trip: counters, the four headers and the hole list
+    uint32_t* hs = h->host_stage;
+    uint32_t* h_ctr = hs;            // [8]
+    uint32_t* h_hdr = hs + 8;        // 4 x 8 words: sent_down, sent_up, recv_down, recv_up
+    uint32_t* h_holes = hs + 64;     // [holes_cap]
+    std::memset(hs, 0, 64 * sizeof(uint32_t));
+    MSIM_CUDA(h, cudaMemcpyAsync(h_ctr, h->shard_ctr, SHARD_CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    const void* hdrs[4] = {h->sent_down, h->sent_up, recv_down, recv_up};
+    for (int i = 0; i < 4; i++)
+        if (hdrs[i]) MSIM_CUDA(h, cudaMemcpyAsync(h_hdr + 8 * i, hdrs[i], sizeof(ShardHeader), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaMemcpyAsync(h_holes, h->holes, static_cast<size_t>(h->holes_cap) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    const uint32_t k_out = h_ctr[SHARD_CTR_HOLES], g_local = h_ctr[SHARD_CTR_LOCAL_GHOSTS];
+    for (int i = 0; i < 4; i++)
+        if (h_hdr[8 * i + 2]) return fail(h, MSIM_ERR_CAPACITY, "shard exchange buffer overflow: raise migrant_capacity / halo_capacity");
+    if (k_out > h->holes_cap) return fail(h, MSIM_ERR_CAPACITY, "more leavers than hole capacity");
+    const uint32_t in_down = recv_down ? h_hdr[16] : 0, halo_down = recv_down ? h_hdr[17] : 0;
+    const uint32_t in_up = recv_up ? h_hdr[24] : 0, halo_up = recv_up ? h_hdr[25] : 0;
+    if (in_down > h->mig_cap || in_up > h->mig_cap || halo_down > h->halo_cap || halo_up > h->halo_cap)
+        return fail(h, MSIM_ERR_CAPACITY, "received shard buffer exceeds the configured capacities");
+    const uint32_t k_in = in_down + in_up;
+    if (k_in > h->holes_cap) return fail(h, MSIM_ERR_CAPACITY, "more arrivals than placement capacity");
+    const uint32_t n_old = h->n;
+    const uint64_t n_new64 = static_cast<uint64_t>(n_old) + k_in - k_out;
+    const uint32_t n_ghost = halo_down + halo_up + g_local;
+    if (n_new64 + n_ghost > h->cap) return fail(h, MSIM_ERR_CAPACITY, "entity_capacity too small for arrivals + ghosts");
+    const uint32_t n_new = static_cast<uint32_t>(n_new64);
+
+    // placement: arrivals fill holes first, then append; left-over holes are closed from the tail
+    uint32_t* h_dst = hs + 64 + h->holes_cap;                                 // [holes_cap]
+    uint2* h_moves = reinterpret_cast<uint2*>(hs + 64 + 2 * h->holes_cap);  // [holes_cap] pairs
+    for (uint32_t i = 0; i < k_in; i++) h_dst[i] = i < k_out ? h_holes[i] : n_old + (i - k_out);
+    uint32_t n_moves = 0;
+    if (k_out > k_in) {
+        // holes still open: h_holes[k_in .. k_out).  Live entities in [n_new, n_old) move into holes < n_new.
+        std::vector<uint32_t> open(h_holes + k_in, h_holes + k_out);
+        std::sort(open.begin(), open.end());
+        std::vector<uint32_t> low;
+        size_t tail_holes_begin = std::lower_bound(open.begin(), open.end(), n_new) - open.begin();
+        low.assign(open.begin(), open.begin() + tail_holes_begin);
+        size_t hp = tail_holes_begin;  // walks the holes inside the tail
+        for (uint32_t src = n_new; src < n_old && n_moves < low.size(); src++) {
+            if (hp < open.size() && open[hp] == src) {
+                hp++;
+                continue;
+            }
+            h_moves[n_moves] = make_uint2(src, low[n_moves]);
+            n_moves++;
+        }
+        if (n_moves != low.size()) return fail(h, MSIM_ERR_INTERNAL, "shard compaction bookkeeping mismatch");
+    }
+    if (k_in) MSIM_CUDA(h, cudaMemcpyAsync(h->place_dst, h_dst, k_in * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    if (n_moves) MSIM_CUDA(h, cudaMemcpyAsync(h->moves, h_moves, n_moves * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+    const ShardArrays a = shard_arrays(h);
+    h->launches += launch_shard_place(h->stream, a, recv_down, in_down, recv_up, in_up, h->place_dst, h->grid, &h->prof);
+    h->launches += launch_shard_relocate(h->stream, a, h->moves, n_moves, &h->prof);
+    h->launches += launch_shard_append_ghosts(h->stream, a, n_new, recv_down, halo_down, recv_up, halo_up, h->local_ghosts, g_local, h->mig_cap,
+                                              h->grid, &h->prof);
+    // the host staging buffers are reused next tick: the copies above must have been consumed
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n = n_new;
+    h->n_ghost = n_ghost;
+    h->keys_valid = true;
+    h->hist_valid = false;
+    h->flags_stale = h->collided;
+    if (owned) *owned = n_new;
+    if (ghosts) *ghosts = n_ghost;
+    return MSIM_OK;
+}
+
+int msim_shard_read_gids(msim_handle* h, uint32_t* dst, uint64_t count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_read_gids: call msim_shard_enable first");
+    if (count > h->n || (count && !dst)) return fail(h, MSIM_ERR_INVALID, "msim_shard_read_gids: bad arguments");
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, h->gid, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSIM_OK;
+}
+
+int msim_shard_row_histogram(msim_handle* h, uint32_t* dst, uint32_t rows) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!dst || rows != static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_row_histogram: rows must equal grid_cells_y");
+    if (!h->row_hist) MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    rc = ensure_keys(h);
+    if (rc != MSIM_OK) return rc;
+    h->launches += launch_shard_row_histogram(h->stream, h->keys, h->n, h->grid.ncx, h->row_hist, rows, &h->prof);
+    MSIM_CUDA(h, cudaMemcpyAsync(dst, h->row_hist, static_cast<size_t>(rows) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSIM_OK;
+}
+
+int msim_grid_rows(float world_w, float world_h, float radius, const float* xy, uint64_t count, uint32_t* rows_out, uint32_t* cells_x, uint32_t* cells_y) {
+    GridParams g{};
+    int bits = 0;
+    compute_grid(world_w, world_h, radius, g, bits);
+    if (cells_x) *cells_x = static_cast<uint32_t>(g.ncx);
+    if (cells_y) *cells_y = static_cast<uint32_t>(g.ncy);
+    if (count && (!xy || !rows_out)) return MSIM_ERR_INVALID;
+    for (uint64_t i = 0; i < count; i++) {
+        const float prod = xy[2 * i + 1] * g.inv_cell;  // the device's cell_key_of: one binary32 multiply, floor, clamp
+        int cy = static_cast<int>(std::floor(prod));
+        if (!(prod == prod)) cy = 0;  // NaN -> 0, like __float2int_rd
+        cy = std::min(std::max(cy, 0), g.ncy - 1);
+        rows_out[i] = static_cast<uint32_t>(cy);
+    }
     return MSIM_OK;
 }
 

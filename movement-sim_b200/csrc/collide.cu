@@ -95,15 +95,22 @@ __device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, in
 // j) — that is the exact unique-pair count and already decides the flag for almost everybody.  Only
 // when nothing was found below does it look at the slots above (rest of its row, row below), and
 // there the first hit is enough.  Half the distance tests of a full 3x3 scan, same flags, same count.
-template <bool COUNT_PAIRS>
+// GHOSTS: slots whose entity index is >= n_owned belong to a neighbouring GPU (halo): they are
+// candidates for everybody else but get no flag and count no pairs here — their owner does that.
+template <bool COUNT_PAIRS, bool GHOSTS>
 __global__ void __launch_bounds__(256)
-query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __restrict__ cell_range,
-             uint8_t* __restrict__ flag_sorted, GridParams grid, Counters* __restrict__ counters) {
+query_kernel(uint32_t n, uint32_t n_owned, const unsigned long long* __restrict__ sorted, const float2* __restrict__ sorted_pos,
+             const uint2* __restrict__ cell_range, uint8_t* __restrict__ flag_sorted, GridParams grid, Counters* __restrict__ counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t pairs = 0;
     bool hit = false;
-    if (j < n) {
+    bool mine = j < n;
+    if (GHOSTS && mine) {
+        mine = static_cast<uint32_t>(__ldcs(sorted + j)) < n_owned;
+        if (!mine) flag_sorted[j] = 0;
+    }
+    if (mine) {
         const float2 p = sorted_pos[j];
         const float thr = grid.hit_threshold;
         int cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
@@ -152,11 +159,12 @@ query_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint2* __r
 }
 
 __global__ void __launch_bounds__(256)
-scatter_flags_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const uint8_t* __restrict__ flag_sorted,
+scatter_flags_kernel(uint32_t n, uint32_t n_owned, const unsigned long long* __restrict__ sorted, const uint8_t* __restrict__ flag_sorted,
                      uint8_t* __restrict__ flag_entity) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t idx = static_cast<uint32_t>(__ldcs(sorted + j));
+    if (idx >= n_owned) return;  // ghost
     flag_entity[idx] = flag_sorted[j] + 1;  // 1 = green, 2 = blue (0 = "no collision pass yet")
 }
 
@@ -174,21 +182,27 @@ int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const
     return 1;
 }
 
-int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted, const GridParams& grid,
-                 bool count_pairs, Counters* counters, Profiler* prof) {
+int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const float2* sorted_pos, const uint2* cell_range,
+                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + 255u) / 256u;
+    const unsigned long long* so = reinterpret_cast<const unsigned long long*>(sorted);
     prof->begin(s, K_QUERY);
-    if (count_pairs) query_kernel<true><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
-    else query_kernel<false><<<blocks, 256, 0, s>>>(n, sorted_pos, cell_range, flag_sorted, grid, counters);
+    if (n_owned < n) {
+        if (count_pairs) query_kernel<true, true><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+        else query_kernel<false, true><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+    } else {
+        if (count_pairs) query_kernel<true, false><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+        else query_kernel<false, false><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+    }
     prof->end(s);
     return 1;
 }
 
-int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
+int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
     if (n == 0) return 0;
     prof->begin(s, K_SCATTER_FLAGS);
-    scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), flag_sorted, flag_entity);
+    scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, n_owned, reinterpret_cast<const unsigned long long*>(sorted), flag_sorted, flag_entity);
     prof->end(s);
     return 1;
 }

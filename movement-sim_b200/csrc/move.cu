@@ -157,7 +157,7 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
     if (EMIT_KEYS) {
         __syncthreads();
         for (int i = threadIdx.x; i < hist_passes * RADIX; i += MOVE_THREADS)
-            if (s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
+            if (ghist && s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
     }
 }
 

@@ -67,7 +67,7 @@ struct Counters {
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
 enum KernelId {
     K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
-    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_COUNT
+    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_COUNT
 };
 
 struct Profiler {
@@ -115,9 +115,10 @@ void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace&
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos,
                        uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof);
-int launch_query(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint2* cell_range, uint8_t* flag_sorted,
-                 const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof);
-int launch_scatter_flags(cudaStream_t s, uint32_t n, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
+// n_owned < n: slots whose entity index is >= n_owned are ghosts (neighbours only; `sorted` is then required)
+int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const float2* sorted_pos, const uint2* cell_range,
+                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof);
+int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu
 struct PackArgs {
@@ -138,6 +139,37 @@ int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& 
 int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target,
                   uint32_t* road, uint4* rng, float4* color0, float2* dir0, uint8_t* init_mask, unsigned int* uninit_count, Profiler* prof);
 int launch_max_road(cudaStream_t s, uint32_t n, const uint32_t* road, unsigned int* out_max);
+
+// ---- multi-GPU sharding (shard.cu) -------------------------------------------------------------
+struct ShardHeader {
+    uint32_t n_migrants;
+    uint32_t n_halo;
+    uint32_t overflow;
+    uint32_t pad[5];
+};
+constexpr uint32_t MIGRANT_BYTES = 72;  // pos, pos_prev, target, rng, color0, road, gid, arrived bit
+enum { SHARD_CTR_HOLES = 0, SHARD_CTR_LOCAL_GHOSTS = 1, SHARD_CTR_COUNT = 8 };
+
+struct ShardArrays {
+    float2* pos_cur;
+    float2* pos_prev;
+    float2* target;
+    uint32_t* road;
+    uint4* rng;
+    float4* color0;
+    uint32_t* gid;
+    uint32_t* keys;
+    uint32_t* arrived;
+};
+
+int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
+                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof);
+int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
+                       const uint32_t* dst, const GridParams& grid, Profiler* prof);
+int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof);
+int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t first, const void* recv_down, uint32_t h_down, const void* recv_up,
+                               uint32_t h_up, const float2* local_ghosts, uint32_t h_local, uint32_t mig_cap, const GridParams& grid, Profiler* prof);
+int launch_shard_row_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, int ncx, uint32_t* rows, uint32_t nrows, Profiler* prof);
 
 // ---- device helpers shared by several translation units ---------------------------------------
 #ifdef __CUDACC__

@@ -1,0 +1,217 @@
+// shard.cu — kernels of the multi-GPU path: one msim handle per GPU owns a band of
+// whole cell rows [row_lo, row_hi) of the neighbour grid; the road graph is replicated.  The reference
+// has no multi-GPU path (one kp::Manager, /root/reference/src/sim/Simulator.cpp:52); this is new work
+// whose results must equal the single-GPU run: same per-entity state, same colour flags, and a global
+// unique-pair count that is the sum of the per-rank counts.
+//
+// Per sim tick, after the move pass:
+//   pack      every owned entity whose new cell row left the band is written as a 72-byte migrant
+//             record into the fixed-size buffer for the neighbour below / above and its slot becomes a
+//             hole; entities staying in the band's first / last row are appended to the halo list
+//             (8-byte positions) of the same buffer.  Leavers are also kept as local ghosts: they
+//             land in the neighbour's boundary row, i.e. within reach of our own boundary row.
+//   (NCCL)    the two buffers go to the neighbours, two come back — torch.distributed plumbing.
+//   place     arrivals are written into holes / appended; relocate closes the remaining holes with
+//             entities from the tail; append_ghosts puts halo + leaver positions after the owned
+//             entities so the radix sort / cell build / query see them as read-only neighbours.
+// Buffer layout (bytes): [32-byte header {n_migrants, n_halo, overflow}] [migrant_capacity x 72]
+// [halo_capacity x 8].
+#include "msim_internal.h"
+
+namespace msim {
+namespace {
+
+__device__ __forceinline__ void set_arrived_bit(uint32_t* mask, uint32_t e, bool value) {
+    uint32_t* w = mask + arrived_word(e);
+    const uint32_t bit = 1u << arrived_bit(e);
+    if (value) atomicOr(w, bit);
+    else atomicAnd(w, ~bit);
+}
+
+__device__ __forceinline__ ShardHeader* header_of(void* buf) { return static_cast<ShardHeader*>(buf); }
+__device__ __forceinline__ uint2* records_of(void* buf) { return reinterpret_cast<uint2*>(static_cast<char*>(buf) + sizeof(ShardHeader)); }
+__device__ __forceinline__ float2* halo_of(void* buf, uint32_t mig_cap) {
+    return reinterpret_cast<float2*>(static_cast<char*>(buf) + sizeof(ShardHeader) + static_cast<size_t>(mig_cap) * MIGRANT_BYTES);
+}
+
+// warp-aggregated append: returns this lane's slot in a list whose length lives at *counter
+__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<uint32_t>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256)
+shard_pack_kernel(ShardArrays a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
+                  uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = e < n;
+    uint32_t row = 0;
+    float2 p = make_float2(0.f, 0.f);
+    if (live) {
+        row = a.keys[e] / static_cast<uint32_t>(ncx);
+        p = a.pos_cur[e];
+    }
+    const bool go_down = live && buf_down && row < row_lo;
+    const bool go_up = live && buf_up && row >= row_hi;
+    if (go_down || go_up) {  // rare: a few hundred entities per boundary per tick
+        void* buf = go_down ? buf_down : buf_up;
+        const uint32_t slot = atomicAdd(&header_of(buf)->n_migrants, 1u);
+        if (slot < mig_cap) {
+            uint2* rec = records_of(buf) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
+            const float2 pp = a.pos_prev[e], t = a.target[e];
+            const uint4 s = a.rng[e];
+            const float4 c = a.color0[e];
+            const uint32_t arrived = (a.arrived[arrived_word(e)] >> arrived_bit(e)) & 1u;
+            rec[0] = make_uint2(__float_as_uint(p.x), __float_as_uint(p.y));
+            rec[1] = make_uint2(__float_as_uint(pp.x), __float_as_uint(pp.y));
+            rec[2] = make_uint2(__float_as_uint(t.x), __float_as_uint(t.y));
+            rec[3] = make_uint2(s.x, s.y);
+            rec[4] = make_uint2(s.z, s.w);
+            rec[5] = make_uint2(__float_as_uint(c.x), __float_as_uint(c.y));
+            rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
+            rec[7] = make_uint2(a.road[e], a.gid[e]);
+            rec[8] = make_uint2(arrived, 0u);
+        } else {
+            header_of(buf)->overflow = 1u;
+        }
+        const uint32_t hslot = atomicAdd(&ctr[SHARD_CTR_HOLES], 1u);
+        if (hslot < holes_cap) holes[hslot] = e;
+        const uint32_t gslot = atomicAdd(&ctr[SHARD_CTR_LOCAL_GHOSTS], 1u);
+        if (gslot < holes_cap) local_ghosts[gslot] = p;
+    }
+    // halo: owned entities that stay, in the band's first / last row
+    const bool halo_down = live && buf_down && !go_down && !go_up && row == row_lo;
+    const bool halo_up = live && buf_up && !go_down && !go_up && row + 1u == row_hi;
+    if (buf_down) {
+        const uint32_t slot = warp_append(halo_down, &header_of(buf_down)->n_halo);
+        if (halo_down) {
+            if (slot < halo_cap) halo_of(buf_down, mig_cap)[slot] = p;
+            else header_of(buf_down)->overflow = 1u;
+        }
+    }
+    if (buf_up) {
+        const uint32_t slot = warp_append(halo_up, &header_of(buf_up)->n_halo);
+        if (halo_up) {
+            if (slot < halo_cap) halo_of(buf_up, mig_cap)[slot] = p;
+            else header_of(buf_up)->overflow = 1u;
+        }
+    }
+}
+
+// arrivals: record i of the concatenation [recv_down migrants][recv_up migrants] goes to slot dst[i]
+__global__ void __launch_bounds__(128)
+shard_place_kernel(ShardArrays a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up, const uint32_t* __restrict__ dst,
+                   GridParams grid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_down + n_up) return;
+    const void* buf = i < n_down ? recv_down : recv_up;
+    const uint32_t r = i < n_down ? i : i - n_down;
+    const uint2* rec = reinterpret_cast<const uint2*>(static_cast<const char*>(buf) + sizeof(ShardHeader)) + static_cast<size_t>(r) * (MIGRANT_BYTES / 8);
+    const uint32_t e = dst[i];
+    const uint2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6], r7 = rec[7], r8 = rec[8];
+    const float2 p = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y));
+    a.pos_cur[e] = p;
+    a.pos_prev[e] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y));
+    a.target[e] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y));
+    a.rng[e] = make_uint4(r3.x, r3.y, r4.x, r4.y);
+    a.color0[e] = make_float4(__uint_as_float(r5.x), __uint_as_float(r5.y), __uint_as_float(r6.x), __uint_as_float(r6.y));
+    a.road[e] = r7.x;
+    a.gid[e] = r7.y;
+    a.keys[e] = cell_key_of(p, grid);
+    set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
+}
+
+// close the remaining holes: entity src[i] moves to slot dst[i]
+__global__ void __launch_bounds__(128) shard_relocate_kernel(ShardArrays a, const uint2* __restrict__ moves, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t src = moves[i].x, dst = moves[i].y;
+    a.pos_cur[dst] = a.pos_cur[src];
+    a.pos_prev[dst] = a.pos_prev[src];
+    a.target[dst] = a.target[src];
+    a.rng[dst] = a.rng[src];
+    a.color0[dst] = a.color0[src];
+    a.road[dst] = a.road[src];
+    a.gid[dst] = a.gid[src];
+    a.keys[dst] = a.keys[src];
+    set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
+}
+
+// ghosts = halo from below + halo from above + our own leavers, appended behind the owned entities
+__global__ void __launch_bounds__(256)
+shard_append_ghosts_kernel(ShardArrays a, uint32_t first, const void* recv_down, uint32_t h_down, const void* recv_up, uint32_t h_up,
+                           const float2* __restrict__ local_ghosts, uint32_t h_local, uint32_t mig_cap, GridParams grid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h_down + h_up + h_local) return;
+    float2 p;
+    if (i < h_down) p = halo_of(const_cast<void*>(recv_down), mig_cap)[i];
+    else if (i < h_down + h_up) p = halo_of(const_cast<void*>(recv_up), mig_cap)[i - h_down];
+    else p = local_ghosts[i - h_down - h_up];
+    a.pos_cur[first + i] = p;
+    a.keys[first + i] = cell_key_of(p, grid);
+}
+
+__global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int ncx, uint32_t* __restrict__ rows) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        atomicAdd(&rows[keys[e] / static_cast<uint32_t>(ncx)], 1u);
+}
+
+}  // namespace
+
+int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
+                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof) {
+    if (buf_down) cudaMemsetAsync(buf_down, 0, sizeof(ShardHeader), s);
+    if (buf_up) cudaMemsetAsync(buf_up, 0, sizeof(ShardHeader), s);
+    cudaMemsetAsync(ctr, 0, SHARD_CTR_COUNT * sizeof(uint32_t), s);
+    if (n == 0) return 0;
+    prof->begin(s, K_SHARD);
+    shard_pack_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(a, n, ncx, row_lo, row_hi, buf_down, buf_up, mig_cap, halo_cap, holes, holes_cap, local_ghosts, ctr);
+    prof->end(s);
+    return 1;
+}
+
+int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
+                       const uint32_t* dst, const GridParams& grid, Profiler* prof) {
+    if (n_down + n_up == 0) return 0;
+    prof->begin(s, K_SHARD);
+    shard_place_kernel<<<(n_down + n_up + 127u) / 128u, 128, 0, s>>>(a, recv_down, n_down, recv_up, n_up, dst, grid);
+    prof->end(s);
+    return 1;
+}
+
+int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof) {
+    if (count == 0) return 0;
+    prof->begin(s, K_SHARD);
+    shard_relocate_kernel<<<(count + 127u) / 128u, 128, 0, s>>>(a, moves, count);
+    prof->end(s);
+    return 1;
+}
+
+int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t first, const void* recv_down, uint32_t h_down, const void* recv_up,
+                               uint32_t h_up, const float2* local_ghosts, uint32_t h_local, uint32_t mig_cap, const GridParams& grid, Profiler* prof) {
+    const uint32_t total = h_down + h_up + h_local;
+    if (total == 0) return 0;
+    prof->begin(s, K_SHARD);
+    shard_append_ghosts_kernel<<<(total + 255u) / 256u, 256, 0, s>>>(a, first, recv_down, h_down, recv_up, h_up, local_ghosts, h_local, mig_cap, grid);
+    prof->end(s);
+    return 1;
+}
+
+int launch_shard_row_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, int ncx, uint32_t* rows, uint32_t nrows, Profiler* prof) {
+    cudaMemsetAsync(rows, 0, static_cast<size_t>(nrows) * sizeof(uint32_t), s);
+    if (n == 0) return 0;
+    uint32_t blocks = (n + 255u) / 256u;
+    if (blocks > 1184u) blocks = 1184u;
+    prof->begin(s, K_SHARD);
+    shard_row_histogram_kernel<<<blocks, 256, 0, s>>>(keys, n, ncx, rows);
+    prof->end(s);
+    return 1;
+}
+
+}  // namespace msim

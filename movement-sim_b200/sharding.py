@@ -1,0 +1,351 @@
+"""Host-side logic of the multi-GPU path: one process per GPU, torch.distributed for the
+plumbing.  The reference is single-device (/root/reference/src/sim/Simulator.cpp:52); this module makes
+N msim handles behave like one.
+
+  collisions off  entities are independent -> contiguous entity ranges, no data-path collective at all
+  collisions on   spatial bands of whole cell rows, road graph replicated; per tick each rank sends ONE
+                  fixed-size device buffer (migrant records + boundary-row halo, packed by the library's
+                  kernels) to the rank below and one to the rank above, and receives two.  Every
+                  REBALANCE_EVERY ticks a (rows x u32) all-reduce of the per-row histogram re-chooses
+                  the split rows; boundaries then walk one row per tick towards the target, which turns
+                  re-balancing into ordinary migration.
+
+The compute object is abstract (`engine`): the product engine is CudaShardEngine (C ABI ->
+hand-written kernels); the CPU tests drive the same orchestration over gloo with an oracle-backed
+engine (tests/shard_oracle_engine.py)."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+REBALANCE_EVERY = 64
+CHUNK = 1 << 20  # entities are generated in seeded chunks so that every rank can rebuild the global population
+
+
+# --------------------------------------------------------------------------------------------------
+# partitioning (pure numpy; unit-tested on CPU)
+# --------------------------------------------------------------------------------------------------
+def balanced_splits(row_hist: np.ndarray, world: int) -> np.ndarray:
+    """Split rows [0, R) into `world` contiguous non-empty bands holding ~equal entity counts.
+    Returns int64 array s of length world+1 with s[0] = 0, s[-1] = R; band r = rows [s[r], s[r+1])."""
+    rows = int(row_hist.shape[0])
+    if world > rows:
+        raise ValueError(f"{world} ranks but only {rows} cell rows")
+    cum = np.concatenate([[0], np.cumsum(row_hist.astype(np.int64))])
+    total = int(cum[-1])
+    s = np.zeros(world + 1, dtype=np.int64)
+    s[-1] = rows
+    for r in range(1, world):
+        want = total * r / world
+        k = int(np.searchsorted(cum, want, side="left"))
+        # the boundary before row k or before row k-1, whichever is closer to the ideal count
+        if k > 0 and abs(cum[k - 1] - want) <= abs(cum[min(k, rows)] - want):
+            k -= 1
+        s[r] = k
+    for r in range(1, world):  # strictly increasing, every band at least one row
+        s[r] = max(s[r], s[r - 1] + 1)
+    for r in range(world - 1, 0, -1):
+        s[r] = min(s[r], s[r + 1] - 1)
+    return s
+
+
+def step_towards(splits: np.ndarray, target: np.ndarray) -> np.ndarray:
+    """Move every interior boundary at most one row towards `target`, keeping bands non-empty."""
+    out = splits.copy()
+    for r in range(1, len(splits) - 1):
+        out[r] += np.sign(target[r] - splits[r])
+    for r in range(1, len(out) - 1):
+        out[r] = max(out[r], out[r - 1] + 1)
+    for r in range(len(out) - 2, 0, -1):
+        out[r] = min(out[r], out[r + 1] - 1)
+    return out
+
+
+def entity_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Collisions off: contiguous index range of `rank` (no collective ever needed)."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def generate_population(M, m, total: int, seed: int, box=None):
+    """Yields (first_gid, entities) chunks of the seeded global population; identical on every rank."""
+    done, chunk = 0, 0
+    while done < total:
+        k = min(CHUNK, total - done)
+        yield done, m.init_entities(k, seed=seed + 1000 * chunk, box=box)
+        done += k
+        chunk += 1
+
+
+def global_row_histogram(M, m, total: int, seed: int, radius: float, box=None):
+    hist, ncx, ncy = None, 0, 0
+    for _, ents in generate_population(M, m, total, seed, box):
+        rows, ncx, ncy = M.grid_rows(m.width, m.height, radius, ents["pos"])
+        h = np.bincount(rows, minlength=ncy).astype(np.int64)
+        hist = h if hist is None else hist + h
+    return hist, ncx, ncy
+
+
+def collect_band(M, m, total: int, seed: int, radius: float, row_lo: int, row_hi: int, box=None):
+    """This rank's slice of the global population: entities whose start row is in [row_lo, row_hi)."""
+    parts, gids = [], []
+    for first, ents in generate_population(M, m, total, seed, box):
+        rows, _, _ = M.grid_rows(m.width, m.height, radius, ents["pos"])
+        keep = (rows >= row_lo) & (rows < row_hi)
+        parts.append(ents[keep])
+        gids.append((first + np.nonzero(keep)[0]).astype(np.uint32))
+    return np.concatenate(parts), np.concatenate(gids)
+
+
+# --------------------------------------------------------------------------------------------------
+# orchestration
+# --------------------------------------------------------------------------------------------------
+class ShardedSimulation:
+    """Drives one rank's engine through sharded sim ticks.  `dist` is torch.distributed (nccl on GPUs,
+    gloo in the CPU tests); buffers are torch tensors on the engine's device."""
+
+    def __init__(self, engine, rank: int, world: int, splits: np.ndarray, rows: int, dist, torch, device, migrant_capacity: int,
+                 halo_capacity: int, buffer_bytes: int, rebalance_every: int = REBALANCE_EVERY):
+        self.engine, self.rank, self.world, self.dist, self.torch = engine, rank, world, dist, torch
+        self.splits = np.asarray(splits, dtype=np.int64).copy()
+        self.target = self.splits.copy()
+        self.rows = rows
+        self.rebalance_every = rebalance_every
+        self.ticks = 0
+        self.device = device
+        mk = lambda: torch.zeros(buffer_bytes, dtype=torch.uint8, device=device)
+        self.has_down, self.has_up = rank > 0, rank + 1 < world
+        self.send_down = mk() if self.has_down else None
+        self.recv_down = mk() if self.has_down else None
+        self.send_up = mk() if self.has_up else None
+        self.recv_up = mk() if self.has_up else None
+        self.migrant_capacity, self.halo_capacity = migrant_capacity, halo_capacity
+        self.exchanged_bytes = 0
+
+    @property
+    def band(self):
+        return int(self.splits[self.rank]), int(self.splits[self.rank + 1])
+
+    def _exchange(self):
+        d = self.dist
+        ops = []
+        if self.has_up:
+            ops += [d.P2POp(d.isend, self.send_up, self.rank + 1), d.P2POp(d.irecv, self.recv_up, self.rank + 1)]
+        if self.has_down:
+            ops += [d.P2POp(d.isend, self.send_down, self.rank - 1), d.P2POp(d.irecv, self.recv_down, self.rank - 1)]
+        if ops:
+            for req in d.batch_isend_irecv(ops):
+                req.wait()
+            self.exchanged_bytes += sum(op.tensor.numel() for op in ops) // 2
+
+    def tick(self, collide: bool = True):
+        """One sim tick: move, migrate/halo exchange, (collision pass)."""
+        if not np.array_equal(self.splits, self.target):
+            self.splits = step_towards(self.splits, self.target)
+        lo, hi = self.band
+        self.engine.move()
+        self.engine.pack(lo, hi, self.send_down, self.send_up)
+        self._exchange()
+        self.engine.integrate(self.recv_down, self.recv_up)
+        if collide:
+            self.engine.collide()
+        self.ticks += 1
+        if self.rebalance_every and self.world > 1 and self.ticks % self.rebalance_every == 0:
+            self.rebalance()
+
+    def rebalance(self):
+        """All-reduce the per-row histogram and re-choose the split rows (dense crowds, config 5)."""
+        hist = self.torch.from_numpy(self.engine.row_histogram(self.rows).astype(np.int64)).to(self.device)
+        self.dist.all_reduce(hist)
+        self.target = balanced_splits(hist.cpu().numpy(), self.world)
+
+    def global_sum(self, value: int) -> int:
+        t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+
+class CudaShardEngine:
+    """The product engine: one msim handle (C ABI, hand-written sm_100a kernels)."""
+
+    def __init__(self, M, sim):
+        self.M, self.sim = M, sim
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else t.data_ptr()
+
+    def move(self):
+        self.sim.enqueue_move()
+
+    def pack(self, lo, hi, send_down, send_up):
+        self.sim.shard_pack(lo, hi, self._ptr(send_down), self._ptr(send_up))
+
+    def integrate(self, recv_down, recv_up):
+        return self.sim.shard_integrate(self._ptr(recv_down), self._ptr(recv_up))
+
+    def collide(self):
+        self.sim.enqueue_collide()
+
+    def row_histogram(self, rows):
+        return self.sim.shard_row_histogram(rows)
+
+    def stats(self):
+        return self.sim.stats()
+
+    def read_owned(self):
+        return self.sim.read_entities(), self.sim.shard_read_gids()
+
+
+def make_cuda_shard(M, m, total: int, seed: int, radius: float, rank: int, world: int, dist, torch, local_rank: int, stream, box=None,
+                    rebalance_every: int = REBALANCE_EVERY):
+    """Builds this rank's band of the seeded global population on its GPU."""
+    hist, ncx, ncy = global_row_histogram(M, m, total, seed, radius, box)
+    splits = balanced_splits(hist, world)
+    lo, hi = int(splits[rank]), int(splits[rank + 1])
+    ents, gids = collect_band(M, m, total, seed, radius, lo, hi, box)
+    max_row = int(hist.max())
+    migrant_capacity = max(4096, 3 * max_row)
+    halo_capacity = max(4096, 3 * max_row)
+    capacity = int(ents.shape[0] * 1.3) + 4 * (migrant_capacity + halo_capacity) + 1024
+    sim = M.Simulation(m, ents, radius=radius, device=local_rank, stream=stream.cuda_stream, capacity=capacity)
+    sim.shard_enable(gids, migrant_capacity, halo_capacity)
+    engine = CudaShardEngine(M, sim)
+    device = torch.device("cuda", local_rank)
+    sh = ShardedSimulation(engine, rank, world, splits, ncy, dist, torch, device, migrant_capacity, halo_capacity,
+                           M.shard_buffer_bytes(migrant_capacity, halo_capacity), rebalance_every)
+    return sh, sim
+
+
+# --------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): launched by torch.distributed.run, one rank per GPU
+# --------------------------------------------------------------------------------------------------
+def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
+    import torch
+    import torch.distributed as dist
+
+    from bench import METRIC, SURVEY_BYTES, ClockSampler, build_workload, load_peaks
+
+    w, m = build_workload(M, args.workload, args.entities)
+    per_gpu = w["entities"]
+    collisions = w["collisions"]
+    total = per_gpu * world  # weak scaling: the per-GPU population is fixed as N grows
+    peak, peak_src = load_peaks()
+    stream = torch.cuda.Stream()
+    device = torch.device("cuda", local_rank)
+    sampler = None
+    with torch.cuda.stream(stream):
+        if collisions:
+            sh, sim = make_cuda_shard(M, m, total, 42, 10.0, rank, world, dist, torch, local_rank, stream)
+            sim.dispatch(2)  # the reference's first dispatch: initialise only
+            step = lambda: sh.tick(True)
+            for _ in range(args.preroll):
+                sh.tick(False)
+        else:
+            lo, hi = entity_range(total, rank, world)
+            parts = [e for _, e in generate_population(M, m, total, 42)]
+            ents = np.concatenate(parts)[lo:hi]
+            sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=M.FLAG_NO_COLLISIONS, stream=stream.cuda_stream)
+            sh = None
+            sim.dispatch(2)
+            sim.enqueue_ticks(args.preroll, False)
+            step = lambda: sim.enqueue_ticks(1, False)
+        for _ in range(max(3, args.warmup)):
+            step()
+        sim.sync()
+        if rank == 0:
+            props = torch.cuda.get_device_properties(local_rank)
+            uuid = getattr(props, "uuid", None)
+            sampler = ClockSampler(f"GPU-{uuid}" if uuid and not str(uuid).startswith("GPU-") else (str(uuid) if uuid else None))
+        launches0 = sim.stats()["kernel_launches"]
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms_local = e0.elapsed_time(e1)
+        t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        ms = float(t.item())
+        launches = sim.stats()["kernel_launches"] - launches0
+        owned = torch.tensor([sim.stats()["entity_count"]], dtype=torch.int64, device=device)
+        gathered = [torch.zeros_like(owned) for _ in range(world)]
+        dist.all_gather(gathered, owned)
+        per_rank = [int(g.item()) for g in gathered]
+        pairs = flagged = None
+        if collisions:
+            st = sim.stats()
+            pairs, flagged = sh.global_sum(st["last_pair_count"]), sh.global_sum(st["last_flagged_count"])
+        # keep the load up for the clock sampler (untimed)
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            step()
+        sim.sync()
+        clocks = sampler.stop() if sampler else None
+
+        # e2e per rank: host (pinned) AoS up, one tick, AoS back; max over ranks
+        n_local = sim.stats()["entity_count"]
+        pinned = torch.empty(int(n_local * 1.2 + 4096) * 64, dtype=torch.uint8, pin_memory=True)
+        ptr = pinned.data_ptr()
+        sim.read_entities_ptr(ptr, n_local)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal n_local, h2d, d2h
+            sim.upload_ptr(ptr, n_local)
+            h2d += n_local * 64
+            step()
+            sim.sync()
+            n_local = sim.stats()["entity_count"]
+            sim.read_entities_ptr(ptr, n_local)
+            d2h += n_local * 64
+
+        e2e_step()
+        h2d = d2h = 0
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        bytes_t = torch.tensor([h2d, d2h], dtype=torch.int64, device=device)
+        dist.all_reduce(bytes_t)
+    value = total * args.steps / (ms * 1e-3)
+    tick_gbs = SURVEY_BYTES[collisions] * value / 1e9
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": args.workload, "entities_per_gpu": per_gpu, "entities_total": total, "collisions": collisions,
+                       "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll,
+                       "parallelism": (f"{world} spatial bands of cell rows, NCCL send/recv of halo + migrants per tick, row-histogram all-reduce every {REBALANCE_EVERY} ticks"
+                                       if collisions else f"{world} entity ranges, no collective"),
+                       "owned_per_rank": per_rank, "l2": "inputs larger than L2 (no flush)",
+                       "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
+                       "global_pairs_last_tick": pairs, "global_flagged_last_tick": flagged},
+            "roofline": None,
+            "tick": {"survey_bytes_per_entity_update": SURVEY_BYTES[collisions], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / (peak * world),
+                     "frac_of_nominal_8tbs": tick_gbs / (8000.0 * world), "peak_source": peak_src},
+            "cpu_baseline": None,
+            "e2e": {"value": total * e2e_steps / float(dt.item()), "unit": "entity-updates/s", "h2d_bytes_per_step": int(bytes_t[0].item()) // e2e_steps,
+                    "d2h_bytes_per_step": int(bytes_t[1].item()) // e2e_steps, "steps": e2e_steps,
+                    "what": "per rank: msim_upload_entities(pinned AoS) + one sharded sim tick + msim_read_entities(pinned AoS); wall clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+    return 0

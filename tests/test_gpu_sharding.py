@@ -1,0 +1,140 @@
+"""GPU tests of the sharded path (include/msim_shard.h): pack / integrate / ghost kernels against the
+unsharded oracle.  Two or three handles on ONE GPU exchange their buffers with device copies (this is
+what the driver's single-GPU `pytest -m gpu` run exercises); with >= 2 GPUs the same worker as the CPU
+gloo test runs over NCCL."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_entities_equal, oracle_map, to_oracle_entities
+from test_sharding import BASE, check_against_reference, free_port
+
+pytestmark = pytest.mark.gpu
+
+
+def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False):
+    import torch
+
+    from movement_sim_b200 import sharding as S
+
+    hist, ncx, ncy = S.global_row_histogram(msim, m, total, seed, radius, box)
+    splits = np.linspace(0, ncy, world + 1).astype(np.int64) if skew else S.balanced_splits(hist, world)
+    target = splits.copy()
+    nbytes = msim.shard_buffer_bytes(capacity, capacity)
+    stream = torch.cuda.current_stream()
+    sims, bufs = [], []
+    for r in range(world):
+        ents, gids = S.collect_band(msim, m, total, seed, radius, int(splits[r]), int(splits[r + 1]), box)
+        sim = msim.Simulation(m, ents, radius=radius, stream=stream.cuda_stream, capacity=total + 8 * capacity)
+        sim.shard_enable(gids, capacity, capacity)
+        sim.dispatch(2)
+        sims.append(sim)
+        bufs.append({k: torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for k in ("sd", "su", "rd", "ru")})
+    pairs, owned = [], []
+    for t in range(ticks):
+        if not np.array_equal(splits, target):
+            splits = S.step_towards(splits, target)
+        for r, sim in enumerate(sims):
+            sim.enqueue_move()
+            sim.shard_pack(int(splits[r]), int(splits[r + 1]), bufs[r]["sd"].data_ptr() if r > 0 else None,
+                           bufs[r]["su"].data_ptr() if r + 1 < world else None)
+        for r in range(world):  # the "exchange": what NCCL send/recv does between processes
+            if r + 1 < world:
+                bufs[r + 1]["rd"].copy_(bufs[r]["su"])
+                bufs[r]["ru"].copy_(bufs[r + 1]["sd"])
+        total_pairs = 0
+        for r, sim in enumerate(sims):
+            sim.shard_integrate(bufs[r]["rd"].data_ptr() if r > 0 else None, bufs[r]["ru"].data_ptr() if r + 1 < world else None)
+            sim.enqueue_collide()
+            sim.sync()
+            total_pairs += sim.stats()["last_pair_count"]
+        pairs.append(total_pairs)
+        owned.append([s.stats()["entity_count"] for s in sims])
+        if rebalance_every and (t + 1) % rebalance_every == 0:
+            h = sum(s.shard_row_histogram(ncy).astype(np.int64) for s in sims)
+            target = S.balanced_splits(h, world)
+    got = np.zeros(total, dtype=msim.ENTITY_DTYPE)
+    seen = np.zeros(total, dtype=np.int32)
+    for sim in sims:
+        e, g = sim.read_entities(), sim.shard_read_gids()
+        got[g] = e
+        seen[g] += 1
+        sim.close()
+    assert (seen == 1).all()
+    return got, pairs, owned
+
+
+def oracle_reference(msim, orc, m, total, seed, radius, ticks, box=None):
+    from movement_sim_b200 import sharding as S
+
+    parts = [e for _, e in S.generate_population(msim, m, total, seed, box)]
+    e = to_oracle_entities(orc, np.concatenate(parts))
+    om = oracle_map(orc, m)
+    orc.move_pass(e, om)
+    pairs = []
+    for _ in range(ticks):
+        orc.move_pass(e, om, threads=8)
+        pairs.append(orc.collide_pass(e, m.width, m.height, radius, threads=8))
+    return e, pairs
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world):
+    total, ticks = 40_000, 50
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14)
+    want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
+    assert_entities_equal(got, want, what=f"{world} bands")
+    assert pairs == want_pairs
+    if world > 1:
+        assert any(o != owned[0] for o in owned), "entities should migrate between bands"
+
+
+def test_bands_rebalance_dense_corner(msim, orc, small_city):
+    """BASELINE config 5 in miniature: everybody starts in one corner, geometric initial split."""
+    total, ticks = 30_000, 80
+    box = [0.0, 0.0, 900.0, 600.0]
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True)
+    want, want_pairs = oracle_reference(msim, orc, small_city, total, 7, 10.0, ticks, box=box)
+    assert_entities_equal(got, want, what="rebalanced bands")
+    assert pairs == want_pairs
+    assert owned[0][0] > 0.8 * total and abs(owned[-1][0] - total / 2) < 0.15 * total
+
+
+def test_capacity_overflow_is_reported(msim, small_city):
+    import torch
+
+    from movement_sim_b200 import sharding as S
+
+    total = 20_000
+    hist, ncx, ncy = S.global_row_histogram(msim, small_city, total, 42, 10.0)
+    ents, gids = S.collect_band(msim, small_city, total, 42, 10.0, 0, ncy // 2)
+    stream = torch.cuda.current_stream()
+    sim = msim.Simulation(small_city, ents, radius=10.0, stream=stream.cuda_stream, capacity=total)
+    sim.shard_enable(gids, 8, 8)  # absurdly small
+    sim.dispatch(2)
+    nbytes = msim.shard_buffer_bytes(8, 8)
+    up = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    rup = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    sim.enqueue_move()
+    sim.shard_pack(0, ncy // 2, None, up.data_ptr())
+    with pytest.raises(msim.MsimError) as ei:
+        sim.shard_integrate(None, rup.data_ptr())
+    assert ei.value.status == msim.MSIM_ERR_CAPACITY
+    sim.close()
+
+
+def test_two_gpus_over_nccl(msim, orc, tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    from shard_worker import run
+
+    world = min(torch.cuda.device_count(), 4)
+    cfg = dict(BASE, entities=60_000, ticks=60, capacity=1 << 14)
+    mp.spawn(run, args=(world, free_port(), "nccl", str(tmp_path), cfg), nprocs=world, join=True)
+    check_against_reference(orc, msim, cfg, str(tmp_path), world)
