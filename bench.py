@@ -37,7 +37,9 @@ METRIC = "entity-updates/sec"
 SURVEY_BYTES = {True: 124.0, False: 24.0}  # B_coll (23-bit keys, 3 passes) / B_move
 # algorithmic HBM bytes per entity per launch of each kernel
 KERNEL_BYTES = {
-    "move": 28.0,  # pos R8 + target R8 + pos W8 + cell key W4 (24.0 when collisions are off)
+    "move": 32.0,  # pos R8 + target R8 + pos W8 + cell key W4 + cell rank W4 (24.0 when collisions are off)
+    "cell_count": 8.0,  # key R4 + rank W4 (only when the keys did not come from a move pass)
+    "cell_scatter": 28.0,  # key R4 + rank R4 + pos R8 + sorted pos W8 + sorted idx W4
     "keygen": 12.0,
     "histogram": 4.0,
     "sort_pass0": 12.0,  # key R4 + pair W8
@@ -231,7 +233,11 @@ def run_b200(args):
     peak, peak_src = load_peaks()
     stream = torch.cuda.Stream()
     ents = m.init_entities(n, seed=42)
-    flags = 0 if collisions else M.FLAG_NO_COLLISIONS
+    if args.presort:  # experiment: spatially coherent storage order (sort the host array by cell row, then x)
+        rows, _, _ = M.grid_rows(m.width, m.height, 10.0, ents["pos"])
+        order = np.lexsort((ents["pos"][:, 0], rows))
+        ents = np.ascontiguousarray(ents[order])
+    flags = (0 if collisions else M.FLAG_NO_COLLISIONS) | (M.FLAG_SORT_COUNTING if args.counting_sort else 0)
     sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=flags, stream=stream.cuda_stream)
     sim.dispatch(2)  # the reference's first dispatch: initialise only
     sim.enqueue_ticks(args.preroll, False)  # disperse the population along the roads (untimed)
@@ -393,6 +399,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1_000_000)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--presort", action="store_true", help="experiment: upload the entities in cell order")
+    ap.add_argument("--counting-sort", action="store_true", help="use the single-digit counting sort instead of onesweep")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

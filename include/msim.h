@@ -96,7 +96,9 @@ typedef struct msim_handle msim_handle;
 enum {
     MSIM_FLAG_NO_COLLISIONS = 1u << 0, /* even-tick dispatches do not emit cell keys; odd ticks are rejected */
     MSIM_FLAG_NO_PAIR_COUNT = 1u << 1, /* collision query stops at the first neighbour (flags only) */
-    MSIM_FLAG_NO_QUADTREE   = 1u << 2  /* msim_read_quadtree_nodes returns the root only */
+    MSIM_FLAG_NO_QUADTREE   = 1u << 2, /* msim_read_quadtree_nodes returns the root only */
+    MSIM_FLAG_SORT_COUNTING = 1u << 3  /* rebuild the neighbour structure with the single-digit (counting) radix sort instead of
+                                          the multi-pass onesweep radix sort; pays off when entity order is spatially coherent */
 };
 
 typedef struct msim_config {

@@ -68,6 +68,7 @@ MSIM_ABI_VERSION = 1
 FLAG_NO_COLLISIONS = 1 << 0
 FLAG_NO_PAIR_COUNT = 1 << 1
 FLAG_NO_QUADTREE = 1 << 2
+FLAG_SORT_COUNTING = 1 << 3
 
 # every symbol include/msim.h declares (tests/test_abi.py checks the library exports exactly these)
 ABI_SYMBOLS = [

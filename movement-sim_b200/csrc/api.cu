@@ -26,6 +26,7 @@ thread_local std::string g_create_error;
 constexpr uint64_t MAX_ENTITIES_PER_HANDLE = 1ull << 30;  // look-back words carry 30-bit counts
 constexpr uint32_t MAX_GRID_CELLS = 1u << 27;
 constexpr uint32_t STAGE_ENTITIES = 1u << 20;  // 64 MiB AoS staging chunk
+constexpr uint32_t CSORT_MAX_CELLS = 1u << 25;  // counter + prefix tables of 2 x 128 MiB at most; beyond that: onesweep
 }  // namespace
 
 struct msim_handle {
@@ -62,8 +63,15 @@ struct msim_handle {
     uint64_t* sort_b{nullptr};
     uint64_t* sorted{nullptr};
     float2* sorted_pos{nullptr};
-    uint2* cell_range{nullptr};
+    uint2* cell_range{nullptr};   // onesweep path: {first, ~end} per cell
     uint32_t cell_capacity{0};
+    uint32_t* cell_count{nullptr};  // counting-sort path: per-cell counters, prefix table, scan scratch, ranks
+    uint32_t* cell_start{nullptr};
+    uint32_t* tile_sums{nullptr};
+    uint32_t* rank{nullptr};
+    uint32_t* sorted_idx{nullptr};
+    bool use_csort{false};
+    bool counts_valid{false};
     uint8_t* flag_sorted{nullptr};
     uint8_t* flag_entity{nullptr};
     void* sort_mem{nullptr};
@@ -72,6 +80,7 @@ struct msim_handle {
     int key_bits{1};
 
     Counters* counters{nullptr};
+    unsigned long long* stripes{nullptr};  // striped per-query counters (collide.cu)
     unsigned int* scratch{nullptr};  // [0] uninitialised count, [1] max road index
     msim_entity* stage{nullptr};
 
@@ -174,8 +183,9 @@ void free_all(msim_handle* h) {
     cudaFree(h->pos[0]); cudaFree(h->pos[1]); cudaFree(h->target); cudaFree(h->road); cudaFree(h->rng);
     cudaFree(h->color0); cudaFree(h->dir0); cudaFree(h->arrived); cudaFree(h->roads); cudaFree(h->conn);
     cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
+    cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums); cudaFree(h->rank); cudaFree(h->sorted_idx);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
-    cudaFree(h->scratch); cudaFree(h->stage);
+    cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -195,12 +205,20 @@ void join_side(msim_handle* h) {
 }
 
 int ensure_cells(msim_handle* h) {
-    if (h->grid.ncells <= h->cell_capacity) return MSIM_OK;
-    cudaFree(h->cell_range);
-    h->cell_range = nullptr;
+    h->use_csort = (h->flags & MSIM_FLAG_SORT_COUNTING) && h->grid.ncells <= CSORT_MAX_CELLS;
+    if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
+    cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums);
+    h->cell_range = nullptr; h->cell_count = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;
     h->cell_capacity = 0;
-    MSIM_CUDA(h, dev_alloc(&h->cell_range, h->grid.ncells));
+    if (h->use_csort) {
+        MSIM_CUDA(h, dev_alloc(&h->cell_count, static_cast<size_t>(h->grid.ncells) + 1));
+        MSIM_CUDA(h, dev_alloc(&h->cell_start, static_cast<size_t>(h->grid.ncells) + 1));
+        MSIM_CUDA(h, dev_alloc(&h->tile_sums, static_cast<size_t>(csort_tiles(h->grid.ncells))));
+    } else {
+        MSIM_CUDA(h, dev_alloc(&h->cell_range, h->grid.ncells));
+    }
     h->cell_capacity = h->grid.ncells;
+    h->counts_valid = false;
     return MSIM_OK;
 }
 
@@ -210,10 +228,14 @@ int alloc_collision_buffers(msim_handle* h) {
     MSIM_CUDA(h, dev_alloc(&h->sort_a, h->cap));
     MSIM_CUDA(h, dev_alloc(&h->sort_b, h->cap));
     MSIM_CUDA(h, dev_alloc(&h->sorted_pos, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->rank, h->cap));
+    MSIM_CUDA(h, dev_alloc(&h->sorted_idx, h->cap));
     MSIM_CUDA(h, dev_alloc(&h->flag_sorted, h->cap));
     MSIM_CUDA(h, dev_alloc(&h->flag_entity, h->cap));
     MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
     const size_t ws_bytes = sort_workspace_bytes(h->cap);
+    MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->stripes), query_stripe_bytes()));
+    MSIM_CUDA(h, cudaMemsetAsync(h->stripes, 0, query_stripe_bytes(), h->stream));
     MSIM_CUDA(h, cudaMalloc(&h->sort_mem, ws_bytes));
     sort_workspace_bind(h->ws, h->sort_mem, h->cap);
     h->ws.error_flag = &h->counters->error_flag;
@@ -241,6 +263,7 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->has_moved = false;
     h->keys_valid = false;
     h->hist_valid = false;
+    h->counts_valid = false;
     h->collided = false;
     h->flags_scattered = false;
     h->n_ghost = 0;
@@ -288,13 +311,18 @@ int enqueue_move(msim_handle* h, bool want_keys) {
         if (rc != MSIM_OK) return rc;
     }
     const int passes = (h->key_bits + RADIX_BITS - 1) / RADIX_BITS;
-    const bool fuse_hist = emit && !h->sharded;  // sharded: the key set changes in the exchange that follows
+    // what the neighbour rebuild can take over from this pass: the counting sort's per-cell ranks, or the
+    // onesweep digit histograms.  Sharded handles change their key set in the exchange that follows.
+    const bool fuse_count = emit && h->use_csort && !h->sharded;
+    const bool fuse_hist = emit && !h->use_csort && !h->sharded;
     h->n_ghost = 0;
+    if (fuse_count) csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
-                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, &h->prof);
+                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof);
+    h->counts_valid = fuse_count;
     if (emit && h->side) {
         // A collision pass follows and needs only the positions and keys of pass A: pass B (gathers
         // into the road tables, latency-bound, little bandwidth) runs beside the sort on a second stream.
@@ -325,11 +353,25 @@ int enqueue_collide(msim_handle* h) {
         h->hist_valid = false;
     }
     const uint32_t total = h->n + h->n_ghost;  // ghosts (multi-GPU halo) sit behind the owned entities
-    h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid && h->n_ghost == 0, &h->prof);
-    h->hist_valid = false;  // the sort consumed the tickets and look-back words
-    h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->cell_range, h->grid, h->counters, &h->prof);
-    h->launches += launch_query(h->stream, total, h->n, h->sorted, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid,
-                                !(h->flags & MSIM_FLAG_NO_PAIR_COUNT), h->counters, &h->prof);
+    const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
+    if (h->use_csort) {
+        if (!h->counts_valid) {  // keys came from keygen or changed in a shard exchange: count them now
+            csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
+            h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, &h->prof);
+        }
+        h->counts_valid = false;
+        h->launches += launch_cell_scan(h->stream, h->cell_count, h->grid.ncells, h->tile_sums, h->cell_start, &h->prof);
+        h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof);
+        h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
+                                    h->counters, h->stripes, &h->prof);
+    } else {
+        h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid && h->n_ghost == 0, &h->prof);
+        h->hist_valid = false;  // the sort consumed the tickets and look-back words
+        h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
+                                          &h->prof);
+        h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
+                                    h->counters, h->stripes, &h->prof);
+    }
     h->collide_total = total;
     h->collide_owned = h->n;
     h->flags_stale = false;
@@ -347,7 +389,7 @@ int bind(msim_handle* h) {
 
 int materialise_flags(msim_handle* h) {
     if (h->collided && !h->flags_scattered) {
-        h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted, h->flag_sorted, h->flag_entity, &h->prof);
+        h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted_idx, h->flag_sorted, h->flag_entity, &h->prof);
         h->flags_scattered = true;
     }
     return MSIM_OK;
@@ -541,6 +583,7 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
         configure_grid(h);
         h->keys_valid = false;
         h->hist_valid = false;
+        h->counts_valid = false;
         if (h->keys) {
             rc = ensure_cells(h);
             if (rc != MSIM_OK) return rc;
@@ -666,7 +709,8 @@ int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32
     if (rc != MSIM_OK) return rc;
     if (!out || !count) return fail(h, MSIM_ERR_INVALID, "msim_profile_end: null argument");
     static const char* const names[K_COUNT] = {"move", "arrive", "keygen", "histogram", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3",
-                                               "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc"};
+                                               "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc", "shard", "cell_count",
+                                               "cell_scan", "cell_scatter"};
     h->prof.enabled = false;
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     double ms[K_COUNT] = {0};
@@ -732,6 +776,7 @@ int ensure_keys(msim_handle* h) {
         h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
         h->keys_valid = true;
         h->hist_valid = false;
+        h->counts_valid = false;
     }
     return MSIM_OK;
 }
@@ -852,6 +897,7 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     h->n_ghost = n_ghost;
     h->keys_valid = true;
     h->hist_valid = false;
+    h->counts_valid = false;
     h->flags_stale = h->collided;
     if (owned) *owned = n_new;
     if (ghosts) *ghosts = n_ghost;

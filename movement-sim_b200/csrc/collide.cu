@@ -19,12 +19,8 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const float2* __restrict__ pos,
-                   float2* __restrict__ sorted_pos, uint2* __restrict__ cell_range, Counters* __restrict__ counters) {
+                   float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx, uint2* __restrict__ cell_range, Counters* __restrict__ counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) {  // per-pass counters of the query that follows
-        counters->pairs_last = 0;
-        counters->flagged_last = 0;
-    }
     const uint32_t lane = threadIdx.x & 31u;
     const bool in = j < n;
     unsigned long long kv = in ? __ldcs(sorted + j) : ~0ull;
@@ -34,6 +30,7 @@ build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, co
     if (lane == 0) prev_key = (j == 0) ? 0xffffffffu : static_cast<uint32_t>(sorted[j - 1] >> 32);
     const uint32_t idx = static_cast<uint32_t>(kv);
     sorted_pos[j] = pos[idx];  // 8-byte gather, coalesced store
+    sorted_idx[j] = idx;
     if (j == 0 || key != prev_key) {
         cell_range[key].x = j;                       // first slot of this cell
         if (j != 0) cell_range[prev_key].y = ~j;     // one past the last slot of the previous cell
@@ -78,7 +75,15 @@ __device__ __forceinline__ bool any_in_range(const float2* __restrict__ sorted_p
 }
 
 // the three cells x0..x1 of one grid row are adjacent keys = one contiguous run [lo, hi) of the sorted order
-__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, int ncx, int yy, int x0, int x1, uint32_t& lo, uint32_t& hi) {
+template <bool PREFIX>
+__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, int ncx, int yy, int x0, int x1,
+                                        uint32_t& lo, uint32_t& hi) {
+    if (PREFIX) {  // counting-sort path: exclusive prefix table, run = [start[first cell], start[last cell + 1])
+        const uint32_t* row = cell_start + static_cast<size_t>(yy) * ncx;
+        lo = __ldg(row + x0);
+        hi = __ldg(row + x1 + 1);
+        return;
+    }
     const uint2* row = cell_range + static_cast<size_t>(yy) * ncx;
     lo = 0xffffffffu;
     hi = 0u;
@@ -90,119 +95,252 @@ __device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, in
     if (lo > hi) lo = hi;  // all three empty
 }
 
+// ---- shared-memory variants of the scans (same arithmetic, candidates already staged) -----------
+__device__ __forceinline__ uint32_t count_in_tile(const float2* __restrict__ tile, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t c = 0;
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = tile[k], q1 = tile[k + 1], q2 = tile[k + 2], q3 = tile[k + 3];
+        c += (dist2(q0, p) < threshold) ? 1u : 0u;
+        c += (dist2(q1, p) < threshold) ? 1u : 0u;
+        c += (dist2(q2, p) < threshold) ? 1u : 0u;
+        c += (dist2(q3, p) < threshold) ? 1u : 0u;
+    }
+    for (; k < b; k++) c += (dist2(tile[k], p) < threshold) ? 1u : 0u;
+    return c;
+}
+
+__device__ __forceinline__ bool any_in_tile(const float2* __restrict__ tile, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = tile[k], q1 = tile[k + 1], q2 = tile[k + 2], q3 = tile[k + 3];
+        if ((dist2(q0, p) < threshold) | (dist2(q1, p) < threshold) | (dist2(q2, p) < threshold) | (dist2(q3, p) < threshold)) return true;
+    }
+    for (; k < b; k++)
+        if (dist2(tile[k], p) < threshold) return true;
+    return false;
+}
+
+constexpr int QUERY_THREADS = 256;
+constexpr int COUNTER_STRIPES = 64;
+constexpr int COUNTER_STRIDE = 16;  // in u64 words: 128 bytes between stripes
+constexpr uint32_t QUERY_WINDOW = 1792;  // candidates staged per window (2 windows x 14 KB of shared memory)
+
 // One thread per sorted slot j.  Every unordered pair is examined from its HIGHER slot only: thread j
-// counts its in-range partners among the slots below it (the whole row above, and its own row up to
-// j) — that is the exact unique-pair count and already decides the flag for almost everybody.  Only
-// when nothing was found below does it look at the slots above (rest of its row, row below), and
-// there the first hit is enough.  Half the distance tests of a full 3x3 scan, same flags, same count.
+// counts its in-range partners among the slots below it — the whole grid row above (cells cx-1..cx+1)
+// and its own row up to j.  That is the exact unique-pair count and already decides the flag for
+// almost everybody; only when nothing was found below does the thread look at the slots above it
+// (rest of its row, row below), where the first hit is enough.
+//
+// The 256 slots of a CTA are consecutive in cell order, so the candidates they need form two short
+// contiguous windows of sorted_pos (one in the row above, one ending at the CTA's own last slot).
+// Both windows are staged in shared memory with coalesced loads and every distance test reads LDS:
+// the first version issued one L2 round trip per four candidates per thread and was 78 % stalled on
+// the long scoreboard (profiles/r1b).  CTAs whose windows do not fit (a row boundary inside the CTA,
+// or a pile-up of thousands of entities in one cell) fall back to the global-memory scan.
+//
 // GHOSTS: slots whose entity index is >= n_owned belong to a neighbouring GPU (halo): they are
 // candidates for everybody else but get no flag and count no pairs here — their owner does that.
-template <bool COUNT_PAIRS, bool GHOSTS>
-__global__ void __launch_bounds__(256)
-query_kernel(uint32_t n, uint32_t n_owned, const unsigned long long* __restrict__ sorted, const float2* __restrict__ sorted_pos,
-             const uint2* __restrict__ cell_range, uint8_t* __restrict__ flag_sorted, GridParams grid, Counters* __restrict__ counters) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
+template <bool COUNT_PAIRS, bool GHOSTS, bool PREFIX>
+__global__ void __launch_bounds__(QUERY_THREADS)
+query_kernel(uint32_t n, uint32_t n_owned, const uint32_t* __restrict__ sorted_idx, const float2* __restrict__ sorted_pos,
+             const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, uint8_t* __restrict__ flag_sorted, GridParams grid,
+             unsigned long long* __restrict__ stripes) {
+    __shared__ float2 s_above[QUERY_WINDOW];
+    __shared__ float2 s_own[QUERY_WINDOW];
+    __shared__ uint32_t s_red[3][QUERY_THREADS / 32];
+
+    const uint32_t block_base = blockIdx.x * QUERY_THREADS;
+    const uint32_t j = block_base + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t pairs = 0;
     bool hit = false;
     bool mine = j < n;
     if (GHOSTS && mine) {
-        mine = static_cast<uint32_t>(__ldcs(sorted + j)) < n_owned;
+        mine = __ldcs(sorted_idx + j) < n_owned;
         if (!mine) flag_sorted[j] = 0;
     }
+
+    float2 p = make_float2(0.f, 0.f);
+    int cx = 0, cy = 0, x0 = 0, x1 = 0;
+    uint32_t own_lo = 0xffffffffu, own_hi = 0, ab_lo = 0xffffffffu, ab_hi = 0;
     if (mine) {
-        const float2 p = sorted_pos[j];
-        const float thr = grid.hit_threshold;
-        int cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
-        int cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
+        p = sorted_pos[j];
+        cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
+        cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
         cx = min(max(cx, 0), grid.ncx - 1);
         cy = min(max(cy, 0), grid.ncy - 1);
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, grid.ncx - 1);
-        uint32_t lo, hi;
-        // own row: slots below j, then (flags-only or nothing found) slots above j
-        uint32_t own_lo, own_hi;
-        row_run(cell_range, grid.ncx, cy, x0, x1, own_lo, own_hi);
-        if (COUNT_PAIRS) {
-            if (cy > 0) {
-                row_run(cell_range, grid.ncx, cy - 1, x0, x1, lo, hi);
-                pairs += count_in_range(sorted_pos, lo, hi, p, thr);
+        x0 = max(cx - 1, 0);
+        x1 = min(cx + 1, grid.ncx - 1);
+        row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy, x0, x1, own_lo, own_hi);
+        if (cy > 0) row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy - 1, x0, x1, ab_lo, ab_hi);
+        else ab_lo = ab_hi = 0;
+    }
+
+    // CTA-wide hull of the windows: min of the run starts, max of the run ends
+    const bool has_above = mine && ab_lo < ab_hi;
+    uint32_t r0 = __reduce_min_sync(0xffffffffu, mine ? own_lo : 0xffffffffu);
+    uint32_t r1 = __reduce_min_sync(0xffffffffu, has_above ? ab_lo : 0xffffffffu);
+    uint32_t r2 = __reduce_max_sync(0xffffffffu, has_above ? ab_hi : 0u);
+    if (lane == 0) {
+        s_red[0][warp] = r0;
+        s_red[1][warp] = r1;
+        s_red[2][warp] = r2;
+    }
+    __syncthreads();
+    uint32_t w_own_lo = 0xffffffffu, w_ab_lo = 0xffffffffu, w_ab_hi = 0;
+#pragma unroll
+    for (int w = 0; w < QUERY_THREADS / 32; w++) {
+        w_own_lo = min(w_own_lo, s_red[0][w]);
+        w_ab_lo = min(w_ab_lo, s_red[1][w]);
+        w_ab_hi = max(w_ab_hi, s_red[2][w]);
+    }
+    const uint32_t w_own_hi = min(block_base + QUERY_THREADS, n);  // nobody needs a slot at or above its own
+    if (w_ab_lo > w_ab_hi) w_ab_lo = w_ab_hi = 0;
+    const bool any_mine = w_own_lo != 0xffffffffu;
+    const bool tiled = any_mine && (w_own_hi - w_own_lo) <= QUERY_WINDOW && (w_ab_hi - w_ab_lo) <= QUERY_WINDOW;  // CTA-uniform
+
+    if (tiled) {
+        for (uint32_t i = threadIdx.x; i < w_own_hi - w_own_lo; i += QUERY_THREADS) s_own[i] = sorted_pos[w_own_lo + i];
+        for (uint32_t i = threadIdx.x; i < w_ab_hi - w_ab_lo; i += QUERY_THREADS) s_above[i] = sorted_pos[w_ab_lo + i];
+    }
+    __syncthreads();
+
+    if (mine) {
+        const float thr = grid.hit_threshold;
+        if (tiled) {
+            if (COUNT_PAIRS) {
+                if (has_above) pairs += count_in_tile(s_above, ab_lo - w_ab_lo, ab_hi - w_ab_lo, p, thr);
+                pairs += count_in_tile(s_own, own_lo - w_own_lo, j - w_own_lo, p, thr);
+                hit = pairs != 0;
+            } else {
+                hit = any_in_tile(s_own, own_lo - w_own_lo, j - w_own_lo, p, thr);
+                if (!hit && has_above) hit = any_in_tile(s_above, ab_lo - w_ab_lo, ab_hi - w_ab_lo, p, thr);
             }
-            pairs += count_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
-            hit = pairs != 0;
         } else {
-            hit = any_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
-            if (!hit && cy > 0) {
-                row_run(cell_range, grid.ncx, cy - 1, x0, x1, lo, hi);
-                hit = any_in_range(sorted_pos, lo, hi, p, thr);
+            if (COUNT_PAIRS) {
+                if (has_above) pairs += count_in_range(sorted_pos, ab_lo, ab_hi, p, thr);
+                pairs += count_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
+                hit = pairs != 0;
+            } else {
+                hit = any_in_range(sorted_pos, own_lo, min(j, own_hi), p, thr);
+                if (!hit && has_above) hit = any_in_range(sorted_pos, ab_lo, ab_hi, p, thr);
             }
         }
+        // nothing below: look above (rare; straight from global memory)
         if (!hit) hit = any_in_range(sorted_pos, max(j + 1, own_lo), own_hi, p, thr);
         if (!hit && cy + 1 < grid.ncy) {
-            row_run(cell_range, grid.ncx, cy + 1, x0, x1, lo, hi);
+            uint32_t lo, hi;
+            row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy + 1, x0, x1, lo, hi);
             hit = any_in_range(sorted_pos, lo, hi, p, thr);
         }
         flag_sorted[j] = hit ? 1 : 0;
     }
-    // per-warp reduction, one atomic per warp per counter
-    const uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit));
-    if (COUNT_PAIRS) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) pairs += __shfl_down_sync(0xffffffffu, pairs, d);
-    }
+    // CTA-level reduction, then ONE atomic per CTA per counter into a striped counter (64 stripes on
+    // separate 128-byte lines).  The first version issued three same-address atomics per warp: ~940 k
+    // atomics on one L2 line serialised to ~630 us and hid everything else (profiles/r1d).
+    uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit));
+    if (COUNT_PAIRS) pairs = __reduce_add_sync(0xffffffffu, pairs);
+    __syncthreads();  // s_red is reused
     if (lane == 0) {
-        if (hits) atomicAdd(&counters->flagged_last, static_cast<unsigned long long>(hits));
-        if (COUNT_PAIRS && pairs) {
-            atomicAdd(&counters->pairs_last, static_cast<unsigned long long>(pairs));
-            atomicAdd(&counters->pairs_total, static_cast<unsigned long long>(pairs));
+        s_red[0][warp] = hits;
+        s_red[1][warp] = pairs;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t h = 0, pr = 0;
+#pragma unroll
+        for (int w = 0; w < QUERY_THREADS / 32; w++) {
+            h += s_red[0][w];
+            pr += s_red[1][w];
         }
+        unsigned long long* stripe = stripes + static_cast<size_t>(blockIdx.x % COUNTER_STRIPES) * COUNTER_STRIDE;
+        if (h) atomicAdd(stripe, static_cast<unsigned long long>(h));
+        if (COUNT_PAIRS && pr) atomicAdd(stripe + 1, static_cast<unsigned long long>(pr));
+    }
+}
+
+// folds the striped counters of one query into Counters and clears them for the next pass
+__global__ void __launch_bounds__(COUNTER_STRIPES) fold_counters_kernel(unsigned long long* __restrict__ stripes, Counters* __restrict__ counters) {
+    __shared__ unsigned long long s_h[COUNTER_STRIPES / 32], s_p[COUNTER_STRIPES / 32];
+    unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
+    unsigned long long h = stripe[0], pr = stripe[1];
+    stripe[0] = 0;
+    stripe[1] = 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        h += __shfl_down_sync(0xffffffffu, h, d);
+        pr += __shfl_down_sync(0xffffffffu, pr, d);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        s_h[threadIdx.x >> 5] = h;
+        s_p[threadIdx.x >> 5] = pr;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        h = pr = 0;
+        for (int w = 0; w < COUNTER_STRIPES / 32; w++) {
+            h += s_h[w];
+            pr += s_p[w];
+        }
+        counters->flagged_last = h;
+        counters->pairs_last = pr;
+        counters->pairs_total += pr;
     }
 }
 
 __global__ void __launch_bounds__(256)
-scatter_flags_kernel(uint32_t n, uint32_t n_owned, const unsigned long long* __restrict__ sorted, const uint8_t* __restrict__ flag_sorted,
+scatter_flags_kernel(uint32_t n, uint32_t n_owned, const uint32_t* __restrict__ sorted_idx, const uint8_t* __restrict__ flag_sorted,
                      uint8_t* __restrict__ flag_entity) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const uint32_t idx = static_cast<uint32_t>(__ldcs(sorted + j));
+    const uint32_t idx = __ldcs(sorted_idx + j);
     if (idx >= n_owned) return;  // ghost
     flag_entity[idx] = flag_sorted[j] + 1;  // 1 = green, 2 = blue (0 = "no collision pass yet")
 }
 
 }  // namespace
 
-int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint2* cell_range,
-                       const GridParams& grid, Counters* counters, Profiler* prof) {
+int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
+                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof) {
     prof->begin(s, K_MEMSET);
     cudaMemsetAsync(cell_range, 0xff, static_cast<size_t>(grid.ncells) * sizeof(uint2), s);
     prof->end(s);
     if (n == 0) return 0;
     prof->begin(s, K_BUILD_CELLS);
-    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, cell_range, counters);
+    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, sorted_idx, cell_range, counters);
     prof->end(s);
     return 1;
 }
 
-int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const float2* sorted_pos, const uint2* cell_range,
-                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof) {
+int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
+                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters,
+                 unsigned long long* stripes, Profiler* prof) {
     if (n == 0) return 0;
-    const uint32_t blocks = (n + 255u) / 256u;
-    const unsigned long long* so = reinterpret_cast<const unsigned long long*>(sorted);
+    const uint32_t blocks = (n + QUERY_THREADS - 1) / QUERY_THREADS;
+    const bool ghosts = n_owned < n, prefix = cell_start != nullptr;
     prof->begin(s, K_QUERY);
-    if (n_owned < n) {
-        if (count_pairs) query_kernel<true, true><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
-        else query_kernel<false, true><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+#define MSIM_QUERY(CP, GH, PF) \
+    query_kernel<CP, GH, PF><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, sorted_idx, sorted_pos, cell_range, cell_start, flag_sorted, grid, stripes)
+    if (count_pairs) {
+        if (ghosts) { if (prefix) MSIM_QUERY(true, true, true); else MSIM_QUERY(true, true, false); }
+        else { if (prefix) MSIM_QUERY(true, false, true); else MSIM_QUERY(true, false, false); }
     } else {
-        if (count_pairs) query_kernel<true, false><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
-        else query_kernel<false, false><<<blocks, 256, 0, s>>>(n, n_owned, so, sorted_pos, cell_range, flag_sorted, grid, counters);
+        if (ghosts) { if (prefix) MSIM_QUERY(false, true, true); else MSIM_QUERY(false, true, false); }
+        else { if (prefix) MSIM_QUERY(false, false, true); else MSIM_QUERY(false, false, false); }
     }
+#undef MSIM_QUERY
+    fold_counters_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
     prof->end(s);
-    return 1;
+    return 2;
 }
 
-int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
+size_t query_stripe_bytes() { return static_cast<size_t>(COUNTER_STRIPES) * COUNTER_STRIDE * sizeof(unsigned long long); }
+
+int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
     if (n == 0) return 0;
     prof->begin(s, K_SCATTER_FLAGS);
-    scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, n_owned, reinterpret_cast<const unsigned long long*>(sorted), flag_sorted, flag_entity);
+    scatter_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, n_owned, sorted_idx, flag_sorted, flag_entity);
     prof->end(s);
     return 1;
 }

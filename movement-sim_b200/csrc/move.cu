@@ -105,7 +105,8 @@ __device__ __forceinline__ float2 walk(float2 p, float2 t, bool& arrived) {
 template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(MOVE_THREADS)
 move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
-            uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes) {
+            uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
+            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank) {
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
     if (EMIT_KEYS) {
         for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
@@ -147,6 +148,12 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
             if (EMIT_KEYS) {
                 const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);
                 keys[pi] = make_uint2(k0, k1);
+                if (cell_count) {  // counting sort: the atomic's return value is the entity's rank inside its cell
+                    uint2 r = make_uint2(0u, 0u);
+                    if (e0 < n) r.x = atomicAdd(&cell_count[k0], 1u);
+                    if (e1 < n) r.y = atomicAdd(&cell_count[k1], 1u);
+                    rank[pi] = r;
+                }
                 for (int p = 0; p < hist_passes; p++) {
                     if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                     if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
@@ -218,7 +225,7 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 }  // namespace
 
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
-                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, Profiler* prof) {
+                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
@@ -229,8 +236,9 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
     prof->begin(s, K_MOVE);
-    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist_passes);
-    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0);
+    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
+                                                          cell_count, reinterpret_cast<uint2*>(rank));
+    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr);
     prof->end(s);
     return 1;
 }

@@ -67,7 +67,7 @@ struct Counters {
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
 enum KernelId {
     K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
-    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_COUNT
+    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_CELL_COUNT, K_CELL_SCAN, K_CELL_SCATTER, K_COUNT
 };
 
 struct Profiler {
@@ -98,7 +98,7 @@ struct Profiler {
 // pass A (streaming) and pass B (next waypoint of the arrived entities) of one move dispatch
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
-                int hist_passes, Profiler* prof);
+                int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof);
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
@@ -112,13 +112,23 @@ int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_
 // zeroes histograms / tickets / look-back words; call before a move pass that fuses the histogram
 void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace& ws, Profiler* prof);
 
+// csort.cu — single-digit radix (counting) sort over the whole cell key
+uint32_t csort_tiles(uint32_t cells);
+void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler* prof);
+int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, Profiler* prof);
+int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
+int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
+                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof);
+
 // collide.cu
-int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos,
+int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
                        uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof);
-// n_owned < n: slots whose entity index is >= n_owned are ghosts (neighbours only; `sorted` is then required)
-int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const float2* sorted_pos, const uint2* cell_range,
-                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, Profiler* prof);
-int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint64_t* sorted, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
+// n_owned < n: slots whose entity index (sorted_idx) is >= n_owned are ghosts (neighbours only).
+// Cell directory: either cell_range ({first, ~end} per cell, onesweep path) or cell_start (prefix table, csort path).
+int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
+                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof);
+size_t query_stripe_bytes();
+int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu
 struct PackArgs {

@@ -57,14 +57,16 @@ def test_enqueue_ticks_matches_dispatch(msim, orc, test_map):
         assert_entities_equal(sim.read_entities(), want, what="300 enqueued move passes")
 
 
+@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 63, 64, 65, 127, 1023, 4096, 4097, 12_345])
-def test_ragged_sizes_full_ticks(msim, orc, small_city, n):
-    """Empty and ragged populations through complete sim ticks (move + collide)."""
+def test_ragged_sizes_full_ticks(msim, orc, small_city, n, counting):
+    """Empty and ragged populations through complete sim ticks (move + collide), with both rebuilds of
+    the neighbour structure: multi-pass onesweep radix sort (default) and single-digit counting sort."""
     ents = small_city.init_entities(n, seed=100 + n)
     omap = oracle_map(orc, small_city)
     ticks = list(range(2, 2 + 2 * 12))
     want, want_pairs = run_oracle(orc, ents, omap, 10.0, ticks)
-    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+    with msim.Simulation(small_city, ents, radius=10.0, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
         got_pairs = []
         for t in ticks:
             sim.dispatch(t)
@@ -75,13 +77,14 @@ def test_ragged_sizes_full_ticks(msim, orc, small_city, n):
     assert got_pairs == want_pairs
 
 
-def test_city_100k_collisions_every_tick(msim, orc, small_city):
+@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
+def test_city_100k_collisions_every_tick(msim, orc, small_city, counting):
     """Munich-style street graph, collisions on: every field and the pair count, tick by tick."""
     n = 100_000
     ents = small_city.init_entities(n, seed=42)
     omap = oracle_map(orc, small_city)
     want = to_oracle_entities(orc, ents)
-    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+    with msim.Simulation(small_city, ents, radius=10.0, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
         for t in range(2, 2 + 2 * 30):
             sim.dispatch(t)
             p = oracle_dispatch(orc, want, omap, 10.0, t)
@@ -110,8 +113,9 @@ def test_flags_only_mode_matches(msim, orc, small_city):
         assert_entities_equal(sim.read_entities(), want, what="flags-only")
 
 
+@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
 @pytest.mark.parametrize("radius", [0.0, 0.5, 3.0, 10.0, 37.5, 250.0])
-def test_point_clouds_vs_brute_force(msim, orc, small_city, radius):
+def test_point_clouds_vs_brute_force(msim, orc, small_city, radius, counting):
     """Collision predicate on arbitrary (off-road) positions, including exact-distance edge cases."""
     rng = np.random.default_rng(int(radius * 10) + 1)
     n = 6000
@@ -128,7 +132,7 @@ def test_point_clouds_vs_brute_force(msim, orc, small_city, radius):
     ents["target"] = xy  # nobody moves anywhere sensible; only the collision pass is exercised
     want = to_oracle_entities(orc, ents)
     want_pairs = orc.collide_pass_brute(want, radius)
-    with msim.Simulation(small_city, ents, radius=radius) as sim:
+    with msim.Simulation(small_city, ents, radius=radius, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
         sim.dispatch(3)
         got = sim.read_entities()
         st = sim.stats()
