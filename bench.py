@@ -399,6 +399,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1_000_000)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
+                    help="N > 1: strong = the workload's population split over N GPUs (BASELINE config 3), weak = that population per GPU")
     ap.add_argument("--presort", action="store_true", help="experiment: upload the entities in cell order")
     ap.add_argument("--counting-sort", action="store_true", help="use the single-digit counting sort instead of onesweep")
     args = ap.parse_args()

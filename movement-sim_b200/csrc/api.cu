@@ -106,7 +106,8 @@ struct msim_handle {
     uint32_t* place_dst{nullptr};
     uint2* moves{nullptr};
     uint32_t* row_hist{nullptr};
-    uint32_t* host_stage{nullptr};  // pinned
+    uint32_t* host_stage{nullptr};  // pinned, two halves
+    bool stage_flip{false};
     void* sent_down{nullptr};
     void* sent_up{nullptr};
 
@@ -806,7 +807,7 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->place_dst, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
-    MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
+    MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), 2 * (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
     if (count) MSIM_CUDA(h, cudaMemcpyAsync(h->gid, gids, count * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->sharded = true;
@@ -834,7 +835,10 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     if (rc != MSIM_OK) return rc;
     if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_integrate: call msim_shard_enable first");
     // one host round trip: counters, the four headers and the hole list
-    uint32_t* hs = h->host_stage;
+    // two staging areas used alternately: the H2D copies of tick t may still be in flight when tick t+1 stages
+    const size_t stage_words = static_cast<size_t>(h->holes_cap) * 4 + 64;
+    uint32_t* hs = h->host_stage + (h->stage_flip ? stage_words : 0);
+    h->stage_flip = !h->stage_flip;
     uint32_t* h_ctr = hs;            // [8]
     uint32_t* h_hdr = hs + 8;        // 4 x 8 words: sent_down, sent_up, recv_down, recv_up
     uint32_t* h_holes = hs + 64;     // [holes_cap]
@@ -891,8 +895,6 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     h->launches += launch_shard_relocate(h->stream, a, h->moves, n_moves, &h->prof);
     h->launches += launch_shard_append_ghosts(h->stream, a, n_new, recv_down, halo_down, recv_up, halo_up, h->local_ghosts, g_local, h->mig_cap,
                                               h->grid, &h->prof);
-    // the host staging buffers are reused next tick: the copies above must have been consumed
-    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n = n_new;
     h->n_ghost = n_ghost;
     h->keys_valid = true;

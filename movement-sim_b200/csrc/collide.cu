@@ -38,11 +38,16 @@ build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, co
     if (j == n - 1) cell_range[key].y = ~n;
 }
 
-// squared distance with individually rounded operations, as the oracle computes it
+// squared distance with individually rounded operations, as the oracle computes it.  The x and y
+// lanes go through Blackwell's packed binary32 pipes (FADD2 / FMUL2, sm_100+): same IEEE round-to-nearest
+// result per lane as two scalar instructions, half the issue slots — the query kernel is issue-bound.
 __device__ __forceinline__ float dist2(float2 a, float2 b) {
-    const float dx = __fsub_rn(a.x, b.x);
-    const float dy = __fsub_rn(a.y, b.y);
-    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    unsigned long long ua, ub, d, sq;
+    ua = (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+    ub = (static_cast<unsigned long long>(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(ua), "l"(ub));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(sq) : "l"(d), "l"(d));
+    return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
 }
 
 // number of slots k in [a, b) with dist2(sorted_pos[k], p) < threshold; four loads in flight

@@ -123,6 +123,7 @@ class ShardedSimulation:
         self.recv_up = mk() if self.has_up else None
         self.migrant_capacity, self.halo_capacity = migrant_capacity, halo_capacity
         self.exchanged_bytes = 0
+        self.phase_us = {}
 
     @property
     def band(self):
@@ -145,12 +146,20 @@ class ShardedSimulation:
         if not np.array_equal(self.splits, self.target):
             self.splits = step_towards(self.splits, self.target)
         lo, hi = self.band
+        t0 = time.perf_counter()
         self.engine.move()
         self.engine.pack(lo, hi, self.send_down, self.send_up)
+        t1 = time.perf_counter()
         self._exchange()
+        t2 = time.perf_counter()
         self.engine.integrate(self.recv_down, self.recv_up)
+        t3 = time.perf_counter()
         if collide:
             self.engine.collide()
+        t4 = time.perf_counter()
+        # host-side wall time per phase (integrate contains the tick's only host<->device round trip)
+        for k, v in (("enqueue_move_pack", t1 - t0), ("exchange_enqueue", t2 - t1), ("integrate", t3 - t2), ("enqueue_collide", t4 - t3)):
+            self.phase_us[k] = 0.9 * self.phase_us.get(k, v * 1e6) + 0.1 * v * 1e6
         self.ticks += 1
         if self.rebalance_every and self.world > 1 and self.ticks % self.rebalance_every == 0:
             self.rebalance()
@@ -230,9 +239,11 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     from bench import METRIC, SURVEY_BYTES, ClockSampler, build_workload, load_peaks
 
     w, m = build_workload(M, args.workload, args.entities)
-    per_gpu = w["entities"]
     collisions = w["collisions"]
-    total = per_gpu * world  # weak scaling: the per-GPU population is fixed as N grows
+    weak = getattr(args, "scaling", "strong") == "weak"
+    # strong (default): BASELINE config 3 names ONE population (10 M) on 1/2/4/8 GPUs.  weak: 10 M per GPU on the same map.
+    total = w["entities"] * world if weak else w["entities"]
+    per_gpu = total // world
     peak, peak_src = load_peaks()
     stream = torch.cuda.Stream()
     device = torch.device("cuda", local_rank)
@@ -326,12 +337,13 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": args.workload, "entities_per_gpu": per_gpu, "entities_total": total, "collisions": collisions,
                        "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll,
                        "parallelism": (f"{world} spatial bands of cell rows, NCCL send/recv of halo + migrants per tick, row-histogram all-reduce every {REBALANCE_EVERY} ticks"
                                        if collisions else f"{world} entity ranges, no collective"),
-                       "owned_per_rank": per_rank, "l2": "inputs larger than L2 (no flush)",
+                       "owned_per_rank": per_rank, "l2": ("inputs larger than L2 (no flush)" if per_gpu * 40 > 200e6 else "per-GPU working set may sit in L2 (strong scaling of a fixed population)"),
+                       "phase_us_rank0": getattr(sh, "phase_us", None),
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
                        "global_pairs_last_tick": pairs, "global_flagged_last_tick": flagged},
             "roofline": None,
