@@ -48,6 +48,7 @@ KERNEL_BYTES = {
     "sort_pass3": 16.0,
     "build_cells": 24.0,  # pair R8 + pos gather R8 + sorted pos W8
     "query": 9.0,  # sorted pos R8 + flag W1 (neighbour reads are cache hits)
+    "reorder": 98.0,  # every 32nd tick: idx R4 + flag R1 + (prev pos 8, target 8, road 4, rng 16, id 4) gathered and written + flag W1 + slot map W4
 }
 
 
@@ -237,7 +238,8 @@ def run_b200(args):
         rows, _, _ = M.grid_rows(m.width, m.height, 10.0, ents["pos"])
         order = np.lexsort((ents["pos"][:, 0], rows))
         ents = np.ascontiguousarray(ents[order])
-    flags = (0 if collisions else M.FLAG_NO_COLLISIONS) | (M.FLAG_SORT_COUNTING if args.counting_sort else 0)
+    flags = (0 if collisions else M.FLAG_NO_COLLISIONS) | (M.FLAG_SORT_COUNTING if args.counting_sort else 0) | (M.FLAG_NO_REORDER if args.no_reorder else 0) | (
+        M.FLAG_SORT_ONESWEEP if args.onesweep else 0)
     sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=flags, stream=stream.cuda_stream)
     sim.dispatch(2)  # the reference's first dispatch: initialise only
     sim.enqueue_ticks(args.preroll, False)  # disperse the population along the roads (untimed)
@@ -402,7 +404,9 @@ def main():
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="N > 1: strong = the workload's population split over N GPUs (BASELINE config 3), weak = that population per GPU")
     ap.add_argument("--presort", action="store_true", help="experiment: upload the entities in cell order")
-    ap.add_argument("--counting-sort", action="store_true", help="use the single-digit counting sort instead of onesweep")
+    ap.add_argument("--counting-sort", action="store_true", help="force the single-digit counting sort")
+    ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")
+    ap.add_argument("--no-reorder", action="store_true", help="keep the state in upload order (onesweep rebuild)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -97,8 +97,10 @@ enum {
     MSIM_FLAG_NO_COLLISIONS = 1u << 0, /* even-tick dispatches do not emit cell keys; odd ticks are rejected */
     MSIM_FLAG_NO_PAIR_COUNT = 1u << 1, /* collision query stops at the first neighbour (flags only) */
     MSIM_FLAG_NO_QUADTREE   = 1u << 2, /* msim_read_quadtree_nodes returns the root only */
-    MSIM_FLAG_SORT_COUNTING = 1u << 3  /* rebuild the neighbour structure with the single-digit (counting) radix sort instead of
-                                          the multi-pass onesweep radix sort; pays off when entity order is spatially coherent */
+    MSIM_FLAG_SORT_COUNTING = 1u << 3, /* always rebuild the neighbour structure with the single-digit (counting) radix sort */
+    MSIM_FLAG_NO_REORDER    = 1u << 4, /* keep the resident state in upload order (default: re-sorted into cell order every
+                                          32 collision passes, with the counting sort as the rebuild) */
+    MSIM_FLAG_SORT_ONESWEEP = 1u << 5  /* always rebuild with the multi-pass onesweep radix sort */
 };
 
 typedef struct msim_config {
@@ -177,7 +179,7 @@ typedef struct msim_stats {
     uint32_t grid_cells_x, grid_cells_y;
     uint32_t key_bits, sort_passes;
     float cell_size;
-    uint32_t reserved;
+    uint32_t reorders;           /* physical re-sorts of the resident state so far */
 } msim_stats;
 int msim_get_stats(msim_handle* h, msim_stats* out);
 
@@ -199,6 +201,7 @@ typedef struct msim_device_view {
     void* road;      /* uint32[count] */
     void* rng;       /* uint4[count] */
     uint64_t count;
+    void* ext_id;    /* uint32[count]: external entity id of each storage slot, or NULL while storage is in upload order */
 } msim_device_view;
 int msim_get_device_view(msim_handle* h, msim_device_view* out);
 

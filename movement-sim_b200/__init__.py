@@ -69,6 +69,8 @@ FLAG_NO_COLLISIONS = 1 << 0
 FLAG_NO_PAIR_COUNT = 1 << 1
 FLAG_NO_QUADTREE = 1 << 2
 FLAG_SORT_COUNTING = 1 << 3
+FLAG_NO_REORDER = 1 << 4
+FLAG_SORT_ONESWEEP = 1 << 5
 
 # every symbol include/msim.h declares (tests/test_abi.py checks the library exports exactly these)
 ABI_SYMBOLS = [
@@ -147,15 +149,16 @@ class Stats(C.Structure):
         ("key_bits", C.c_uint32),
         ("sort_passes", C.c_uint32),
         ("cell_size", C.c_float),
-        ("reserved", C.c_uint32),
+        ("reorders", C.c_uint32),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class DeviceView(C.Structure):
-    _fields_ = [("pos", C.c_void_p), ("target", C.c_void_p), ("road", C.c_void_p), ("rng", C.c_void_p), ("count", C.c_uint64)]
+    _fields_ = [("pos", C.c_void_p), ("target", C.c_void_p), ("road", C.c_void_p), ("rng", C.c_void_p), ("count", C.c_uint64),
+                ("ext_id", C.c_void_p)]
 
 
 class KernelTime(C.Structure):

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <new>
 #include <string>
@@ -92,6 +94,21 @@ struct msim_handle {
     bool flags_scattered{false};
     uint64_t move_passes{0}, collide_passes{0}, launches{0}, initialised_total{0};
     uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0};
+
+    // cell-ordered storage: periodic physical re-sort of the state (pack.cu), slot <-> external id maps
+    bool reorder_enabled{false};
+    bool perm_active{false};
+    uint32_t reorder_every{32};
+    uint32_t since_reorder{0};
+    uint64_t reorders{0};
+    float2* pos_spare{nullptr};
+    float2* target_alt{nullptr};
+    uint32_t* road_alt{nullptr};
+    uint4* rng_alt{nullptr};
+    uint32_t* arrived_alt{nullptr};
+    uint32_t* ext_id{nullptr};
+    uint32_t* ext_id_alt{nullptr};
+    uint32_t* slot_of{nullptr};
 
     // multi-GPU sharding (msim_shard.h): band of cell rows per handle, ghosts behind the owned entities
     bool sharded{false};
@@ -187,6 +204,8 @@ void free_all(msim_handle* h) {
     cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums); cudaFree(h->rank); cudaFree(h->sorted_idx);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
     cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes);
+    cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
+    cudaFree(h->ext_id); cudaFree(h->ext_id_alt); cudaFree(h->slot_of);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -206,7 +225,10 @@ void join_side(msim_handle* h) {
 }
 
 int ensure_cells(msim_handle* h) {
-    h->use_csort = (h->flags & MSIM_FLAG_SORT_COUNTING) && h->grid.ncells <= CSORT_MAX_CELLS;
+    // counting sort: on request, or by default whenever the storage is kept in cell order
+    const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
+    h->use_csort = want_counting && !h->sharded && h->grid.ncells <= CSORT_MAX_CELLS;
+    if ((h->flags & MSIM_FLAG_SORT_COUNTING) && h->grid.ncells <= CSORT_MAX_CELLS) h->use_csort = true;
     if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
     cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums);
     h->cell_range = nullptr; h->cell_count = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;
@@ -269,6 +291,8 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->flags_scattered = false;
     h->n_ghost = 0;
     h->flags_stale = false;
+    h->perm_active = false;                 // uploaded state is in external order again
+    h->since_reorder = h->reorder_every;    // re-sort right after the first collision pass
     if (h->flag_entity) MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
     if (count && host_scratch[1] >= h->road_count) {
         h->n = 0;
@@ -343,6 +367,55 @@ int enqueue_move(msim_handle* h, bool want_keys) {
     return MSIM_OK;
 }
 
+// Permute the resident state into the cell order of the collision pass that just ran.
+int reorder_storage(msim_handle* h) {
+    if (!h->pos_spare) {
+        MSIM_CUDA(h, dev_alloc(&h->pos_spare, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->target_alt, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->road_alt, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->rng_alt, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->arrived_alt, h->cap / 32 + 2));
+        MSIM_CUDA(h, dev_alloc(&h->ext_id, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->ext_id_alt, h->cap));
+        MSIM_CUDA(h, dev_alloc(&h->slot_of, h->cap));
+        MSIM_CUDA(h, cudaMemsetAsync(h->pos_spare, 0, sizeof(float2) * h->cap, h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->target_alt, 0, sizeof(float2) * h->cap, h->stream));
+    }
+    join_side(h);  // pass B of the last move rewrites target / road / rng
+    ReorderArrays a{};
+    a.pos_prev = h->pos[h->cur ^ 1];
+    a.pos_prev_new = h->pos_spare;
+    a.target = h->target;      a.target_new = h->target_alt;
+    a.road = h->road;          a.road_new = h->road_alt;
+    a.rng = h->rng;            a.rng_new = h->rng_alt;
+    a.ext_id = h->perm_active ? h->ext_id : nullptr;
+    a.ext_id_new = h->ext_id_alt;
+    a.slot_of = h->slot_of;
+    a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
+    a.flag_entity = h->flag_entity;
+    h->launches += launch_reorder(h->stream, h->n, h->sorted_idx, h->flag_sorted, a, &h->prof);
+    // the sorted positions ARE the new current positions: swap buffers instead of copying
+    float2* old_cur = h->pos[h->cur];
+    float2* old_prev = h->pos[h->cur ^ 1];
+    h->pos[h->cur] = h->sorted_pos;
+    h->sorted_pos = old_cur;
+    h->pos[h->cur ^ 1] = h->pos_spare;
+    h->pos_spare = old_prev;
+    std::swap(h->target, h->target_alt);
+    std::swap(h->road, h->road_alt);
+    std::swap(h->rng, h->rng_alt);
+    std::swap(h->arrived, h->arrived_alt);
+    std::swap(h->ext_id, h->ext_id_alt);
+    h->perm_active = true;
+    h->flags_scattered = true;   // flag_entity was written in slot order by the re-sort
+    h->keys_valid = false;       // keys / ranks were indexed by the old slots
+    h->hist_valid = false;
+    h->counts_valid = false;
+    h->since_reorder = 0;
+    h->reorders++;
+    return MSIM_OK;
+}
+
 int enqueue_collide(msim_handle* h) {
     if (h->flags & MSIM_FLAG_NO_COLLISIONS) return fail(h, MSIM_ERR_INVALID, "collision dispatch on a handle created with MSIM_FLAG_NO_COLLISIONS");
     if (consume_init_dispatch(h)) return MSIM_OK;
@@ -379,6 +452,8 @@ int enqueue_collide(msim_handle* h) {
     h->collided = true;
     h->flags_scattered = false;
     h->collide_passes++;
+    h->since_reorder++;
+    if (h->reorder_enabled && !h->sharded && h->has_moved && h->n > 1 && h->since_reorder >= h->reorder_every) return reorder_storage(h);
     return MSIM_OK;
 }
 
@@ -457,6 +532,13 @@ int msim_create(const msim_config* cfg, msim_handle** out) {
     h->qt_cap = cfg->quadtree_node_cap ? cfg->quadtree_node_cap : 10;
     h->road_count = cfg->road_count;
     h->conn_count = cfg->connection_count;
+    h->reorder_enabled = !(cfg->flags & (MSIM_FLAG_NO_COLLISIONS | MSIM_FLAG_NO_REORDER));
+    if (const char* env = std::getenv("MSIM_REORDER_EVERY")) {
+        const long v = std::atol(env);
+        if (v > 0) h->reorder_every = static_cast<uint32_t>(v);
+        else h->reorder_enabled = false;
+    }
+    h->since_reorder = h->reorder_every;
     h->cap = static_cast<uint32_t>((capacity + 63ull) & ~63ull);
     if (h->cap == 0) h->cap = 64;
 
@@ -614,6 +696,7 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     a.arrived = h->arrived;
     a.flag_entity = h->collided ? h->flag_entity : nullptr;
     a.init_mask = nullptr;
+    a.slot_of = h->perm_active ? h->slot_of : nullptr;
     a.initialized_all = h->uninitialised ? 0u : 1u;
     a.has_moved = h->has_moved ? 1u : 0u;
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
@@ -629,7 +712,13 @@ int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count) {
     if (rc != MSIM_OK) return rc;
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: count exceeds the resident entity count");
     if (count && !dst_xy) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: dst is null");
-    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst_xy, h->pos[h->cur], count * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+    const float2* src = h->pos[h->cur];
+    if (count && h->perm_active) {  // storage is in cell order: gather into external order first
+        float2* tmp = reinterpret_cast<float2*>(h->sort_a);
+        h->launches += launch_gather_pos(h->stream, static_cast<uint32_t>(count), h->slot_of, h->pos[h->cur], tmp);
+        src = tmp;
+    }
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst_xy, src, count * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
     return check_device_errors(h);
 }
 
@@ -643,7 +732,13 @@ int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count) {
         return MSIM_OK;
     }
     materialise_flags(h);
-    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, h->flag_entity, count, cudaMemcpyDeviceToHost, h->stream));
+    const uint8_t* fsrc = h->flag_entity;
+    if (count && h->perm_active) {
+        uint8_t* tmp = reinterpret_cast<uint8_t*>(h->sort_b);
+        h->launches += launch_gather_flag(h->stream, static_cast<uint32_t>(count), h->slot_of, h->flag_entity, tmp);
+        fsrc = tmp;
+    }
+    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, fsrc, count, cudaMemcpyDeviceToHost, h->stream));
     rc = check_device_errors(h);
     for (uint64_t i = 0; i < count; i++) dst[i] = dst[i] == 2 ? 1 : 0;
     return rc;
@@ -693,6 +788,7 @@ int msim_get_stats(msim_handle* h, msim_stats* out) {
     out->key_bits = static_cast<uint32_t>(h->key_bits);
     out->sort_passes = static_cast<uint32_t>((h->key_bits + RADIX_BITS - 1) / RADIX_BITS);
     out->cell_size = h->grid.inv_cell > 0.0f ? 1.0f / h->grid.inv_cell : 0.0f;
+    out->reorders = static_cast<uint32_t>(h->reorders);
     return rc;
 }
 
@@ -711,7 +807,7 @@ int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32
     if (!out || !count) return fail(h, MSIM_ERR_INVALID, "msim_profile_end: null argument");
     static const char* const names[K_COUNT] = {"move", "arrive", "keygen", "histogram", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3",
                                                "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc", "shard", "cell_count",
-                                               "cell_scan", "cell_scatter"};
+                                               "cell_scan", "cell_scatter", "reorder"};
     h->prof.enabled = false;
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     double ms[K_COUNT] = {0};
@@ -748,6 +844,7 @@ int msim_get_device_view(msim_handle* h, msim_device_view* out) {
     out->road = h->road;
     out->rng = h->rng;
     out->count = h->n;
+    out->ext_id = h->perm_active ? h->ext_id : nullptr;
     return MSIM_OK;
 }
 
@@ -811,7 +908,8 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     if (count) MSIM_CUDA(h, cudaMemcpyAsync(h->gid, gids, count * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->sharded = true;
-    return MSIM_OK;
+    h->reorder_enabled = false;  // the shard exchange relocates entities itself; gid is the id map
+    return ensure_cells(h);
 }
 
 int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up) {

@@ -67,7 +67,7 @@ struct Counters {
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
 enum KernelId {
     K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
-    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_CELL_COUNT, K_CELL_SCAN, K_CELL_SCATTER, K_COUNT
+    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_CELL_COUNT, K_CELL_SCAN, K_CELL_SCATTER, K_REORDER, K_COUNT
 };
 
 struct Profiler {
@@ -142,6 +142,7 @@ struct PackArgs {
     const uint32_t* arrived;
     const uint8_t* flag_entity;  // nullable: no collision pass since upload -> colour as uploaded
     const uint8_t* init_mask;    // nullable
+    const uint32_t* slot_of;     // nullable: external id -> storage slot (cell-ordered storage)
     uint32_t initialized_all;    // value of `initialized` when init_mask == nullptr
     uint32_t has_moved;          // 0: direction = dir0
 };
@@ -149,6 +150,21 @@ int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& 
 int launch_unpack(cudaStream_t s, uint32_t first, uint32_t count, const msim_entity* src, float2* pos, float2* target,
                   uint32_t* road, uint4* rng, float4* color0, float2* dir0, uint8_t* init_mask, unsigned int* uninit_count, Profiler* prof);
 int launch_max_road(cudaStream_t s, uint32_t n, const uint32_t* road, unsigned int* out_max);
+
+// cell-ordered storage: permute the resident state into the order of the last collision pass
+struct ReorderArrays {
+    const float2* pos_prev;  float2* pos_prev_new;
+    const float2* target;    float2* target_new;
+    const uint32_t* road;    uint32_t* road_new;
+    const uint4* rng;        uint4* rng_new;
+    const uint32_t* ext_id;  uint32_t* ext_id_new;   // ext_id may be NULL (identity)
+    uint32_t* slot_of;
+    const uint32_t* arrived; uint32_t* arrived_new;
+    uint8_t* flag_entity;
+};
+int launch_reorder(cudaStream_t s, uint32_t n, const uint32_t* sorted_idx, const uint8_t* flag_sorted, const ReorderArrays& a, Profiler* prof);
+int launch_gather_pos(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const float2* pos, float2* out);
+int launch_gather_flag(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const uint8_t* flag, uint8_t* out);
 
 // ---- multi-GPU sharding (shard.cu) -------------------------------------------------------------
 struct ShardHeader {

@@ -28,7 +28,8 @@ __device__ __forceinline__ float2 direction_from(float2 from, float2 target) {
 __global__ void __launch_bounds__(256) pack_kernel(uint32_t first, uint32_t count, PackArgs a, float4* __restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const uint32_t e = first + i;
+    // external entity id first + i lives in storage slot slot_of[first + i] once the state has been re-sorted
+    const uint32_t e = a.slot_of ? a.slot_of[first + i] : first + i;
     const float2 p = a.pos_cur[e];
     const float2 t = a.target[e];
     float2 dir;
@@ -80,7 +81,60 @@ __global__ void __launch_bounds__(256) max_road_kernel(uint32_t n, const uint32_
     if ((threadIdx.x & 31u) == 0) atomicMax(out_max, m);
 }
 
+// ---- cell-ordered storage ---------------------------------------------------------------------
+// Every REORDER_EVERY collision passes the resident state is physically permuted into the cell order
+// the pass has just computed (new slot j <- old slot sorted_idx[j]).  Consecutive slots then hold
+// entities of the same or neighbouring cells for the next few dozen ticks, which turns the scattered
+// stores / atomics / gathers of the neighbour rebuild into L2-local traffic (profiles/r1_sort_paths.md).
+// ext_id maps slot -> external entity id, slot_of is its inverse; both stay NULL until the first re-sort.
+__global__ void __launch_bounds__(256)
+reorder_kernel(uint32_t n, const uint32_t* __restrict__ sorted_idx, const uint8_t* __restrict__ flag_sorted, ReorderArrays a) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t src = __ldcs(sorted_idx + j);
+    a.pos_prev_new[j] = a.pos_prev[src];
+    a.target_new[j] = a.target[src];
+    a.road_new[j] = a.road[src];
+    a.rng_new[j] = a.rng[src];
+    const uint32_t ext = a.ext_id ? a.ext_id[src] : src;
+    a.ext_id_new[j] = ext;
+    a.slot_of[ext] = j;
+    a.flag_entity[j] = flag_sorted[j] + 1;  // 1 = green, 2 = blue: the flags are in slot order already
+    if ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) atomicOr(a.arrived_new + arrived_word(j), 1u << arrived_bit(j));
+}
+
+__global__ void __launch_bounds__(256) gather_pos_kernel(uint32_t n, const uint32_t* __restrict__ slot_of, const float2* __restrict__ pos, float2* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos[slot_of[i]];
+}
+
+__global__ void __launch_bounds__(256) gather_flag_kernel(uint32_t n, const uint32_t* __restrict__ slot_of, const uint8_t* __restrict__ flag, uint8_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flag[slot_of ? slot_of[i] : i];
+}
+
 }  // namespace
+
+int launch_reorder(cudaStream_t s, uint32_t n, const uint32_t* sorted_idx, const uint8_t* flag_sorted, const ReorderArrays& a, Profiler* prof) {
+    if (n == 0) return 0;
+    prof->begin(s, K_REORDER);
+    cudaMemsetAsync(a.arrived_new, 0, (static_cast<size_t>(n + 63u) / 64u) * 2u * sizeof(uint32_t), s);
+    reorder_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, sorted_idx, flag_sorted, a);
+    prof->end(s);
+    return 1;
+}
+
+int launch_gather_pos(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const float2* pos, float2* out) {
+    if (n == 0) return 0;
+    gather_pos_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, slot_of, pos, out);
+    return 1;
+}
+
+int launch_gather_flag(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const uint8_t* flag, uint8_t* out) {
+    if (n == 0) return 0;
+    gather_flag_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, slot_of, flag, out);
+    return 1;
+}
 
 int launch_pack(cudaStream_t s, uint32_t first, uint32_t count, const PackArgs& a, msim_entity* dst, Profiler* prof) {
     if (count == 0) return 0;

@@ -13,6 +13,12 @@ from conftest import assert_entities_equal, oracle_dispatch, oracle_map, to_orac
 pytestmark = pytest.mark.gpu
 
 
+def MODES(msim):
+    """flag sets selecting the neighbour-structure rebuild (include/msim.h)"""
+    return {"default": 0, "onesweep": msim.FLAG_NO_REORDER, "counting": msim.FLAG_NO_REORDER | msim.FLAG_SORT_COUNTING,
+            "reorder+onesweep": msim.FLAG_SORT_ONESWEEP}
+
+
 def run_oracle(O, ents, omap, radius, ticks):
     """ticks = list of dispatch tick numbers, as Simulator::sim_tick issues them (2,3,4,5,...)."""
     e = to_oracle_entities(O, ents)
@@ -57,16 +63,19 @@ def test_enqueue_ticks_matches_dispatch(msim, orc, test_map):
         assert_entities_equal(sim.read_entities(), want, what="300 enqueued move passes")
 
 
-@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
+@pytest.mark.parametrize("mode", ["default", "onesweep", "counting", "reorder+onesweep"])
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 63, 64, 65, 127, 1023, 4096, 4097, 12_345])
-def test_ragged_sizes_full_ticks(msim, orc, small_city, n, counting):
-    """Empty and ragged populations through complete sim ticks (move + collide), with both rebuilds of
-    the neighbour structure: multi-pass onesweep radix sort (default) and single-digit counting sort."""
+def test_ragged_sizes_full_ticks(msim, orc, small_city, n, mode, monkeypatch):
+    """Empty and ragged populations through complete sim ticks (move + collide), with every rebuild of
+    the neighbour structure: cell-ordered storage + counting sort (default), onesweep radix sort and
+    counting sort on upload-ordered storage, onesweep on cell-ordered storage.  The state is re-sorted
+    every 3 collision passes here so that several re-sorts happen inside the test."""
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
     ents = small_city.init_entities(n, seed=100 + n)
     omap = oracle_map(orc, small_city)
     ticks = list(range(2, 2 + 2 * 12))
     want, want_pairs = run_oracle(orc, ents, omap, 10.0, ticks)
-    with msim.Simulation(small_city, ents, radius=10.0, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
+    with msim.Simulation(small_city, ents, radius=10.0, flags=MODES(msim)[mode]) as sim:
         got_pairs = []
         for t in ticks:
             sim.dispatch(t)
@@ -77,14 +86,15 @@ def test_ragged_sizes_full_ticks(msim, orc, small_city, n, counting):
     assert got_pairs == want_pairs
 
 
-@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
-def test_city_100k_collisions_every_tick(msim, orc, small_city, counting):
+@pytest.mark.parametrize("mode", ["default", "onesweep", "counting", "reorder+onesweep"])
+def test_city_100k_collisions_every_tick(msim, orc, small_city, mode, monkeypatch):
     """Munich-style street graph, collisions on: every field and the pair count, tick by tick."""
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "4")
     n = 100_000
     ents = small_city.init_entities(n, seed=42)
     omap = oracle_map(orc, small_city)
     want = to_oracle_entities(orc, ents)
-    with msim.Simulation(small_city, ents, radius=10.0, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
+    with msim.Simulation(small_city, ents, radius=10.0, flags=MODES(msim)[mode]) as sim:
         for t in range(2, 2 + 2 * 30):
             sim.dispatch(t)
             p = oracle_dispatch(orc, want, omap, 10.0, t)
@@ -97,8 +107,10 @@ def test_city_100k_collisions_every_tick(msim, orc, small_city, counting):
         assert_entities_equal(sim.read_entities(), want, what="final")
         flags = sim.read_collision_flags()
         assert (flags == orc.collision_flags(want)).all()
+        assert (sim.read_positions() == want["pos"]).all()
         dbg = sim.read_debug()
         assert dbg[0] == n
+        assert (sim.stats()["reorders"] > 2) == (mode in ("default", "reorder+onesweep"))
 
 
 def test_flags_only_mode_matches(msim, orc, small_city):
@@ -113,9 +125,9 @@ def test_flags_only_mode_matches(msim, orc, small_city):
         assert_entities_equal(sim.read_entities(), want, what="flags-only")
 
 
-@pytest.mark.parametrize("counting", [False, True], ids=["onesweep", "counting"])
+@pytest.mark.parametrize("mode", ["default", "onesweep", "counting", "reorder+onesweep"])
 @pytest.mark.parametrize("radius", [0.0, 0.5, 3.0, 10.0, 37.5, 250.0])
-def test_point_clouds_vs_brute_force(msim, orc, small_city, radius, counting):
+def test_point_clouds_vs_brute_force(msim, orc, small_city, radius, mode):
     """Collision predicate on arbitrary (off-road) positions, including exact-distance edge cases."""
     rng = np.random.default_rng(int(radius * 10) + 1)
     n = 6000
@@ -132,7 +144,7 @@ def test_point_clouds_vs_brute_force(msim, orc, small_city, radius, counting):
     ents["target"] = xy  # nobody moves anywhere sensible; only the collision pass is exercised
     want = to_oracle_entities(orc, ents)
     want_pairs = orc.collide_pass_brute(want, radius)
-    with msim.Simulation(small_city, ents, radius=radius, flags=msim.FLAG_SORT_COUNTING if counting else 0) as sim:
+    with msim.Simulation(small_city, ents, radius=radius, flags=MODES(msim)[mode]) as sim:
         sim.dispatch(3)
         got = sim.read_entities()
         st = sim.stats()

@@ -30,8 +30,8 @@ def test_munich_1m_vs_oracle(msim, orc, munich):
 
 def test_munich_10m_properties(msim, orc, munich):
     """BASELINE config 3 size on one GPU.  Properties that hold at any size:
-    * the two neighbour-structure rebuilds (onesweep radix sort / counting sort) agree on every flag and
-      on the pair count, and with the flags-only query;
+    * the two neighbour-structure rebuilds (cell-ordered storage + counting sort / upload order + onesweep
+      radix sort) agree on every flag and on the pair count, and with the flags-only query;
     * flagged entities = entities with a partner: sum over blue == 'last_flagged_count';
     * a 200 k-entity sample of the 10 M state equals an oracle continuation of that sample for the
       movement fields (movement never reads another entity);
@@ -39,7 +39,7 @@ def test_munich_10m_properties(msim, orc, munich):
     n = 10_000_000
     ents = munich.init_entities(n, seed=42)
     results = []
-    for flags in (0, msim.FLAG_SORT_COUNTING, msim.FLAG_NO_PAIR_COUNT):
+    for flags in (0, msim.FLAG_NO_REORDER, msim.FLAG_NO_PAIR_COUNT):
         with msim.Simulation(munich, ents, radius=10.0, flags=flags) as sim:
             sim.dispatch(2)
             sim.enqueue_ticks(12, True)
