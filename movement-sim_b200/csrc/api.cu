@@ -39,6 +39,7 @@ struct msim_handle {
     cudaStream_t side{nullptr};  // pass B of a move runs here while the collision pass uses `stream`
     cudaEvent_t ev_moved{nullptr}, ev_arrived{nullptr};
     bool side_pending{false};
+    bool arrive_deferred{false};  // pass B of the last move has not been launched yet (it will ride beside the query)
     uint32_t flags{0};
 
     uint32_t n{0};
@@ -84,6 +85,7 @@ struct msim_handle {
     Counters* counters{nullptr};
     unsigned long long* stripes{nullptr};  // striped per-query counters (collide.cu)
     unsigned int* scratch{nullptr};  // [0] uninitialised count, [1] max road index
+    uint32_t* leaf_hist{nullptr};    // display quadtree: entities per finest cell
     msim_entity* stage{nullptr};
 
     bool uninitialised{false};
@@ -203,7 +205,7 @@ void free_all(msim_handle* h) {
     cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
     cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums); cudaFree(h->rank); cudaFree(h->sorted_idx);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
-    cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes);
+    cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes); cudaFree(h->leaf_hist);
     cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
     cudaFree(h->ext_id); cudaFree(h->ext_id_alt); cudaFree(h->slot_of);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
@@ -217,7 +219,24 @@ void free_all(msim_handle* h) {
 }
 
 // make the main stream wait for a pass B still running on the side stream
+void launch_deferred_arrive(msim_handle* h, bool beside) {
+    if (!h->arrive_deferred) return;
+    h->arrive_deferred = false;
+    if (beside && h->side) {
+        // pass B (dependent gathers, latency-bound, few issue slots) runs on the side stream from here on:
+        // called right before the query, which is issue-bound and leaves the memory system idle
+        cudaEventRecord(h->ev_moved, h->stream);
+        cudaStreamWaitEvent(h->side, h->ev_moved, 0);
+        h->launches += launch_arrive(h->side, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+        cudaEventRecord(h->ev_arrived, h->side);
+        h->side_pending = true;
+    } else {
+        h->launches += launch_arrive(h->stream, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+    }
+}
+
 void join_side(msim_handle* h) {
+    launch_deferred_arrive(h, false);
     if (h->side_pending) {
         cudaStreamWaitEvent(h->stream, h->ev_arrived, 0);
         h->side_pending = false;
@@ -348,14 +367,8 @@ int enqueue_move(msim_handle* h, bool want_keys) {
                                emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof);
     h->counts_valid = fuse_count;
-    if (emit && h->side) {
-        // A collision pass follows and needs only the positions and keys of pass A: pass B (gathers
-        // into the road tables, latency-bound, little bandwidth) runs beside the sort on a second stream.
-        cudaEventRecord(h->ev_moved, h->stream);
-        cudaStreamWaitEvent(h->side, h->ev_moved, 0);
-        h->launches += launch_arrive(h->side, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
-        cudaEventRecord(h->ev_arrived, h->side);
-        h->side_pending = true;
+    if (emit && h->side && !h->sharded) {
+        h->arrive_deferred = true;  // a collision pass follows and needs only positions and keys: pass B is launched beside its query
     } else {
         h->launches += launch_arrive(h->stream, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
     }
@@ -436,6 +449,7 @@ int enqueue_collide(msim_handle* h) {
         h->counts_valid = false;
         h->launches += launch_cell_scan(h->stream, h->cell_count, h->grid.ncells, h->tile_sums, h->cell_start, &h->prof);
         h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof);
+        launch_deferred_arrive(h, true);
         h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof);
     } else {
@@ -443,6 +457,7 @@ int enqueue_collide(msim_handle* h) {
         h->hist_valid = false;  // the sort consumed the tickets and look-back words
         h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
                                           &h->prof);
+        launch_deferred_arrive(h, true);
         h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof);
     }
@@ -744,18 +759,81 @@ int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count) {
     return rc;
 }
 
+namespace {
+// Emits the subtree of the node covering finest cells [x0, x0+size) x [y0, y0+size); returns its index.
+struct QuadBuilder {
+    const std::vector<std::vector<uint32_t>>* sums;  // sums[l][iy * side_l + ix]: entities in the level-l cell (l = 0: finest)
+    int levels;
+    uint32_t node_cap;
+    msim_quadtree_node* out;
+    uint64_t cap;
+    uint64_t used;
+    bool overflow;
+
+    uint32_t emit(int level_up, uint32_t ix, uint32_t iy, float off_x, float off_y, float w, float hgt, uint32_t parent) {
+        if (used >= cap) {
+            overflow = true;
+            return 0;
+        }
+        const uint32_t self = static_cast<uint32_t>(used++);
+        msim_quadtree_node& nd = out[self];
+        std::memset(&nd, 0, sizeof(nd));
+        nd.offset_x = off_x;
+        nd.offset_y = off_y;
+        nd.width = w;
+        nd.height = hgt;
+        nd.prev_node_index = parent;
+        const uint32_t side = 1u << (levels - level_up);
+        const uint32_t count = (*sums)[level_up][static_cast<size_t>(iy) * side + ix];
+        if (count > node_cap && level_up > 0) {  // random_move.comp:354: split unless there is room or maxDepth is reached
+            nd.content_type = 1;  // NODE
+            const float hw = w * 0.5f, hh = hgt * 0.5f;  // quad_tree_split_up_node, :285-295
+            nd.next_tl = emit(level_up - 1, 2 * ix, 2 * iy, off_x, off_y, hw, hh, self);
+            nd.next_tr = emit(level_up - 1, 2 * ix + 1, 2 * iy, off_x + hw, off_y, hw, hh, self);
+            nd.next_bl = emit(level_up - 1, 2 * ix, 2 * iy + 1, off_x, off_y + hh, hw, hh, self);
+            nd.next_br = emit(level_up - 1, 2 * ix + 1, 2 * iy + 1, off_x + hw, off_y + hh, hw, hh, self);
+        } else {
+            nd.content_type = 2;  // ENTITY leaf
+            nd.entity_count = count;
+        }
+        return self;
+    }
+};
+}  // namespace
+
 int msim_read_quadtree_nodes(msim_handle* h, msim_quadtree_node* dst, uint64_t cap, uint64_t* count) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!dst || cap == 0 || !count) return fail(h, MSIM_ERR_INVALID, "msim_read_quadtree_nodes: bad arguments");
-    // Root only for now (gpu_quad_tree::init_node_zero, GpuQuadTree.cpp:6-10): a single ENTITY leaf
-    // spanning the world.  The display tree built from the sorted cell keys is SURVEY §8f row 1.
-    std::memset(dst, 0, sizeof(msim_quadtree_node));
-    dst[0].width = h->world_w;
-    dst[0].height = h->world_h;
-    dst[0].content_type = 2;
-    dst[0].entity_count = h->uninitialised ? 0 : h->n;
-    *count = 1;
+    const int depth = static_cast<int>(std::min<uint32_t>(std::max<uint32_t>(h->qt_depth, 1u), 8u));  // 4^7 finest cells fit one CTA's shared memory; the reference uses 8
+    const int levels = depth - 1;  // the root is depth 1 (quad_tree_insert(index, 0, 1), :864)
+    const bool root_only = (h->flags & MSIM_FLAG_NO_QUADTREE) || h->uninitialised || h->n == 0 || levels == 0;
+    std::vector<std::vector<uint32_t>> sums(levels + 1);
+    if (!root_only) {
+        const size_t bins = static_cast<size_t>(1) << (2 * levels);
+        if (!h->leaf_hist) MSIM_CUDA(h, dev_alloc(&h->leaf_hist, static_cast<size_t>(1) << 16));
+        h->launches += launch_leaf_histogram(h->stream, h->sm_count, h->n, h->pos[h->cur], h->world_w, h->world_h, levels, h->leaf_hist);
+        sums[0].resize(bins);
+        MSIM_CUDA(h, cudaMemcpyAsync(sums[0].data(), h->leaf_hist, bins * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        rc = check_device_errors(h);
+        if (rc != MSIM_OK) return rc;
+        for (int l = 1; l <= levels; l++) {  // bottom-up sums
+            const uint32_t side = 1u << (levels - l);
+            sums[l].resize(static_cast<size_t>(side) * side);
+            for (uint32_t y = 0; y < side; y++)
+                for (uint32_t x = 0; x < side; x++) {
+                    const std::vector<uint32_t>& f = sums[l - 1];
+                    const size_t fs = static_cast<size_t>(side) * 2;
+                    sums[l][static_cast<size_t>(y) * side + x] = f[(2 * y) * fs + 2 * x] + f[(2 * y) * fs + 2 * x + 1] + f[(2 * y + 1) * fs + 2 * x] + f[(2 * y + 1) * fs + 2 * x + 1];
+                }
+        }
+    } else {
+        sums.assign(1, std::vector<uint32_t>(1, (h->uninitialised || (h->flags & MSIM_FLAG_NO_QUADTREE)) ? 0u : h->n));
+    }
+    QuadBuilder b{&sums, root_only ? 0 : levels, h->qt_cap, dst, cap, 0, false};
+    b.emit(root_only ? 0 : levels, 0, 0, 0.0f, 0.0f, h->world_w, h->world_h, 0);
+    if (b.overflow) return fail(h, MSIM_ERR_CAPACITY, "msim_read_quadtree_nodes: node buffer too small (calc_node_count(maxDepth) entries suffice)");
+    *count = b.used;
     return MSIM_OK;
 }
 

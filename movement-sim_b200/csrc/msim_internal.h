@@ -166,6 +166,9 @@ int launch_reorder(cudaStream_t s, uint32_t n, const uint32_t* sorted_idx, const
 int launch_gather_pos(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const float2* pos, float2* out);
 int launch_gather_flag(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const uint8_t* flag, uint8_t* out);
 
+// quadtree.cu — histogram over the finest display-quadtree cells (levels = maxDepth - 1, <= 8)
+int launch_leaf_histogram(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, float world_w, float world_h, int levels, uint32_t* hist);
+
 // ---- multi-GPU sharding (shard.cu) -------------------------------------------------------------
 struct ShardHeader {
     uint32_t n_migrants;

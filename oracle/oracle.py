@@ -210,6 +210,8 @@ def ref():
         R.ref_get_positions.restype = None
         R.ref_get_positions.argtypes = [C.c_void_p, C.c_size_t]
         R.ref_count_entities_in_tree.restype = C.c_size_t
+        R.ref_dump_tree.restype = C.c_size_t
+        R.ref_dump_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         _ref = R
     return _ref
 
@@ -241,6 +243,15 @@ class RefQuadTree:
 
     def count_in_tree(self) -> int:
         return int(self.R.ref_count_entities_in_tree())
+
+    def dump_tree(self):
+        """Depth-first (TL, TR, BL, BR) list of the reference tree's nodes: (rects[n,4], types[n], counts[n])."""
+        cap = int(self.R.ref_node_count())
+        rects = np.zeros((cap, 4), dtype=np.float32)
+        types = np.zeros(cap, dtype=np.uint32)
+        counts = np.zeros(cap, dtype=np.uint32)
+        n = int(self.R.ref_dump_tree(rects.ctypes.data, types.ctypes.data, counts.ctypes.data, cap))
+        return rects[:n], types[:n], counts[:n]
 
 
 def run_ref_kat() -> subprocess.CompletedProcess:
