@@ -42,6 +42,15 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
  * (NULL = none).  One host round trip (counts + hole list).  Returns the new owned / ghost counts. */
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts);
 
+/* Asynchronous variant: the same integration done by kernels on the handle's stream, NO host round trip.
+ * The owned / ghost counts stay in device memory and every following kernel of the handle reads them
+ * there, so a whole sharded tick (move, pack, exchange, integrate, collide) can be enqueued without
+ * waiting for the GPU.  Overflow is reported by the next call that synchronises (msim_sync, msim_get_stats,
+ * msim_read_*, msim_shard_counts). */
+int msim_shard_integrate_async(msim_handle* h, const void* recv_down, const void* recv_up);
+/* Current owned / ghost counts (synchronises the stream when asynchronous ticks are outstanding). */
+int msim_shard_counts(msim_handle* h, uint64_t* owned, uint64_t* ghosts);
+
 /* Global ids of the owned entities, in the order msim_read_entities returns them. */
 int msim_shard_read_gids(msim_handle* h, uint32_t* dst, uint64_t count);
 

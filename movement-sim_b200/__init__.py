@@ -84,7 +84,8 @@ ABI_SYMBOLS = [
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
     "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
     # include/msim_shard.h
-    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_integrate", "msim_shard_read_gids",
+    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_integrate", "msim_shard_integrate_async",
+    "msim_shard_counts", "msim_shard_read_gids",
     "msim_shard_row_histogram", "msim_grid_rows",
 ]
 
@@ -205,6 +206,8 @@ def lib():
         "msim_shard_enable": (i32, [vp, vp, u64, u32, u32]),
         "msim_shard_pack": (i32, [vp, u32, u32, vp, vp]),
         "msim_shard_integrate": (i32, [vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+        "msim_shard_integrate_async": (i32, [vp, vp, vp]),
+        "msim_shard_counts": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "msim_shard_read_gids": (i32, [vp, vp, u64]),
         "msim_shard_row_histogram": (i32, [vp, vp, u32]),
         "msim_grid_rows": (i32, [f32, f32, f32, vp, u64, vp, C.POINTER(u32), C.POINTER(u32)]),
@@ -343,6 +346,7 @@ class Simulation:
         if rc != MSIM_OK:
             raise MsimError(rc, L.msim_last_error(None).decode())
         self.count = ents.shape[0]
+        self._sharded_async = False
         self.quadtree_depth, self.quadtree_cap = quadtree_depth, quadtree_cap
 
     # -- lifetime
@@ -403,6 +407,8 @@ class Simulation:
         self.count = count
 
     def read_entities(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None and self._sharded_async:
+            self.shard_counts()
         if out is None:
             out = np.empty(self.count, dtype=ENTITY_DTYPE)
         assert out.dtype == ENTITY_DTYPE and out.flags.c_contiguous
@@ -453,7 +459,18 @@ class Simulation:
         self.count = owned.value
         return owned.value, ghosts.value
 
+    def shard_integrate_async(self, recv_down_ptr: int | None, recv_up_ptr: int | None):
+        self._sharded_async = True
+        self._check(lib().msim_shard_integrate_async(self._h, recv_down_ptr, recv_up_ptr))
+
+    def shard_counts(self):
+        owned, ghosts = C.c_uint64(), C.c_uint64()
+        self._check(lib().msim_shard_counts(self._h, C.byref(owned), C.byref(ghosts)))
+        self.count = owned.value
+        return owned.value, ghosts.value
+
     def shard_read_gids(self) -> np.ndarray:
+        self.shard_counts()
         out = np.empty(self.count, dtype=np.uint32)
         self._check(lib().msim_shard_read_gids(self._h, out.ctypes.data, self.count))
         return out

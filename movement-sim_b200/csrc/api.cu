@@ -129,6 +129,8 @@ struct msim_handle {
     bool stage_flip{false};
     void* sent_down{nullptr};
     void* sent_up{nullptr};
+    uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
+    bool async_counts{false};       // host-side n / n_ghost are stale (upper bound = capacity) until the next refresh
 
     Profiler prof;
     std::string error;
@@ -208,6 +210,7 @@ void free_all(msim_handle* h) {
     cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes); cudaFree(h->leaf_hist);
     cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
     cudaFree(h->ext_id); cudaFree(h->ext_id_alt); cudaFree(h->slot_of);
+    cudaFree(h->dev_counts);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -219,6 +222,13 @@ void free_all(msim_handle* h) {
 }
 
 // make the main stream wait for a pass B still running on the side stream
+// element counts for launches: exact host values, or (asynchronous sharded ticks) the capacity as an upper
+// bound for grid sizing plus device pointers the kernels read the exact counts from
+inline uint32_t launch_owned(const msim_handle* h) { return h->async_counts ? h->cap : h->n; }
+inline uint32_t launch_total(const msim_handle* h) { return h->async_counts ? h->cap : h->n + h->n_ghost; }
+inline const uint32_t* dev_owned(const msim_handle* h) { return h->async_counts ? h->dev_counts + DEV_N_OWNED : nullptr; }
+inline const uint32_t* dev_total(const msim_handle* h) { return h->async_counts ? h->dev_counts + DEV_N_TOTAL : nullptr; }
+
 void launch_deferred_arrive(msim_handle* h, bool beside) {
     if (!h->arrive_deferred) return;
     h->arrive_deferred = false;
@@ -227,11 +237,13 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
         // called right before the query, which is issue-bound and leaves the memory system idle
         cudaEventRecord(h->ev_moved, h->stream);
         cudaStreamWaitEvent(h->side, h->ev_moved, 0);
-        h->launches += launch_arrive(h->side, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+        h->launches += launch_arrive(h->side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
+                                     dev_owned(h));
         cudaEventRecord(h->ev_arrived, h->side);
         h->side_pending = true;
     } else {
-        h->launches += launch_arrive(h->stream, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+        h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
+                                     dev_owned(h));
     }
 }
 
@@ -241,6 +253,31 @@ void join_side(msim_handle* h) {
         cudaStreamWaitEvent(h->stream, h->ev_arrived, 0);
         h->side_pending = false;
     }
+}
+
+int write_dev_counts(msim_handle* h) {
+    if (!h->dev_counts) return MSIM_OK;
+    const uint32_t v[DEV_COUNT_WORDS] = {h->n, h->n_ghost, h->n + h->n_ghost, 0, 0, 0, 0, 0};
+    MSIM_CUDA(h, cudaMemcpyAsync(h->dev_counts, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged before return
+    return MSIM_OK;
+}
+
+// asynchronous sharded ticks: bring the host-side counts up to date (one small D2H + stream sync)
+int refresh_counts(msim_handle* h) {
+    if (!h->async_counts) return MSIM_OK;
+    uint32_t v[DEV_COUNT_WORDS] = {0};
+    MSIM_CUDA(h, cudaMemcpyAsync(v, h->dev_counts, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n = v[DEV_N_OWNED];
+    h->n_ghost = v[DEV_N_GHOST];
+    h->async_counts = false;
+    if (!h->flags_stale) {  // counts only change in an integrate, which marks the flags stale: these are the last collision pass's
+        h->collide_owned = h->n;
+        h->collide_total = h->n + h->n_ghost;
+    }
+    if (v[DEV_SHARD_ERROR] & 7u) return fail(h, MSIM_ERR_CAPACITY, "shard exchange overflow (migrant / halo / entity capacity) during asynchronous ticks");
+    if (v[DEV_SHARD_ERROR]) return fail(h, MSIM_ERR_INTERNAL, "shard compaction bookkeeping mismatch");
+    return MSIM_OK;
 }
 
 int ensure_cells(msim_handle* h) {
@@ -310,6 +347,11 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->flags_scattered = false;
     h->n_ghost = 0;
     h->flags_stale = false;
+    h->async_counts = false;
+    {
+        const int wrc = write_dev_counts(h);
+        if (wrc != MSIM_OK) return wrc;
+    }
     h->perm_active = false;                 // uploaded state is in external order again
     h->since_reorder = h->reorder_every;    // re-sort right after the first collision pass
     if (h->flag_entity) MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
@@ -327,6 +369,10 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
 
 int check_device_errors(msim_handle* h) {
     join_side(h);
+    {
+        const int rc = refresh_counts(h);
+        if (rc != MSIM_OK) return rc;
+    }
     Counters c{};
     MSIM_CUDA(h, cudaMemcpyAsync(&c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -363,14 +409,16 @@ int enqueue_move(msim_handle* h, bool want_keys) {
     if (fuse_count) csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
-    h->launches += launch_move(h->stream, h->sm_count, h->n, h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
+    h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
-                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof);
+                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof,
+                               dev_owned(h));
     h->counts_valid = fuse_count;
     if (emit && h->side && !h->sharded) {
         h->arrive_deferred = true;  // a collision pass follows and needs only positions and keys: pass B is launched beside its query
     } else {
-        h->launches += launch_arrive(h->stream, h->n, h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof);
+        h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
+                                     dev_owned(h));
     }
     h->cur ^= 1;
     h->has_moved = true;
@@ -439,7 +487,11 @@ int enqueue_collide(msim_handle* h) {
         h->keys_valid = true;
         h->hist_valid = false;
     }
-    const uint32_t total = h->n + h->n_ghost;  // ghosts (multi-GPU halo) sit behind the owned entities
+    if (h->async_counts && h->use_csort) {  // the counting-sort path sizes its scatter from exact host counts
+        rc = refresh_counts(h);
+        if (rc != MSIM_OK) return rc;
+    }
+    const uint32_t total = launch_total(h);  // ghosts (multi-GPU halo) sit behind the owned entities
     const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
     if (h->use_csort) {
         if (!h->counts_valid) {  // keys came from keygen or changed in a shard exchange: count them now
@@ -453,16 +505,17 @@ int enqueue_collide(msim_handle* h) {
         h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof);
     } else {
-        h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted, h->hist_valid && h->n_ghost == 0, &h->prof);
+        h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted,
+                                   h->hist_valid && h->n_ghost == 0 && !h->async_counts, &h->prof, dev_total(h));
         h->hist_valid = false;  // the sort consumed the tickets and look-back words
         h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
-                                          &h->prof);
+                                          &h->prof, dev_total(h));
         launch_deferred_arrive(h, true);
-        h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
-                                    h->counters, h->stripes, &h->prof);
+        h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
+                                    h->counters, h->stripes, &h->prof, dev_total(h), dev_owned(h));
     }
     h->collide_total = total;
-    h->collide_owned = h->n;
+    h->collide_owned = launch_owned(h);
     h->flags_stale = false;
     h->collided = true;
     h->flags_scattered = false;
@@ -480,6 +533,11 @@ int bind(msim_handle* h) {
 
 int materialise_flags(msim_handle* h) {
     if (h->collided && !h->flags_scattered) {
+        if (h->async_counts) {  // the collision pass ran on device-resident counts: fetch them (they have not changed since)
+            if (refresh_counts(h) != MSIM_OK) return MSIM_ERR_CAPACITY;
+            h->collide_owned = h->n;
+            h->collide_total = h->n + h->n_ghost;
+        }
         h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted_idx, h->flag_sorted, h->flag_entity, &h->prof);
         h->flags_scattered = true;
     }
@@ -694,6 +752,8 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
 
 int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    rc = refresh_counts(h);
     if (rc != MSIM_OK) return rc;
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
     if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
@@ -982,6 +1042,9 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->place_dst, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_COUNT_WORDS));
+    rc = write_dev_counts(h);
+    if (rc != MSIM_OK) return rc;
     MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), 2 * (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
     if (count) MSIM_CUDA(h, cudaMemcpyAsync(h->gid, gids, count * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -999,8 +1062,8 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
     rc = ensure_keys(h);
     if (rc != MSIM_OK) return rc;
     h->n_ghost = 0;
-    h->launches += launch_shard_pack(h->stream, shard_arrays(h), h->n, h->grid.ncx, row_lo, row_hi, send_down, send_up, h->mig_cap, h->halo_cap,
-                                     h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof);
+    h->launches += launch_shard_pack(h->stream, shard_arrays(h), launch_owned(h), h->grid.ncx, row_lo, row_hi, send_down, send_up, h->mig_cap, h->halo_cap,
+                                     h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof, dev_owned(h));
     h->sent_down = send_down;
     h->sent_up = send_up;
     return MSIM_OK;
@@ -1010,6 +1073,8 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_integrate: call msim_shard_enable first");
+    rc = refresh_counts(h);
+    if (rc != MSIM_OK) return rc;
     // one host round trip: counters, the four headers and the hole list
     // two staging areas used alternately: the H2D copies of tick t may still be in flight when tick t+1 stages
     const size_t stage_words = static_cast<size_t>(h->holes_cap) * 4 + 64;
@@ -1073,6 +1138,8 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
                                               h->grid, &h->prof);
     h->n = n_new;
     h->n_ghost = n_ghost;
+    rc = write_dev_counts(h);
+    if (rc != MSIM_OK) return rc;
     h->keys_valid = true;
     h->hist_valid = false;
     h->counts_valid = false;
@@ -1082,10 +1149,37 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     return MSIM_OK;
 }
 
+int msim_shard_integrate_async(msim_handle* h, const void* recv_down, const void* recv_up) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_integrate_async: call msim_shard_enable first");
+    h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
+                                                 h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
+                                                 h->grid, &h->prof);
+    h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
+    h->keys_valid = true;
+    h->hist_valid = false;
+    h->counts_valid = false;
+    h->flags_stale = h->collided;
+    return MSIM_OK;
+}
+
+int msim_shard_counts(msim_handle* h, uint64_t* owned, uint64_t* ghosts) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    rc = refresh_counts(h);
+    if (rc != MSIM_OK) return rc;
+    if (owned) *owned = h->n;
+    if (ghosts) *ghosts = h->n_ghost;
+    return MSIM_OK;
+}
+
 int msim_shard_read_gids(msim_handle* h, uint32_t* dst, uint64_t count) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_read_gids: call msim_shard_enable first");
+    rc = refresh_counts(h);
+    if (rc != MSIM_OK) return rc;
     if (count > h->n || (count && !dst)) return fail(h, MSIM_ERR_INVALID, "msim_shard_read_gids: bad arguments");
     if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, h->gid, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1097,6 +1191,8 @@ int msim_shard_row_histogram(msim_handle* h, uint32_t* dst, uint32_t rows) {
     if (rc != MSIM_OK) return rc;
     if (!dst || rows != static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_row_histogram: rows must equal grid_cells_y");
     if (!h->row_hist) MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    rc = refresh_counts(h);
+    if (rc != MSIM_OK) return rc;
     rc = ensure_keys(h);
     if (rc != MSIM_OK) return rc;
     h->launches += launch_shard_row_histogram(h->stream, h->keys, h->n, h->grid.ncx, h->row_hist, rows, &h->prof);

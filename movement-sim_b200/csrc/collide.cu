@@ -18,8 +18,9 @@ namespace msim {
 namespace {
 
 __global__ void __launch_bounds__(256)
-build_cells_kernel(uint32_t n, const unsigned long long* __restrict__ sorted, const float2* __restrict__ pos,
+build_cells_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const unsigned long long* __restrict__ sorted, const float2* __restrict__ pos,
                    float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx, uint2* __restrict__ cell_range, Counters* __restrict__ counters) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     const bool in = j < n;
@@ -148,14 +149,18 @@ constexpr uint32_t QUERY_WINDOW = 1792;  // candidates staged per window (2 wind
 // candidates for everybody else but get no flag and count no pairs here — their owner does that.
 template <bool COUNT_PAIRS, bool GHOSTS, bool PREFIX>
 __global__ void __launch_bounds__(QUERY_THREADS)
-query_kernel(uint32_t n, uint32_t n_owned, const uint32_t* __restrict__ sorted_idx, const float2* __restrict__ sorted_pos,
+query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ n_owned_dev,
+             const uint32_t* __restrict__ sorted_idx, const float2* __restrict__ sorted_pos,
              const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, uint8_t* __restrict__ flag_sorted, GridParams grid,
              unsigned long long* __restrict__ stripes) {
     __shared__ float2 s_above[QUERY_WINDOW];
     __shared__ float2 s_own[QUERY_WINDOW];
     __shared__ uint32_t s_red[3][QUERY_THREADS / 32];
 
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t n_owned = n_owned_dev ? *n_owned_dev : n_owned_host;
     const uint32_t block_base = blockIdx.x * QUERY_THREADS;
+    if (block_base >= n) return;  // grid sized for an upper bound of n (whole CTA, uniform)
     const uint32_t j = block_base + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t pairs = 0;
@@ -307,26 +312,26 @@ scatter_flags_kernel(uint32_t n, uint32_t n_owned, const uint32_t* __restrict__ 
 }  // namespace
 
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
-                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof) {
+                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof, const uint32_t* n_dev) {
     prof->begin(s, K_MEMSET);
     cudaMemsetAsync(cell_range, 0xff, static_cast<size_t>(grid.ncells) * sizeof(uint2), s);
     prof->end(s);
     if (n == 0) return 0;
     prof->begin(s, K_BUILD_CELLS);
-    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, sorted_idx, cell_range, counters);
+    build_cells_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, n_dev, reinterpret_cast<const unsigned long long*>(sorted), pos, sorted_pos, sorted_idx, cell_range, counters);
     prof->end(s);
     return 1;
 }
 
 int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
                  const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters,
-                 unsigned long long* stripes, Profiler* prof) {
+                 unsigned long long* stripes, Profiler* prof, const uint32_t* n_dev, const uint32_t* n_owned_dev) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + QUERY_THREADS - 1) / QUERY_THREADS;
-    const bool ghosts = n_owned < n, prefix = cell_start != nullptr;
+    const bool ghosts = n_owned < n || n_owned_dev != nullptr, prefix = cell_start != nullptr;
     prof->begin(s, K_QUERY);
 #define MSIM_QUERY(CP, GH, PF) \
-    query_kernel<CP, GH, PF><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, sorted_idx, sorted_pos, cell_range, cell_start, flag_sorted, grid, stripes)
+    query_kernel<CP, GH, PF><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, n_dev, n_owned_dev, sorted_idx, sorted_pos, cell_range, cell_start, flag_sorted, grid, stripes)
     if (count_pairs) {
         if (ghosts) { if (prefix) MSIM_QUERY(true, true, true); else MSIM_QUERY(true, true, false); }
         else { if (prefix) MSIM_QUERY(true, false, true); else MSIM_QUERY(true, false, false); }

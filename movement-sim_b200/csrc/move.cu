@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t run_rank(uint32_t* __restrict__ cell_count, 
 // rebuild needs no separate histogram read of the keys.
 template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(MOVE_THREADS)
-move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
+move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
             uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
             uint32_t* __restrict__ cell_count, uint2* __restrict__ rank) {
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
@@ -130,6 +130,7 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
         for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
         __syncthreads();
     }
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t pairs_pad = (pairs + 31u) & ~31u;  // arrays are padded, whole warps stay converged
     const uint32_t lane = threadIdx.x & 31u;
@@ -191,9 +192,11 @@ move_kernel(uint32_t n, const float4* __restrict__ pos_in, float4* __restrict__ 
 constexpr int ARRIVE_THREADS = 256;
 
 __global__ void __launch_bounds__(ARRIVE_THREADS)
-arrive_kernel(uint32_t n, uint32_t words, const uint32_t* __restrict__ arrived_mask, float2* __restrict__ target,
+arrive_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ arrived_mask, float2* __restrict__ target,
               uint32_t* __restrict__ road, uint4* __restrict__ rng, const uint4* __restrict__ roads,
               const uint32_t* __restrict__ conn, uint64_t conn_count) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t words = ((n + 63u) >> 6) << 1;  // two mask words per 64-entity chunk
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t w = blockIdx.x * ARRIVE_THREADS + threadIdx.x;  // one mask word per lane
     const uint32_t mask = (w < words) ? __ldcs(arrived_mask + w) : 0u;
@@ -240,7 +243,8 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 }  // namespace
 
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
-                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof) {
+                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
+                const uint32_t* n_dev) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
@@ -251,20 +255,20 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
     prof->begin(s, K_MOVE);
-    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
+    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
                                                           cell_count, reinterpret_cast<uint2*>(rank));
-    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr);
+    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr);
     prof->end(s);
     return 1;
 }
 
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof) {
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
-    const uint32_t words = ((n + 63u) >> 6) << 1;  // two mask words per 64-entity chunk
+    const uint32_t words = ((n + 63u) >> 6) << 1;  // grid size (n is an upper bound when n_dev is given)
     prof->begin(s, K_ARRIVE);
     arrive_kernel<<<(words + ARRIVE_THREADS - 1) / ARRIVE_THREADS, ARRIVE_THREADS, 0, s>>>(
-        n, words, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
+        n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
     prof->end(s);
     return 1;
 }

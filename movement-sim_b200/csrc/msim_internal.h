@@ -96,11 +96,15 @@ struct Profiler {
 // ---- kernel launchers (each returns the number of kernels it launched) ------------------------
 // move.cu
 // pass A (streaming) and pass B (next waypoint of the arrived entities) of one move dispatch
+// Device-resident counts (asynchronous sharded ticks): when `n_dev` is non-NULL a kernel takes its element
+// count from *n_dev (written by an earlier kernel on the stream) and the host-side `n` is only an upper
+// bound used to size the grid.
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
-                int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof);
+                int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
+                const uint32_t* n_dev = nullptr);
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof);
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
 
 // sort.cu
@@ -108,7 +112,7 @@ size_t sort_workspace_bytes(uint32_t capacity);
 void sort_workspace_bind(SortWorkspace& ws, void* base, uint32_t capacity);
 // sorts (key, index) by key; result lands in *result (either buf_a or buf_b)
 int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits,
-                const SortWorkspace& ws, uint64_t** result, bool hist_ready, Profiler* prof);
+                const SortWorkspace& ws, uint64_t** result, bool hist_ready, Profiler* prof, const uint32_t* n_dev = nullptr);
 // zeroes histograms / tickets / look-back words; call before a move pass that fuses the histogram
 void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace& ws, Profiler* prof);
 
@@ -122,11 +126,12 @@ int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const 
 
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
-                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof);
+                       uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof, const uint32_t* n_dev = nullptr);
 // n_owned < n: slots whose entity index (sorted_idx) is >= n_owned are ghosts (neighbours only).
 // Cell directory: either cell_range ({first, ~end} per cell, onesweep path) or cell_start (prefix table, csort path).
 int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
-                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof);
+                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
+                 const uint32_t* n_dev = nullptr, const uint32_t* n_owned_dev = nullptr);
 size_t query_stripe_bytes();
 int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
@@ -192,7 +197,14 @@ struct ShardArrays {
 };
 
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
-                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof);
+                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
+                      const uint32_t* n_dev = nullptr);
+// device-side integrate (asynchronous sharded tick): placement, tail compaction and the new counts without a host round trip
+enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_SHARD_ERROR = 3, DEV_COUNT_WORDS = 8 };
+int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
+                                  const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
+                                  uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
+                                  const GridParams& grid, Profiler* prof);
 int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
                        const uint32_t* dst, const GridParams& grid, Profiler* prof);
 int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof);

@@ -47,8 +47,9 @@ __device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
 }
 
 __global__ void __launch_bounds__(256)
-shard_pack_kernel(ShardArrays a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
+shard_pack_kernel(ShardArrays a, uint32_t n_host, const uint32_t* __restrict__ n_dev, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
                   uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = e < n;
     uint32_t row = 0;
@@ -157,6 +158,131 @@ shard_append_ghosts_kernel(ShardArrays a, uint32_t first, const void* recv_down,
     a.keys[first + i] = cell_key_of(p, grid);
 }
 
+// ---- device-side integrate (asynchronous sharded tick) ------------------------------------------
+// Same bookkeeping as msim_shard_integrate's host code, done by ONE CTA so that the tick needs no host
+// round trip: arrivals fill the leavers' holes (then append), remaining holes are closed with the live
+// entities of the tail, and the new owned / ghost / total counts are left in device memory for the
+// kernels that follow on the stream.  Lists are short (hundreds to a few thousand entries per tick).
+__device__ __forceinline__ void copy_entity(const ShardArrays& a, uint32_t src, uint32_t dst) {
+    a.pos_cur[dst] = a.pos_cur[src];
+    a.pos_prev[dst] = a.pos_prev[src];
+    a.target[dst] = a.target[src];
+    a.rng[dst] = a.rng[src];
+    a.color0[dst] = a.color0[src];
+    a.road[dst] = a.road[src];
+    a.gid[dst] = a.gid[src];
+    a.keys[dst] = a.keys[src];
+    set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
+}
+
+__device__ __forceinline__ void place_record(const ShardArrays& a, const void* buf, uint32_t r, uint32_t e, const GridParams& grid) {
+    const uint2* rec = reinterpret_cast<const uint2*>(static_cast<const char*>(buf) + sizeof(ShardHeader)) + static_cast<size_t>(r) * (MIGRANT_BYTES / 8);
+    const uint2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6], r7 = rec[7], r8 = rec[8];
+    const float2 p = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y));
+    a.pos_cur[e] = p;
+    a.pos_prev[e] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y));
+    a.target[e] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y));
+    a.rng[e] = make_uint4(r3.x, r3.y, r4.x, r4.y);
+    a.color0[e] = make_float4(__uint_as_float(r5.x), __uint_as_float(r5.y), __uint_as_float(r6.x), __uint_as_float(r6.y));
+    a.road[e] = r7.x;
+    a.gid[e] = r7.y;
+    a.keys[e] = cell_key_of(p, grid);
+    set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
+}
+
+constexpr int INTEGRATE_THREADS = 1024;
+
+__global__ void __launch_bounds__(INTEGRATE_THREADS)
+shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const void* sent_down, const void* sent_up, const void* recv_down,
+                       const void* recv_up, const uint32_t* __restrict__ holes, const uint32_t* __restrict__ ctr, uint32_t mig_cap, uint32_t halo_cap,
+                       uint32_t holes_cap, uint32_t entity_cap, uint32_t* __restrict__ tail_bits, uint2* __restrict__ moves, GridParams grid) {
+    __shared__ uint32_t s_n_old, s_n_new, s_k_out, s_in_down, s_in_up, s_ghosts, s_low, s_live, s_err;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        uint32_t err = 0;
+        const uint32_t n_old = dev_counts[DEV_N_OWNED];
+        uint32_t k_out = ctr[SHARD_CTR_HOLES], g_local = ctr[SHARD_CTR_LOCAL_GHOSTS];
+        uint32_t in_down = 0, in_up = 0, halo_down = 0, halo_up = 0;
+        if (sent_down && static_cast<const ShardHeader*>(sent_down)->overflow) err |= 1u;
+        if (sent_up && static_cast<const ShardHeader*>(sent_up)->overflow) err |= 1u;
+        if (recv_down) {
+            const ShardHeader* hd = static_cast<const ShardHeader*>(recv_down);
+            in_down = hd->n_migrants;
+            halo_down = hd->n_halo;
+            if (hd->overflow) err |= 1u;
+        }
+        if (recv_up) {
+            const ShardHeader* hd = static_cast<const ShardHeader*>(recv_up);
+            in_up = hd->n_migrants;
+            halo_up = hd->n_halo;
+            if (hd->overflow) err |= 1u;
+        }
+        if (k_out > holes_cap || g_local > holes_cap) { err |= 2u; k_out = min(k_out, holes_cap); g_local = min(g_local, holes_cap); }
+        if (in_down > mig_cap || in_up > mig_cap || halo_down > halo_cap || halo_up > halo_cap) {
+            err |= 2u;
+            in_down = min(in_down, mig_cap); in_up = min(in_up, mig_cap); halo_down = min(halo_down, halo_cap); halo_up = min(halo_up, halo_cap);
+        }
+        uint32_t n_new = n_old + in_down + in_up - min(k_out, n_old + in_down + in_up);
+        uint32_t ghosts = halo_down + halo_up + g_local;
+        if (static_cast<unsigned long long>(n_new) + ghosts > entity_cap) {  // keep every later kernel inside its arrays
+            err |= 4u;
+            if (n_new > entity_cap) n_new = entity_cap;
+            ghosts = entity_cap - n_new;
+        }
+        s_n_old = n_old; s_n_new = n_new; s_k_out = k_out; s_in_down = in_down; s_in_up = in_up; s_ghosts = ghosts;
+        s_low = 0; s_live = 0; s_err = err;
+    }
+    __syncthreads();
+    const uint32_t n_old = s_n_old, n_new = s_n_new, k_out = s_k_out, in_down = s_in_down, in_up = s_in_up, k_in = in_down + in_up;
+    // 1. arrivals: holes first, then append
+    for (uint32_t i = tid; i < k_in; i += INTEGRATE_THREADS) {
+        const uint32_t dst = i < k_out ? holes[i] : n_old + (i - k_out);
+        if (dst < entity_cap) place_record(a, i < in_down ? recv_down : recv_up, i < in_down ? i : i - in_down, dst, grid);
+    }
+    // 2. more leavers than arrivals: the tail [n_new, n_old) goes away; its live entities move into the open holes below n_new
+    if (k_out > k_in) {
+        const uint32_t tail = n_old - n_new;
+        for (uint32_t w = tid; w < (tail + 31u) / 32u; w += INTEGRATE_THREADS) tail_bits[w] = 0;
+        __syncthreads();
+        for (uint32_t i = k_in + tid; i < k_out; i += INTEGRATE_THREADS) {
+            const uint32_t hole = holes[i];
+            if (hole >= n_new) atomicOr(&tail_bits[(hole - n_new) >> 5], 1u << ((hole - n_new) & 31u));
+            else moves[atomicAdd(&s_low, 1u)].y = hole;
+        }
+        __syncthreads();
+        for (uint32_t t = tid; t < tail; t += INTEGRATE_THREADS)
+            if (!((tail_bits[t >> 5] >> (t & 31u)) & 1u)) moves[atomicAdd(&s_live, 1u)].x = n_new + t;
+        __syncthreads();
+        if (tid == 0 && s_low != s_live) s_err |= 8u;
+        const uint32_t m = min(s_low, s_live);
+        for (uint32_t i = tid; i < m; i += INTEGRATE_THREADS) copy_entity(a, moves[i].x, moves[i].y);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        dev_counts[DEV_N_OWNED] = n_new;
+        dev_counts[DEV_N_GHOST] = s_ghosts;
+        dev_counts[DEV_N_TOTAL] = n_new + s_ghosts;
+        if (s_err) atomicOr(&dev_counts[DEV_SHARD_ERROR], s_err);
+    }
+}
+
+// ghosts behind the owned entities, counts taken from device memory (grid sized for the capacities)
+__global__ void __launch_bounds__(256)
+shard_append_ghosts_device_kernel(ShardArrays a, const uint32_t* __restrict__ dev_counts, const void* recv_down, const void* recv_up,
+                                  const float2* __restrict__ local_ghosts, uint32_t mig_cap, uint32_t halo_cap, GridParams grid) {
+    const uint32_t first = dev_counts[DEV_N_OWNED], ghosts = dev_counts[DEV_N_GHOST];
+    const uint32_t h_down = recv_down ? min(static_cast<const ShardHeader*>(recv_down)->n_halo, halo_cap) : 0u;
+    const uint32_t h_up = recv_up ? min(static_cast<const ShardHeader*>(recv_up)->n_halo, halo_cap) : 0u;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ghosts) return;
+    float2 p;
+    if (i < h_down) p = halo_of(const_cast<void*>(recv_down), mig_cap)[i];
+    else if (i < h_down + h_up) p = halo_of(const_cast<void*>(recv_up), mig_cap)[i - h_down];
+    else p = local_ghosts[i - h_down - h_up];
+    a.pos_cur[first + i] = p;
+    a.keys[first + i] = cell_key_of(p, grid);
+}
+
 __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int ncx, uint32_t* __restrict__ rows) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
         atomicAdd(&rows[keys[e] / static_cast<uint32_t>(ncx)], 1u);
@@ -165,13 +291,14 @@ __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t
 }  // namespace
 
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
-                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof) {
+                      uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
+                      const uint32_t* n_dev) {
     if (buf_down) cudaMemsetAsync(buf_down, 0, sizeof(ShardHeader), s);
     if (buf_up) cudaMemsetAsync(buf_up, 0, sizeof(ShardHeader), s);
     cudaMemsetAsync(ctr, 0, SHARD_CTR_COUNT * sizeof(uint32_t), s);
     if (n == 0) return 0;
     prof->begin(s, K_SHARD);
-    shard_pack_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(a, n, ncx, row_lo, row_hi, buf_down, buf_up, mig_cap, halo_cap, holes, holes_cap, local_ghosts, ctr);
+    shard_pack_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(a, n, n_dev, ncx, row_lo, row_hi, buf_down, buf_up, mig_cap, halo_cap, holes, holes_cap, local_ghosts, ctr);
     prof->end(s);
     return 1;
 }
@@ -201,6 +328,19 @@ int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t fi
     shard_append_ghosts_kernel<<<(total + 255u) / 256u, 256, 0, s>>>(a, first, recv_down, h_down, recv_up, h_up, local_ghosts, h_local, mig_cap, grid);
     prof->end(s);
     return 1;
+}
+
+int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
+                                  const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
+                                  uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
+                                  const GridParams& grid, Profiler* prof) {
+    prof->begin(s, K_SHARD);
+    shard_integrate_kernel<<<1, INTEGRATE_THREADS, 0, s>>>(a, dev_counts, sent_down, sent_up, recv_down, recv_up, holes, ctr, mig_cap, halo_cap, holes_cap,
+                                                           entity_cap, scratch_bits, scratch_moves, grid);
+    const uint32_t max_ghosts = 2u * halo_cap + holes_cap;
+    shard_append_ghosts_device_kernel<<<(max_ghosts + 255u) / 256u, 256, 0, s>>>(a, dev_counts, recv_down, recv_up, local_ghosts, mig_cap, halo_cap, grid);
+    prof->end(s);
+    return 2;
 }
 
 int launch_shard_row_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, int ncx, uint32_t* rows, uint32_t nrows, Profiler* prof) {

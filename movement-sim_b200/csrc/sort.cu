@@ -31,8 +31,9 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
 }
 
 // ---- histogram of every digit in one read of the keys -----------------------------------------
-__global__ void __launch_bounds__(256) histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist, int passes) {
+__global__ void __launch_bounds__(256) histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n_host, const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ hist, int passes) {
     __shared__ uint32_t sh[MAX_SORT_PASSES * RADIX];
+    const uint32_t n = n_dev ? *n_dev : n_host;
     for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const uint32_t quads = n >> 2;
@@ -75,7 +76,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // ---- one onesweep pass ------------------------------------------------------------------------
 // FIRST: input is the bare u32 key array, the payload (entity index) is the element's position.
 template <bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const void* __restrict__ in_raw, uint64_t* __restrict__ out, uint32_t n, int shift,
+__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const void* __restrict__ in_raw, uint64_t* __restrict__ out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int shift,
                                                                 const uint32_t* __restrict__ hist /* [RADIX], this pass */,
                                                                 uint32_t* __restrict__ tile_state /* [tiles][RADIX] */,
                                                                 uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ error_flag) {
@@ -90,8 +91,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const void* _
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * SORT_TILE;
+    if (tile_base >= n) return;  // grid sized for an upper bound of n: surplus CTAs (whole CTA, uniform) have nothing to sort
 
     // -- load: warp-striped, item i of lane l = warp chunk + i*32 + l (coalesced, order-preserving)
     uint64_t kv[SORT_ITEMS];
@@ -246,7 +249,7 @@ void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace&
 }
 
 int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_a, uint64_t* buf_b, int key_bits, const SortWorkspace& ws,
-                uint64_t** result, bool hist_ready, Profiler* prof) {
+                uint64_t** result, bool hist_ready, Profiler* prof, const uint32_t* n_dev) {
     *result = buf_a;
     if (n == 0) return 0;
     const int passes = sort_passes_for(key_bits);
@@ -258,7 +261,7 @@ int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_
         if (hblocks > 148u * 8u) hblocks = 148u * 8u;
         if (hblocks < 1) hblocks = 1;
         prof->begin(s, K_HISTOGRAM);
-        histogram_kernel<<<hblocks, 256, 0, s>>>(keys, n, ws.hist, passes);
+        histogram_kernel<<<hblocks, 256, 0, s>>>(keys, n, n_dev, ws.hist, passes);
         prof->end(s);
         launches++;
     }
@@ -268,9 +271,9 @@ int launch_sort(cudaStream_t s, uint32_t n, const uint32_t* keys, uint64_t* buf_
         uint32_t* state = ws.tile_state + static_cast<size_t>(p) * tiles * RADIX;
         prof->begin(s, K_SORT_PASS0 + p);
         if (p == 0)
-            onesweep_kernel<true><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
+            onesweep_kernel<true><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, n_dev, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
         else
-            onesweep_kernel<false><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
+            onesweep_kernel<false><<<tiles, SORT_THREADS, 0, s>>>(in, out, n, n_dev, p * RADIX_BITS, ws.hist + p * RADIX, state, ws.tile_counter + p, ws.error_flag);
         prof->end(s);
         launches++;
         *result = out;

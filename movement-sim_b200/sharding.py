@@ -195,8 +195,8 @@ class ShardedSimulation:
 class CudaShardEngine:
     """The product engine: one msim handle (C ABI, hand-written sm_100a kernels)."""
 
-    def __init__(self, M, sim):
-        self.M, self.sim = M, sim
+    def __init__(self, M, sim, asynchronous: bool = True):
+        self.M, self.sim, self.asynchronous = M, sim, asynchronous
 
     @staticmethod
     def _ptr(t):
@@ -209,6 +209,8 @@ class CudaShardEngine:
         self.sim.shard_pack(lo, hi, self._ptr(send_down), self._ptr(send_up))
 
     def integrate(self, recv_down, recv_up):
+        if self.asynchronous:  # device-side integrate: nothing to wait for, the host keeps enqueueing
+            return self.sim.shard_integrate_async(self._ptr(recv_down), self._ptr(recv_up))
         return self.sim.shard_integrate(self._ptr(recv_down), self._ptr(recv_up))
 
     def collide(self):
@@ -221,6 +223,7 @@ class CudaShardEngine:
         return self.sim.stats()
 
     def read_owned(self):
+        self.sim.shard_counts()
         return self.sim.read_entities(), self.sim.shard_read_gids()
 
 
@@ -310,9 +313,23 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         if collisions:
             st = sim.stats()
             pairs, flagged = sh.global_sum(st["last_pair_count"]), sh.global_sum(st["last_flagged_count"])
-        # keep the load up for the clock sampler (untimed)
-        t_end = time.time() + 1.0
-        while time.time() < t_end:
+        # per-kernel device time on rank 0 over a second pass of the same K steps (events around every launch)
+        kernels = None
+        if rank == 0:
+            sim.profile_begin()
+        ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ep0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ep1.record(stream)
+        ep1.synchronize()
+        if rank == 0:
+            kt = sim.profile_end()
+            kernels = {name: round(t / args.steps * 1e3, 1) for name, (cnt, t) in sorted(kt.items(), key=lambda kv: -kv[1][1])}
+            kernels["_step_us_with_events"] = round(ep0.elapsed_time(ep1) / args.steps * 1e3, 1)
+        # keep the load up for the clock sampler (untimed).  A FIXED number of steps derived from the all-reduced
+        # time: every rank must enqueue the same number of exchanges (a wall-clock loop would not)
+        for _ in range(max(10, min(5000, int(1000.0 / max(ms / args.steps, 0.01))))):
             step()
         sim.sync()
         clocks = sampler.stop() if sampler else None
@@ -358,7 +375,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
                        "parallelism": (f"{world} spatial bands of cell rows, NCCL send/recv of halo + migrants per tick, row-histogram all-reduce every {REBALANCE_EVERY} ticks"
                                        if collisions else f"{world} entity ranges, no collective"),
                        "owned_per_rank": per_rank, "l2": ("inputs larger than L2 (no flush)" if per_gpu * 40 > 200e6 else "per-GPU working set may sit in L2 (strong scaling of a fixed population)"),
-                       "phase_us_rank0": getattr(sh, "phase_us", None),
+                       "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels,
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
                        "global_pairs_last_tick": pairs, "global_flagged_last_tick": flagged},
             "roofline": None,

@@ -14,16 +14,28 @@ from test_sharding import BASE, check_against_reference, free_port
 pytestmark = pytest.mark.gpu
 
 
-def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False):
+def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False):
     import torch
 
     from movement_sim_b200 import sharding as S
 
     hist, ncx, ncy = S.global_row_histogram(msim, m, total, seed, radius, box)
     splits = np.linspace(0, ncy, world + 1).astype(np.int64) if skew else S.balanced_splits(hist, world)
+    # an explicit stream: torch's default stream has handle 0, which the C ABI reads as "create your own stream",
+    # and the exchange copies below would then not be ordered with the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream)
+
+
+def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream):
+    import torch
+
+    from movement_sim_b200 import sharding as S
+
     target = splits.copy()
     nbytes = msim.shard_buffer_bytes(capacity, capacity)
-    stream = torch.cuda.current_stream()
     sims, bufs = [], []
     for r in range(world):
         ents, gids = S.collect_band(msim, m, total, seed, radius, int(splits[r]), int(splits[r + 1]), box)
@@ -46,12 +58,17 @@ def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capaci
                 bufs[r]["ru"].copy_(bufs[r + 1]["sd"])
         total_pairs = 0
         for r, sim in enumerate(sims):
-            sim.shard_integrate(bufs[r]["rd"].data_ptr() if r > 0 else None, bufs[r]["ru"].data_ptr() if r + 1 < world else None)
+            integrate = sim.shard_integrate_async if asynchronous else sim.shard_integrate
+            integrate(bufs[r]["rd"].data_ptr() if r > 0 else None, bufs[r]["ru"].data_ptr() if r + 1 < world else None)
             sim.enqueue_collide()
-            sim.sync()
-            total_pairs += sim.stats()["last_pair_count"]
+            if not asynchronous:
+                sim.sync()
+                total_pairs += sim.stats()["last_pair_count"]
+        if asynchronous:  # everything of this tick is enqueued on every band before anybody waits
+            total_pairs = sum(sim.stats()["last_pair_count"] for sim in sims)
         pairs.append(total_pairs)
-        owned.append([s.stats()["entity_count"] for s in sims])
+        if not asynchronous or t % 7 == 0 or t == ticks - 1:  # asynchronous ticks: do not force the counts to the host every tick
+            owned.append([s.stats()["entity_count"] for s in sims])
         if rebalance_every and (t + 1) % rebalance_every == 0:
             h = sum(s.shard_row_histogram(ncy).astype(np.int64) for s in sims)
             target = S.balanced_splits(h, world)
@@ -62,7 +79,9 @@ def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capaci
         got[g] = e
         seen[g] += 1
         sim.close()
-    assert (seen == 1).all()
+    stream.synchronize()
+    assert (seen == 1).all(), (f"gids missing {np.nonzero(seen == 0)[0][:8].tolist()} ({int((seen == 0).sum())}), "
+                               f"duplicated {np.nonzero(seen > 1)[0][:8].tolist()} ({int((seen > 1).sum())}); owned history tail {owned[-3:]}")
     return got, pairs, owned
 
 
@@ -80,10 +99,11 @@ def oracle_reference(msim, orc, m, total, seed, radius, ticks, box=None):
     return e, pairs
 
 
+@pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world):
+def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, asynchronous):
     total, ticks = 40_000, 50
-    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14)
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14, asynchronous=asynchronous)
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
     assert_entities_equal(got, want, what=f"{world} bands")
     assert pairs == want_pairs
@@ -91,11 +111,13 @@ def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world):
         assert any(o != owned[0] for o in owned), "entities should migrate between bands"
 
 
-def test_bands_rebalance_dense_corner(msim, orc, small_city):
+@pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
+def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous):
     """BASELINE config 5 in miniature: everybody starts in one corner, geometric initial split."""
     total, ticks = 30_000, 80
     box = [0.0, 0.0, 900.0, 600.0]
-    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True)
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True,
+                                             asynchronous=asynchronous)
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 7, 10.0, ticks, box=box)
     assert_entities_equal(got, want, what="rebalanced bands")
     assert pairs == want_pairs
@@ -110,17 +132,42 @@ def test_capacity_overflow_is_reported(msim, small_city):
     total = 20_000
     hist, ncx, ncy = S.global_row_histogram(msim, small_city, total, 42, 10.0)
     ents, gids = S.collect_band(msim, small_city, total, 42, 10.0, 0, ncy // 2)
-    stream = torch.cuda.current_stream()
-    sim = msim.Simulation(small_city, ents, radius=10.0, stream=stream.cuda_stream, capacity=total)
+    sim = msim.Simulation(small_city, ents, radius=10.0, capacity=total)  # library-owned stream
     sim.shard_enable(gids, 8, 8)  # absurdly small
     sim.dispatch(2)
     nbytes = msim.shard_buffer_bytes(8, 8)
     up = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     rup = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the buffers are zeroed on torch's stream
     sim.enqueue_move()
     sim.shard_pack(0, ncy // 2, None, up.data_ptr())
     with pytest.raises(msim.MsimError) as ei:
         sim.shard_integrate(None, rup.data_ptr())
+    assert ei.value.status == msim.MSIM_ERR_CAPACITY
+    sim.close()
+
+
+def test_capacity_overflow_is_reported_by_async_ticks(msim, small_city):
+    import torch
+
+    from movement_sim_b200 import sharding as S
+
+    total = 20_000
+    hist, ncx, ncy = S.global_row_histogram(msim, small_city, total, 42, 10.0)
+    ents, gids = S.collect_band(msim, small_city, total, 42, 10.0, 0, ncy // 2)
+    sim = msim.Simulation(small_city, ents, radius=10.0, capacity=total)  # library-owned stream
+    sim.shard_enable(gids, 8, 8)
+    sim.dispatch(2)
+    nbytes = msim.shard_buffer_bytes(8, 8)
+    up = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    rup = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the buffers are zeroed on torch's stream
+    sim.enqueue_move()
+    sim.shard_pack(0, ncy // 2, None, up.data_ptr())
+    sim.shard_integrate_async(None, rup.data_ptr())  # enqueue only: cannot fail yet
+    sim.enqueue_collide()
+    with pytest.raises(msim.MsimError) as ei:
+        sim.sync()
     assert ei.value.status == msim.MSIM_ERR_CAPACITY
     sim.close()
 
