@@ -52,6 +52,30 @@ KERNEL_BYTES = {
 }
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+    fd 1 when NCCL_DEBUG is set), so everything else is sent to stderr and only emit() reaches the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+        os.environ["MSIM_BENCH_RESULT_FD"] = str(_RESULT_FD)  # sharding.py imports this file a second time as module "bench"
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    fd = _RESULT_FD if _RESULT_FD is not None else (int(os.environ["MSIM_BENCH_RESULT_FD"]) if "MSIM_BENCH_RESULT_FD" in os.environ else None)
+    if fd is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(fd, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -200,7 +224,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -400,7 +424,7 @@ def run_b200(args):
         "clocks": clocks,
     }
     sim.close()
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -426,6 +450,7 @@ def main():
     ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")
     ap.add_argument("--no-reorder", action="store_true", help="keep the state in upload order (onesweep rebuild)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -129,6 +129,10 @@ struct msim_handle {
     bool stage_flip{false};
     void* sent_down{nullptr};
     void* sent_up{nullptr};
+    uint32_t* gid_alt{nullptr};
+    uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
+    bool packed{false};
+    bool band_valid{false};           // false between a move pass and the integrate that follows it
     uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
     bool async_counts{false};       // host-side n / n_ghost are stale (upper bound = capacity) until the next refresh
 
@@ -210,7 +214,7 @@ void free_all(msim_handle* h) {
     cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes); cudaFree(h->leaf_hist);
     cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
     cudaFree(h->ext_id); cudaFree(h->ext_id_alt); cudaFree(h->slot_of);
-    cudaFree(h->dev_counts);
+    cudaFree(h->dev_counts); cudaFree(h->gid_alt);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -283,7 +287,7 @@ int refresh_counts(msim_handle* h) {
 int ensure_cells(msim_handle* h) {
     // counting sort: on request, or by default whenever the storage is kept in cell order
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
-    h->use_csort = want_counting && !h->sharded && h->grid.ncells <= CSORT_MAX_CELLS;
+    h->use_csort = want_counting && h->grid.ncells <= CSORT_MAX_CELLS;
     if ((h->flags & MSIM_FLAG_SORT_COUNTING) && h->grid.ncells <= CSORT_MAX_CELLS) h->use_csort = true;
     if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
     cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums);
@@ -422,6 +426,7 @@ int enqueue_move(msim_handle* h, bool want_keys) {
     }
     h->cur ^= 1;
     h->has_moved = true;
+    h->band_valid = false;  // entities may have crossed the band's rows until the next pack + integrate
     h->keys_valid = emit;
     h->hist_valid = fuse_hist;
     h->move_passes++;
@@ -443,6 +448,41 @@ int reorder_storage(msim_handle* h) {
         MSIM_CUDA(h, cudaMemsetAsync(h->target_alt, 0, sizeof(float2) * h->cap, h->stream));
     }
     join_side(h);  // pass B of the last move rewrites target / road / rng
+    if (h->sharded) {
+        // gid is the id map; the owned entities are the run of the sorted order that starts at the band's first row
+        if (!h->gid_alt) MSIM_CUDA(h, dev_alloc(&h->gid_alt, h->cap));
+        ReorderArrays a{};
+        a.pos_prev = h->pos[h->cur ^ 1];
+        a.pos_prev_new = h->pos_spare;
+        a.target = h->target;      a.target_new = h->target_alt;
+        a.road = h->road;          a.road_new = h->road_alt;
+        a.rng = h->rng;            a.rng_new = h->rng_alt;
+        a.ext_id = h->gid;         a.ext_id_new = h->gid_alt;
+        a.slot_of = nullptr;
+        a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
+        a.flag_entity = h->flag_entity;
+        a.first_owned = h->cell_start + static_cast<size_t>(h->band_lo) * static_cast<size_t>(h->grid.ncx);
+        a.n_owned_dev = h->dev_counts + DEV_N_OWNED;
+        a.sorted_pos = h->sorted_pos;
+        a.pos_cur_new = h->pos[h->cur];  // not read by the kernel: sorted_pos holds the same positions in the new order
+        a.error_word = h->dev_counts + DEV_SHARD_ERROR;
+        h->launches += launch_reorder_sharded(h->stream, launch_owned(h), h->cap / 32 + 2, h->sorted_idx, h->flag_sorted, a, &h->prof);
+        float2* old_prev = h->pos[h->cur ^ 1];
+        h->pos[h->cur ^ 1] = h->pos_spare;
+        h->pos_spare = old_prev;
+        std::swap(h->target, h->target_alt);
+        std::swap(h->road, h->road_alt);
+        std::swap(h->rng, h->rng_alt);
+        std::swap(h->arrived, h->arrived_alt);
+        std::swap(h->gid, h->gid_alt);
+        h->flags_scattered = true;
+        h->keys_valid = false;
+        h->hist_valid = false;
+        h->counts_valid = false;
+        h->since_reorder = 0;
+        h->reorders++;
+        return MSIM_OK;
+    }
     ReorderArrays a{};
     a.pos_prev = h->pos[h->cur ^ 1];
     a.pos_prev_new = h->pos_spare;
@@ -483,27 +523,32 @@ int enqueue_collide(msim_handle* h) {
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
     if (!h->keys_valid) {
+        rc = refresh_counts(h);  // (asynchronous sharded ticks) keygen is sized by the exact owned count
+        if (rc != MSIM_OK) return rc;
         h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
         h->keys_valid = true;
         h->hist_valid = false;
     }
-    if (h->async_counts && h->use_csort) {  // the counting-sort path sizes its scatter from exact host counts
-        rc = refresh_counts(h);
-        if (rc != MSIM_OK) return rc;
-    }
     const uint32_t total = launch_total(h);  // ghosts (multi-GPU halo) sit behind the owned entities
     const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
     if (h->use_csort) {
+        // sharded handles: the counter table is cleared / scanned over the band's cell range only, keys outside it
+        // (a leaver that jumped two rows while the boundary moved: out of everybody's reach) are left out of the
+        // order, and the number of sorted slots is the scan's grand total, read by the query from the table itself
+        uint32_t c0 = 0, c1 = h->grid.ncells;
+        const bool band = h->sharded && h->band_valid;
+        if (band) csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &c0, &c1);
         if (!h->counts_valid) {  // keys came from keygen or changed in a shard exchange: count them now
-            csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
-            h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, &h->prof);
+            csort_clear(h->stream, h->cell_count + c0, c1 - c0, &h->prof);
+            h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, c0, c1, &h->prof, dev_total(h));
         }
         h->counts_valid = false;
-        h->launches += launch_cell_scan(h->stream, h->cell_count, h->grid.ncells, h->tile_sums, h->cell_start, &h->prof);
-        h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof);
+        h->launches += launch_cell_scan(h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->cell_start + c0, &h->prof);
+        h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
+                                           dev_total(h));
         launch_deferred_arrive(h, true);
-        h->launches += launch_query(h->stream, total, h->n, h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
-                                    h->counters, h->stripes, &h->prof);
+        h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
+                                    h->counters, h->stripes, &h->prof, h->sharded ? h->cell_start + c1 : nullptr, dev_owned(h));
     } else {
         h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted,
                                    h->hist_valid && h->n_ghost == 0 && !h->async_counts, &h->prof, dev_total(h));
@@ -521,7 +566,9 @@ int enqueue_collide(msim_handle* h) {
     h->flags_scattered = false;
     h->collide_passes++;
     h->since_reorder++;
-    if (h->reorder_enabled && !h->sharded && h->has_moved && h->n > 1 && h->since_reorder >= h->reorder_every) return reorder_storage(h);
+    if (h->reorder_enabled && h->use_csort && h->has_moved && (h->n > 1 || h->async_counts) && h->since_reorder >= h->reorder_every &&
+        (!h->sharded || h->band_valid))
+        return reorder_storage(h);
     return MSIM_OK;
 }
 
@@ -1009,6 +1056,8 @@ int ensure_keys(msim_handle* h) {
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
     if (!h->keys_valid) {
+        rc = refresh_counts(h);
+        if (rc != MSIM_OK) return rc;
         h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
         h->keys_valid = true;
         h->hist_valid = false;
@@ -1049,7 +1098,8 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     if (count) MSIM_CUDA(h, cudaMemcpyAsync(h->gid, gids, count * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->sharded = true;
-    h->reorder_enabled = false;  // the shard exchange relocates entities itself; gid is the id map
+    h->band_valid = false;
+    h->perm_active = false;  // gid is the id map of a sharded handle; a cell re-sort permutes it with the state
     return ensure_cells(h);
 }
 
@@ -1066,6 +1116,10 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
                                      h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof, dev_owned(h));
     h->sent_down = send_down;
     h->sent_up = send_up;
+    // rows that can hold owned entities once the leavers are gone: without a neighbour nobody leaves on that side
+    h->band_lo = send_down ? row_lo : 0u;
+    h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
+    h->packed = true;
     return MSIM_OK;
 }
 
@@ -1140,6 +1194,8 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     h->n_ghost = n_ghost;
     rc = write_dev_counts(h);
     if (rc != MSIM_OK) return rc;
+    h->band_valid = h->packed;
+    h->packed = false;
     h->keys_valid = true;
     h->hist_valid = false;
     h->counts_valid = false;
@@ -1157,6 +1213,8 @@ int msim_shard_integrate_async(msim_handle* h, const void* recv_down, const void
                                                  h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
                                                  h->grid, &h->prof);
     h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
+    h->band_valid = h->packed;
+    h->packed = false;
     h->keys_valid = true;
     h->hist_valid = false;
     h->counts_valid = false;

@@ -26,10 +26,17 @@ namespace {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096 cells per CTA
+constexpr uint32_t CSORT_SKIP = 0xffffffffu;          // rank of an entity that is left out of the order
 
 __global__ void __launch_bounds__(256)
-cell_count_kernel(uint32_t n, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ rank) {
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) rank[e] = atomicAdd(&cell_count[__ldcs(keys + e)], 1u);
+cell_count_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
+                  uint32_t* __restrict__ rank, uint32_t c0, uint32_t c1) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t k = __ldcs(keys + e);
+        // keys outside the counted cell range [c0, c1) (sharded handles only) stay out of the order
+        rank[e] = (k - c0 < c1 - c0) ? atomicAdd(&cell_count[k], 1u) : CSORT_SKIP;
+    }
 }
 
 __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* s_warp) {
@@ -139,17 +146,20 @@ scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uin
 
 // two entities per thread: 128-bit position loads, 64-bit key / rank loads
 __global__ void __launch_bounds__(256)
-cell_scatter_kernel(uint32_t n, const uint2* __restrict__ keys, const uint2* __restrict__ rank, const float4* __restrict__ pos,
-                    const uint32_t* __restrict__ starts, float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx) {
+cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint2* __restrict__ keys, const uint2* __restrict__ rank,
+                    const float4* __restrict__ pos, const uint32_t* __restrict__ starts, float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t pairs = (n + 1u) >> 1;
     for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < pairs; pi += gridDim.x * blockDim.x) {
         const uint2 k = __ldcs(keys + pi), r = __ldcs(rank + pi);
         const float4 p = __ldcs(pos + pi);
         const uint32_t e0 = pi * 2u, e1 = e0 + 1u;
-        const uint32_t s0 = __ldg(starts + k.x) + r.x;
-        sorted_pos[s0] = make_float2(p.x, p.y);
-        sorted_idx[s0] = e0;
-        if (e1 < n) {
+        if (r.x != CSORT_SKIP) {
+            const uint32_t s0 = __ldg(starts + k.x) + r.x;
+            sorted_pos[s0] = make_float2(p.x, p.y);
+            sorted_idx[s0] = e0;
+        }
+        if (e1 < n && r.y != CSORT_SKIP) {
             const uint32_t s1 = __ldg(starts + k.y) + r.y;
             sorted_pos[s1] = make_float2(p.z, p.w);
             sorted_idx[s1] = e1;
@@ -167,12 +177,25 @@ void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler*
     prof->end(s);
 }
 
-int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, Profiler* prof) {
+// A sharded handle only ever holds keys of its band's rows plus one ghost row on either side: the counter
+// table is cleared and scanned over that cell range [c0, c1) only (c0 rounded down to the scan kernels'
+// 16-byte vector alignment), so the per-tick table work shrinks with the band instead of staying
+// grid-sized on every GPU.  cell_start is valid on [c0, c1]; nothing outside is read (collide.cu).
+void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int ncy, uint32_t* c0, uint32_t* c1) {
+    const uint32_t r0 = row_lo > 0 ? row_lo - 1 : 0;
+    const uint32_t r1 = row_hi + 1 < static_cast<uint32_t>(ncy) ? row_hi + 1 : static_cast<uint32_t>(ncy);
+    *c0 = (r0 * static_cast<uint32_t>(ncx)) & ~3u;
+    *c1 = r1 * static_cast<uint32_t>(ncx);
+    if (*c1 > cells) *c1 = cells;
+}
+
+int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
+                      const uint32_t* n_dev) {
     if (n == 0) return 0;
     uint32_t blocks = (n + 255u) / 256u;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
     prof->begin(s, K_CELL_COUNT);
-    cell_count_kernel<<<blocks, 256, 0, s>>>(n, keys, cell_count, rank);
+    cell_count_kernel<<<blocks, 256, 0, s>>>(n, n_dev, keys, cell_count, rank, c0, c1);
     prof->end(s);
     return 1;
 }
@@ -188,13 +211,13 @@ int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells,
 }
 
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
-                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof) {
+                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     uint32_t blocks = (pairs + 255u) / 256u;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
     prof->begin(s, K_CELL_SCATTER);
-    cell_scatter_kernel<<<blocks, 256, 0, s>>>(n, reinterpret_cast<const uint2*>(keys), reinterpret_cast<const uint2*>(rank),
+    cell_scatter_kernel<<<blocks, 256, 0, s>>>(n, n_dev, reinterpret_cast<const uint2*>(keys), reinterpret_cast<const uint2*>(rank),
                                                reinterpret_cast<const float4*>(pos), cell_start, sorted_pos, sorted_idx);
     prof->end(s);
     return 1;

@@ -119,10 +119,12 @@ void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace&
 // csort.cu — single-digit radix (counting) sort over the whole cell key
 uint32_t csort_tiles(uint32_t cells);
 void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler* prof);
-int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, Profiler* prof);
+void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int ncy, uint32_t* c0, uint32_t* c1);
+int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
+                      const uint32_t* n_dev = nullptr);
 int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
-                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof);
+                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
 
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
@@ -166,8 +168,18 @@ struct ReorderArrays {
     uint32_t* slot_of;
     const uint32_t* arrived; uint32_t* arrived_new;
     uint8_t* flag_entity;
+    // sharded handles (ext_id = gid, slot_of = NULL): the owned entities are the middle run of the sorted order,
+    // between the ghost rows below and above the band; it starts at *first_owned (an entry of the prefix table),
+    // its length is *n_owned_dev, and the current positions are copied out of sorted_pos instead of swapped in
+    const uint32_t* first_owned;
+    const uint32_t* n_owned_dev;
+    const float2* sorted_pos;
+    float2* pos_cur_new;
+    uint32_t* error_word;  // |= 16 when a slot of the middle run turns out to be a ghost
 };
 int launch_reorder(cudaStream_t s, uint32_t n, const uint32_t* sorted_idx, const uint8_t* flag_sorted, const ReorderArrays& a, Profiler* prof);
+int launch_reorder_sharded(cudaStream_t s, uint32_t n_upper, uint32_t arrived_words, const uint32_t* sorted_idx, const uint8_t* flag_sorted,
+                           const ReorderArrays& a, Profiler* prof);
 int launch_gather_pos(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const float2* pos, float2* out);
 int launch_gather_flag(cudaStream_t s, uint32_t n, const uint32_t* slot_of, const uint8_t* flag, uint8_t* out);
 

@@ -103,6 +103,28 @@ reorder_kernel(uint32_t n, const uint32_t* __restrict__ sorted_idx, const uint8_
     if ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) atomicOr(a.arrived_new + arrived_word(j), 1u << arrived_bit(j));
 }
 
+// Sharded handles: new slot j <- old slot sorted_idx[first + j], j < n_owned.  Ghost rows sort before and
+// after the band's own rows (row-major keys), so the owned entities are one contiguous run of the order.
+__global__ void __launch_bounds__(256)
+reorder_sharded_kernel(const uint32_t* __restrict__ sorted_idx, const uint8_t* __restrict__ flag_sorted, ReorderArrays a) {
+    const uint32_t n = *a.n_owned_dev, first = *a.first_owned;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t src = __ldcs(sorted_idx + first + j);
+    if (src >= n) {  // cannot happen while every owned entity lies inside the band (msim_shard_pack guarantees it)
+        atomicOr(a.error_word, 16u);
+        return;
+    }
+    a.pos_cur_new[j] = a.sorted_pos[first + j];
+    a.pos_prev_new[j] = a.pos_prev[src];
+    a.target_new[j] = a.target[src];
+    a.road_new[j] = a.road[src];
+    a.rng_new[j] = a.rng[src];
+    a.ext_id_new[j] = a.ext_id[src];
+    a.flag_entity[j] = flag_sorted[first + j] + 1;
+    if ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) atomicOr(a.arrived_new + arrived_word(j), 1u << arrived_bit(j));
+}
+
 __global__ void __launch_bounds__(256) gather_pos_kernel(uint32_t n, const uint32_t* __restrict__ slot_of, const float2* __restrict__ pos, float2* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = pos[slot_of[i]];
@@ -120,6 +142,16 @@ int launch_reorder(cudaStream_t s, uint32_t n, const uint32_t* sorted_idx, const
     prof->begin(s, K_REORDER);
     cudaMemsetAsync(a.arrived_new, 0, (static_cast<size_t>(n + 63u) / 64u) * 2u * sizeof(uint32_t), s);
     reorder_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, sorted_idx, flag_sorted, a);
+    prof->end(s);
+    return 1;
+}
+
+int launch_reorder_sharded(cudaStream_t s, uint32_t n_upper, uint32_t arrived_words, const uint32_t* sorted_idx, const uint8_t* flag_sorted,
+                           const ReorderArrays& a, Profiler* prof) {
+    if (n_upper == 0) return 0;
+    prof->begin(s, K_REORDER);
+    cudaMemsetAsync(a.arrived_new, 0, static_cast<size_t>(arrived_words) * sizeof(uint32_t), s);
+    reorder_sharded_kernel<<<(n_upper + 255u) / 256u, 256, 0, s>>>(sorted_idx, flag_sorted, a);
     prof->end(s);
     return 1;
 }

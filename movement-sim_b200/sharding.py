@@ -254,7 +254,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     import torch
     import torch.distributed as dist
 
-    from bench import METRIC, SURVEY_BYTES, ClockSampler, build_workload, load_peaks
+    from bench import METRIC, SURVEY_BYTES, ClockSampler, build_workload, emit, load_peaks
 
     w, m = build_workload(M, args.workload, args.entities)
     collisions = w["collisions"]
@@ -388,7 +388,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     sim.close()
     dist.destroy_process_group()

@@ -14,7 +14,7 @@ from test_sharding import BASE, check_against_reference, free_port
 pytestmark = pytest.mark.gpu
 
 
-def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False):
+def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False, flags=0):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -26,10 +26,10 @@ def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capaci
     stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream)
+        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags)
 
 
-def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream):
+def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -39,7 +39,7 @@ def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebala
     sims, bufs = [], []
     for r in range(world):
         ents, gids = S.collect_band(msim, m, total, seed, radius, int(splits[r]), int(splits[r + 1]), box)
-        sim = msim.Simulation(m, ents, radius=radius, stream=stream.cuda_stream, capacity=total + 8 * capacity)
+        sim = msim.Simulation(m, ents, radius=radius, stream=stream.cuda_stream, capacity=total + 8 * capacity, flags=flags)
         sim.shard_enable(gids, capacity, capacity)
         sim.dispatch(2)
         sims.append(sim)
@@ -72,6 +72,8 @@ def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebala
         if rebalance_every and (t + 1) % rebalance_every == 0:
             h = sum(s.shard_row_histogram(ncy).astype(np.int64) for s in sims)
             target = S.balanced_splits(h, world)
+    if not flags & msim.FLAG_NO_REORDER and ticks >= 8:  # the bands must actually have been re-sorted into cell order
+        assert all(s.stats()["reorders"] >= 2 for s in sims), [s.stats()["reorders"] for s in sims]
     got = np.zeros(total, dtype=msim.ENTITY_DTYPE)
     seen = np.zeros(total, dtype=np.int32)
     for sim in sims:
@@ -99,11 +101,25 @@ def oracle_reference(msim, orc, m, total, seed, radius, ticks, box=None):
     return e, pairs
 
 
+REBUILDS = ["cell-ordered", "onesweep"]
+
+
+def rebuild_flags(msim, monkeypatch, rebuild):
+    """cell-ordered = the default (counting sort + periodic physical re-sort, here every 3rd collision pass so that the
+    re-sort of a band is exercised many times); onesweep = the radix-sort rebuild on storage left in arrival order."""
+    if rebuild == "cell-ordered":
+        monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
+        return 0
+    return msim.FLAG_SORT_ONESWEEP | msim.FLAG_NO_REORDER
+
+
+@pytest.mark.parametrize("rebuild", REBUILDS)
 @pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, asynchronous):
+def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, asynchronous, rebuild, monkeypatch):
     total, ticks = 40_000, 50
-    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14, asynchronous=asynchronous)
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14, asynchronous=asynchronous,
+                                             flags=rebuild_flags(msim, monkeypatch, rebuild))
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
     assert_entities_equal(got, want, what=f"{world} bands")
     assert pairs == want_pairs
@@ -111,13 +127,14 @@ def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, a
         assert any(o != owned[0] for o in owned), "entities should migrate between bands"
 
 
+@pytest.mark.parametrize("rebuild", REBUILDS)
 @pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
-def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous):
+def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous, rebuild, monkeypatch):
     """BASELINE config 5 in miniature: everybody starts in one corner, geometric initial split."""
     total, ticks = 30_000, 80
     box = [0.0, 0.0, 900.0, 600.0]
     got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True,
-                                             asynchronous=asynchronous)
+                                             asynchronous=asynchronous, flags=rebuild_flags(msim, monkeypatch, rebuild))
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 7, 10.0, ticks, box=box)
     assert_entities_equal(got, want, what="rebalanced bands")
     assert pairs == want_pairs
