@@ -38,6 +38,13 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
  * buffers of msim_shard_buffer_bytes() (NULL when there is no neighbour on that side).  Enqueue only. */
 int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up);
 
+/* msim_enqueue_move + msim_shard_pack in ONE kernel: the move kernel classifies the entities it has just
+ * moved and writes leavers / halo straight into the buffers, so the population is not read a second
+ * time.  Migrant records then carry the state before the next-waypoint pass (arrival bit set); that pass
+ * runs after msim_shard_integrate, beside the collision query, on the GPU that owns the entity by then.
+ * Until the integrate call the handle accepts no move pass and no entity readback.  Enqueue only. */
+int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up);
+
 /* After the exchange: recv_down / recv_up are the DEVICE buffers received from the rank below / above
  * (NULL = none).  One host round trip (counts + hole list).  Returns the new owned / ghost counts. */
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts);

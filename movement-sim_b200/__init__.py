@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
     "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
     # include/msim_shard.h
-    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_integrate", "msim_shard_integrate_async",
+    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_integrate", "msim_shard_integrate_async",
     "msim_shard_counts", "msim_shard_read_gids",
     "msim_shard_row_histogram", "msim_grid_rows",
 ]
@@ -205,6 +205,7 @@ def lib():
         "msim_shard_buffer_bytes": (u64, [u32, u32]),
         "msim_shard_enable": (i32, [vp, vp, u64, u32, u32]),
         "msim_shard_pack": (i32, [vp, u32, u32, vp, vp]),
+        "msim_shard_move_pack": (i32, [vp, u32, u32, vp, vp]),
         "msim_shard_integrate": (i32, [vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "msim_shard_integrate_async": (i32, [vp, vp, vp]),
         "msim_shard_counts": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -452,6 +453,10 @@ class Simulation:
 
     def shard_pack(self, row_lo: int, row_hi: int, send_down_ptr: int | None, send_up_ptr: int | None):
         self._check(lib().msim_shard_pack(self._h, row_lo, row_hi, send_down_ptr, send_up_ptr))
+
+    def shard_move_pack(self, row_lo: int, row_hi: int, send_down_ptr: int | None, send_up_ptr: int | None):
+        """Move pass and shard pack fused into one kernel (msim_shard.h)."""
+        self._check(lib().msim_shard_move_pack(self._h, row_lo, row_hi, send_down_ptr, send_up_ptr))
 
     def shard_integrate(self, recv_down_ptr: int | None, recv_up_ptr: int | None):
         owned, ghosts = C.c_uint64(), C.c_uint64()

@@ -132,6 +132,7 @@ struct msim_handle {
     uint32_t* gid_alt{nullptr};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
+    bool awaiting_integrate{false};   // a fused move + pack has run: pass B stays deferred until the exchange has been integrated
     bool band_valid{false};           // false between a move pass and the integrate that follows it
     uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
     bool async_counts{false};       // host-side n / n_ghost are stale (upper bound = capacity) until the next refresh
@@ -235,6 +236,7 @@ inline const uint32_t* dev_total(const msim_handle* h) { return h->async_counts 
 
 void launch_deferred_arrive(msim_handle* h, bool beside) {
     if (!h->arrive_deferred) return;
+    if (h->awaiting_integrate) return;  // migrants travel with their pre-arrival state: pass B must see the integrated population
     h->arrive_deferred = false;
     if (beside && h->side) {
         // pass B (dependent gathers, latency-bound, few issue slots) runs on the side stream from here on:
@@ -397,7 +399,8 @@ bool consume_init_dispatch(msim_handle* h) {
     return true;
 }
 
-int enqueue_move(msim_handle* h, bool want_keys) {
+int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nullptr) {
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "move pass on a sharded handle whose last msim_shard_move_pack has not been integrated");
     if (consume_init_dispatch(h)) return MSIM_OK;
     const bool emit = want_keys && !(h->flags & MSIM_FLAG_NO_COLLISIONS);
     if (emit) {
@@ -416,9 +419,9 @@ int enqueue_move(msim_handle* h, bool want_keys) {
     h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof,
-                               dev_owned(h));
+                               dev_owned(h), shard);
     h->counts_valid = fuse_count;
-    if (emit && h->side && !h->sharded) {
+    if (emit && h->side && (!h->sharded || shard)) {
         h->arrive_deferred = true;  // a collision pass follows and needs only positions and keys: pass B is launched beside its query
     } else {
         h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
@@ -804,6 +807,7 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     if (rc != MSIM_OK) return rc;
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
     if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_move_pack and msim_shard_integrate");
     if (h->flags_stale) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_integrate and the collision pass");
     materialise_flags(h);
     join_side(h);
@@ -1123,6 +1127,47 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
     return MSIM_OK;
 }
 
+int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: call msim_shard_enable first");
+    if (row_lo >= row_hi || row_hi > static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: bad row range");
+    if (h->uninitialised) {  // the reference's first dispatch moves nobody (random_move.comp:863-867): plain pack of the resident positions
+        rc = enqueue_move(h, true);
+        if (rc != MSIM_OK) return rc;
+        return msim_shard_pack(h, row_lo, row_hi, send_down, send_up);
+    }
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: the previous exchange has not been integrated");
+    join_side(h);  // pass B of the previous tick: the records read target / road / rng
+    h->launches += launch_shard_reset(h->stream, send_down, send_up, h->shard_ctr);
+    ShardMoveArgs sh{};
+    sh.lo_key = row_lo * static_cast<uint32_t>(h->grid.ncx);
+    sh.hi_key = row_hi * static_cast<uint32_t>(h->grid.ncx);
+    sh.ncx = static_cast<uint32_t>(h->grid.ncx);
+    sh.buf_down = send_down;
+    sh.buf_up = send_up;
+    sh.mig_cap = h->mig_cap;
+    sh.halo_cap = h->halo_cap;
+    sh.holes_cap = h->holes_cap;
+    sh.holes = h->holes;
+    sh.local_ghosts = h->local_ghosts;
+    sh.ctr = h->shard_ctr;
+    sh.rng = h->rng;
+    sh.color0 = h->color0;
+    sh.road = h->road;
+    sh.gid = h->gid;
+    rc = enqueue_move(h, true, &sh);
+    if (rc != MSIM_OK) return rc;
+    h->n_ghost = 0;
+    h->sent_down = send_down;
+    h->sent_up = send_up;
+    h->band_lo = send_down ? row_lo : 0u;
+    h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
+    h->packed = true;
+    h->awaiting_integrate = true;
+    return MSIM_OK;
+}
+
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
@@ -1196,6 +1241,7 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     if (rc != MSIM_OK) return rc;
     h->band_valid = h->packed;
     h->packed = false;
+    h->awaiting_integrate = false;
     h->keys_valid = true;
     h->hist_valid = false;
     h->counts_valid = false;
@@ -1215,6 +1261,7 @@ int msim_shard_integrate_async(msim_handle* h, const void* recv_down, const void
     h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
     h->band_valid = h->packed;
     h->packed = false;
+    h->awaiting_integrate = false;
     h->keys_valid = true;
     h->hist_valid = false;
     h->counts_valid = false;

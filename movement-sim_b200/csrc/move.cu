@@ -117,14 +117,74 @@ __device__ __forceinline__ uint32_t run_rank(uint32_t* __restrict__ cell_count, 
     return base + (lane - my_head);
 }
 
+// ---- fused shard pack (multi-GPU bands, shard.cu) ------------------------------------------------
+// A leaver: its new cell row is outside the band.  Rare (a few hundred per boundary per tick), so it is
+// kept out of line.  The record carries the state BEFORE pass B (target of the waypoint just reached,
+// arrival bit set): pass B runs on whichever GPU owns the entity after the exchange, and yields the same
+// result there because new_target() reads nothing but the entity and the replicated road graph.
+__device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bool down, float2 p_new, float2 p_old, float2 tgt, bool arrived) {
+    void* buf = down ? sh.buf_down : sh.buf_up;
+    const uint32_t slot = atomicAdd(&header_of(buf)->n_migrants, 1u);
+    if (slot < sh.mig_cap) {
+        uint2* rec = records_of(buf) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
+        const uint4 s = sh.rng[e];
+        const float4 c = sh.color0[e];
+        rec[0] = make_uint2(__float_as_uint(p_new.x), __float_as_uint(p_new.y));
+        rec[1] = make_uint2(__float_as_uint(p_old.x), __float_as_uint(p_old.y));
+        rec[2] = make_uint2(__float_as_uint(tgt.x), __float_as_uint(tgt.y));
+        rec[3] = make_uint2(s.x, s.y);
+        rec[4] = make_uint2(s.z, s.w);
+        rec[5] = make_uint2(__float_as_uint(c.x), __float_as_uint(c.y));
+        rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
+        rec[7] = make_uint2(sh.road[e], sh.gid[e]);
+        rec[8] = make_uint2(arrived ? 1u : 0u, 0u);
+    } else {
+        header_of(buf)->overflow = 1u;
+    }
+    const uint32_t hslot = atomicAdd(&sh.ctr[SHARD_CTR_HOLES], 1u);
+    if (hslot < sh.holes_cap) sh.holes[hslot] = e;
+    const uint32_t gslot = atomicAdd(&sh.ctr[SHARD_CTR_LOCAL_GHOSTS], 1u);
+    if (gslot < sh.holes_cap) sh.local_ghosts[gslot] = p_new;  // it lands in the neighbour's boundary row: still within reach of ours
+}
+
+// whole warp calls this once per entity slot; does what shard_pack_kernel does for one entity
+__device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, float2 p_old, float2 tgt,
+                                               bool arrived) {
+    const bool go_down = valid && sh.buf_down && key < sh.lo_key;
+    const bool go_up = valid && sh.buf_up && key >= sh.hi_key;
+    if (go_down || go_up) shard_leave(sh, e, go_down, p_new, p_old, tgt, arrived);
+    const bool stays = valid && !go_down && !go_up;
+    if (sh.buf_down) {  // halo: owned entities that stay, in the band's first / last row
+        const bool halo = stays && key < sh.lo_key + sh.ncx;
+        if (__any_sync(0xffffffffu, halo)) {
+            const uint32_t slot = warp_append(halo, &header_of(sh.buf_down)->n_halo);
+            if (halo) {
+                if (slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
+                else header_of(sh.buf_down)->overflow = 1u;
+            }
+        }
+    }
+    if (sh.buf_up) {
+        const bool halo = stays && key >= sh.hi_key - sh.ncx;
+        if (__any_sync(0xffffffffu, halo)) {
+            const uint32_t slot = warp_append(halo, &header_of(sh.buf_up)->n_halo);
+            if (halo) {
+                if (slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
+                else header_of(sh.buf_up)->overflow = 1u;
+            }
+        }
+    }
+}
+
 // EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
 // sort's digit histograms for all passes in shared memory (flushed once per CTA), so the neighbour
 // rebuild needs no separate histogram read of the keys.
-template <bool EMIT_KEYS>
+// SHARD (multi-GPU bands) additionally does the shard pack for the entities it has just moved (see above).
+template <bool EMIT_KEYS, bool SHARD>
 __global__ void __launch_bounds__(MOVE_THREADS)
 move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
             uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
-            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank) {
+            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh) {
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
     if (EMIT_KEYS) {
         for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
@@ -173,6 +233,10 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                 for (int p = 0; p < hist_passes; p++) {
                     if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                     if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+                }
+                if (SHARD) {
+                    shard_classify(sh, e0, e0 < n, k0, q0, make_float2(P[k].x, P[k].y), make_float2(T[k].x, T[k].y), arr0);
+                    shard_classify(sh, e1, e1 < n, k1, q1, make_float2(P[k].z, P[k].w), make_float2(T[k].z, T[k].w), arr1);
                 }
             }
         }
@@ -244,7 +308,7 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev) {
+                const uint32_t* n_dev, const ShardMoveArgs* shard) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
@@ -255,9 +319,15 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
     prof->begin(s, K_MOVE);
-    if (keys) move_kernel<true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
-                                                          cell_count, reinterpret_cast<uint2*>(rank));
-    else move_kernel<false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr);
+    const ShardMoveArgs none{};
+    if (keys && shard)
+        move_kernel<true, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
+                                                                cell_count, reinterpret_cast<uint2*>(rank), *shard);
+    else if (keys)
+        move_kernel<true, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
+                                                                 cell_count, reinterpret_cast<uint2*>(rank), none);
+    else
+        move_kernel<false, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr, none);
     prof->end(s);
     return 1;
 }

@@ -64,6 +64,24 @@ struct Counters {
     unsigned int pad;
 };
 
+// ---- fused move + shard pack (move.cu, shard.cu): what the move kernel needs to classify the entities it has
+// just moved against the band [lo_key, hi_key) of cell keys and to write leavers / halo straight into the
+// exchange buffers (local send buffers, or the neighbour's receive buffers over NVLink peer memory)
+struct ShardMoveArgs {
+    uint32_t lo_key, hi_key;  // first key of the band's first row, first key past its last row
+    uint32_t ncx;
+    void* buf_down;           // NULL: no neighbour below (nobody leaves that way, no halo)
+    void* buf_up;
+    uint32_t mig_cap, halo_cap, holes_cap;
+    uint32_t* holes;
+    float2* local_ghosts;
+    uint32_t* ctr;
+    const uint4* rng;
+    const float4* color0;
+    const uint32_t* road;
+    const uint32_t* gid;
+};
+
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
 enum KernelId {
     K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
@@ -102,7 +120,7 @@ struct Profiler {
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
                 int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev = nullptr);
+                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr);
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
@@ -208,6 +226,7 @@ struct ShardArrays {
     uint32_t* arrived;
 };
 
+int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr);
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
                       const uint32_t* n_dev = nullptr);
@@ -233,6 +252,24 @@ __device__ __forceinline__ uint32_t cell_key_of(float2 p, const GridParams& g) {
     cx = min(max(cx, 0), g.ncx - 1);
     cy = min(max(cy, 0), g.ncy - 1);
     return static_cast<uint32_t>(cy) * static_cast<uint32_t>(g.ncx) + static_cast<uint32_t>(cx);
+}
+
+// exchange buffer accessors and the warp-aggregated list append shared by shard.cu and the fused move kernel
+__device__ __forceinline__ ShardHeader* header_of(void* buf) { return static_cast<ShardHeader*>(buf); }
+__device__ __forceinline__ uint2* records_of(void* buf) { return reinterpret_cast<uint2*>(static_cast<char*>(buf) + sizeof(ShardHeader)); }
+__device__ __forceinline__ float2* halo_of(void* buf, uint32_t mig_cap) {
+    return reinterpret_cast<float2*>(static_cast<char*>(buf) + sizeof(ShardHeader) + static_cast<size_t>(mig_cap) * MIGRANT_BYTES);
+}
+// returns this lane's slot in a list whose length lives at *counter (one atomic per warp); whole warp must call
+__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<uint32_t>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
 }
 
 // bit position of entity e inside the `arrived` mask written by the move kernel: entities are

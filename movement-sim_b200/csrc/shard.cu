@@ -28,22 +28,14 @@ __device__ __forceinline__ void set_arrived_bit(uint32_t* mask, uint32_t e, bool
     else atomicAnd(w, ~bit);
 }
 
-__device__ __forceinline__ ShardHeader* header_of(void* buf) { return static_cast<ShardHeader*>(buf); }
-__device__ __forceinline__ uint2* records_of(void* buf) { return reinterpret_cast<uint2*>(static_cast<char*>(buf) + sizeof(ShardHeader)); }
-__device__ __forceinline__ float2* halo_of(void* buf, uint32_t mig_cap) {
-    return reinterpret_cast<float2*>(static_cast<char*>(buf) + sizeof(ShardHeader) + static_cast<size_t>(mig_cap) * MIGRANT_BYTES);
-}
-
-// warp-aggregated append: returns this lane's slot in a list whose length lives at *counter
-__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
-    const uint32_t m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return 0;
-    const uint32_t lane = threadIdx.x & 31u;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<uint32_t>(__popc(m)));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
+// one tiny launch instead of three memsets: clears the two headers and the hole / ghost counters
+__global__ void shard_reset_kernel(void* buf_down, void* buf_up, uint32_t* ctr) {
+    const uint32_t t = threadIdx.x;
+    if (t < 8u) {
+        if (buf_down) reinterpret_cast<uint32_t*>(buf_down)[t] = 0u;
+        if (buf_up) reinterpret_cast<uint32_t*>(buf_up)[t] = 0u;
+        if (t < SHARD_CTR_COUNT) ctr[t] = 0u;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -289,6 +281,11 @@ __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t
 }
 
 }  // namespace
+
+int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr) {
+    shard_reset_kernel<<<1, 32, 0, s>>>(buf_down, buf_up, ctr);
+    return 1;
+}
 
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,

@@ -133,6 +133,7 @@ class ShardedSimulation:
         self.migrant_capacity, self.halo_capacity = migrant_capacity, halo_capacity
         self.exchanged_bytes = 0
         self.phase_us = {}
+        self.fused_move_pack = hasattr(engine, "move_pack")  # one kernel moves and packs (msim_shard_move_pack)
 
     @property
     def band(self):
@@ -162,8 +163,11 @@ class ShardedSimulation:
             self.splits = step_towards(self.splits, self.target)
         lo, hi = self.band
         t0 = time.perf_counter()
-        self.engine.move()
-        self.engine.pack(lo, hi, self.send_down, self.send_up)
+        if self.fused_move_pack:
+            self.engine.move_pack(lo, hi, self.send_down, self.send_up)
+        else:
+            self.engine.move()
+            self.engine.pack(lo, hi, self.send_down, self.send_up)
         t1 = time.perf_counter()
         self._exchange()
         t2 = time.perf_counter()
@@ -207,6 +211,9 @@ class CudaShardEngine:
 
     def pack(self, lo, hi, send_down, send_up):
         self.sim.shard_pack(lo, hi, self._ptr(send_down), self._ptr(send_up))
+
+    def move_pack(self, lo, hi, send_down, send_up):
+        self.sim.shard_move_pack(lo, hi, self._ptr(send_down), self._ptr(send_up))
 
     def integrate(self, recv_down, recv_up):
         if self.asynchronous:  # device-side integrate: nothing to wait for, the host keeps enqueueing

@@ -14,7 +14,7 @@ from test_sharding import BASE, check_against_reference, free_port
 pytestmark = pytest.mark.gpu
 
 
-def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False, flags=0):
+def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False, flags=0, fused=False):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -26,10 +26,10 @@ def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capaci
     stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags)
+        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused)
 
 
-def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags):
+def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -49,9 +49,12 @@ def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebala
         if not np.array_equal(splits, target):
             splits = S.step_towards(splits, target)
         for r, sim in enumerate(sims):
-            sim.enqueue_move()
-            sim.shard_pack(int(splits[r]), int(splits[r + 1]), bufs[r]["sd"].data_ptr() if r > 0 else None,
-                           bufs[r]["su"].data_ptr() if r + 1 < world else None)
+            band = (int(splits[r]), int(splits[r + 1]), bufs[r]["sd"].data_ptr() if r > 0 else None, bufs[r]["su"].data_ptr() if r + 1 < world else None)
+            if fused:  # one kernel moves and packs; the next-waypoint pass then runs after the integrate
+                sim.shard_move_pack(*band)
+            else:
+                sim.enqueue_move()
+                sim.shard_pack(*band)
         for r in range(world):  # the "exchange": what NCCL send/recv does between processes
             if r + 1 < world:
                 bufs[r + 1]["rd"].copy_(bufs[r]["su"])
@@ -113,13 +116,14 @@ def rebuild_flags(msim, monkeypatch, rebuild):
     return msim.FLAG_SORT_ONESWEEP | msim.FLAG_NO_REORDER
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["move+pack", "fused-move-pack"])
 @pytest.mark.parametrize("rebuild", REBUILDS)
 @pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, asynchronous, rebuild, monkeypatch):
+def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, asynchronous, rebuild, fused, monkeypatch):
     total, ticks = 40_000, 50
     got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14, asynchronous=asynchronous,
-                                             flags=rebuild_flags(msim, monkeypatch, rebuild))
+                                             flags=rebuild_flags(msim, monkeypatch, rebuild), fused=fused)
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
     assert_entities_equal(got, want, what=f"{world} bands")
     assert pairs == want_pairs
@@ -127,14 +131,15 @@ def test_bands_on_one_gpu_match_unsharded_oracle(msim, orc, small_city, world, a
         assert any(o != owned[0] for o in owned), "entities should migrate between bands"
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["move+pack", "fused-move-pack"])
 @pytest.mark.parametrize("rebuild", REBUILDS)
 @pytest.mark.parametrize("asynchronous", [False, True], ids=["host-integrate", "device-integrate"])
-def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous, rebuild, monkeypatch):
+def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous, rebuild, fused, monkeypatch):
     """BASELINE config 5 in miniature: everybody starts in one corner, geometric initial split."""
     total, ticks = 30_000, 80
     box = [0.0, 0.0, 900.0, 600.0]
     got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True,
-                                             asynchronous=asynchronous, flags=rebuild_flags(msim, monkeypatch, rebuild))
+                                             asynchronous=asynchronous, flags=rebuild_flags(msim, monkeypatch, rebuild), fused=fused)
     want, want_pairs = oracle_reference(msim, orc, small_city, total, 7, 10.0, ticks, box=box)
     assert_entities_equal(got, want, what="rebalanced bands")
     assert pairs == want_pairs
