@@ -445,6 +445,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="N > 1: strong = the workload's population split over N GPUs (BASELINE config 3), weak = that population per GPU")
+    ap.add_argument("--exchange", choices=["p2p", "collective"], default="p2p",
+                    help="N > 1 with collisions: p2p = move kernel stores into the neighbours' buffers over peer memory; collective = NCCL all_to_all per tick")
     ap.add_argument("--presort", action="store_true", help="experiment: upload the entities in cell order")
     ap.add_argument("--counting-sort", action="store_true", help="force the single-digit counting sort")
     ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")

@@ -45,6 +45,27 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
  * Until the integrate call the handle accepts no move pass and no entity readback.  Enqueue only. */
 int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up);
 
+/* ---- peer-memory exchange: no collective call per tick ------------------------------------------------
+ * The fused move + pack kernel writes leavers and halo DIRECTLY into the neighbours' receive buffers
+ * (NVLink / NVSwitch peer stores and atomics), its last CTA raises a flag in the neighbour's memory after a
+ * system-scope fence, and the neighbour's integrate kernel spins on that flag before it reads.  Two
+ * receive buffers per side are used alternately, so tick t+1's stores never meet tick t's reads.  Per tick
+ * and rank the host enqueues msim_shard_p2p_move_pack, msim_shard_p2p_integrate, msim_enqueue_collide and
+ * never waits.  A neighbour that does not signal within MSIM_P2P_TIMEOUT_MS (default 10 000) is reported
+ * as MSIM_ERR_INTERNAL by the next synchronising call; the GPU never hangs on it.
+ *   msim_shard_p2p_create         allocates this handle's receive arena; returns its CUDA IPC handle
+ *                                 (MSIM_P2P_HANDLE_BYTES bytes, for neighbours in other processes) and / or
+ *                                 its device pointer (for neighbours driven by this process)
+ *   msim_shard_p2p_connect        opens the neighbours' arenas from their IPC handles (NULL = no neighbour)
+ *   msim_shard_p2p_connect_local  same, from device pointers of arenas living in this process
+ * All ranks must use the same migrant / halo capacities (they fix the buffer layout). */
+#define MSIM_P2P_HANDLE_BYTES 64
+int msim_shard_p2p_create(msim_handle* h, void* ipc_handle_out, void** arena_out);
+int msim_shard_p2p_connect(msim_handle* h, const void* down_ipc_handle, const void* up_ipc_handle);
+int msim_shard_p2p_connect_local(msim_handle* h, void* down_arena, void* up_arena);
+int msim_shard_p2p_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi);
+int msim_shard_p2p_integrate(msim_handle* h);
+
 /* After the exchange: recv_down / recv_up are the DEVICE buffers received from the rank below / above
  * (NULL = none).  One host round trip (counts + hole list).  Returns the new owned / ghost counts. */
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts);

@@ -84,7 +84,8 @@ ABI_SYMBOLS = [
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
     "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
     # include/msim_shard.h
-    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_integrate", "msim_shard_integrate_async",
+    "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_p2p_create", "msim_shard_p2p_connect",
+    "msim_shard_p2p_connect_local", "msim_shard_p2p_move_pack", "msim_shard_p2p_integrate", "msim_shard_integrate", "msim_shard_integrate_async",
     "msim_shard_counts", "msim_shard_read_gids",
     "msim_shard_row_histogram", "msim_grid_rows",
 ]
@@ -206,6 +207,11 @@ def lib():
         "msim_shard_enable": (i32, [vp, vp, u64, u32, u32]),
         "msim_shard_pack": (i32, [vp, u32, u32, vp, vp]),
         "msim_shard_move_pack": (i32, [vp, u32, u32, vp, vp]),
+        "msim_shard_p2p_create": (i32, [vp, vp, C.POINTER(vp)]),
+        "msim_shard_p2p_connect": (i32, [vp, vp, vp]),
+        "msim_shard_p2p_connect_local": (i32, [vp, vp, vp]),
+        "msim_shard_p2p_move_pack": (i32, [vp, u32, u32]),
+        "msim_shard_p2p_integrate": (i32, [vp]),
         "msim_shard_integrate": (i32, [vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "msim_shard_integrate_async": (i32, [vp, vp, vp]),
         "msim_shard_counts": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -463,6 +469,27 @@ class Simulation:
         self._check(lib().msim_shard_integrate(self._h, recv_down_ptr, recv_up_ptr, C.byref(owned), C.byref(ghosts)))
         self.count = owned.value
         return owned.value, ghosts.value
+
+    # -- peer-memory exchange (msim_shard.h): no collective call per tick
+    def shard_p2p_create(self) -> tuple[bytes, int]:
+        """Returns (CUDA IPC handle of this handle's receive arena, its device pointer)."""
+        buf = C.create_string_buffer(64)
+        arena = C.c_void_p()
+        self._check(lib().msim_shard_p2p_create(self._h, buf, C.byref(arena)))
+        return bytes(buf.raw), int(arena.value or 0)
+
+    def shard_p2p_connect(self, down_handle: bytes | None, up_handle: bytes | None):
+        self._check(lib().msim_shard_p2p_connect(self._h, down_handle, up_handle))
+
+    def shard_p2p_connect_local(self, down_arena: int | None, up_arena: int | None):
+        self._check(lib().msim_shard_p2p_connect_local(self._h, down_arena, up_arena))
+
+    def shard_p2p_move_pack(self, row_lo: int, row_hi: int):
+        self._check(lib().msim_shard_p2p_move_pack(self._h, row_lo, row_hi))
+
+    def shard_p2p_integrate(self):
+        self._sharded_async = True
+        self._check(lib().msim_shard_p2p_integrate(self._h))
 
     def shard_integrate_async(self, recv_down_ptr: int | None, recv_up_ptr: int | None):
         self._sharded_async = True

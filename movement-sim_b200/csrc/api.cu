@@ -130,6 +130,16 @@ struct msim_handle {
     void* sent_down{nullptr};
     void* sent_up{nullptr};
     uint32_t* gid_alt{nullptr};
+    // peer-memory exchange (msim_shard_p2p_*): our receive arena, the neighbours' arenas as peer pointers
+    char* p2p_arena{nullptr};
+    size_t p2p_buf_bytes{0};
+    char* p2p_peer_down{nullptr};
+    char* p2p_peer_up{nullptr};
+    bool p2p_down_ipc{false}, p2p_up_ipc{false};
+    bool p2p_connected{false};
+    uint32_t p2p_tick{0};
+    uint32_t* p2p_done{nullptr};
+    unsigned long long p2p_timeout_ns{10000000000ull};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
     bool awaiting_integrate{false};   // a fused move + pack has run: pass B stays deferred until the exchange has been integrated
@@ -216,6 +226,9 @@ void free_all(msim_handle* h) {
     cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
     cudaFree(h->ext_id); cudaFree(h->ext_id_alt); cudaFree(h->slot_of);
     cudaFree(h->dev_counts); cudaFree(h->gid_alt);
+    if (h->p2p_peer_down && h->p2p_down_ipc) cudaIpcCloseMemHandle(h->p2p_peer_down);
+    if (h->p2p_peer_up && h->p2p_up_ipc) cudaIpcCloseMemHandle(h->p2p_peer_up);
+    cudaFree(h->p2p_arena); cudaFree(h->p2p_done);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -281,6 +294,7 @@ int refresh_counts(msim_handle* h) {
         h->collide_owned = h->n;
         h->collide_total = h->n + h->n_ghost;
     }
+    if (v[DEV_SHARD_ERROR] & 32u) return fail(h, MSIM_ERR_INTERNAL, "peer-memory exchange: a neighbour never signalled its tick (timeout)");
     if (v[DEV_SHARD_ERROR] & 7u) return fail(h, MSIM_ERR_CAPACITY, "shard exchange overflow (migrant / halo / entity capacity) during asynchronous ticks");
     if (v[DEV_SHARD_ERROR]) return fail(h, MSIM_ERR_INTERNAL, "shard compaction bookkeeping mismatch");
     return MSIM_OK;
@@ -673,7 +687,13 @@ int msim_create(const msim_config* cfg, msim_handle** out) {
             MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             h->own_stream = true;
         }
-        MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        {
+            // the side stream carries pass B beside the (issue-bound, ~20 k CTA) collision query: highest priority, so that its
+            // few CTAs are placed as soon as query CTAs retire instead of queueing behind all of them
+            int prio_low = 0, prio_high = 0;
+            MSIM_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+            MSIM_CUDA(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_high));
+        }
         MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
         MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
         MSIM_CUDA(h, dev_alloc(&h->pos[0], h->cap));
@@ -1127,19 +1147,29 @@ int msim_shard_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send
     return MSIM_OK;
 }
 
-int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up) {
-    int rc = bind(h);
-    if (rc != MSIM_OK) return rc;
-    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: call msim_shard_enable first");
-    if (row_lo >= row_hi || row_hi > static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: bad row range");
-    if (h->uninitialised) {  // the reference's first dispatch moves nobody (random_move.comp:863-867): plain pack of the resident positions
-        rc = enqueue_move(h, true);
-        if (rc != MSIM_OK) return rc;
-        return msim_shard_pack(h, row_lo, row_hi, send_down, send_up);
-    }
-    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_shard_move_pack: the previous exchange has not been integrated");
+namespace {
+// arena of one handle: [flag from below @0][flag from above @128][256: receive buffers, index 2 * parity + side]
+// side 0 = written by the neighbour below, side 1 = written by the neighbour above
+constexpr size_t P2P_FLAG_BYTES = 256;
+inline uint32_t* p2p_flag(char* arena, int side) { return reinterpret_cast<uint32_t*>(arena + 128 * side); }
+inline char* p2p_recv(const msim_handle* h, char* arena, uint32_t parity, int side) { return arena + P2P_FLAG_BYTES + (2u * parity + side) * h->p2p_buf_bytes; }
+
+struct P2PSignal {
+    uint32_t* flag_down;
+    uint32_t* flag_up;
+    uint32_t value;
+};
+
+int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up, const P2PSignal* sig) {
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": call msim_shard_enable first");
+    if (row_lo >= row_hi || row_hi > static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": bad row range");
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": the previous exchange has not been integrated");
+    int rc = MSIM_OK;
+    const bool init_only = h->uninitialised;  // the reference's first dispatch moves nobody (random_move.comp:863-867)
+    if (init_only) consume_init_dispatch(h);
     join_side(h);  // pass B of the previous tick: the records read target / road / rng
-    h->launches += launch_shard_reset(h->stream, send_down, send_up, h->shard_ctr);
+    // local send buffers: headers cleared here; peer receive buffers: cleared by their owner's integrate kernel
+    h->launches += launch_shard_reset(h->stream, sig ? nullptr : send_down, sig ? nullptr : send_up, h->shard_ctr);
     ShardMoveArgs sh{};
     sh.lo_key = row_lo * static_cast<uint32_t>(h->grid.ncx);
     sh.hi_key = row_hi * static_cast<uint32_t>(h->grid.ncx);
@@ -1156,16 +1186,153 @@ int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void*
     sh.color0 = h->color0;
     sh.road = h->road;
     sh.gid = h->gid;
-    rc = enqueue_move(h, true, &sh);
-    if (rc != MSIM_OK) return rc;
+    if (sig) {
+        sh.done_ctr = h->p2p_done;
+        sh.peer_flag_down = sig->flag_down;
+        sh.peer_flag_up = sig->flag_up;
+        sh.signal_value = sig->value;
+    }
+    if (init_only) {
+        // nobody moves: pack the resident positions with the stand-alone kernel, then raise the flags
+        rc = ensure_keys(h);
+        if (rc != MSIM_OK) return rc;
+        h->launches += launch_shard_pack(h->stream, shard_arrays(h), launch_owned(h), h->grid.ncx, row_lo, row_hi, send_down, send_up, h->mig_cap, h->halo_cap,
+                                         h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof, dev_owned(h), /*reset=*/false);
+        if (sig) h->launches += launch_shard_signal(h->stream, sig->flag_down, sig->flag_up, sig->value);
+    } else {
+        rc = enqueue_move(h, true, &sh);
+        if (rc != MSIM_OK) return rc;
+        h->awaiting_integrate = true;  // pass B is deferred until the exchange has been integrated
+    }
     h->n_ghost = 0;
-    h->sent_down = send_down;
-    h->sent_up = send_up;
+    h->sent_down = sig ? nullptr : send_down;  // peer buffers: their owner checks the overflow flag
+    h->sent_up = sig ? nullptr : send_up;
     h->band_lo = send_down ? row_lo : 0u;
     h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
     h->packed = true;
-    h->awaiting_integrate = true;
     return MSIM_OK;
+}
+
+int integrate_device_common(msim_handle* h, const void* recv_down, const void* recv_up, const ShardWait* wait) {
+    h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
+                                                 h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
+                                                 h->grid, &h->prof, wait);
+    h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
+    h->band_valid = h->packed;
+    h->packed = false;
+    h->awaiting_integrate = false;
+    h->keys_valid = true;
+    h->hist_valid = false;
+    h->counts_valid = false;
+    h->flags_stale = h->collided;
+    return MSIM_OK;
+}
+}  // namespace
+
+int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    return move_pack_common(h, "msim_shard_move_pack", row_lo, row_hi, send_down, send_up, nullptr);
+}
+
+// ---- peer-memory exchange ---------------------------------------------------------------------------
+int msim_shard_p2p_create(msim_handle* h, void* ipc_handle_out, void** arena_out) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_create: call msim_shard_enable first");
+    if (!h->p2p_arena) {
+        h->p2p_buf_bytes = (msim_shard_buffer_bytes(h->mig_cap, h->halo_cap) + 255ull) & ~255ull;
+        const size_t bytes = P2P_FLAG_BYTES + 4 * h->p2p_buf_bytes;
+        MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->p2p_arena), bytes));
+        MSIM_CUDA(h, dev_alloc(&h->p2p_done, 1));
+        MSIM_CUDA(h, cudaMemsetAsync(h->p2p_arena, 0, bytes, h->stream));
+        MSIM_CUDA(h, cudaMemsetAsync(h->p2p_done, 0, sizeof(uint32_t), h->stream));
+        MSIM_CUDA(h, cudaStreamSynchronize(h->stream));  // neighbours may write as soon as they hold the pointer
+        if (const char* env = std::getenv("MSIM_P2P_TIMEOUT_MS")) {
+            const long v = std::atol(env);
+            if (v > 0) h->p2p_timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
+        }
+    }
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == MSIM_P2P_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+        cudaIpcMemHandle_t ipc{};
+        MSIM_CUDA(h, cudaIpcGetMemHandle(&ipc, h->p2p_arena));
+        std::memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+    }
+    if (arena_out) *arena_out = h->p2p_arena;
+    return MSIM_OK;
+}
+
+int msim_shard_p2p_connect(msim_handle* h, const void* down_ipc_handle, const void* up_ipc_handle) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->p2p_arena) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_connect: call msim_shard_p2p_create first");
+    if (h->p2p_connected) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_connect: already connected");
+    auto open = [&](const void* src, char** out) -> int {
+        cudaIpcMemHandle_t ipc{};
+        std::memcpy(&ipc, src, sizeof(ipc));
+        void* p = nullptr;
+        MSIM_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        *out = static_cast<char*>(p);
+        return MSIM_OK;
+    };
+    if (down_ipc_handle) {
+        rc = open(down_ipc_handle, &h->p2p_peer_down);
+        if (rc != MSIM_OK) return rc;
+        h->p2p_down_ipc = true;
+    }
+    if (up_ipc_handle) {
+        rc = open(up_ipc_handle, &h->p2p_peer_up);
+        if (rc != MSIM_OK) return rc;
+        h->p2p_up_ipc = true;
+    }
+    h->p2p_connected = true;
+    return MSIM_OK;
+}
+
+int msim_shard_p2p_connect_local(msim_handle* h, void* down_arena, void* up_arena) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->p2p_arena) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_connect_local: call msim_shard_p2p_create first");
+    if (h->p2p_connected) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_connect_local: already connected");
+    h->p2p_peer_down = static_cast<char*>(down_arena);
+    h->p2p_peer_up = static_cast<char*>(up_arena);
+    h->p2p_connected = true;
+    return MSIM_OK;
+}
+
+int msim_shard_p2p_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->p2p_connected) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_move_pack: call msim_shard_p2p_connect first");
+    const uint32_t parity = h->p2p_tick & 1u;
+    // we are the neighbour ABOVE the rank below us (its side 1) and the neighbour BELOW the rank above us (its side 0)
+    P2PSignal sig{};
+    sig.flag_down = h->p2p_peer_down ? p2p_flag(h->p2p_peer_down, 1) : nullptr;
+    sig.flag_up = h->p2p_peer_up ? p2p_flag(h->p2p_peer_up, 0) : nullptr;
+    sig.value = h->p2p_tick + 1u;
+    return move_pack_common(h, "msim_shard_p2p_move_pack", row_lo, row_hi, h->p2p_peer_down ? p2p_recv(h, h->p2p_peer_down, parity, 1) : nullptr,
+                            h->p2p_peer_up ? p2p_recv(h, h->p2p_peer_up, parity, 0) : nullptr, &sig);
+}
+
+int msim_shard_p2p_integrate(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!h->p2p_connected) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_integrate: call msim_shard_p2p_connect first");
+    if (!h->packed) return fail(h, MSIM_ERR_INVALID, "msim_shard_p2p_integrate: call msim_shard_p2p_move_pack first");
+    const uint32_t parity = h->p2p_tick & 1u;
+    void* recv_down = h->p2p_peer_down ? p2p_recv(h, h->p2p_arena, parity, 0) : nullptr;
+    void* recv_up = h->p2p_peer_up ? p2p_recv(h, h->p2p_arena, parity, 1) : nullptr;
+    ShardWait w{};
+    w.flag_down = recv_down ? p2p_flag(h->p2p_arena, 0) : nullptr;
+    w.flag_up = recv_up ? p2p_flag(h->p2p_arena, 1) : nullptr;
+    w.expected = h->p2p_tick + 1u;
+    w.timeout_ns = h->p2p_timeout_ns;
+    w.zero_headers = 1;
+    w.zero_recv_down = recv_down;
+    w.zero_recv_up = recv_up;
+    h->p2p_tick++;
+    return integrate_device_common(h, recv_down, recv_up, &w);
 }
 
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts) {
@@ -1255,18 +1422,7 @@ int msim_shard_integrate_async(msim_handle* h, const void* recv_down, const void
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!h->sharded) return fail(h, MSIM_ERR_INVALID, "msim_shard_integrate_async: call msim_shard_enable first");
-    h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
-                                                 h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
-                                                 h->grid, &h->prof);
-    h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
-    h->band_valid = h->packed;
-    h->packed = false;
-    h->awaiting_integrate = false;
-    h->keys_valid = true;
-    h->hist_valid = false;
-    h->counts_valid = false;
-    h->flags_stale = h->collided;
-    return MSIM_OK;
+    return integrate_device_common(h, recv_down, recv_up, nullptr);
 }
 
 int msim_shard_counts(msim_handle* h, uint64_t* owned, uint64_t* ghosts) {

@@ -147,31 +147,31 @@ __device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bo
     if (gslot < sh.holes_cap) sh.local_ghosts[gslot] = p_new;  // it lands in the neighbour's boundary row: still within reach of ours
 }
 
-// whole warp calls this once per entity slot; does what shard_pack_kernel does for one entity
+// whole warp calls this once per entity slot; does what shard_pack_kernel does for one entity.  Storage is in
+// cell order, so only the warps at either end of the slot range ever see a boundary row: everybody else
+// leaves after one vote.
 __device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, float2 p_old, float2 tgt,
                                                bool arrived) {
-    const bool go_down = valid && sh.buf_down && key < sh.lo_key;
-    const bool go_up = valid && sh.buf_up && key >= sh.hi_key;
+    const bool low = valid && sh.buf_down && key < sh.lo_key + sh.ncx;   // leaves downwards or sits in the first row
+    const bool high = valid && sh.buf_up && key >= sh.hi_key - sh.ncx;   // leaves upwards or sits in the last row
+    if (!__any_sync(0xffffffffu, low || high)) return;
+    const bool go_down = low && key < sh.lo_key;
+    const bool go_up = high && key >= sh.hi_key;
     if (go_down || go_up) shard_leave(sh, e, go_down, p_new, p_old, tgt, arrived);
-    const bool stays = valid && !go_down && !go_up;
     if (sh.buf_down) {  // halo: owned entities that stay, in the band's first / last row
-        const bool halo = stays && key < sh.lo_key + sh.ncx;
-        if (__any_sync(0xffffffffu, halo)) {
-            const uint32_t slot = warp_append(halo, &header_of(sh.buf_down)->n_halo);
-            if (halo) {
-                if (slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
-                else header_of(sh.buf_down)->overflow = 1u;
-            }
+        const bool halo = low && !go_down && !go_up;
+        const uint32_t slot = warp_append(halo, &header_of(sh.buf_down)->n_halo);
+        if (halo) {
+            if (slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
+            else header_of(sh.buf_down)->overflow = 1u;
         }
     }
     if (sh.buf_up) {
-        const bool halo = stays && key >= sh.hi_key - sh.ncx;
-        if (__any_sync(0xffffffffu, halo)) {
-            const uint32_t slot = warp_append(halo, &header_of(sh.buf_up)->n_halo);
-            if (halo) {
-                if (slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
-                else header_of(sh.buf_up)->overflow = 1u;
-            }
+        const bool halo = high && !go_down && !go_up;
+        const uint32_t slot = warp_append(halo, &header_of(sh.buf_up)->n_halo);
+        if (halo) {
+            if (slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
+            else header_of(sh.buf_up)->overflow = 1u;
         }
     }
 }
@@ -246,6 +246,21 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
         for (int i = threadIdx.x; i < hist_passes * RADIX; i += MOVE_THREADS)
             if (ghist && s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
     }
+    if (SHARD && sh.done_ctr) {
+        // peer-memory exchange: everything this CTA wrote into the neighbours' buffers is made visible system-wide, then the
+        // CTA checks out; the last one to do so raises the neighbours' flags (their integrate kernels spin on them)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t prev = atomicAdd(sh.done_ctr, 1u);
+            if (prev == gridDim.x - 1u) {
+                *sh.done_ctr = 0u;  // next launch on this stream starts from zero
+                __threadfence_system();
+                if (sh.peer_flag_down) st_release_sys(sh.peer_flag_down, sh.signal_value);
+                if (sh.peer_flag_up) st_release_sys(sh.peer_flag_up, sh.signal_value);
+            }
+        }
+    }
 }
 
 // ---- pass B: next waypoint for the entities that arrived (new_target, :778-828) ----------------
@@ -309,10 +324,11 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
                 const uint32_t* n_dev, const ShardMoveArgs* shard) {
-    if (n == 0) return 0;
+    if (n == 0 && !(shard && shard->done_ctr)) return 0;  // an empty band still has to signal its neighbours
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
     uint32_t blocks = (pairs + per_block - 1) / per_block;
+    if (blocks == 0) blocks = 1;
     const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;  // 8 x 256 threads = 2048 threads per SM
     if (blocks > resident) blocks = resident;  // grid-stride: a whole number of CTAs per SM
     const float4* pin = reinterpret_cast<const float4*>(pos_in);

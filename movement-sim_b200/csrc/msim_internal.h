@@ -80,6 +80,12 @@ struct ShardMoveArgs {
     const float4* color0;
     const uint32_t* road;
     const uint32_t* gid;
+    // peer-memory exchange: buf_down / buf_up are the NEIGHBOURS' receive buffers (NVLink peer pointers); the last
+    // CTA of the kernel publishes `signal_value` into their flag words after a system-scope fence
+    uint32_t* done_ctr;        // NULL: no signalling (buffers are local, the caller moves them)
+    uint32_t* peer_flag_down;
+    uint32_t* peer_flag_up;
+    uint32_t signal_value;
 };
 
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
@@ -229,13 +235,24 @@ struct ShardArrays {
 int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr);
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
-                      const uint32_t* n_dev = nullptr);
+                      const uint32_t* n_dev = nullptr, bool reset = true);
+int launch_shard_signal(cudaStream_t s, uint32_t* flag_down, uint32_t* flag_up, uint32_t value);
 // device-side integrate (asynchronous sharded tick): placement, tail compaction and the new counts without a host round trip
-enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_SHARD_ERROR = 3, DEV_COUNT_WORDS = 8 };
+enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_SHARD_ERROR = 3, DEV_HALO_DOWN = 4, DEV_HALO_UP = 5, DEV_COUNT_WORDS = 8 };
+// device-side wait of the peer-memory exchange: the integrate kernel spins until both flag words reach `expected`
+struct ShardWait {
+    const uint32_t* flag_down;  // NULL: nothing to wait for on that side
+    const uint32_t* flag_up;
+    uint32_t expected;
+    unsigned long long timeout_ns;
+    int zero_headers;           // the receive buffers are ours: clear their headers for the tick after next
+    void* zero_recv_down;
+    void* zero_recv_up;
+};
 int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
                                   uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
-                                  const GridParams& grid, Profiler* prof);
+                                  const GridParams& grid, Profiler* prof, const ShardWait* wait = nullptr);
 int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
                        const uint32_t* dst, const GridParams& grid, Profiler* prof);
 int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof);
@@ -270,6 +287,14 @@ __device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
     if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<uint32_t>(__popc(m)));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// system-scope flag accesses of the peer-memory exchange (the flag lives in another GPU's memory or is written by one)
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // bit position of entity e inside the `arrived` mask written by the move kernel: entities are

@@ -169,7 +169,9 @@ __device__ __forceinline__ void copy_entity(const ShardArrays& a, uint32_t src, 
 
 __device__ __forceinline__ void place_record(const ShardArrays& a, const void* buf, uint32_t r, uint32_t e, const GridParams& grid) {
     const uint2* rec = reinterpret_cast<const uint2*>(static_cast<const char*>(buf) + sizeof(ShardHeader)) + static_cast<size_t>(r) * (MIGRANT_BYTES / 8);
-    const uint2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6], r7 = rec[7], r8 = rec[8];
+    // .cg: the buffer may have been written by another GPU (peer-memory exchange); L2 is the point of coherence
+    const uint2 r0 = __ldcg(rec), r1 = __ldcg(rec + 1), r2 = __ldcg(rec + 2), r3 = __ldcg(rec + 3), r4 = __ldcg(rec + 4), r5 = __ldcg(rec + 5),
+                r6 = __ldcg(rec + 6), r7 = __ldcg(rec + 7), r8 = __ldcg(rec + 8);
     const float2 p = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y));
     a.pos_cur[e] = p;
     a.pos_prev[e] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y));
@@ -182,32 +184,55 @@ __device__ __forceinline__ void place_record(const ShardArrays& a, const void* b
     set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *flag >= expected; false on timeout (a neighbour that never enqueued its tick must not hang this GPU)
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t expected, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_timer_ns();
+    // signed distance: the counter may wrap after 2^32 ticks
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - expected) < 0) {
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
 constexpr int INTEGRATE_THREADS = 1024;
 
 __global__ void __launch_bounds__(INTEGRATE_THREADS)
 shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const void* sent_down, const void* sent_up, const void* recv_down,
                        const void* recv_up, const uint32_t* __restrict__ holes, const uint32_t* __restrict__ ctr, uint32_t mig_cap, uint32_t halo_cap,
-                       uint32_t holes_cap, uint32_t entity_cap, uint32_t* __restrict__ tail_bits, uint2* __restrict__ moves, GridParams grid) {
+                       uint32_t holes_cap, uint32_t entity_cap, uint32_t* __restrict__ tail_bits, uint2* __restrict__ moves, GridParams grid, ShardWait wait) {
     __shared__ uint32_t s_n_old, s_n_new, s_k_out, s_in_down, s_in_up, s_ghosts, s_low, s_live, s_err;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         uint32_t err = 0;
+        // peer-memory exchange: the neighbours' move kernels write into our receive buffers and then raise our flags
+        if ((wait.flag_down || wait.flag_up) && !(dev_counts[DEV_SHARD_ERROR] & 32u)) {  // after one timeout nobody waits again
+            if (wait.flag_down && !wait_flag(wait.flag_down, wait.expected, wait.timeout_ns)) err |= 32u;
+            if (wait.flag_up && !(err & 32u) && !wait_flag(wait.flag_up, wait.expected, wait.timeout_ns)) err |= 32u;
+        }
+        if ((err | dev_counts[DEV_SHARD_ERROR]) & 32u) recv_down = recv_up = nullptr;  // timed out: this tick integrates nothing from outside
         const uint32_t n_old = dev_counts[DEV_N_OWNED];
         uint32_t k_out = ctr[SHARD_CTR_HOLES], g_local = ctr[SHARD_CTR_LOCAL_GHOSTS];
         uint32_t in_down = 0, in_up = 0, halo_down = 0, halo_up = 0;
         if (sent_down && static_cast<const ShardHeader*>(sent_down)->overflow) err |= 1u;
         if (sent_up && static_cast<const ShardHeader*>(sent_up)->overflow) err |= 1u;
         if (recv_down) {
-            const ShardHeader* hd = static_cast<const ShardHeader*>(recv_down);
-            in_down = hd->n_migrants;
-            halo_down = hd->n_halo;
-            if (hd->overflow) err |= 1u;
+            const uint32_t* hd = static_cast<const uint32_t*>(recv_down);  // ShardHeader {n_migrants, n_halo, overflow}
+            in_down = __ldcg(hd);
+            halo_down = __ldcg(hd + 1);
+            if (__ldcg(hd + 2)) err |= 1u;
         }
         if (recv_up) {
-            const ShardHeader* hd = static_cast<const ShardHeader*>(recv_up);
-            in_up = hd->n_migrants;
-            halo_up = hd->n_halo;
-            if (hd->overflow) err |= 1u;
+            const uint32_t* hd = static_cast<const uint32_t*>(recv_up);
+            in_up = __ldcg(hd);
+            halo_up = __ldcg(hd + 1);
+            if (__ldcg(hd + 2)) err |= 1u;
         }
         if (k_out > holes_cap || g_local > holes_cap) { err |= 2u; k_out = min(k_out, holes_cap); g_local = min(g_local, holes_cap); }
         if (in_down > mig_cap || in_up > mig_cap || halo_down > halo_cap || halo_up > halo_cap) {
@@ -221,6 +246,14 @@ shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const v
             if (n_new > entity_cap) n_new = entity_cap;
             ghosts = entity_cap - n_new;
         }
+        // the ghost kernel that follows takes the (clamped) halo counts from here, not from the headers
+        if (halo_down + halo_up + g_local > ghosts) {  // capacity error above: drop ghosts from the end
+            uint32_t room = ghosts;
+            halo_down = min(halo_down, room); room -= halo_down;
+            halo_up = min(halo_up, room);
+        }
+        dev_counts[DEV_HALO_DOWN] = halo_down;
+        dev_counts[DEV_HALO_UP] = halo_up;
         s_n_old = n_old; s_n_new = n_new; s_k_out = k_out; s_in_down = in_down; s_in_up = in_up; s_ghosts = ghosts;
         s_low = 0; s_live = 0; s_err = err;
     }
@@ -256,6 +289,12 @@ shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const v
         dev_counts[DEV_N_TOTAL] = n_new + s_ghosts;
         if (s_err) atomicOr(&dev_counts[DEV_SHARD_ERROR], s_err);
     }
+    if (wait.zero_headers && tid < 8u) {
+        // peer-memory exchange: the headers are counters the neighbour's NEXT-BUT-ONE move kernel adds to (two buffers per
+        // side, used alternately); it cannot start before it has seen the flag our next move kernel raises
+        if (wait.zero_recv_down) static_cast<uint32_t*>(wait.zero_recv_down)[tid] = 0u;
+        if (wait.zero_recv_up) static_cast<uint32_t*>(wait.zero_recv_up)[tid] = 0u;
+    }
 }
 
 // ghosts behind the owned entities, counts taken from device memory (grid sized for the capacities)
@@ -263,13 +302,12 @@ __global__ void __launch_bounds__(256)
 shard_append_ghosts_device_kernel(ShardArrays a, const uint32_t* __restrict__ dev_counts, const void* recv_down, const void* recv_up,
                                   const float2* __restrict__ local_ghosts, uint32_t mig_cap, uint32_t halo_cap, GridParams grid) {
     const uint32_t first = dev_counts[DEV_N_OWNED], ghosts = dev_counts[DEV_N_GHOST];
-    const uint32_t h_down = recv_down ? min(static_cast<const ShardHeader*>(recv_down)->n_halo, halo_cap) : 0u;
-    const uint32_t h_up = recv_up ? min(static_cast<const ShardHeader*>(recv_up)->n_halo, halo_cap) : 0u;
+    const uint32_t h_down = dev_counts[DEV_HALO_DOWN], h_up = dev_counts[DEV_HALO_UP];  // validated by the integrate kernel
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ghosts) return;
     float2 p;
-    if (i < h_down) p = halo_of(const_cast<void*>(recv_down), mig_cap)[i];
-    else if (i < h_down + h_up) p = halo_of(const_cast<void*>(recv_up), mig_cap)[i - h_down];
+    if (i < h_down) p = __ldcg(halo_of(const_cast<void*>(recv_down), mig_cap) + i);
+    else if (i < h_down + h_up) p = __ldcg(halo_of(const_cast<void*>(recv_up), mig_cap) + (i - h_down));
     else p = local_ghosts[i - h_down - h_up];
     a.pos_cur[first + i] = p;
     a.keys[first + i] = cell_key_of(p, grid);
@@ -280,7 +318,19 @@ __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t
         atomicAdd(&rows[keys[e] / static_cast<uint32_t>(ncx)], 1u);
 }
 
+// raises the neighbours' flags after a pack that was not fused into a move kernel (the init-only first dispatch)
+__global__ void shard_signal_kernel(uint32_t* flag_down, uint32_t* flag_up, uint32_t value) {
+    __threadfence_system();
+    if (flag_down) st_release_sys(flag_down, value);
+    if (flag_up) st_release_sys(flag_up, value);
+}
+
 }  // namespace
+
+int launch_shard_signal(cudaStream_t s, uint32_t* flag_down, uint32_t* flag_up, uint32_t value) {
+    shard_signal_kernel<<<1, 1, 0, s>>>(flag_down, flag_up, value);
+    return 1;
+}
 
 int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr) {
     shard_reset_kernel<<<1, 32, 0, s>>>(buf_down, buf_up, ctr);
@@ -289,10 +339,8 @@ int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* c
 
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
-                      const uint32_t* n_dev) {
-    if (buf_down) cudaMemsetAsync(buf_down, 0, sizeof(ShardHeader), s);
-    if (buf_up) cudaMemsetAsync(buf_up, 0, sizeof(ShardHeader), s);
-    cudaMemsetAsync(ctr, 0, SHARD_CTR_COUNT * sizeof(uint32_t), s);
+                      const uint32_t* n_dev, bool reset) {
+    if (reset) shard_reset_kernel<<<1, 32, 0, s>>>(buf_down, buf_up, ctr);
     if (n == 0) return 0;
     prof->begin(s, K_SHARD);
     shard_pack_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(a, n, n_dev, ncx, row_lo, row_hi, buf_down, buf_up, mig_cap, halo_cap, holes, holes_cap, local_ghosts, ctr);
@@ -330,10 +378,11 @@ int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t fi
 int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
                                   uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
-                                  const GridParams& grid, Profiler* prof) {
+                                  const GridParams& grid, Profiler* prof, const ShardWait* wait) {
     prof->begin(s, K_SHARD);
+    const ShardWait none{};
     shard_integrate_kernel<<<1, INTEGRATE_THREADS, 0, s>>>(a, dev_counts, sent_down, sent_up, recv_down, recv_up, holes, ctr, mig_cap, halo_cap, holes_cap,
-                                                           entity_cap, scratch_bits, scratch_moves, grid);
+                                                           entity_cap, scratch_bits, scratch_moves, grid, wait ? *wait : none);
     const uint32_t max_ghosts = 2u * halo_cap + holes_cap;
     shard_append_ghosts_device_kernel<<<(max_ghosts + 255u) / 256u, 256, 0, s>>>(a, dev_counts, recv_down, recv_up, local_ghosts, mig_cap, halo_cap, grid);
     prof->end(s);

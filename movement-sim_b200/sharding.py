@@ -107,7 +107,7 @@ class ShardedSimulation:
     gloo in the CPU tests); buffers are torch tensors on the engine's device."""
 
     def __init__(self, engine, rank: int, world: int, splits: np.ndarray, rows: int, dist, torch, device, migrant_capacity: int,
-                 halo_capacity: int, buffer_bytes: int, rebalance_every: int = REBALANCE_EVERY):
+                 halo_capacity: int, buffer_bytes: int, rebalance_every: int = REBALANCE_EVERY, exchange: str = "collective"):
         self.engine, self.rank, self.world, self.dist, self.torch = engine, rank, world, dist, torch
         self.splits = np.asarray(splits, dtype=np.int64).copy()
         self.target = self.splits.copy()
@@ -134,6 +134,29 @@ class ShardedSimulation:
         self.exchanged_bytes = 0
         self.phase_us = {}
         self.fused_move_pack = hasattr(engine, "move_pack")  # one kernel moves and packs (msim_shard_move_pack)
+        # exchange = "p2p": the move kernel stores into the neighbours' receive buffers over NVLink peer memory and the
+        # integrate kernel waits on a flag: no collective call per tick.  "collective": one all_to_all_single per tick.
+        self.exchange = exchange if world > 1 else "collective"
+        if self.exchange == "p2p":
+            self.exchange = "p2p" if self._connect_p2p() else "collective"
+
+    def _connect_p2p(self) -> bool:
+        """Exchange the CUDA IPC handles of the receive arenas and open the neighbours'.  All ranks agree on the outcome."""
+        ok, handle = 1, b""
+        try:
+            handle = self.engine.p2p_create()
+        except Exception as e:  # e.g. IPC not permitted in this container
+            ok, self.p2p_error = 0, str(e)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, (ok, handle))
+        if all(h[0] for h in handles):
+            try:
+                self.engine.p2p_connect(handles[self.rank - 1][1] if self.has_down else None, handles[self.rank + 1][1] if self.has_up else None)
+            except Exception as e:
+                ok, self.p2p_error = 0, str(e)
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok)
+        return all(flags)
 
     @property
     def band(self):
@@ -162,6 +185,21 @@ class ShardedSimulation:
         if not np.array_equal(self.splits, self.target):
             self.splits = step_towards(self.splits, self.target)
         lo, hi = self.band
+        if self.exchange == "p2p":
+            t0 = time.perf_counter()
+            self.engine.p2p_move_pack(lo, hi)
+            t2 = time.perf_counter()
+            self.engine.p2p_integrate()
+            t3 = time.perf_counter()
+            if collide:
+                self.engine.collide()
+            t4 = time.perf_counter()
+            for k, v in (("enqueue_move_pack", t2 - t0), ("exchange_enqueue", 0.0), ("integrate", t3 - t2), ("enqueue_collide", t4 - t3)):
+                self.phase_us[k] = 0.9 * self.phase_us.get(k, v * 1e6) + 0.1 * v * 1e6
+            self.ticks += 1
+            if self.rebalance_every and self.world > 1 and self.ticks % self.rebalance_every == 0:
+                self.rebalance()
+            return
         t0 = time.perf_counter()
         if self.fused_move_pack:
             self.engine.move_pack(lo, hi, self.send_down, self.send_up)
@@ -215,6 +253,18 @@ class CudaShardEngine:
     def move_pack(self, lo, hi, send_down, send_up):
         self.sim.shard_move_pack(lo, hi, self._ptr(send_down), self._ptr(send_up))
 
+    def p2p_create(self) -> bytes:
+        return self.sim.shard_p2p_create()[0]
+
+    def p2p_connect(self, down_handle, up_handle):
+        self.sim.shard_p2p_connect(down_handle, up_handle)
+
+    def p2p_move_pack(self, lo, hi):
+        self.sim.shard_p2p_move_pack(lo, hi)
+
+    def p2p_integrate(self):
+        self.sim.shard_p2p_integrate()
+
     def integrate(self, recv_down, recv_up):
         if self.asynchronous:  # device-side integrate: nothing to wait for, the host keeps enqueueing
             return self.sim.shard_integrate_async(self._ptr(recv_down), self._ptr(recv_up))
@@ -235,7 +285,7 @@ class CudaShardEngine:
 
 
 def make_cuda_shard(M, m, total: int, seed: int, radius: float, rank: int, world: int, dist, torch, local_rank: int, stream, box=None,
-                    rebalance_every: int = REBALANCE_EVERY):
+                    rebalance_every: int = REBALANCE_EVERY, exchange: str = "p2p"):
     """Builds this rank's band of the seeded global population on its GPU."""
     hist, ncx, ncy = global_row_histogram(M, m, total, seed, radius, box)
     splits = balanced_splits(hist, world)
@@ -250,7 +300,7 @@ def make_cuda_shard(M, m, total: int, seed: int, radius: float, rank: int, world
     engine = CudaShardEngine(M, sim)
     device = torch.device("cuda", local_rank)
     sh = ShardedSimulation(engine, rank, world, splits, ncy, dist, torch, device, migrant_capacity, halo_capacity,
-                           M.shard_buffer_bytes(migrant_capacity, halo_capacity), rebalance_every)
+                           M.shard_buffer_bytes(migrant_capacity, halo_capacity), rebalance_every, exchange)
     return sh, sim
 
 
@@ -275,7 +325,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     sampler = None
     with torch.cuda.stream(stream):
         if collisions:
-            sh, sim = make_cuda_shard(M, m, total, 42, 10.0, rank, world, dist, torch, local_rank, stream)
+            sh, sim = make_cuda_shard(M, m, total, 42, 10.0, rank, world, dist, torch, local_rank, stream, exchange=getattr(args, "exchange", "p2p"))
             sim.dispatch(2)  # the reference's first dispatch: initialise only
             step = lambda: sh.tick(True)
             for _ in range(args.preroll):
@@ -379,8 +429,12 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": args.workload, "entities_per_gpu": per_gpu, "entities_total": total, "collisions": collisions,
                        "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll,
-                       "parallelism": (f"{world} spatial bands of cell rows, NCCL send/recv of halo + migrants per tick, row-histogram all-reduce every {REBALANCE_EVERY} ticks"
+                       "parallelism": (f"{world} spatial bands of cell rows; halo + migrants per tick "
+                                       + ("stored by the move kernel into the neighbours' buffers over NVLink peer memory, flag-synchronised (no collective call)"
+                                          if sh.exchange == "p2p" else "through one NCCL all_to_all_single")
+                                       + f"; row-histogram all-reduce every {REBALANCE_EVERY} ticks"
                                        if collisions else f"{world} entity ranges, no collective"),
+                       "exchange": (sh.exchange if sh else None), "p2p_fallback_reason": getattr(sh, "p2p_error", None),
                        "owned_per_rank": per_rank, "l2": ("inputs larger than L2 (no flush)" if per_gpu * 40 > 200e6 else "per-GPU working set may sit in L2 (strong scaling of a fixed population)"),
                        "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels,
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),

@@ -60,7 +60,8 @@ def run(rank, world, port, backend, outdir, cfg):
         engine = OracleShardEngine(O, M, m, ents, gids, radius, mig_cap, hal_cap)
         engine.move()  # the init-only first dispatch
         device = torch.device("cpu")
-    sh = S.ShardedSimulation(engine, rank, world, splits, ncy, dist, torch, device, mig_cap, hal_cap, nbytes, cfg.get("rebalance_every", 8))
+    sh = S.ShardedSimulation(engine, rank, world, splits, ncy, dist, torch, device, mig_cap, hal_cap, nbytes, cfg.get("rebalance_every", 8),
+                             exchange=cfg.get("exchange", "collective"))
     pairs, owned_hist, split_hist = [], [], []
     for t in range(cfg["ticks"]):
         sh.tick(True)
@@ -74,7 +75,8 @@ def run(rank, world, port, backend, outdir, cfg):
     np.save(os.path.join(outdir, f"ents_{rank}.npy"), np.ascontiguousarray(e).view(np.uint8))
     np.save(os.path.join(outdir, f"gids_{rank}.npy"), g)
     with open(os.path.join(outdir, f"meta_{rank}.json"), "w") as f:
-        json.dump({"pairs": pairs, "owned": owned_hist, "splits": split_hist, "exchanged_bytes": sh.exchanged_bytes}, f)
+        json.dump({"pairs": pairs, "owned": owned_hist, "splits": split_hist, "exchanged_bytes": sh.exchanged_bytes, "exchange": sh.exchange,
+                   "p2p_error": getattr(sh, "p2p_error", None)}, f)
     dist.barrier()
     if backend == "nccl":
         sim.close()

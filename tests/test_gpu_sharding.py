@@ -14,7 +14,7 @@ from test_sharding import BASE, check_against_reference, free_port
 pytestmark = pytest.mark.gpu
 
 
-def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False, flags=0, fused=False):
+def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capacity, box=None, rebalance_every=0, skew=False, asynchronous=False, flags=0, fused=False, p2p=False):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -26,10 +26,10 @@ def run_bands_on_one_gpu(msim, orc, m, total, seed, radius, world, ticks, capaci
     stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused)
+        return _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused, p2p)
 
 
-def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused):
+def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebalance_every, asynchronous, splits, ncy, stream, flags, fused, p2p):
     import torch
 
     from movement_sim_b200 import sharding as S
@@ -44,10 +44,29 @@ def _run_bands(msim, m, total, seed, radius, world, ticks, capacity, box, rebala
         sim.dispatch(2)
         sims.append(sim)
         bufs.append({k: torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for k in ("sd", "su", "rd", "ru")})
+    if p2p:  # the bands' receive arenas live in this process: connect them by device pointer
+        arenas = [sim.shard_p2p_create()[1] for sim in sims]
+        for r, sim in enumerate(sims):
+            sim.shard_p2p_connect_local(arenas[r - 1] if r > 0 else None, arenas[r + 1] if r + 1 < world else None)
     pairs, owned = [], []
     for t in range(ticks):
         if not np.array_equal(splits, target):
             splits = S.step_towards(splits, target)
+        if p2p:
+            # every band's move kernel (stores into the neighbours' buffers, raises their flags) is enqueued before any
+            # integrate kernel (spins on the flags): on ONE stream the opposite order would wait for itself
+            for r, sim in enumerate(sims):
+                sim.shard_p2p_move_pack(int(splits[r]), int(splits[r + 1]))
+            for sim in sims:
+                sim.shard_p2p_integrate()
+                sim.enqueue_collide()
+            pairs.append(sum(sim.stats()["last_pair_count"] for sim in sims))
+            if t % 7 == 0 or t == ticks - 1:
+                owned.append([s.stats()["entity_count"] for s in sims])
+            if rebalance_every and (t + 1) % rebalance_every == 0:
+                h = sum(s.shard_row_histogram(ncy).astype(np.int64) for s in sims)
+                target = S.balanced_splits(h, world)
+            continue
         for r, sim in enumerate(sims):
             band = (int(splits[r]), int(splits[r + 1]), bufs[r]["sd"].data_ptr() if r > 0 else None, bufs[r]["su"].data_ptr() if r + 1 < world else None)
             if fused:  # one kernel moves and packs; the next-waypoint pass then runs after the integrate
@@ -146,6 +165,59 @@ def test_bands_rebalance_dense_corner(msim, orc, small_city, asynchronous, rebui
     assert owned[0][0] > 0.8 * total and abs(owned[-1][0] - total / 2) < 0.15 * total
 
 
+@pytest.mark.parametrize("rebuild", REBUILDS)
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_bands_peer_memory_exchange_matches_unsharded_oracle(msim, orc, small_city, world, rebuild, monkeypatch):
+    """msim_shard_p2p_*: the move kernel stores into the neighbours' receive buffers, the integrate kernel waits on a flag."""
+    total, ticks = 40_000, 50
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 42, 10.0, world, ticks, capacity=1 << 14, asynchronous=True,
+                                             flags=rebuild_flags(msim, monkeypatch, rebuild), p2p=True)
+    want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
+    assert_entities_equal(got, want, what=f"{world} bands, peer-memory exchange")
+    assert pairs == want_pairs
+    if world > 1:
+        assert any(o != owned[0] for o in owned), "entities should migrate between bands"
+
+
+def test_bands_peer_memory_exchange_rebalance_dense_corner(msim, orc, small_city, monkeypatch):
+    total, ticks = 30_000, 80
+    box = [0.0, 0.0, 900.0, 600.0]
+    got, pairs, owned = run_bands_on_one_gpu(msim, orc, small_city, total, 7, 10.0, 2, ticks, capacity=1 << 15, box=box, rebalance_every=4, skew=True,
+                                             asynchronous=True, flags=rebuild_flags(msim, monkeypatch, "cell-ordered"), p2p=True)
+    want, want_pairs = oracle_reference(msim, orc, small_city, total, 7, 10.0, ticks, box=box)
+    assert_entities_equal(got, want, what="rebalanced bands, peer-memory exchange")
+    assert pairs == want_pairs
+
+
+def test_peer_memory_exchange_times_out_instead_of_hanging(msim, small_city, monkeypatch):
+    """A neighbour that never enqueues its tick: the integrate kernel gives up after MSIM_P2P_TIMEOUT_MS and the error surfaces."""
+    import torch
+
+    from movement_sim_b200 import sharding as S
+
+    monkeypatch.setenv("MSIM_P2P_TIMEOUT_MS", "200")
+    total = 20_000
+    hist, ncx, ncy = S.global_row_histogram(msim, small_city, total, 42, 10.0)
+    sims = []
+    for lo, hi in ((0, ncy // 2), (ncy // 2, ncy)):
+        ents, gids = S.collect_band(msim, small_city, total, 42, 10.0, lo, hi)
+        sim = msim.Simulation(small_city, ents, radius=10.0, capacity=total + (1 << 14))
+        sim.shard_enable(gids, 1 << 12, 1 << 12)
+        sim.dispatch(2)
+        sims.append(sim)
+    arenas = [s.shard_p2p_create()[1] for s in sims]
+    sims[0].shard_p2p_connect_local(None, arenas[1])
+    sims[1].shard_p2p_connect_local(arenas[0], None)
+    sims[0].shard_p2p_move_pack(0, ncy // 2)  # band 1 never moves: band 0 waits for a flag that is not coming
+    sims[0].shard_p2p_integrate()
+    sims[0].enqueue_collide()
+    with pytest.raises(msim.MsimError) as ei:
+        sims[0].sync()
+    assert ei.value.status == msim.MSIM_ERR_INTERNAL and "timeout" in str(ei.value)
+    for s in sims:
+        s.close()
+
+
 def test_capacity_overflow_is_reported(msim, small_city):
     import torch
 
@@ -194,7 +266,10 @@ def test_capacity_overflow_is_reported_by_async_ticks(msim, small_city):
     sim.close()
 
 
-def test_two_gpus_over_nccl(msim, orc, tmp_path):
+@pytest.mark.parametrize("exchange", ["collective", "p2p"])
+def test_two_gpus_over_nccl(msim, orc, tmp_path, exchange):
+    import json
+
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -204,6 +279,9 @@ def test_two_gpus_over_nccl(msim, orc, tmp_path):
     from shard_worker import run
 
     world = min(torch.cuda.device_count(), 4)
-    cfg = dict(BASE, entities=60_000, ticks=60, capacity=1 << 14)
+    cfg = dict(BASE, entities=60_000, ticks=60, capacity=1 << 14, exchange=exchange)
     mp.spawn(run, args=(world, free_port(), "nccl", str(tmp_path), cfg), nprocs=world, join=True)
     check_against_reference(orc, msim, cfg, str(tmp_path), world)
+    with open(tmp_path / "meta_0.json") as f:
+        meta = json.load(f)
+    assert meta["exchange"] == exchange, f"fell back to {meta['exchange']}: {meta.get('p2p_error')}"
