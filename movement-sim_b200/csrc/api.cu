@@ -142,6 +142,7 @@ struct msim_handle {
     unsigned long long p2p_timeout_ns{10000000000ull};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
+    bool count_fused{false};          // the last move + pack ranked the stayers: place / relocate / ghost kernels complete the per-cell counters
     bool awaiting_integrate{false};   // a fused move + pack has run: pass B stays deferred until the exchange has been integrated
     bool band_valid{false};           // false between a move pass and the integrate that follows it
     uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
@@ -424,10 +425,15 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     const int passes = (h->key_bits + RADIX_BITS - 1) / RADIX_BITS;
     // what the neighbour rebuild can take over from this pass: the counting sort's per-cell ranks, or the
     // onesweep digit histograms.  Sharded handles change their key set in the exchange that follows.
-    const bool fuse_count = emit && h->use_csort && !h->sharded;
+    const bool fuse_count = emit && h->use_csort && (!h->sharded || shard);
     const bool fuse_hist = emit && !h->use_csort && !h->sharded;
     h->n_ghost = 0;
-    if (fuse_count) csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
+    h->count_fused = fuse_count && h->sharded;
+    if (fuse_count) {
+        uint32_t c0 = 0, c1 = h->grid.ncells;
+        if (h->sharded) csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &c0, &c1);  // band set by the caller (move_pack_common)
+        csort_clear(h->stream, h->cell_count + c0, c1 - c0, &h->prof);
+    }
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
@@ -583,8 +589,9 @@ int enqueue_collide(msim_handle* h) {
     h->flags_scattered = false;
     h->collide_passes++;
     h->since_reorder++;
-    if (h->reorder_enabled && h->use_csort && h->has_moved && (h->n > 1 || h->async_counts) && h->since_reorder >= h->reorder_every &&
-        (!h->sharded || h->band_valid))
+    // a sharded handle finds its owned run through the counting sort's prefix table and only while every owned entity lies in the band
+    if (h->reorder_enabled && h->has_moved && (h->n > 1 || h->async_counts) && h->since_reorder >= h->reorder_every &&
+        (!h->sharded || (h->use_csort && h->band_valid)))
         return reorder_storage(h);
     return MSIM_OK;
 }
@@ -1073,6 +1080,11 @@ ShardArrays shard_arrays(msim_handle* h) {
     a.gid = h->gid;
     a.keys = h->keys;
     a.arrived = h->arrived;
+    if (h->count_fused) {
+        a.cell_count = h->cell_count;
+        a.rank = h->rank;
+        csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &a.c0, &a.c1);
+    }
     return a;
 }
 
@@ -1116,6 +1128,8 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
     MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_COUNT_WORDS));
+    MSIM_CUDA(h, dev_alloc(&h->p2p_done, 1));
+    MSIM_CUDA(h, cudaMemsetAsync(h->p2p_done, 0, sizeof(uint32_t), h->stream));
     rc = write_dev_counts(h);
     if (rc != MSIM_OK) return rc;
     MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), 2 * (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
@@ -1168,8 +1182,9 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     const bool init_only = h->uninitialised;  // the reference's first dispatch moves nobody (random_move.comp:863-867)
     if (init_only) consume_init_dispatch(h);
     join_side(h);  // pass B of the previous tick: the records read target / road / rng
-    // local send buffers: headers cleared here; peer receive buffers: cleared by their owner's integrate kernel
-    h->launches += launch_shard_reset(h->stream, sig ? nullptr : send_down, sig ? nullptr : send_up, h->shard_ctr);
+    // the fused kernel counts in h->shard_ctr and writes the buffer headers itself (last CTA); the stand-alone pack kernel
+    // (init-only dispatch below) counts in the headers of the buffers, which the reset clears when they are local
+    h->launches += launch_shard_reset(h->stream, (sig || !init_only) ? nullptr : send_down, (sig || !init_only) ? nullptr : send_up, h->shard_ctr);
     ShardMoveArgs sh{};
     sh.lo_key = row_lo * static_cast<uint32_t>(h->grid.ncx);
     sh.hi_key = row_hi * static_cast<uint32_t>(h->grid.ncx);
@@ -1186,13 +1201,17 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     sh.color0 = h->color0;
     sh.road = h->road;
     sh.gid = h->gid;
+    sh.done_ctr = h->p2p_done;
     if (sig) {
-        sh.done_ctr = h->p2p_done;
         sh.peer_flag_down = sig->flag_down;
         sh.peer_flag_up = sig->flag_up;
         sh.signal_value = sig->value;
     }
+    // rows that can hold owned entities once the leavers are gone: without a neighbour nobody leaves on that side
+    h->band_lo = send_down ? row_lo : 0u;
+    h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
     if (init_only) {
+        h->count_fused = false;
         // nobody moves: pack the resident positions with the stand-alone kernel, then raise the flags
         rc = ensure_keys(h);
         if (rc != MSIM_OK) return rc;
@@ -1207,8 +1226,6 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     h->n_ghost = 0;
     h->sent_down = sig ? nullptr : send_down;  // peer buffers: their owner checks the overflow flag
     h->sent_up = sig ? nullptr : send_up;
-    h->band_lo = send_down ? row_lo : 0u;
-    h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
     h->packed = true;
     return MSIM_OK;
 }
@@ -1223,7 +1240,7 @@ int integrate_device_common(msim_handle* h, const void* recv_down, const void* r
     h->awaiting_integrate = false;
     h->keys_valid = true;
     h->hist_valid = false;
-    h->counts_valid = false;
+    h->counts_valid = h->count_fused;  // ranks and per-cell counters were completed by the placement kernels
     h->flags_stale = h->collided;
     return MSIM_OK;
 }
@@ -1244,9 +1261,7 @@ int msim_shard_p2p_create(msim_handle* h, void* ipc_handle_out, void** arena_out
         h->p2p_buf_bytes = (msim_shard_buffer_bytes(h->mig_cap, h->halo_cap) + 255ull) & ~255ull;
         const size_t bytes = P2P_FLAG_BYTES + 4 * h->p2p_buf_bytes;
         MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->p2p_arena), bytes));
-        MSIM_CUDA(h, dev_alloc(&h->p2p_done, 1));
         MSIM_CUDA(h, cudaMemsetAsync(h->p2p_arena, 0, bytes, h->stream));
-        MSIM_CUDA(h, cudaMemsetAsync(h->p2p_done, 0, sizeof(uint32_t), h->stream));
         MSIM_CUDA(h, cudaStreamSynchronize(h->stream));  // neighbours may write as soon as they hold the pointer
         if (const char* env = std::getenv("MSIM_P2P_TIMEOUT_MS")) {
             const long v = std::atol(env);
@@ -1328,9 +1343,7 @@ int msim_shard_p2p_integrate(msim_handle* h) {
     w.flag_up = recv_up ? p2p_flag(h->p2p_arena, 1) : nullptr;
     w.expected = h->p2p_tick + 1u;
     w.timeout_ns = h->p2p_timeout_ns;
-    w.zero_headers = 1;
-    w.zero_recv_down = recv_down;
-    w.zero_recv_up = recv_up;
+    w.zero_headers = 0;  // headers are overwritten every tick by the sender's last CTA
     h->p2p_tick++;
     return integrate_device_common(h, recv_down, recv_up, &w);
 }
@@ -1411,7 +1424,7 @@ int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv
     h->awaiting_integrate = false;
     h->keys_valid = true;
     h->hist_valid = false;
-    h->counts_valid = false;
+    h->counts_valid = h->count_fused;  // ranks and per-cell counters were completed by the placement kernels
     h->flags_stale = h->collided;
     if (owned) *owned = n_new;
     if (ghosts) *ghosts = n_ghost;

@@ -26,7 +26,6 @@ namespace {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096 cells per CTA
-constexpr uint32_t CSORT_SKIP = 0xffffffffu;          // rank of an entity that is left out of the order
 
 __global__ void __launch_bounds__(256)
 cell_count_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,

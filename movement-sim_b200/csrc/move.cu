@@ -28,6 +28,7 @@ constexpr int MOVE_ITEMS = 2;  // float4 pairs per thread -> 4 entities per thre
 constexpr float SPEED = 1.4f;  // random_move.comp:750
 
 __device__ __forceinline__ float as_f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
 // random_move.comp:725-736
 __device__ __forceinline__ uint32_t xorshift128(uint4& s) {
@@ -124,8 +125,8 @@ __device__ __forceinline__ uint32_t run_rank(uint32_t* __restrict__ cell_count, 
 // result there because new_target() reads nothing but the entity and the replicated road graph.
 __device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bool down, float2 p_new, float2 p_old, float2 tgt, bool arrived) {
     void* buf = down ? sh.buf_down : sh.buf_up;
-    const uint32_t slot = atomicAdd(&header_of(buf)->n_migrants, 1u);
-    if (slot < sh.mig_cap) {
+    const uint32_t slot = atomicAdd(&sh.ctr[down ? SHARD_CTR_MIG_DOWN : SHARD_CTR_MIG_UP], 1u);
+    if (slot < sh.mig_cap) {  // beyond the capacity the count alone reports the overflow
         uint2* rec = records_of(buf) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
         const uint4 s = sh.rng[e];
         const float4 c = sh.color0[e];
@@ -138,8 +139,6 @@ __device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bo
         rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
         rec[7] = make_uint2(sh.road[e], sh.gid[e]);
         rec[8] = make_uint2(arrived ? 1u : 0u, 0u);
-    } else {
-        header_of(buf)->overflow = 1u;
     }
     const uint32_t hslot = atomicAdd(&sh.ctr[SHARD_CTR_HOLES], 1u);
     if (hslot < sh.holes_cap) sh.holes[hslot] = e;
@@ -149,31 +148,28 @@ __device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bo
 
 // whole warp calls this once per entity slot; does what shard_pack_kernel does for one entity.  Storage is in
 // cell order, so only the warps at either end of the slot range ever see a boundary row: everybody else
-// leaves after one vote.
-__device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, float2 p_old, float2 tgt,
+// leaves after one vote.  List slots come from LOCAL counters; the buffers (which may live in a neighbour's
+// memory) receive plain stores only.  Returns true iff this thread stored into an exchange buffer (it then
+// owes a system-scope fence).
+__device__ __forceinline__ bool shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, float2 p_old, float2 tgt,
                                                bool arrived) {
     const bool low = valid && sh.buf_down && key < sh.lo_key + sh.ncx;   // leaves downwards or sits in the first row
     const bool high = valid && sh.buf_up && key >= sh.hi_key - sh.ncx;   // leaves upwards or sits in the last row
-    if (!__any_sync(0xffffffffu, low || high)) return;
+    if (!__any_sync(0xffffffffu, low || high)) return false;
     const bool go_down = low && key < sh.lo_key;
     const bool go_up = high && key >= sh.hi_key;
     if (go_down || go_up) shard_leave(sh, e, go_down, p_new, p_old, tgt, arrived);
     if (sh.buf_down) {  // halo: owned entities that stay, in the band's first / last row
         const bool halo = low && !go_down && !go_up;
-        const uint32_t slot = warp_append(halo, &header_of(sh.buf_down)->n_halo);
-        if (halo) {
-            if (slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
-            else header_of(sh.buf_down)->overflow = 1u;
-        }
+        const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_DOWN]);
+        if (halo && slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
     }
     if (sh.buf_up) {
         const bool halo = high && !go_down && !go_up;
-        const uint32_t slot = warp_append(halo, &header_of(sh.buf_up)->n_halo);
-        if (halo) {
-            if (slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
-            else header_of(sh.buf_up)->overflow = 1u;
-        }
+        const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_UP]);
+        if (halo && slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
     }
+    return low || high;
 }
 
 // EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
@@ -195,6 +191,7 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
     const uint32_t pairs_pad = (pairs + 31u) & ~31u;  // arrays are padded, whole warps stay converged
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t PER_BLOCK = MOVE_THREADS * MOVE_ITEMS;
+    bool wrote_exchange = false;
 
     for (uint32_t base = blockIdx.x * PER_BLOCK; base < pairs_pad; base += gridDim.x * PER_BLOCK) {
         float4 P[MOVE_ITEMS], T[MOVE_ITEMS];
@@ -228,15 +225,20 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                 const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);
                 keys[pi] = make_uint2(k0, k1);
                 if (cell_count) {  // counting sort: the atomic's return value is the entity's rank inside its cell
-                    rank[pi] = make_uint2(run_rank(cell_count, k0, e0 < n, lane), run_rank(cell_count, k1, e1 < n, lane));
+                    bool v0 = e0 < n, v1 = e1 < n;
+                    if (SHARD) {  // leavers are not part of this band's order any more; arrivals take their rank in the integrate kernel
+                        v0 = v0 && !((sh.buf_down && k0 < sh.lo_key) || (sh.buf_up && k0 >= sh.hi_key));
+                        v1 = v1 && !((sh.buf_down && k1 < sh.lo_key) || (sh.buf_up && k1 >= sh.hi_key));
+                    }
+                    rank[pi] = make_uint2(run_rank(cell_count, k0, v0, lane), run_rank(cell_count, k1, v1, lane));
                 }
                 for (int p = 0; p < hist_passes; p++) {
                     if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                     if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                 }
                 if (SHARD) {
-                    shard_classify(sh, e0, e0 < n, k0, q0, make_float2(P[k].x, P[k].y), make_float2(T[k].x, T[k].y), arr0);
-                    shard_classify(sh, e1, e1 < n, k1, q1, make_float2(P[k].z, P[k].w), make_float2(T[k].z, T[k].w), arr1);
+                    wrote_exchange |= shard_classify(sh, e0, e0 < n, k0, q0, make_float2(P[k].x, P[k].y), make_float2(T[k].x, T[k].y), arr0);
+                    wrote_exchange |= shard_classify(sh, e1, e1 < n, k1, q1, make_float2(P[k].z, P[k].w), make_float2(T[k].z, T[k].w), arr1);
                 }
             }
         }
@@ -246,15 +248,33 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
         for (int i = threadIdx.x; i < hist_passes * RADIX; i += MOVE_THREADS)
             if (ghist && s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
     }
-    if (SHARD && sh.done_ctr) {
-        // peer-memory exchange: everything this CTA wrote into the neighbours' buffers is made visible system-wide, then the
-        // CTA checks out; the last one to do so raises the neighbours' flags (their integrate kernels spin on them)
-        __threadfence_system();
+    if (SHARD) {
+        // Every thread that stored into an exchange buffer makes its stores visible system-wide (only the few threads at
+        // either end of the slot range ever do), the CTA meets at a barrier and checks out with a fence + atomic (release
+        // pattern, cumulative over the barrier).  The last CTA to check out publishes the list lengths into the buffer
+        // headers and, for the peer-memory exchange, raises the neighbours' flags, on which their integrate kernels spin.
+        if (wrote_exchange) __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();
             const uint32_t prev = atomicAdd(sh.done_ctr, 1u);
             if (prev == gridDim.x - 1u) {
                 *sh.done_ctr = 0u;  // next launch on this stream starts from zero
+                __threadfence();
+                if (sh.buf_down) {
+                    const uint32_t m = ld_volatile(sh.ctr + SHARD_CTR_MIG_DOWN), hl = ld_volatile(sh.ctr + SHARD_CTR_HALO_DOWN);
+                    ShardHeader* hd = header_of(sh.buf_down);
+                    hd->n_migrants = m;
+                    hd->n_halo = hl;
+                    hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+                }
+                if (sh.buf_up) {
+                    const uint32_t m = ld_volatile(sh.ctr + SHARD_CTR_MIG_UP), hl = ld_volatile(sh.ctr + SHARD_CTR_HALO_UP);
+                    ShardHeader* hd = header_of(sh.buf_up);
+                    hd->n_migrants = m;
+                    hd->n_halo = hl;
+                    hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+                }
                 __threadfence_system();
                 if (sh.peer_flag_down) st_release_sys(sh.peer_flag_down, sh.signal_value);
                 if (sh.peer_flag_up) st_release_sys(sh.peer_flag_up, sh.signal_value);
@@ -324,7 +344,7 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
                 const uint32_t* n_dev, const ShardMoveArgs* shard) {
-    if (n == 0 && !(shard && shard->done_ctr)) return 0;  // an empty band still has to signal its neighbours
+    if (n == 0 && !shard) return 0;  // an empty band still has to publish its (empty) headers and signal its neighbours
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
     uint32_t blocks = (pairs + per_block - 1) / per_block;

@@ -82,7 +82,7 @@ struct ShardMoveArgs {
     const uint32_t* gid;
     // peer-memory exchange: buf_down / buf_up are the NEIGHBOURS' receive buffers (NVLink peer pointers); the last
     // CTA of the kernel publishes `signal_value` into their flag words after a system-scope fence
-    uint32_t* done_ctr;        // NULL: no signalling (buffers are local, the caller moves them)
+    uint32_t* done_ctr;        // CTA check-out counter: the last CTA publishes the headers (and the flags, if any)
     uint32_t* peer_flag_down;
     uint32_t* peer_flag_up;
     uint32_t signal_value;
@@ -218,7 +218,11 @@ struct ShardHeader {
     uint32_t pad[5];
 };
 constexpr uint32_t MIGRANT_BYTES = 72;  // pos, pos_prev, target, rng, color0, road, gid, arrived bit
-enum { SHARD_CTR_HOLES = 0, SHARD_CTR_LOCAL_GHOSTS = 1, SHARD_CTR_COUNT = 8 };
+// counters of one pack (device, cleared per tick).  The fused move + pack kernel counts migrants / halo entries HERE, in local
+// memory, and publishes the totals into the (possibly remote) buffer headers once, from its last CTA: the exchange buffers
+// only ever see plain stores, never an atomic round trip over NVLink
+enum { SHARD_CTR_HOLES = 0, SHARD_CTR_LOCAL_GHOSTS = 1, SHARD_CTR_MIG_DOWN = 2, SHARD_CTR_MIG_UP = 3, SHARD_CTR_HALO_DOWN = 4, SHARD_CTR_HALO_UP = 5,
+       SHARD_CTR_COUNT = 8 };
 
 struct ShardArrays {
     float2* pos_cur;
@@ -230,7 +234,14 @@ struct ShardArrays {
     uint32_t* gid;
     uint32_t* keys;
     uint32_t* arrived;
+    // counting-sort ranks maintained through the exchange (NULL cell_count: a count kernel runs later instead): the fused
+    // move + pack kernel has ranked the entities that stay, so whoever is placed, relocated or appended as a ghost
+    // afterwards takes / keeps its own rank and the per-cell counters are complete when the integrate is done
+    uint32_t* cell_count;
+    uint32_t* rank;
+    uint32_t c0, c1;  // counted cell range; keys outside it get CSORT_SKIP
 };
+constexpr uint32_t CSORT_SKIP = 0xffffffffu;  // rank of an entity that is left out of the cell order
 
 int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr);
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,

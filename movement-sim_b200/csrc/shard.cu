@@ -28,6 +28,11 @@ __device__ __forceinline__ void set_arrived_bit(uint32_t* mask, uint32_t e, bool
     else atomicAnd(w, ~bit);
 }
 
+// rank of an entity that joins the cell order after the move kernel has ranked the ones that stayed
+__device__ __forceinline__ void take_rank(const ShardArrays& a, uint32_t e, uint32_t key) {
+    if (a.cell_count) a.rank[e] = (key - a.c0 < a.c1 - a.c0) ? atomicAdd(&a.cell_count[key], 1u) : CSORT_SKIP;
+}
+
 // one tiny launch instead of three memsets: clears the two headers and the hole / ghost counters
 __global__ void shard_reset_kernel(void* buf_down, void* buf_up, uint32_t* ctr) {
     const uint32_t t = threadIdx.x;
@@ -116,7 +121,9 @@ shard_place_kernel(ShardArrays a, const void* recv_down, uint32_t n_down, const 
     a.color0[e] = make_float4(__uint_as_float(r5.x), __uint_as_float(r5.y), __uint_as_float(r6.x), __uint_as_float(r6.y));
     a.road[e] = r7.x;
     a.gid[e] = r7.y;
-    a.keys[e] = cell_key_of(p, grid);
+    const uint32_t key = cell_key_of(p, grid);
+    a.keys[e] = key;
+    take_rank(a, e, key);
     set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
 }
 
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(128) shard_relocate_kernel(ShardArrays a, cons
     a.road[dst] = a.road[src];
     a.gid[dst] = a.gid[src];
     a.keys[dst] = a.keys[src];
+    if (a.cell_count) a.rank[dst] = a.rank[src];
     set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
 }
 
@@ -147,7 +155,9 @@ shard_append_ghosts_kernel(ShardArrays a, uint32_t first, const void* recv_down,
     else if (i < h_down + h_up) p = halo_of(const_cast<void*>(recv_up), mig_cap)[i - h_down];
     else p = local_ghosts[i - h_down - h_up];
     a.pos_cur[first + i] = p;
-    a.keys[first + i] = cell_key_of(p, grid);
+    const uint32_t key = cell_key_of(p, grid);
+    a.keys[first + i] = key;
+    take_rank(a, first + i, key);
 }
 
 // ---- device-side integrate (asynchronous sharded tick) ------------------------------------------
@@ -164,6 +174,7 @@ __device__ __forceinline__ void copy_entity(const ShardArrays& a, uint32_t src, 
     a.road[dst] = a.road[src];
     a.gid[dst] = a.gid[src];
     a.keys[dst] = a.keys[src];
+    if (a.cell_count) a.rank[dst] = a.rank[src];
     set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
 }
 
@@ -180,7 +191,9 @@ __device__ __forceinline__ void place_record(const ShardArrays& a, const void* b
     a.color0[e] = make_float4(__uint_as_float(r5.x), __uint_as_float(r5.y), __uint_as_float(r6.x), __uint_as_float(r6.y));
     a.road[e] = r7.x;
     a.gid[e] = r7.y;
-    a.keys[e] = cell_key_of(p, grid);
+    const uint32_t key = cell_key_of(p, grid);
+    a.keys[e] = key;
+    take_rank(a, e, key);
     set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
 }
 
@@ -310,7 +323,9 @@ shard_append_ghosts_device_kernel(ShardArrays a, const uint32_t* __restrict__ de
     else if (i < h_down + h_up) p = __ldcg(halo_of(const_cast<void*>(recv_up), mig_cap) + (i - h_down));
     else p = local_ghosts[i - h_down - h_up];
     a.pos_cur[first + i] = p;
-    a.keys[first + i] = cell_key_of(p, grid);
+    const uint32_t key = cell_key_of(p, grid);
+    a.keys[first + i] = key;
+    take_rank(a, first + i, key);
 }
 
 __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int ncx, uint32_t* __restrict__ rows) {
