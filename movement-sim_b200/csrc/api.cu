@@ -138,7 +138,6 @@ struct msim_handle {
     bool p2p_down_ipc{false}, p2p_up_ipc{false};
     bool p2p_connected{false};
     uint32_t p2p_tick{0};
-    uint32_t* p2p_done{nullptr};
     unsigned long long p2p_timeout_ns{10000000000ull};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
@@ -229,7 +228,7 @@ void free_all(msim_handle* h) {
     cudaFree(h->dev_counts); cudaFree(h->gid_alt);
     if (h->p2p_peer_down && h->p2p_down_ipc) cudaIpcCloseMemHandle(h->p2p_peer_down);
     if (h->p2p_peer_up && h->p2p_up_ipc) cudaIpcCloseMemHandle(h->p2p_peer_up);
-    cudaFree(h->p2p_arena); cudaFree(h->p2p_done);
+    cudaFree(h->p2p_arena);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -1128,8 +1127,6 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
     MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_COUNT_WORDS));
-    MSIM_CUDA(h, dev_alloc(&h->p2p_done, 1));
-    MSIM_CUDA(h, cudaMemsetAsync(h->p2p_done, 0, sizeof(uint32_t), h->stream));
     rc = write_dev_counts(h);
     if (rc != MSIM_OK) return rc;
     MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), 2 * (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
@@ -1201,7 +1198,7 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     sh.color0 = h->color0;
     sh.road = h->road;
     sh.gid = h->gid;
-    sh.done_ctr = h->p2p_done;
+    sh.error_word = h->dev_counts + DEV_SHARD_ERROR;
     if (sig) {
         sh.peer_flag_down = sig->flag_down;
         sh.peer_flag_up = sig->flag_up;
@@ -1221,6 +1218,7 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     } else {
         rc = enqueue_move(h, true, &sh);
         if (rc != MSIM_OK) return rc;
+        h->launches += launch_shard_emit(h->stream, shard_arrays(h), sh, &h->prof);  // leavers -> records, headers, flags
         h->awaiting_integrate = true;  // pass B is deferred until the exchange has been integrated
     }
     h->n_ghost = 0;

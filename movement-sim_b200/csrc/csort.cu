@@ -7,7 +7,7 @@
 // key and one pass suffices:
 //   count    rank[e] = atomicAdd(&cell_count[key[e]], 1)   — fused into the move kernel (move.cu), or
 //            cell_count_kernel below when the keys did not come from a move pass (sharded / keygen)
-//   scan     cell_start = exclusive prefix sum of cell_count (three small kernels over the table)
+//   scan     cell_start = exclusive prefix sum of cell_count (two small kernels over the table)
 //   scatter  slot = cell_start[key] + rank: sorted_pos[slot] = pos[e], sorted_idx[slot] = e
 // Per entity that is key W4 + rank W4 in the move pass and key R4 + rank R4 + pos R8 + pos W8 + idx W4
 // in the scatter = 36 B, against 44 B + 24 B for three onesweep passes plus the gather — and far fewer
@@ -63,37 +63,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// phase 2: exclusive scan of the tile totals (one CTA, serial over chunks of 256)
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets_kernel(uint32_t* __restrict__ tile_sums, uint32_t tiles) {
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < tiles; base += SCAN_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < tiles ? tile_sums[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= static_cast<uint32_t>(d)) incl += up;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t before = s_carry;
-        for (uint32_t w = 0; w < warp; w++) before += s_warp[w];
-        if (i < tiles) tile_sums[i] = before + incl - v;
-        __syncthreads();
-        if (threadIdx.x == SCAN_THREADS - 1) s_carry = before + incl;
-        __syncthreads();
-    }
-}
-
-// phase 3: exclusive scan inside each tile + tile offset.  Thread t owns SCAN_ITEMS consecutive cells.
+// phase 2: exclusive scan inside each tile + the sum of the earlier tiles' totals.  Thread t owns SCAN_ITEMS consecutive cells.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ starts) {
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets /* per-tile TOTALS */,
+                  uint32_t* __restrict__ starts) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_before[SCAN_THREADS / 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
@@ -117,10 +91,20 @@ scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uin
         const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= static_cast<uint32_t>(d)) incl += up;
     }
+    // offset of this tile = sum of the totals of the tiles before it (at most ~1.2 k words, L2-resident): cheaper than
+    // a third kernel that scans the totals with one CTA between the two passes over the table
+    uint32_t before = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) before += __ldcg(tile_offsets + t);
+    before = __reduce_add_sync(0xffffffffu, before);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_before[warp] = before;
     __syncthreads();
-    uint32_t run = tile_offsets[blockIdx.x] + incl - sum;
-    for (uint32_t w = 0; w < warp; w++) run += s_warp[w];
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        run += s_before[w];
+        if (static_cast<uint32_t>(w) < warp) run += s_warp[w];
+    }
     // starts has cells + 1 entries: entry `cells` receives the grand total
     if (first + SCAN_ITEMS <= cells) {
         uint4* dst = reinterpret_cast<uint4*>(starts + first);
@@ -143,7 +127,8 @@ scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uin
     }
 }
 
-// two entities per thread: 128-bit position loads, 64-bit key / rank loads
+// two entities per thread: 128-bit position loads, 64-bit key / rank loads.  (Four per thread, with every load hoisted
+// above the first dependent gather, was measured 20 % SLOWER: a warp's stores then spread over 128 slots and coalesce less.)
 __global__ void __launch_bounds__(256)
 cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint2* __restrict__ keys, const uint2* __restrict__ rank,
                     const float4* __restrict__ pos, const uint32_t* __restrict__ starts, float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx) {
@@ -203,10 +188,9 @@ int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells,
     const uint32_t tiles = csort_tiles(cells);
     prof->begin(s, K_CELL_SCAN);
     scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums);
-    scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(tile_sums, tiles);
     scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
     prof->end(s);
-    return 3;
+    return 2;
 }
 
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,

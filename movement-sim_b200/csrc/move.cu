@@ -28,7 +28,6 @@ constexpr int MOVE_ITEMS = 2;  // float4 pairs per thread -> 4 entities per thre
 constexpr float SPEED = 1.4f;  // random_move.comp:750
 
 __device__ __forceinline__ float as_f(uint32_t u) { return __uint_as_float(u); }
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
 // random_move.comp:725-736
 __device__ __forceinline__ uint32_t xorshift128(uint4& s) {
@@ -104,72 +103,55 @@ __device__ __forceinline__ float2 walk(float2 p, float2 t, bool& arrived) {
 // cell order, so neighbouring lanes mostly hold the same key: each run of equal keys in adjacent lanes
 // issues ONE atomic (by its first lane) and shares the result — a few times fewer L2 atomics than one per
 // entity.  Ranks inside a cell are a permutation either way; nothing observable depends on their order.
-__device__ __forceinline__ uint32_t run_rank(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, uint32_t lane) {
+struct RunRank {
+    uint32_t base;     // the run head's atomic result (valid in the head lane only, until finished)
+    uint32_t my_head;  // lane of the head of this lane's run
+};
+// phase 1: find the runs and issue the heads' atomics; the result is not consumed here, so several of these can be
+// in flight per thread before anybody waits (the atomics' L2 round trips dominated the kernel: profiles/r1m)
+__device__ __forceinline__ RunRank run_rank_issue(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, uint32_t lane) {
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool prev_valid = __shfl_up_sync(0xffffffffu, valid ? 1u : 0u, 1) != 0u;
     const bool head = lane == 0 || key != prev || !valid || !prev_valid;
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t my_head = 31u - __clz(heads & ((2u << lane) - 1u));        // nearest head at or below this lane (lane 0 is one)
-    const uint32_t above = my_head == 31u ? 0u : (heads >> (my_head + 1u)) << (my_head + 1u);
+    RunRank r;
+    r.my_head = 31u - __clz(heads & ((2u << lane) - 1u));        // nearest head at or below this lane (lane 0 is one)
+    const uint32_t above = r.my_head == 31u ? 0u : (heads >> (r.my_head + 1u)) << (r.my_head + 1u);
     const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
-    uint32_t base = 0;
-    if (lane == my_head && valid) base = atomicAdd(&cell_count[key], next_head - my_head);
-    base = __shfl_sync(0xffffffffu, base, my_head);
-    return base + (lane - my_head);
+    r.base = 0;
+    if (lane == r.my_head && valid) r.base = atomicAdd(&cell_count[key], next_head - r.my_head);
+    return r;
+}
+// phase 2: every lane of a run takes the head's result plus its distance from the head
+__device__ __forceinline__ uint32_t run_rank_finish(const RunRank& r, uint32_t lane) {
+    return __shfl_sync(0xffffffffu, r.base, r.my_head) + (lane - r.my_head);
 }
 
 // ---- fused shard pack (multi-GPU bands, shard.cu) ------------------------------------------------
-// A leaver: its new cell row is outside the band.  Rare (a few hundred per boundary per tick), so it is
-// kept out of line.  The record carries the state BEFORE pass B (target of the waypoint just reached,
-// arrival bit set): pass B runs on whichever GPU owns the entity after the exchange, and yields the same
-// result there because new_target() reads nothing but the entity and the replicated road graph.
-__device__ __noinline__ void shard_leave(const ShardMoveArgs& sh, uint32_t e, bool down, float2 p_new, float2 p_old, float2 tgt, bool arrived) {
-    void* buf = down ? sh.buf_down : sh.buf_up;
-    const uint32_t slot = atomicAdd(&sh.ctr[down ? SHARD_CTR_MIG_DOWN : SHARD_CTR_MIG_UP], 1u);
-    if (slot < sh.mig_cap) {  // beyond the capacity the count alone reports the overflow
-        uint2* rec = records_of(buf) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
-        const uint4 s = sh.rng[e];
-        const float4 c = sh.color0[e];
-        rec[0] = make_uint2(__float_as_uint(p_new.x), __float_as_uint(p_new.y));
-        rec[1] = make_uint2(__float_as_uint(p_old.x), __float_as_uint(p_old.y));
-        rec[2] = make_uint2(__float_as_uint(tgt.x), __float_as_uint(tgt.y));
-        rec[3] = make_uint2(s.x, s.y);
-        rec[4] = make_uint2(s.z, s.w);
-        rec[5] = make_uint2(__float_as_uint(c.x), __float_as_uint(c.y));
-        rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
-        rec[7] = make_uint2(sh.road[e], sh.gid[e]);
-        rec[8] = make_uint2(arrived ? 1u : 0u, 0u);
-    }
-    const uint32_t hslot = atomicAdd(&sh.ctr[SHARD_CTR_HOLES], 1u);
-    if (hslot < sh.holes_cap) sh.holes[hslot] = e;
-    const uint32_t gslot = atomicAdd(&sh.ctr[SHARD_CTR_LOCAL_GHOSTS], 1u);
-    if (gslot < sh.holes_cap) sh.local_ghosts[gslot] = p_new;  // it lands in the neighbour's boundary row: still within reach of ours
-}
-
-// whole warp calls this once per entity slot; does what shard_pack_kernel does for one entity.  Storage is in
-// cell order, so only the warps at either end of the slot range ever see a boundary row: everybody else
-// leaves after one vote.  List slots come from LOCAL counters; the buffers (which may live in a neighbour's
-// memory) receive plain stores only.  Returns true iff this thread stored into an exchange buffer (it then
-// owes a system-scope fence).
-__device__ __forceinline__ bool shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, float2 p_old, float2 tgt,
-                                               bool arrived) {
+// Whole warp calls this once per entity slot.  Storage is in cell order, so only the warps at either end of
+// the slot range ever see a boundary row: everybody else leaves after one vote.
+//   leaver (new cell row outside the band)  -> its slot goes on the hole list; shard_emit_kernel (shard.cu), a
+//                                              one-CTA kernel right behind this one, writes the migrant records
+//   stays in the band's first / last row    -> its position is appended to the halo list of that side's exchange
+//                                              buffer (local send buffer, or the neighbour's receive buffer over
+//                                              NVLink peer memory: plain stores, the slot comes from a LOCAL counter)
+__device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new) {
     const bool low = valid && sh.buf_down && key < sh.lo_key + sh.ncx;   // leaves downwards or sits in the first row
     const bool high = valid && sh.buf_up && key >= sh.hi_key - sh.ncx;   // leaves upwards or sits in the last row
-    if (!__any_sync(0xffffffffu, low || high)) return false;
-    const bool go_down = low && key < sh.lo_key;
-    const bool go_up = high && key >= sh.hi_key;
-    if (go_down || go_up) shard_leave(sh, e, go_down, p_new, p_old, tgt, arrived);
-    if (sh.buf_down) {  // halo: owned entities that stay, in the band's first / last row
-        const bool halo = low && !go_down && !go_up;
+    if (!__any_sync(0xffffffffu, low || high)) return;
+    const bool leaves = (low && key < sh.lo_key) || (high && key >= sh.hi_key);
+    const uint32_t hslot = warp_append(leaves, &sh.ctr[SHARD_CTR_HOLES]);
+    if (leaves && hslot < sh.holes_cap) sh.holes[hslot] = e;
+    if (sh.buf_down) {
+        const bool halo = low && !leaves;
         const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_DOWN]);
         if (halo && slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
     }
     if (sh.buf_up) {
-        const bool halo = high && !go_down && !go_up;
+        const bool halo = high && !leaves;
         const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_UP]);
         if (halo && slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
     }
-    return low || high;
 }
 
 // EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
@@ -191,7 +173,6 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
     const uint32_t pairs_pad = (pairs + 31u) & ~31u;  // arrays are padded, whole warps stay converged
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t PER_BLOCK = MOVE_THREADS * MOVE_ITEMS;
-    bool wrote_exchange = false;
 
     for (uint32_t base = blockIdx.x * PER_BLOCK; base < pairs_pad; base += gridDim.x * PER_BLOCK) {
         float4 P[MOVE_ITEMS], T[MOVE_ITEMS];
@@ -205,6 +186,7 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                 T[k] = __ldcs(target + pi);
             }
         }
+        RunRank R0[MOVE_ITEMS], R1[MOVE_ITEMS];
 #pragma unroll
         for (int k = 0; k < MOVE_ITEMS; k++) {
             if (!live[k]) continue;  // warp-uniform
@@ -230,16 +212,25 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                         v0 = v0 && !((sh.buf_down && k0 < sh.lo_key) || (sh.buf_up && k0 >= sh.hi_key));
                         v1 = v1 && !((sh.buf_down && k1 < sh.lo_key) || (sh.buf_up && k1 >= sh.hi_key));
                     }
-                    rank[pi] = make_uint2(run_rank(cell_count, k0, v0, lane), run_rank(cell_count, k1, v1, lane));
+                    R0[k] = run_rank_issue(cell_count, k0, v0, lane);
+                    R1[k] = run_rank_issue(cell_count, k1, v1, lane);
                 }
                 for (int p = 0; p < hist_passes; p++) {
                     if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                     if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                 }
                 if (SHARD) {
-                    wrote_exchange |= shard_classify(sh, e0, e0 < n, k0, q0, make_float2(P[k].x, P[k].y), make_float2(T[k].x, T[k].y), arr0);
-                    wrote_exchange |= shard_classify(sh, e1, e1 < n, k1, q1, make_float2(P[k].z, P[k].w), make_float2(T[k].z, T[k].w), arr1);
+                    shard_classify(sh, e0, e0 < n, k0, q0);
+                    shard_classify(sh, e1, e1 < n, k1, q1);
                 }
+            }
+        }
+        if (EMIT_KEYS && cell_count) {  // all of this thread's rank atomics are in flight by now
+#pragma unroll
+            for (int k = 0; k < MOVE_ITEMS; k++) {
+                if (!live[k]) continue;
+                const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
+                rank[pi] = make_uint2(run_rank_finish(R0[k], lane), run_rank_finish(R1[k], lane));
             }
         }
     }
@@ -247,39 +238,6 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
         __syncthreads();
         for (int i = threadIdx.x; i < hist_passes * RADIX; i += MOVE_THREADS)
             if (ghist && s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
-    }
-    if (SHARD) {
-        // Every thread that stored into an exchange buffer makes its stores visible system-wide (only the few threads at
-        // either end of the slot range ever do), the CTA meets at a barrier and checks out with a fence + atomic (release
-        // pattern, cumulative over the barrier).  The last CTA to check out publishes the list lengths into the buffer
-        // headers and, for the peer-memory exchange, raises the neighbours' flags, on which their integrate kernels spin.
-        if (wrote_exchange) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const uint32_t prev = atomicAdd(sh.done_ctr, 1u);
-            if (prev == gridDim.x - 1u) {
-                *sh.done_ctr = 0u;  // next launch on this stream starts from zero
-                __threadfence();
-                if (sh.buf_down) {
-                    const uint32_t m = ld_volatile(sh.ctr + SHARD_CTR_MIG_DOWN), hl = ld_volatile(sh.ctr + SHARD_CTR_HALO_DOWN);
-                    ShardHeader* hd = header_of(sh.buf_down);
-                    hd->n_migrants = m;
-                    hd->n_halo = hl;
-                    hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
-                }
-                if (sh.buf_up) {
-                    const uint32_t m = ld_volatile(sh.ctr + SHARD_CTR_MIG_UP), hl = ld_volatile(sh.ctr + SHARD_CTR_HALO_UP);
-                    ShardHeader* hd = header_of(sh.buf_up);
-                    hd->n_migrants = m;
-                    hd->n_halo = hl;
-                    hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
-                }
-                __threadfence_system();
-                if (sh.peer_flag_down) st_release_sys(sh.peer_flag_down, sh.signal_value);
-                if (sh.peer_flag_up) st_release_sys(sh.peer_flag_up, sh.signal_value);
-            }
-        }
     }
 }
 
@@ -344,11 +302,10 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
                 const uint32_t* n_dev, const ShardMoveArgs* shard) {
-    if (n == 0 && !shard) return 0;  // an empty band still has to publish its (empty) headers and signal its neighbours
+    if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
     uint32_t blocks = (pairs + per_block - 1) / per_block;
-    if (blocks == 0) blocks = 1;
     const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;  // 8 x 256 threads = 2048 threads per SM
     if (blocks > resident) blocks = resident;  // grid-stride: a whole number of CTAs per SM
     const float4* pin = reinterpret_cast<const float4*>(pos_in);

@@ -80,10 +80,10 @@ struct ShardMoveArgs {
     const float4* color0;
     const uint32_t* road;
     const uint32_t* gid;
-    // peer-memory exchange: buf_down / buf_up are the NEIGHBOURS' receive buffers (NVLink peer pointers); the last
-    // CTA of the kernel publishes `signal_value` into their flag words after a system-scope fence
-    uint32_t* done_ctr;        // CTA check-out counter: the last CTA publishes the headers (and the flags, if any)
-    uint32_t* peer_flag_down;
+    // peer-memory exchange: buf_down / buf_up are the NEIGHBOURS' receive buffers (NVLink peer pointers); the emit
+    // kernel behind the move kernel publishes `signal_value` into their flag words after a system-scope fence
+    uint32_t* error_word;      // |= 2 when the hole list overflows
+    uint32_t* peer_flag_down;  // raised by shard_emit_kernel once everything of this tick is in the buffers
     uint32_t* peer_flag_up;
     uint32_t signal_value;
 };
@@ -218,9 +218,9 @@ struct ShardHeader {
     uint32_t pad[5];
 };
 constexpr uint32_t MIGRANT_BYTES = 72;  // pos, pos_prev, target, rng, color0, road, gid, arrived bit
-// counters of one pack (device, cleared per tick).  The fused move + pack kernel counts migrants / halo entries HERE, in local
-// memory, and publishes the totals into the (possibly remote) buffer headers once, from its last CTA: the exchange buffers
-// only ever see plain stores, never an atomic round trip over NVLink
+// counters of one pack (device, cleared per tick).  The fused move + pack kernels count leavers / halo entries HERE, in local
+// memory, and publish the totals into the (possibly remote) buffer headers once: the exchange buffers only ever see plain
+// stores, never an atomic round trip over NVLink
 enum { SHARD_CTR_HOLES = 0, SHARD_CTR_LOCAL_GHOSTS = 1, SHARD_CTR_MIG_DOWN = 2, SHARD_CTR_MIG_UP = 3, SHARD_CTR_HALO_DOWN = 4, SHARD_CTR_HALO_UP = 5,
        SHARD_CTR_COUNT = 8 };
 
@@ -248,6 +248,7 @@ int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
                       const uint32_t* n_dev = nullptr, bool reset = true);
 int launch_shard_signal(cudaStream_t s, uint32_t* flag_down, uint32_t* flag_up, uint32_t value);
+int launch_shard_emit(cudaStream_t s, const ShardArrays& a, const struct ShardMoveArgs& sh, Profiler* prof);
 // device-side integrate (asynchronous sharded tick): placement, tail compaction and the new counts without a host round trip
 enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_SHARD_ERROR = 3, DEV_HALO_DOWN = 4, DEV_HALO_UP = 5, DEV_COUNT_WORDS = 8 };
 // device-side wait of the peer-memory exchange: the integrate kernel spins until both flag words reach `expected`

@@ -160,6 +160,75 @@ shard_append_ghosts_kernel(ShardArrays a, uint32_t first, const void* recv_down,
     take_rank(a, first + i, key);
 }
 
+// ---- second half of the fused move + pack ---------------------------------------------------------
+// One CTA right behind the move kernel: turns the hole list the move kernel left (slots of the leavers, a few hundred
+// per boundary per tick) into migrant records in the exchange buffers, keeps the leavers' positions as local ghosts,
+// publishes the list lengths into the buffer headers and - peer-memory exchange - raises the neighbours' flags.
+// Records carry the state BEFORE pass B (target = the waypoint just reached, arrival bit set): pass B runs on
+// whichever GPU owns the entity after the exchange and yields the same result there, because new_target() reads
+// nothing but the entity and the replicated road graph.
+// The buffers may live in a neighbour's memory: they only ever see plain stores; every counter is local.  The move
+// kernel's halo stores are complete when this kernel starts (stream order); this kernel's own stores are fenced at
+// system scope before the flags go up.
+constexpr int EMIT_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+__global__ void __launch_bounds__(EMIT_THREADS) shard_emit_kernel(ShardArrays a, ShardMoveArgs sh) {
+    __shared__ uint32_t s_mig[2];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 2) s_mig[tid] = 0;
+    __syncthreads();
+    const uint32_t k_out = min(sh.ctr[SHARD_CTR_HOLES], sh.holes_cap);
+    for (uint32_t i = tid; i < k_out; i += EMIT_THREADS) {
+        const uint32_t e = sh.holes[i];
+        const bool down = sh.buf_down && a.keys[e] < sh.lo_key;
+        const float2 p = a.pos_cur[e];
+        const uint32_t slot = atomicAdd(&s_mig[down ? 0 : 1], 1u);
+        if (slot < sh.mig_cap) {  // beyond the capacity the count alone reports the overflow
+            uint2* rec = records_of(down ? sh.buf_down : sh.buf_up) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
+            const float2 pp = a.pos_prev[e], t = a.target[e];
+            const uint4 r = a.rng[e];
+            const float4 c = a.color0[e];
+            const uint32_t arrived = (a.arrived[arrived_word(e)] >> arrived_bit(e)) & 1u;
+            rec[0] = make_uint2(__float_as_uint(p.x), __float_as_uint(p.y));
+            rec[1] = make_uint2(__float_as_uint(pp.x), __float_as_uint(pp.y));
+            rec[2] = make_uint2(__float_as_uint(t.x), __float_as_uint(t.y));
+            rec[3] = make_uint2(r.x, r.y);
+            rec[4] = make_uint2(r.z, r.w);
+            rec[5] = make_uint2(__float_as_uint(c.x), __float_as_uint(c.y));
+            rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
+            rec[7] = make_uint2(a.road[e], a.gid[e]);
+            rec[8] = make_uint2(arrived, 0u);
+        }
+        sh.local_ghosts[i] = p;  // it lands in the neighbour's boundary row: still within reach of ours
+    }
+    // barrier, then ONE thread writes the headers and fences at system scope (fences are cumulative over the barrier)
+    // before it raises the flags
+    __syncthreads();
+    if (tid == 0) {
+        sh.ctr[SHARD_CTR_LOCAL_GHOSTS] = k_out;
+        if (sh.ctr[SHARD_CTR_HOLES] > sh.holes_cap) atomicOr(sh.error_word, 2u);
+        if (sh.buf_down) {
+            const uint32_t m = s_mig[0], hl = ld_volatile_u32(sh.ctr + SHARD_CTR_HALO_DOWN);
+            ShardHeader* hd = header_of(sh.buf_down);
+            hd->n_migrants = m;
+            hd->n_halo = hl;
+            hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+        }
+        if (sh.buf_up) {
+            const uint32_t m = s_mig[1], hl = ld_volatile_u32(sh.ctr + SHARD_CTR_HALO_UP);
+            ShardHeader* hd = header_of(sh.buf_up);
+            hd->n_migrants = m;
+            hd->n_halo = hl;
+            hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+        }
+        __threadfence_system();
+        if (sh.peer_flag_down) st_release_sys(sh.peer_flag_down, sh.signal_value);
+        if (sh.peer_flag_up) st_release_sys(sh.peer_flag_up, sh.signal_value);
+    }
+}
+
 // ---- device-side integrate (asynchronous sharded tick) ------------------------------------------
 // Same bookkeeping as msim_shard_integrate's host code, done by ONE CTA so that the tick needs no host
 // round trip: arrivals fill the leavers' holes (then append), remaining holes are closed with the live
@@ -341,6 +410,13 @@ __global__ void shard_signal_kernel(uint32_t* flag_down, uint32_t* flag_up, uint
 }
 
 }  // namespace
+
+int launch_shard_emit(cudaStream_t s, const ShardArrays& a, const ShardMoveArgs& sh, Profiler* prof) {
+    prof->begin(s, K_SHARD);
+    shard_emit_kernel<<<1, EMIT_THREADS, 0, s>>>(a, sh);
+    prof->end(s);
+    return 1;
+}
 
 int launch_shard_signal(cudaStream_t s, uint32_t* flag_down, uint32_t* flag_up, uint32_t value) {
     shard_signal_kernel<<<1, 1, 0, s>>>(flag_down, flag_up, value);
