@@ -75,6 +75,7 @@ struct msim_handle {
     uint32_t* sorted_idx{nullptr};
     bool use_csort{false};
     bool counts_valid{false};
+    bool counts_dirty{true};   // the counter table is not all-zero (every scan leaves it zeroed: no per-tick memset in steady state)
     uint8_t* flag_sorted{nullptr};
     uint8_t* flag_entity{nullptr};
     void* sort_mem{nullptr};
@@ -300,6 +301,14 @@ int refresh_counts(msim_handle* h) {
     return MSIM_OK;
 }
 
+// The scan that consumes the per-cell counters also zeroes them (csort.cu), so between two collision passes the table is
+// all zero and the next count needs no memset.  Only a count that was never scanned (a move pass that fused the count and
+// was not followed by a collision pass, an upload in between, ...) leaves it dirty: then the whole table is cleared.
+void prepare_counts(msim_handle* h) {
+    if (h->counts_dirty) csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
+    h->counts_dirty = true;  // about to be counted into
+}
+
 int ensure_cells(msim_handle* h) {
     // counting sort: on request, or by default whenever the storage is kept in cell order
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
@@ -311,6 +320,7 @@ int ensure_cells(msim_handle* h) {
     h->cell_capacity = 0;
     if (h->use_csort) {
         MSIM_CUDA(h, dev_alloc(&h->cell_count, static_cast<size_t>(h->grid.ncells) + 1));
+        h->counts_dirty = true;
         MSIM_CUDA(h, dev_alloc(&h->cell_start, static_cast<size_t>(h->grid.ncells) + 1));
         MSIM_CUDA(h, dev_alloc(&h->tile_sums, static_cast<size_t>(csort_tiles(h->grid.ncells))));
     } else {
@@ -429,9 +439,7 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     h->n_ghost = 0;
     h->count_fused = fuse_count && h->sharded;
     if (fuse_count) {
-        uint32_t c0 = 0, c1 = h->grid.ncells;
-        if (h->sharded) csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &c0, &c1);  // band set by the caller (move_pack_common)
-        csort_clear(h->stream, h->cell_count + c0, c1 - c0, &h->prof);
+        prepare_counts(h);
     }
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
@@ -561,11 +569,12 @@ int enqueue_collide(msim_handle* h) {
         const bool band = h->sharded && h->band_valid;
         if (band) csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &c0, &c1);
         if (!h->counts_valid) {  // keys came from keygen or changed in a shard exchange: count them now
-            csort_clear(h->stream, h->cell_count + c0, c1 - c0, &h->prof);
+            prepare_counts(h);
             h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, c0, c1, &h->prof, dev_total(h));
         }
         h->counts_valid = false;
         h->launches += launch_cell_scan(h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->cell_start + c0, &h->prof);
+        h->counts_dirty = false;  // the scan zeroed every counter it read, and nothing was counted outside [c0, c1)
         h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
                                            dev_total(h));
         launch_deferred_arrive(h, true);

@@ -189,21 +189,36 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
 
     // CTA-wide hull of the windows: min of the run starts, max of the run ends
     const bool has_above = mine && ab_lo < ab_hi;
-    uint32_t r0 = __reduce_min_sync(0xffffffffu, mine ? own_lo : 0xffffffffu);
-    uint32_t r1 = __reduce_min_sync(0xffffffffu, has_above ? ab_lo : 0xffffffffu);
-    uint32_t r2 = __reduce_max_sync(0xffffffffu, has_above ? ab_hi : 0u);
-    if (lane == 0) {
-        s_red[0][warp] = r0;
-        s_red[1][warp] = r1;
-        s_red[2][warp] = r2;
-    }
-    __syncthreads();
     uint32_t w_own_lo = 0xffffffffu, w_ab_lo = 0xffffffffu, w_ab_hi = 0;
+    if (PREFIX && !GHOSTS) {
+        // every slot is a querying entity and the run bounds come from ONE prefix table: they are non-decreasing in the
+        // slot index, so the hull is [bound of the CTA's first slot, bound of its last slot] - no reduction needed.
+        // (Row 0 has no row above: bound 0, which keeps the hull a superset; such a CTA may fall back to the global scan.)
+        if (threadIdx.x == 0) {
+            s_red[0][0] = own_lo;
+            s_red[1][0] = cy > 0 ? ab_lo : 0u;
+        }
+        if (j == min(block_base + QUERY_THREADS, n) - 1u) s_red[2][0] = cy > 0 ? ab_hi : 0u;
+        __syncthreads();
+        w_own_lo = s_red[0][0];
+        w_ab_lo = s_red[1][0];
+        w_ab_hi = s_red[2][0];
+    } else {
+        uint32_t r0 = __reduce_min_sync(0xffffffffu, mine ? own_lo : 0xffffffffu);
+        uint32_t r1 = __reduce_min_sync(0xffffffffu, has_above ? ab_lo : 0xffffffffu);
+        uint32_t r2 = __reduce_max_sync(0xffffffffu, has_above ? ab_hi : 0u);
+        if (lane == 0) {
+            s_red[0][warp] = r0;
+            s_red[1][warp] = r1;
+            s_red[2][warp] = r2;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int w = 0; w < QUERY_THREADS / 32; w++) {
-        w_own_lo = min(w_own_lo, s_red[0][w]);
-        w_ab_lo = min(w_ab_lo, s_red[1][w]);
-        w_ab_hi = max(w_ab_hi, s_red[2][w]);
+        for (int w = 0; w < QUERY_THREADS / 32; w++) {
+            w_own_lo = min(w_own_lo, s_red[0][w]);
+            w_ab_lo = min(w_ab_lo, s_red[1][w]);
+            w_ab_hi = max(w_ab_hi, s_red[2][w]);
+        }
     }
     const uint32_t w_own_hi = min(block_base + QUERY_THREADS, n);  // nobody needs a slot at or above its own
     if (w_ab_lo > w_ab_hi) w_ab_lo = w_ab_hi = 0;

@@ -65,23 +65,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint
 
 // phase 2: exclusive scan inside each tile + the sum of the earlier tiles' totals.  Thread t owns SCAN_ITEMS consecutive cells.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets /* per-tile TOTALS */,
+scan_tiles_kernel(uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets /* per-tile TOTALS */,
                   uint32_t* __restrict__ starts) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_before[SCAN_THREADS / 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
+    // the counters are consumed here: they are zeroed on the way, so the next tick's count needs no memset of the table
     if (first + SCAN_ITEMS <= cells) {
-        const uint4* src = reinterpret_cast<const uint4*>(counts + first);  // first is a multiple of 16: 64-byte aligned
+        uint4* src = reinterpret_cast<uint4*>(counts + first);  // first is a multiple of 16 and the base 16-byte aligned
 #pragma unroll
         for (int q = 0; q < SCAN_ITEMS / 4; q++) {
             const uint4 c = __ldcs(src + q);
             v[4 * q] = c.x; v[4 * q + 1] = c.y; v[4 * q + 2] = c.z; v[4 * q + 3] = c.w;
+            src[q] = make_uint4(0u, 0u, 0u, 0u);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) v[i] = (first + i < cells) ? counts[first + i] : 0u;
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = 0u;
+            if (first + i < cells) {
+                v[i] = counts[first + i];
+                counts[first + i] = 0u;
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) sum += v[i];
@@ -127,8 +135,9 @@ scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t cells, const uin
     }
 }
 
-// two entities per thread: 128-bit position loads, 64-bit key / rank loads.  (Four per thread, with every load hoisted
-// above the first dependent gather, was measured 20 % SLOWER: a warp's stores then spread over 128 slots and coalesce less.)
+// two entities per thread: 128-bit position loads, 64-bit key / rank loads.  Measured and rejected (profiles/r1_final.md):
+// four entities per thread (+20 %: a warp's stores spread over 128 slots and coalesce less) and a software pipeline that
+// issues the next pair's streaming loads before the dependent cell-start gathers (+3 %).
 __global__ void __launch_bounds__(256)
 cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint2* __restrict__ keys, const uint2* __restrict__ rank,
                     const float4* __restrict__ pos, const uint32_t* __restrict__ starts, float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx) {
@@ -184,7 +193,7 @@ int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t
     return 1;
 }
 
-int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof) {
+int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof) {
     const uint32_t tiles = csort_tiles(cells);
     prof->begin(s, K_CELL_SCAN);
     scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums);

@@ -146,7 +146,7 @@ void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler*
 void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int ncy, uint32_t* c0, uint32_t* c1);
 int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
                       const uint32_t* n_dev = nullptr);
-int launch_cell_scan(cudaStream_t s, const uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
+int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
                         float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
 
