@@ -218,7 +218,7 @@ def run_reference(args):
                       if use_ref else "oracle port (move + cell-grid collisions) on all threads"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32",
         "data": "synthetic", "config": {"workload": args.workload, "entities_sampled": sample, "collisions": w["collisions"], "map": w["map_desc"]},
         "cpu_baseline": {"value": value, "unit": "entity-updates/s", "cores": threads, "kind": kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -408,7 +408,7 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
         "config": {"workload": args.workload, "entities": n, "collisions": collisions, "collision_radius_m": 10.0, "map": w["map_desc"],
                    "entity_seed": 42, "preroll_move_passes": args.preroll, "pair_count": collisions,
                    "l2": ("flushed between timed steps (512 MiB fill)" if small else "inputs larger than L2 (no flush)"),
