@@ -57,7 +57,11 @@ int msim_shard_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi, void*
  *                                 (MSIM_P2P_HANDLE_BYTES bytes, for neighbours in other processes) and / or
  *                                 its device pointer (for neighbours driven by this process)
  *   msim_shard_p2p_connect        opens the neighbours' arenas from their IPC handles (NULL = no neighbour)
- *   msim_shard_p2p_connect_local  same, from device pointers of arenas living in this process
+ *   msim_shard_p2p_connect_local  same, from device pointers of arenas living in this process.  Handles connected
+ *                                 this way may share one stream if every band's move_pack is enqueued before
+ *                                 any band's integrate (the flag wait would otherwise wait for a kernel queued
+ *                                 behind itself); handles connected over IPC publish, wait and integrate in ONE
+ *                                 kernel launched by msim_shard_p2p_integrate
  * All ranks must use the same migrant / halo capacities (they fix the buffer layout). */
 #define MSIM_P2P_HANDLE_BYTES 64
 int msim_shard_p2p_create(msim_handle* h, void* ipc_handle_out, void** arena_out);

@@ -142,6 +142,9 @@ struct msim_handle {
     unsigned long long p2p_timeout_ns{10000000000ull};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
+    bool p2p_merged{true};            // emit rides in the exchange kernel (false: separate launch right behind the move kernel)
+    bool emit_pending{false};         // peer-memory exchange: the emit step rides in the exchange kernel of msim_shard_p2p_integrate
+    ShardMoveArgs pending_emit{};
     bool count_fused{false};          // the last move + pack ranked the stayers: place / relocate / ghost kernels complete the per-cell counters
     bool awaiting_integrate{false};   // a fused move + pack has run: pass B stays deferred until the exchange has been integrated
     bool band_valid{false};           // false between a move pass and the integrate that follows it
@@ -1227,7 +1230,12 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     } else {
         rc = enqueue_move(h, true, &sh);
         if (rc != MSIM_OK) return rc;
-        h->launches += launch_shard_emit(h->stream, shard_arrays(h), sh, &h->prof);  // leavers -> records, headers, flags
+        if (sig && h->p2p_merged) {  // peer-memory exchange: emit, wait, integrate and ghosts are ONE kernel, launched by msim_shard_p2p_integrate
+            h->pending_emit = sh;
+            h->emit_pending = true;
+        } else {
+            h->launches += launch_shard_emit(h->stream, shard_arrays(h), sh, &h->prof);  // leavers -> records, headers
+        }
         h->awaiting_integrate = true;  // pass B is deferred until the exchange has been integrated
     }
     h->n_ghost = 0;
@@ -1237,10 +1245,11 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     return MSIM_OK;
 }
 
-int integrate_device_common(msim_handle* h, const void* recv_down, const void* recv_up, const ShardWait* wait) {
-    h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
-                                                 h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
-                                                 h->grid, &h->prof, wait);
+int integrate_device_common(msim_handle* h, const void* recv_down, const void* recv_up, const ShardWait* wait, bool launch = true) {
+    if (launch)
+        h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
+                                                     h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
+                                                     h->grid, &h->prof, wait);
     h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
     h->band_valid = h->packed;
     h->packed = false;
@@ -1320,6 +1329,12 @@ int msim_shard_p2p_connect_local(msim_handle* h, void* down_arena, void* up_aren
     h->p2p_peer_down = static_cast<char*>(down_arena);
     h->p2p_peer_up = static_cast<char*>(up_arena);
     h->p2p_connected = true;
+    // Neighbours driven by ONE process are usually enqueued on one stream, band after band.  The merged exchange kernel
+    // raises its flags and then waits for the neighbours' in the same launch, which on a single stream would wait for a
+    // kernel queued behind itself; so here the emit step stays a separate launch right behind the move kernel.
+    // MSIM_P2P_MERGED=1 (handles on separate streams) selects the merged kernel anyway.
+    const char* env = std::getenv("MSIM_P2P_MERGED");
+    h->p2p_merged = env && std::atoi(env) != 0;
     return MSIM_OK;
 }
 
@@ -1352,7 +1367,11 @@ int msim_shard_p2p_integrate(msim_handle* h) {
     w.timeout_ns = h->p2p_timeout_ns;
     w.zero_headers = 0;  // headers are overwritten every tick by the sender's last CTA
     h->p2p_tick++;
-    return integrate_device_common(h, recv_down, recv_up, &w);
+    h->launches += launch_shard_exchange(h->stream, shard_arrays(h), h->emit_pending ? &h->pending_emit : nullptr, h->dev_counts, recv_down, recv_up, h->holes,
+                                         h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves, h->grid,
+                                         &h->prof, w);
+    h->emit_pending = false;
+    return integrate_device_common(h, recv_down, recv_up, nullptr, /*launch=*/false);
 }
 
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts) {

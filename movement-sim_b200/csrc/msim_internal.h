@@ -265,6 +265,9 @@ int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
                                   uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
                                   const GridParams& grid, Profiler* prof, const ShardWait* wait = nullptr);
+int launch_shard_exchange(cudaStream_t s, const ShardArrays& a, const struct ShardMoveArgs* emit, uint32_t* dev_counts, const void* recv_down, const void* recv_up,
+                          const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts, uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap,
+                          uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves, const GridParams& grid, Profiler* prof, const ShardWait& wait);
 int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
                        const uint32_t* dst, const GridParams& grid, Profiler* prof);
 int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof);

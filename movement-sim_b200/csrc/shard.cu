@@ -174,7 +174,7 @@ constexpr int EMIT_THREADS = 1024;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
-__global__ void __launch_bounds__(EMIT_THREADS) shard_emit_kernel(ShardArrays a, ShardMoveArgs sh) {
+__device__ __forceinline__ void emit_body(const ShardArrays& a, const ShardMoveArgs& sh) {
     __shared__ uint32_t s_mig[2];
     const uint32_t tid = threadIdx.x;
     if (tid < 2) s_mig[tid] = 0;
@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) shard_emit_kernel(ShardArrays a,
         if (sh.peer_flag_up) st_release_sys(sh.peer_flag_up, sh.signal_value);
     }
 }
+
+__global__ void __launch_bounds__(EMIT_THREADS) shard_emit_kernel(ShardArrays a, ShardMoveArgs sh) { emit_body(a, sh); }
 
 // ---- device-side integrate (asynchronous sharded tick) ------------------------------------------
 // Same bookkeeping as msim_shard_integrate's host code, done by ONE CTA so that the tick needs no host
@@ -285,10 +287,31 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t expecte
 
 constexpr int INTEGRATE_THREADS = 1024;
 
-__global__ void __launch_bounds__(INTEGRATE_THREADS)
-shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const void* sent_down, const void* sent_up, const void* recv_down,
-                       const void* recv_up, const uint32_t* __restrict__ holes, const uint32_t* __restrict__ ctr, uint32_t mig_cap, uint32_t halo_cap,
-                       uint32_t holes_cap, uint32_t entity_cap, uint32_t* __restrict__ tail_bits, uint2* __restrict__ moves, GridParams grid, ShardWait wait) {
+struct IntegrateArgs {
+    uint32_t* dev_counts;
+    const void* sent_down;
+    const void* sent_up;
+    const void* recv_down;
+    const void* recv_up;
+    const uint32_t* holes;
+    const uint32_t* ctr;
+    const float2* local_ghosts;
+    uint32_t mig_cap, halo_cap, holes_cap, entity_cap;
+    uint32_t* tail_bits;
+    uint2* moves;
+};
+
+__device__ __forceinline__ void integrate_body(const ShardArrays& a, const IntegrateArgs& ia, const GridParams& grid, const ShardWait& wait) {
+    uint32_t* __restrict__ dev_counts = ia.dev_counts;
+    const void* sent_down = ia.sent_down;
+    const void* sent_up = ia.sent_up;
+    const void* recv_down = ia.recv_down;
+    const void* recv_up = ia.recv_up;
+    const uint32_t* __restrict__ holes = ia.holes;
+    const uint32_t* __restrict__ ctr = ia.ctr;
+    const uint32_t mig_cap = ia.mig_cap, halo_cap = ia.halo_cap, holes_cap = ia.holes_cap, entity_cap = ia.entity_cap;
+    uint32_t* __restrict__ tail_bits = ia.tail_bits;
+    uint2* __restrict__ moves = ia.moves;
     __shared__ uint32_t s_n_old, s_n_new, s_k_out, s_in_down, s_in_up, s_ghosts, s_low, s_live, s_err;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
@@ -379,22 +402,47 @@ shard_integrate_kernel(ShardArrays a, uint32_t* __restrict__ dev_counts, const v
     }
 }
 
-// ghosts behind the owned entities, counts taken from device memory (grid sized for the capacities)
+// ghosts behind the owned entities, counts taken from device memory
+__device__ __forceinline__ void ghosts_body(const ShardArrays& a, const uint32_t* __restrict__ dev_counts, const void* recv_down, const void* recv_up,
+                                            const float2* __restrict__ local_ghosts, uint32_t mig_cap, const GridParams& grid, uint32_t first_thread,
+                                            uint32_t stride) {
+    const uint32_t first = dev_counts[DEV_N_OWNED], ghosts = dev_counts[DEV_N_GHOST];
+    const uint32_t h_down = dev_counts[DEV_HALO_DOWN], h_up = dev_counts[DEV_HALO_UP];  // validated by the integrate step
+    for (uint32_t i = first_thread; i < ghosts; i += stride) {
+        float2 p;
+        if (i < h_down) p = __ldcg(halo_of(const_cast<void*>(recv_down), mig_cap) + i);
+        else if (i < h_down + h_up) p = __ldcg(halo_of(const_cast<void*>(recv_up), mig_cap) + (i - h_down));
+        else p = local_ghosts[i - h_down - h_up];
+        a.pos_cur[first + i] = p;
+        const uint32_t key = cell_key_of(p, grid);
+        a.keys[first + i] = key;
+        take_rank(a, first + i, key);
+    }
+}
+
+__global__ void __launch_bounds__(INTEGRATE_THREADS) shard_integrate_kernel(ShardArrays a, IntegrateArgs ia, GridParams grid, ShardWait wait) {
+    integrate_body(a, ia, grid, wait);
+}
+
 __global__ void __launch_bounds__(256)
 shard_append_ghosts_device_kernel(ShardArrays a, const uint32_t* __restrict__ dev_counts, const void* recv_down, const void* recv_up,
-                                  const float2* __restrict__ local_ghosts, uint32_t mig_cap, uint32_t halo_cap, GridParams grid) {
-    const uint32_t first = dev_counts[DEV_N_OWNED], ghosts = dev_counts[DEV_N_GHOST];
-    const uint32_t h_down = dev_counts[DEV_HALO_DOWN], h_up = dev_counts[DEV_HALO_UP];  // validated by the integrate kernel
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ghosts) return;
-    float2 p;
-    if (i < h_down) p = __ldcg(halo_of(const_cast<void*>(recv_down), mig_cap) + i);
-    else if (i < h_down + h_up) p = __ldcg(halo_of(const_cast<void*>(recv_up), mig_cap) + (i - h_down));
-    else p = local_ghosts[i - h_down - h_up];
-    a.pos_cur[first + i] = p;
-    const uint32_t key = cell_key_of(p, grid);
-    a.keys[first + i] = key;
-    take_rank(a, first + i, key);
+                                  const float2* __restrict__ local_ghosts, uint32_t mig_cap, GridParams grid) {
+    ghosts_body(a, dev_counts, recv_down, recv_up, local_ghosts, mig_cap, grid, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// Peer-memory exchange, the whole middle of a sharded tick in ONE single-CTA launch: publish what the move kernel left
+// (emit: records, headers, flags), wait for both neighbours' flags, integrate their buffers, append the ghosts.  Three
+// latency-bound launches became one; the ghost lists are a few thousand entries, well within one CTA's reach.
+__global__ void __launch_bounds__(INTEGRATE_THREADS)
+shard_exchange_kernel(ShardArrays a, ShardMoveArgs sh, int do_emit, IntegrateArgs ia, GridParams grid, ShardWait wait) {
+    if (do_emit) {
+        emit_body(a, sh);
+        __syncthreads();
+    }
+    integrate_body(a, ia, grid, wait);
+    __threadfence_block();
+    __syncthreads();  // dev_counts written by thread 0 above
+    ghosts_body(a, ia.dev_counts, ia.recv_down, ia.recv_up, ia.local_ghosts, ia.mig_cap, grid, threadIdx.x, INTEGRATE_THREADS);
 }
 
 __global__ void __launch_bounds__(256) shard_row_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int ncx, uint32_t* __restrict__ rows) {
@@ -466,18 +514,54 @@ int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t fi
     return 1;
 }
 
+namespace {
+IntegrateArgs integrate_args(uint32_t* dev_counts, const void* sent_down, const void* sent_up, const void* recv_down, const void* recv_up,
+                             const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts, uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap,
+                             uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves) {
+    IntegrateArgs ia{};
+    ia.dev_counts = dev_counts;
+    ia.sent_down = sent_down;
+    ia.sent_up = sent_up;
+    ia.recv_down = recv_down;
+    ia.recv_up = recv_up;
+    ia.holes = holes;
+    ia.ctr = ctr;
+    ia.local_ghosts = local_ghosts;
+    ia.mig_cap = mig_cap;
+    ia.halo_cap = halo_cap;
+    ia.holes_cap = holes_cap;
+    ia.entity_cap = entity_cap;
+    ia.tail_bits = scratch_bits;
+    ia.moves = scratch_moves;
+    return ia;
+}
+}  // namespace
+
 int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
                                   uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
                                   const GridParams& grid, Profiler* prof, const ShardWait* wait) {
     prof->begin(s, K_SHARD);
     const ShardWait none{};
-    shard_integrate_kernel<<<1, INTEGRATE_THREADS, 0, s>>>(a, dev_counts, sent_down, sent_up, recv_down, recv_up, holes, ctr, mig_cap, halo_cap, holes_cap,
-                                                           entity_cap, scratch_bits, scratch_moves, grid, wait ? *wait : none);
+    const IntegrateArgs ia = integrate_args(dev_counts, sent_down, sent_up, recv_down, recv_up, holes, ctr, local_ghosts, mig_cap, halo_cap, holes_cap,
+                                            entity_cap, scratch_bits, scratch_moves);
+    shard_integrate_kernel<<<1, INTEGRATE_THREADS, 0, s>>>(a, ia, grid, wait ? *wait : none);
     const uint32_t max_ghosts = 2u * halo_cap + holes_cap;
-    shard_append_ghosts_device_kernel<<<(max_ghosts + 255u) / 256u, 256, 0, s>>>(a, dev_counts, recv_down, recv_up, local_ghosts, mig_cap, halo_cap, grid);
+    shard_append_ghosts_device_kernel<<<(max_ghosts + 255u) / 256u, 256, 0, s>>>(a, dev_counts, recv_down, recv_up, local_ghosts, mig_cap, grid);
     prof->end(s);
     return 2;
+}
+
+int launch_shard_exchange(cudaStream_t s, const ShardArrays& a, const ShardMoveArgs* emit, uint32_t* dev_counts, const void* recv_down, const void* recv_up,
+                          const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts, uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap,
+                          uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves, const GridParams& grid, Profiler* prof, const ShardWait& wait) {
+    prof->begin(s, K_SHARD);
+    const ShardMoveArgs none{};
+    const IntegrateArgs ia = integrate_args(dev_counts, nullptr, nullptr, recv_down, recv_up, holes, ctr, local_ghosts, mig_cap, halo_cap, holes_cap,
+                                            entity_cap, scratch_bits, scratch_moves);
+    shard_exchange_kernel<<<1, INTEGRATE_THREADS, 0, s>>>(a, emit ? *emit : none, emit ? 1 : 0, ia, grid, wait);
+    prof->end(s);
+    return 1;
 }
 
 int launch_shard_row_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, int ncx, uint32_t* rows, uint32_t nrows, Profiler* prof) {

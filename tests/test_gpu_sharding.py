@@ -189,6 +189,46 @@ def test_bands_peer_memory_exchange_rebalance_dense_corner(msim, orc, small_city
     assert pairs == want_pairs
 
 
+def test_peer_memory_exchange_merged_kernel_on_separate_streams(msim, orc, small_city, monkeypatch):
+    """The kernel multi-process ranks run (publish + wait + integrate + ghosts in one launch), exercised on one GPU: each band
+    on its own library-owned stream, so that a band's wait can overlap the neighbour's launch."""
+    from movement_sim_b200 import sharding as S
+
+    monkeypatch.setenv("MSIM_P2P_MERGED", "1")
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
+    total, ticks, world, cap = 40_000, 40, 3, 1 << 14
+    hist, ncx, ncy = S.global_row_histogram(msim, small_city, total, 42, 10.0)
+    splits = S.balanced_splits(hist, world)
+    sims = []
+    for r in range(world):
+        ents, gids = S.collect_band(msim, small_city, total, 42, 10.0, int(splits[r]), int(splits[r + 1]))
+        sim = msim.Simulation(small_city, ents, radius=10.0, capacity=total + 8 * cap)  # own stream
+        sim.shard_enable(gids, cap, cap)
+        sim.dispatch(2)
+        sims.append(sim)
+    arenas = [s.shard_p2p_create()[1] for s in sims]
+    for r, s in enumerate(sims):
+        s.shard_p2p_connect_local(arenas[r - 1] if r > 0 else None, arenas[r + 1] if r + 1 < world else None)
+    pairs = []
+    for t in range(ticks):
+        for r, s in enumerate(sims):  # nothing here waits for the GPU: three streams run three bands concurrently
+            s.shard_p2p_move_pack(int(splits[r]), int(splits[r + 1]))
+            s.shard_p2p_integrate()
+            s.enqueue_collide()
+        pairs.append(sum(s.stats()["last_pair_count"] for s in sims))
+    got = np.zeros(total, dtype=msim.ENTITY_DTYPE)
+    seen = np.zeros(total, dtype=np.int32)
+    for s in sims:
+        e, g = s.read_entities(), s.shard_read_gids()
+        got[g] = e
+        seen[g] += 1
+        s.close()
+    assert (seen == 1).all()
+    want, want_pairs = oracle_reference(msim, orc, small_city, total, 42, 10.0, ticks)
+    assert_entities_equal(got, want, what="3 bands, merged exchange kernel")
+    assert pairs == want_pairs
+
+
 def test_peer_memory_exchange_times_out_instead_of_hanging(msim, small_city, monkeypatch):
     """A neighbour that never enqueues its tick: the integrate kernel gives up after MSIM_P2P_TIMEOUT_MS and the error surfaces."""
     import torch
