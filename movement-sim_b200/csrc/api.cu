@@ -1365,7 +1365,6 @@ int msim_shard_p2p_integrate(msim_handle* h) {
     w.flag_up = recv_up ? p2p_flag(h->p2p_arena, 1) : nullptr;
     w.expected = h->p2p_tick + 1u;
     w.timeout_ns = h->p2p_timeout_ns;
-    w.zero_headers = 0;  // headers are overwritten every tick by the sender's last CTA
     h->p2p_tick++;
     h->launches += launch_shard_exchange(h->stream, shard_arrays(h), h->emit_pending ? &h->pending_emit : nullptr, h->dev_counts, recv_down, recv_up, h->holes,
                                          h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves, h->grid,

@@ -257,9 +257,6 @@ struct ShardWait {
     const uint32_t* flag_up;
     uint32_t expected;
     unsigned long long timeout_ns;
-    int zero_headers;           // the receive buffers are ours: clear their headers for the tick after next
-    void* zero_recv_down;
-    void* zero_recv_up;
 };
 int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,

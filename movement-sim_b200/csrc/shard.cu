@@ -394,12 +394,6 @@ __device__ __forceinline__ void integrate_body(const ShardArrays& a, const Integ
         dev_counts[DEV_N_TOTAL] = n_new + s_ghosts;
         if (s_err) atomicOr(&dev_counts[DEV_SHARD_ERROR], s_err);
     }
-    if (wait.zero_headers && tid < 8u) {
-        // peer-memory exchange: the headers are counters the neighbour's NEXT-BUT-ONE move kernel adds to (two buffers per
-        // side, used alternately); it cannot start before it has seen the flag our next move kernel raises
-        if (wait.zero_recv_down) static_cast<uint32_t*>(wait.zero_recv_down)[tid] = 0u;
-        if (wait.zero_recv_up) static_cast<uint32_t*>(wait.zero_recv_up)[tid] = 0u;
-    }
 }
 
 // ghosts behind the owned entities, counts taken from device memory

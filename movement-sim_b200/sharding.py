@@ -3,10 +3,16 @@ plumbing.  The reference is single-device (/root/reference/src/sim/Simulator.cpp
 N msim handles behave like one.
 
   collisions off  entities are independent -> contiguous entity ranges, no data-path collective at all
-  collisions on   spatial bands of whole cell rows, road graph replicated; per tick each rank sends ONE
-                  fixed-size device buffer (migrant records + boundary-row halo, packed by the library's
-                  kernels) to the rank below and one to the rank above, and receives two.  Every
-                  REBALANCE_EVERY ticks a (rows x u32) all-reduce of the per-row histogram re-chooses
+  collisions on   spatial bands of whole cell rows, road graph replicated.  Per tick each rank enqueues
+                  move+pack, integrate, collide and never waits for its GPU.  Two transports:
+                    p2p         (default on GPUs) the library's move / exchange kernels store leavers and halo
+                                straight into the neighbours' receive buffers over NVLink peer memory and
+                                synchronise through flag words; this module only exchanges the CUDA IPC
+                                handles once (msim_shard.h, "peer-memory exchange")
+                    collective  each rank sends ONE fixed-size device buffer (migrant records + boundary-row
+                                halo, packed by the library's kernels) to the rank below and one to the rank
+                                above with a single all_to_all_single (send/recv pairs over gloo)
+                  Every REBALANCE_EVERY ticks a (rows x u32) all-reduce of the per-row histogram re-chooses
                   the split rows; boundaries then walk one row per tick towards the target, which turns
                   re-balancing into ordinary migration.
 

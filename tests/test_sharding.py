@@ -71,6 +71,20 @@ def test_sharded_gloo_matches_unsharded_oracle(orc, msim, tmp_path, world):
     assert metas[0]["exchanged_bytes"] > 0
 
 
+def test_peer_memory_request_falls_back_to_the_collective_when_unavailable(orc, msim, tmp_path):
+    """exchange="p2p" on an engine / box that cannot do it (here: the CPU oracle engine over gloo): every rank must agree on
+    the fall-back and the run must still match."""
+    import torch.multiprocessing as mp
+
+    from shard_worker import run
+
+    cfg = dict(BASE, exchange="p2p", ticks=20)
+    mp.spawn(run, args=(2, free_port(), "gloo", str(tmp_path), cfg), nprocs=2, join=True)
+    metas = check_against_reference(orc, msim, cfg, str(tmp_path), 2)
+    assert all(m["exchange"] == "collective" and m["p2p_error"] for m in metas)
+    assert metas[0]["exchanged_bytes"] > 0
+
+
 def test_rebalancing_from_a_skewed_partition(orc, msim, tmp_path):
     """Dense crowd (BASELINE config 5 in miniature): everybody starts in one corner and the initial
     split is geometric; the histogram all-reduce must walk the boundary until the load is even."""
