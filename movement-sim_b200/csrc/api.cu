@@ -357,6 +357,7 @@ int alloc_collision_buffers(msim_handle* h) {
 int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     if (count > h->cap) return fail(h, MSIM_ERR_CAPACITY, "msim_upload_entities: count exceeds entity_capacity");
     if (count && !src) return fail(h, MSIM_ERR_INVALID, "msim_upload_entities: null source");
+    if (h->awaiting_integrate) h->arrive_deferred = false;  // pass B of a move whose exchange never completed: the population is being replaced
     join_side(h);
     MSIM_CUDA(h, cudaMemsetAsync(h->scratch, 0, 2 * sizeof(unsigned int), h->stream));
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
@@ -381,6 +382,11 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->n_ghost = 0;
     h->flags_stale = false;
     h->async_counts = false;
+    h->awaiting_integrate = false;          // a pending exchange refers to the population that has just been replaced
+    h->emit_pending = false;
+    h->packed = false;
+    h->band_valid = false;
+    h->count_fused = false;
     {
         const int wrc = write_dev_counts(h);
         if (wrc != MSIM_OK) return wrc;
