@@ -127,10 +127,37 @@ __device__ __forceinline__ bool any_in_tile(const float2* __restrict__ tile, uin
     return false;
 }
 
+// ---- bulk asynchronous copy (TMA, 1-D) of a contiguous window of sorted_pos into shared memory ----------------
+// One elected thread arms an mbarrier with the byte count and issues cp.async.bulk; the copy engine fills the window while
+// no thread spends issue slots on LDG + STS (the query kernel is issue-bound: the two staging loops were ~10 % of its
+// instructions).  Source, destination and size must be multiples of 16 bytes: windows are widened to even slot indices.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_global, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_global),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
 constexpr int QUERY_THREADS = 256;
 constexpr int COUNTER_STRIPES = 64;
 constexpr int COUNTER_STRIDE = 16;  // in u64 words: 128 bytes between stripes
-constexpr uint32_t QUERY_WINDOW = 1792;  // candidates staged per window (2 windows x 14 KB of shared memory)
+constexpr uint32_t QUERY_WINDOW = 1728;  // candidates staged per window: 2 x 13.5 KB, so that 8 CTAs (64 warps) fit one SM with the 1 KB per-CTA reserve
 
 // One thread per sorted slot j.  Every unordered pair is examined from its HIGHER slot only: thread j
 // counts its in-range partners among the slots below it — the whole grid row above (cells cx-1..cx+1)
@@ -153,14 +180,16 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
              const uint32_t* __restrict__ sorted_idx, const float2* __restrict__ sorted_pos,
              const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, uint8_t* __restrict__ flag_sorted, GridParams grid,
              unsigned long long* __restrict__ stripes) {
-    __shared__ float2 s_above[QUERY_WINDOW];
-    __shared__ float2 s_own[QUERY_WINDOW];
+    __shared__ __align__(16) float2 s_above[QUERY_WINDOW];
+    __shared__ __align__(16) float2 s_own[QUERY_WINDOW];
     __shared__ uint32_t s_red[3][QUERY_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t n_owned = n_owned_dev ? *n_owned_dev : n_owned_host;
     const uint32_t block_base = blockIdx.x * QUERY_THREADS;
     if (block_base >= n) return;  // grid sized for an upper bound of n (whole CTA, uniform)
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);  // made visible to the CTA by the barrier behind the hull computation
     const uint32_t j = block_base + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t pairs = 0;
@@ -223,13 +252,22 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
     const uint32_t w_own_hi = min(block_base + QUERY_THREADS, n);  // nobody needs a slot at or above its own
     if (w_ab_lo > w_ab_hi) w_ab_lo = w_ab_hi = 0;
     const bool any_mine = w_own_lo != 0xffffffffu;
-    const bool tiled = any_mine && (w_own_hi - w_own_lo) <= QUERY_WINDOW && (w_ab_hi - w_ab_lo) <= QUERY_WINDOW;  // CTA-uniform
+    // windows widened to even slot indices: 16-byte aligned source and size for the bulk copy (sorted_pos holds a multiple of
+    // 64 slots, so the widened end stays inside the array; the extra slots are never used as candidates)
+    w_own_lo &= ~1u;
+    w_ab_lo &= ~1u;
+    const uint32_t own_slots = any_mine ? ((w_own_hi - w_own_lo + 1u) & ~1u) : 0u;
+    const uint32_t ab_slots = (w_ab_hi - w_ab_lo + 1u) & ~1u;
+    const bool tiled = any_mine && own_slots <= QUERY_WINDOW && ab_slots <= QUERY_WINDOW;  // CTA-uniform
 
     if (tiled) {
-        for (uint32_t i = threadIdx.x; i < w_own_hi - w_own_lo; i += QUERY_THREADS) s_own[i] = sorted_pos[w_own_lo + i];
-        for (uint32_t i = threadIdx.x; i < w_ab_hi - w_ab_lo; i += QUERY_THREADS) s_above[i] = sorted_pos[w_ab_lo + i];
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, (own_slots + ab_slots) * static_cast<uint32_t>(sizeof(float2)));
+            bulk_copy_g2s(s_own, sorted_pos + w_own_lo, own_slots * static_cast<uint32_t>(sizeof(float2)), &s_bar);
+            if (ab_slots) bulk_copy_g2s(s_above, sorted_pos + w_ab_lo, ab_slots * static_cast<uint32_t>(sizeof(float2)), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
     }
-    __syncthreads();
 
     if (mine) {
         const float thr = grid.hit_threshold;
