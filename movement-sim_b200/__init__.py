@@ -88,7 +88,20 @@ ABI_SYMBOLS = [
     "msim_shard_p2p_connect_local", "msim_shard_p2p_move_pack", "msim_shard_p2p_integrate", "msim_shard_integrate", "msim_shard_integrate_async",
     "msim_shard_counts", "msim_shard_read_gids",
     "msim_shard_row_histogram", "msim_grid_rows",
+    # include/msim_mapgen.h
+    "msim_map_from_geojson", "msim_map_save_binary", "msim_map_load_binary", "msim_map_load", "msim_map_from_arrays", "msim_haversine_m",
 ]
+MAPGEN_EXACT_TRAVERSAL = 1 << 0
+MAPGEN_NO_DUPLICATE_END = 1 << 1
+
+
+class MapgenStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("features", "line_strings", "road_pieces", "skipped_zero", "skipped_duplicate", "connected",
+                                          "coordinates")] + [
+        (n, C.c_double) for n in ("min_dist_lat", "max_dist_lat", "min_dist_long", "max_dist_long", "ref_lat", "ref_long")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class MsimError(RuntimeError):
@@ -233,6 +246,12 @@ def lib():
         "msim_entities_init": (i32, [vp, u64, u64, u64, vp, vp]),
         "msim_calc_node_count": (u64, [u32]),
         "msim_abi_version": (u32, []),
+        "msim_map_from_geojson": (i32, [C.c_char_p, u32, C.POINTER(vp), C.POINTER(MapgenStats)]),
+        "msim_map_save_binary": (i32, [vp, C.c_char_p]),
+        "msim_map_load_binary": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "msim_map_load": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "msim_map_from_arrays": (i32, [f32, f32, vp, u64, vp, u64, C.POINTER(vp)]),
+        "msim_haversine_m": (C.c_double, [C.c_double] * 4),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -277,6 +296,43 @@ class Map:
         if rc != MSIM_OK:
             raise MsimError(rc, L.msim_map_last_error().decode())
         return cls._take(h)
+
+    @classmethod
+    def load(cls, path: str) -> "Map":
+        """Any supported map file: binary cache, GeoJSON export, or the reference's map JSON (msim_map_load)."""
+        L = lib()
+        h = C.c_void_p()
+        rc = L.msim_map_load(os.fsencode(path), C.byref(h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        return cls._take(h)
+
+    @classmethod
+    def from_geojson(cls, path: str, flags: int = 0, with_stats: bool = False):
+        """/root/reference/map/generate_map.py as a native pipeline (include/msim_mapgen.h)."""
+        L = lib()
+        h = C.c_void_p()
+        st = MapgenStats()
+        rc = L.msim_map_from_geojson(os.fsencode(path), flags, C.byref(h), C.byref(st))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        m = cls._take(h)
+        return (m, st.as_dict()) if with_stats else m
+
+    def save_binary(self, path: str) -> None:
+        """Binary map cache (msim_map_save_binary)."""
+        L = lib()
+        h = C.c_void_p()
+        rc = L.msim_map_from_arrays(self.width, self.height, self.roads.ctypes.data, self.roads.shape[0], self.connections.ctypes.data,
+                                    self.connections.shape[0], C.byref(h))
+        if rc != MSIM_OK:
+            raise MsimError(rc, L.msim_map_last_error().decode())
+        try:
+            rc = L.msim_map_save_binary(h, os.fsencode(path))
+            if rc != MSIM_OK:
+                raise MsimError(rc, L.msim_map_last_error().decode())
+        finally:
+            L.msim_map_free(h)
 
     @classmethod
     def city(cls, world_w: float = 29007.4609, world_h: float = 16463.7656, spacing: float = 35.0, jitter: float = 0.3,

@@ -8,7 +8,7 @@
 //   Simulator::add_entities      /root/reference/src/sim/Simulator.cpp:114-129
 //   Map::get_random_road_index   /root/reference/src/sim/Map.cpp:152-157
 //   Rgba::random_color / Vec4U::random_vec   /root/reference/src/sim/Entity.cpp:44-60
-#include "../../include/msim.h"
+#include "host_map.h"
 
 #include <algorithm>
 #include <cctype>
@@ -24,115 +24,32 @@
 #include <string>
 #include <vector>
 
-struct msim_map {
-    float width{0};
-    float height{0};
-    std::vector<msim_road> roads;
-    std::vector<uint32_t> connections;
-};
-
+namespace msim_host {
 namespace {
 thread_local std::string g_map_error;
-
+}
 int map_fail(int code, const std::string& msg) {
     g_map_error = msg;
     return code;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Minimal JSON reader for the map schema (the reference uses nlohmann::json; any conforming parser
-// yields the same doubles, which are then narrowed to float exactly like json::get_to<float>).
-// ---------------------------------------------------------------------------------------------
-class JsonCursor {
- public:
-    JsonCursor(const char* begin, const char* end) : p_(begin), end_(end) {}
-
-    void ws() {
-        while (p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')) p_++;
-    }
-    bool eof() {
-        ws();
-        return p_ >= end_;
-    }
-    char peek() {
-        ws();
-        return p_ < end_ ? *p_ : '\0';
-    }
-    bool consume(char c) {
-        if (peek() == c) {
-            p_++;
-            return true;
-        }
+const std::string& map_error() { return g_map_error; }
+bool read_file(const char* path, std::string& text) {
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) {
+        map_fail(MSIM_ERR_IO, std::string("Failed to open map from '") + path + "'. File does not exist.");
         return false;
     }
-    void expect(char c) {
-        if (!consume(c)) fail(std::string("expected '") + c + "'");
-    }
-    std::string string() {
-        expect('"');
-        std::string out;
-        while (p_ < end_ && *p_ != '"') {
-            if (*p_ == '\\' && p_ + 1 < end_) {
-                p_++;
-                switch (*p_) {
-                    case 'n': out.push_back('\n'); break;
-                    case 't': out.push_back('\t'); break;
-                    case 'r': out.push_back('\r'); break;
-                    case 'b': out.push_back('\b'); break;
-                    case 'f': out.push_back('\f'); break;
-                    case 'u': p_ += 4; out.push_back('?'); break;
-                    default: out.push_back(*p_); break;
-                }
-                p_++;
-            } else {
-                out.push_back(*p_++);
-            }
-        }
-        if (p_ >= end_) fail("unterminated string");
-        p_++;
-        return out;
-    }
-    double number() {
-        ws();
-        char* stop = nullptr;
-        errno = 0;
-        const double v = std::strtod(p_, &stop);
-        if (stop == p_) fail("expected a number");
-        p_ = stop;
-        return v;
-    }
-    void skip_value() {
-        const char c = peek();
-        if (c == '{') {
-            p_++;
-            if (consume('}')) return;
-            do {
-                (void)string();
-                expect(':');
-                skip_value();
-            } while (consume(','));
-            expect('}');
-        } else if (c == '[') {
-            p_++;
-            if (consume(']')) return;
-            do {
-                skip_value();
-            } while (consume(','));
-            expect(']');
-        } else if (c == '"') {
-            (void)string();
-        } else if (c == 't' || c == 'f' || c == 'n') {
-            while (p_ < end_ && std::isalpha(static_cast<unsigned char>(*p_))) p_++;
-        } else {
-            (void)number();
-        }
-    }
-    [[noreturn]] void fail(const std::string& what) { throw std::runtime_error("Failed to parse map. JSON syntax: " + what); }
+    char buf[1 << 16];
+    size_t got = 0;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    return true;
+}
+}  // namespace msim_host
 
- private:
-    const char* p_;
-    const char* end_;
-};
+namespace {
+using msim_host::JsonCursor;
+using msim_host::map_fail;
 
 struct Present {
     bool v{false};
@@ -320,18 +237,13 @@ uint32_t uf_find(std::vector<uint32_t>& parent, uint32_t x) {
 
 extern "C" {
 
-const char* msim_map_last_error(void) { return g_map_error.c_str(); }
+const char* msim_map_last_error(void) { return msim_host::map_error().c_str(); }
 
 int msim_map_load_json(const char* path, msim_map** out) {
     if (!path || !out) return map_fail(MSIM_ERR_INVALID, "msim_map_load_json: null argument");
     *out = nullptr;
-    std::FILE* f = std::fopen(path, "rb");
-    if (!f) return map_fail(MSIM_ERR_IO, std::string("Failed to open map from '") + path + "'. File does not exist.");
     std::string text;
-    char buf[1 << 16];
-    size_t got = 0;
-    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
-    std::fclose(f);
+    if (!msim_host::read_file(path, text)) return MSIM_ERR_IO;
     msim_map* m = new (std::nothrow) msim_map();
     if (!m) return map_fail(MSIM_ERR_OOM, "out of host memory");
     try {

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/msim.h"
+#include "../../include/msim_mapgen.h"
 
 namespace sim {
 

@@ -42,7 +42,8 @@ std::shared_ptr<Map> Map::adopt(msim_map* handle) {
 std::shared_ptr<Map> Map::load_from_file(const std::filesystem::path& path) {
     log_line("Loading map from '" + path.string() + "'...");
     msim_map* handle = nullptr;
-    const int status = msim_map_load_json(path.c_str(), &handle);
+    // the reference's map JSON (Map.cpp:28-150), a GeoJSON export (map/generate_map.py) or a binary map cache
+    const int status = msim_map_load(path.c_str(), &handle);
     if (status == MSIM_ERR_IO) {
         log_line(msim_map_last_error());
         return nullptr;
