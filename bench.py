@@ -32,6 +32,9 @@ WORKLOADS = {
     "munich_10m_collisions": dict(entities=10_000_000, collisions=True, map="city"),
     "munich_1m_nocollisions": dict(entities=1_000_000, collisions=False, map="city"),
     "test_map_10k_nocollisions": dict(entities=10_000, collisions=False, map="test_map"),
+    # BASELINE configs[3] / configs[4]: sized for --gpus 8 (ONE population split over the GPUs; they also fit one B200)
+    "grid4096_100m_collisions": dict(entities=100_000_000, collisions=True, map="grid4096", survey_bytes=140.0),  # 26-bit keys: k = 4 passes
+    "munich_50m_dense": dict(entities=50_000_000, collisions=True, map="city", box_frac=(0.45, 0.45, 0.55, 0.55)),
 }
 METRIC = "entity-updates/sec"
 SURVEY_BYTES = {True: 124.0, False: 24.0}  # B_coll (23-bit keys, 3 passes) / B_move
@@ -152,9 +155,19 @@ def build_workload(M, name: str, entities_override: int | None, seed: int = 42):
     if w["map"] == "city":
         m = M.Map.city()  # 29007.4609 x 16463.7656 m Munich stand-in, seed 2022
         w["map_desc"] = f"synthetic Munich stand-in {m.width:.1f}x{m.height:.1f} m, {m.roads.shape[0]} roads (munich.json absent from the reference checkout)"
+    elif w["map"] == "grid4096":
+        side = int(os.environ.get("MSIM_BENCH_GRID_SIDE", "4096"))  # smaller lattices for dry runs
+        m = M.Map.grid(side, side, 20.0)  # nodes at (20 i, 20 j): every coordinate exact in binary32
+        w["map_desc"] = f"synthetic {side}x{side} lattice, 20 m spacing, {m.width:.0f}x{m.height:.0f} m, {m.roads.shape[0]} roads"
     else:
         m = M.Map.load_json(os.path.join(ROOT, "tests", "golden", "test_map.json"))
         w["map_desc"] = "test_map.json (4 roads)"
+    w.setdefault("survey_bytes", SURVEY_BYTES[w["collisions"]])
+    w["box"] = None
+    if w.get("box_frac"):  # dense crowd: initial roads drawn only from roads with both ends inside the central box
+        fx0, fy0, fx1, fy1 = w["box_frac"]
+        w["box"] = np.array([fx0 * m.width, fy0 * m.height, fx1 * m.width, fy1 * m.height], dtype=np.float32)
+        w["map_desc"] += f"; entities start on roads inside the central box {w['box'].tolist()}"
     return w, m
 
 
@@ -204,7 +217,7 @@ def run_reference(args):
     use_ref = O.ref_available() and w["collisions"]
     sample = min(w["entities"], args.ref_sample, int(O.ref().ref_capacity()) if use_ref else 1 << 62)
     omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
-    ents = m.init_entities(sample, seed=42)
+    ents = m.init_entities(sample, seed=42, box=w["box"])
     e = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()
     O.move_pass(e, omap, threads=threads)  # init dispatch
     for _ in range(args.preroll):
@@ -257,7 +270,7 @@ def run_b200(args):
     collisions = w["collisions"]
     peak, peak_src = load_peaks()
     stream = torch.cuda.Stream()
-    ents = m.init_entities(n, seed=42)
+    ents = m.init_entities(n, seed=42, box=w["box"])
     if args.presort:  # experiment: spatially coherent storage order (sort the host array by cell row, then x)
         rows, _, _ = M.grid_rows(m.width, m.height, 10.0, ents["pos"])
         order = np.lexsort((ents["pos"][:, 0], rows))
@@ -332,7 +345,7 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": dom["frac"], "traffic": traffic.get(dom["name"]), "peak_source": peak_src,
                     "alg_bytes_per_launch": dom["alg_bytes_per_entity"] * n, "avg_launch_us": dom["avg_us"], "share_of_step": dom["share"]}
-    tick_gbs = SURVEY_BYTES[collisions] * n * args.steps / (ms * 1e-3) / 1e9
+    tick_gbs = w["survey_bytes"] * n * args.steps / (ms * 1e-3) / 1e9
     if roofline and traffic.get("_issue_active_pct", {}).get(roofline["kernel"]) is not None:
         roofline["issue_active_pct_ncu"] = traffic["_issue_active_pct"][roofline["kernel"]]
         roofline["note"] = ("this kernel is instruction-issue-bound, not HBM-bound (ncu smsp__issue_active, profiles/r1_ncu_full.md); "
@@ -414,7 +427,7 @@ def run_b200(args):
                    "l2": ("flushed between timed steps (512 MiB fill)" if small else "inputs larger than L2 (no flush)"),
                    "grid": sim.stats()},
         "roofline": roofline,
-        "tick": {"survey_bytes_per_entity_update": SURVEY_BYTES[collisions], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / peak,
+        "tick": {"survey_bytes_per_entity_update": w["survey_bytes"], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / peak,
                  "frac_of_nominal_8tbs": tick_gbs / 8000.0, "kernel_time_ms_per_step": total_kernel_ms / args.steps},
         "kernels": kernels,
         "move_only": move_only,

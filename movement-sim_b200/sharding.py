@@ -331,14 +331,15 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     sampler = None
     with torch.cuda.stream(stream):
         if collisions:
-            sh, sim = make_cuda_shard(M, m, total, 42, 10.0, rank, world, dist, torch, local_rank, stream, exchange=getattr(args, "exchange", "p2p"))
+            sh, sim = make_cuda_shard(M, m, total, 42, 10.0, rank, world, dist, torch, local_rank, stream, box=w["box"],
+                                      exchange=getattr(args, "exchange", "p2p"))
             sim.dispatch(2)  # the reference's first dispatch: initialise only
             step = lambda: sh.tick(True)
             for _ in range(args.preroll):
                 sh.tick(False)
         else:
             lo, hi = entity_range(total, rank, world)
-            parts = [e for _, e in generate_population(M, m, total, 42)]
+            parts = [e for _, e in generate_population(M, m, total, 42, w["box"])]
             ents = np.concatenate(parts)[lo:hi]
             sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=M.FLAG_NO_COLLISIONS, stream=stream.cuda_stream)
             sh = None
@@ -428,7 +429,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         bytes_t = torch.tensor([h2d, d2h], dtype=torch.int64, device=device)
         dist.all_reduce(bytes_t)
     value = total * args.steps / (ms * 1e-3)
-    tick_gbs = SURVEY_BYTES[collisions] * value / 1e9
+    tick_gbs = w["survey_bytes"] * value / 1e9
     roofline = None
     if rank == 0 and kernels:
         # dominant kernel on rank 0 (events around every launch, second pass of the same K steps): algorithmic bytes of ONE launch
@@ -465,7 +466,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
                        "global_pairs_last_tick": pairs, "global_flagged_last_tick": flagged},
             "roofline": roofline,
-            "tick": {"survey_bytes_per_entity_update": SURVEY_BYTES[collisions], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / (peak * world),
+            "tick": {"survey_bytes_per_entity_update": w["survey_bytes"], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / (peak * world),
                      "frac_of_nominal_8tbs": tick_gbs / (8000.0 * world), "peak_source": peak_src},
             "cpu_baseline": None,
             "e2e": {"value": total * e2e_steps / float(dt.item()), "unit": "entity-updates/s", "h2d_bytes_per_step": int(bytes_t[0].item()) // e2e_steps,

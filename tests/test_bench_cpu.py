@@ -1,0 +1,77 @@
+"""bench.py's CPU-side pieces: the reference arm (--impl reference) prints the contract's JSON line, and the workload
+builders of BASELINE configs 3-5 produce what the GPU arm will be given.  No GPU needed."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+
+
+def run_bench(*argv, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *argv], capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, f"stdout must carry exactly one JSON line, got {len(lines)}"
+    return json.loads(lines[0])
+
+
+def check_reference_line(line, workload):
+    assert line["impl"] == "reference" and line["metric"] == "entity-updates/sec" and line["unit"] == "entity-updates/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["data"] == "synthetic"
+    assert line["config"]["workload"] == workload
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
+
+
+def test_reference_arm_config1():
+    line = run_bench("--impl", "reference", "--workload", "test_map_10k_nocollisions", "--steps", "3", "--warmup", "1", "--preroll", "4")
+    check_reference_line(line, "test_map_10k_nocollisions")
+    assert line["config"]["collisions"] is False and line["config"]["entities_sampled"] == 10_000
+    assert line["cpu_baseline"]["kind"] == "port"  # the reference's CPU harness has no road-graph movement
+
+
+def test_reference_arm_dense_crowd_sample():
+    line = run_bench("--impl", "reference", "--workload", "munich_50m_dense", "--steps", "1", "--warmup", "1", "--preroll", "8", "--ref-sample", "3000")
+    check_reference_line(line, "munich_50m_dense")
+    assert line["config"]["collisions"] is True and line["config"]["entities_sampled"] == 3000
+    assert "central box" in line["config"]["map"]
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"], capture_output=True, text=True,
+                       timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_workload_builders(msim, monkeypatch):
+    import bench
+
+    monkeypatch.setenv("MSIM_BENCH_GRID_SIDE", "33")
+    w, m = bench.build_workload(msim, "grid4096_100m_collisions", None)
+    assert m.roads.shape[0] == 2 * 33 * 32 and m.width == 640.0 and m.height == 640.0
+    assert w["entities"] == 100_000_000 and w["collisions"] and w["box"] is None and w["survey_bytes"] == 140.0
+    # lattice coordinates are multiples of 20 m: exact in binary32
+    assert np.all(np.mod(m.roads["start_pos"], 20.0) == 0)
+
+    w, m = bench.build_workload(msim, "munich_50m_dense", 5000)
+    assert w["entities"] == 5000 and w["survey_bytes"] == 124.0
+    x0, y0, x1, y1 = w["box"].tolist()
+    assert abs((x1 - x0) / m.width - 0.1) < 1e-3 and abs((y1 - y0) / m.height - 0.1) < 1e-3
+    ents = m.init_entities(5000, seed=42, box=w["box"])
+    for end in ("start_pos", "end_pos"):  # every chosen road lies inside the central box with both ends
+        p = m.roads[end][ents["road_index"]]
+        assert np.all((p[:, 0] >= x0) & (p[:, 0] <= x1) & (p[:, 1] >= y0) & (p[:, 1] <= y1))
+    assert len(np.unique(ents["road_index"])) > 1000  # ~1 % of 701 590 roads are eligible
+
+    w, m = bench.build_workload(msim, "munich_10m_collisions", None)
+    assert w["entities"] == 10_000_000 and w["box"] is None and w["survey_bytes"] == 124.0
