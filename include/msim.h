@@ -100,7 +100,10 @@ enum {
     MSIM_FLAG_SORT_COUNTING = 1u << 3, /* always rebuild the neighbour structure with the single-digit (counting) radix sort */
     MSIM_FLAG_NO_REORDER    = 1u << 4, /* keep the resident state in upload order (default: re-sorted into cell order every
                                           32 collision passes, with the counting sort as the rebuild) */
-    MSIM_FLAG_SORT_ONESWEEP = 1u << 5  /* always rebuild with the multi-pass onesweep radix sort */
+    MSIM_FLAG_SORT_ONESWEEP = 1u << 5, /* always rebuild with the multi-pass onesweep radix sort */
+    MSIM_FLAG_FUSED_ARRIVE  = 1u << 6  /* opt-in: the next-waypoint pass of a move is served by the NEXT move kernel instead of a
+                                          kernel of its own (asynchronous msim_enqueue_* sequences on unsharded handles; every
+                                          synchronising call completes a pending pass first, results are identical) */
 };
 
 typedef struct msim_config {
@@ -149,7 +152,7 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc);
 int msim_enqueue_move(msim_handle* h);
 int msim_enqueue_collide(msim_handle* h);
 /* `sim_ticks` x (move pass [+ collision pass]) == that many Simulator::sim_tick calls
- * (Simulator.cpp:213-241) without the host round trips; replayed from a CUDA graph. */
+ * (Simulator.cpp:213-241) without the host round trips: everything is enqueued, nothing is waited for. */
 int msim_enqueue_ticks(msim_handle* h, uint32_t sim_ticks, int with_collisions);
 int msim_sync(msim_handle* h);
 int msim_set_stream(msim_handle* h, void* cuda_stream);

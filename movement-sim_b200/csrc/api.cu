@@ -155,6 +155,21 @@ struct msim_handle {
     std::string error;
 };
 
+namespace msim {
+const Tuning& tuning() {
+    static const Tuning t = [] {
+        Tuning v{0, false};
+        if (const char* e = std::getenv("MSIM_MOVE_MIN_BLOCKS")) {
+            const int k = std::atoi(e);
+            if (k == 5 || k == 6) v.move_min_blocks = k;
+        }
+        if (const char* e = std::getenv("MSIM_MOVE_GRID")) v.move_grid_by_occupancy = std::strcmp(e, "occupancy") == 0;
+        return v;
+    }();
+    return t;
+}
+}  // namespace msim
+
 namespace {
 
 int fail(msim_handle* h, int code, const std::string& msg) {
@@ -269,6 +284,8 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
                                      dev_owned(h));
     }
 }
+
+inline bool fused_arrive(const msim_handle* h) { return (h->flags & MSIM_FLAG_FUSED_ARRIVE) && !h->sharded; }
 
 void join_side(msim_handle* h) {
     launch_deferred_arrive(h, false);
@@ -451,13 +468,23 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
         prepare_counts(h);
     }
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
+    // MSIM_FLAG_FUSED_ARRIVE (unsharded handles): pass B of a move is left pending and served by the NEXT move kernel itself;
+    // anything else that reads target / road / rng joins it first (join_side launches the stand-alone kernel)
+    const bool fused = fused_arrive(h);
+    FusedArriveArgs fa{h->target, h->road, h->rng, h->roads, h->conn, h->conn_count, false};
+    if (fused && h->arrive_deferred && !h->side_pending) {
+        fa.consume = true;
+        h->arrive_deferred = false;
+    }
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof,
-                               dev_owned(h), shard);
+                               dev_owned(h), shard, fused ? &fa : nullptr);
     h->counts_valid = fuse_count;
-    if (emit && h->side && (!h->sharded || shard)) {
+    if (fused) {
+        h->arrive_deferred = true;
+    } else if (emit && h->side && (!h->sharded || shard)) {
         h->arrive_deferred = true;  // a collision pass follows and needs only positions and keys: pass B is launched beside its query
     } else {
         h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
@@ -586,7 +613,7 @@ int enqueue_collide(msim_handle* h) {
         h->counts_dirty = false;  // the scan zeroed every counter it read, and nothing was counted outside [c0, c1)
         h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
                                            dev_total(h));
-        launch_deferred_arrive(h, true);
+        if (!fused_arrive(h)) launch_deferred_arrive(h, true);  // fused: stays pending for the next move kernel
         h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof, h->sharded ? h->cell_start + c1 : nullptr, dev_owned(h));
     } else {
@@ -595,7 +622,7 @@ int enqueue_collide(msim_handle* h) {
         h->hist_valid = false;  // the sort consumed the tickets and look-back words
         h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
                                           &h->prof, dev_total(h));
-        launch_deferred_arrive(h, true);
+        if (!fused_arrive(h)) launch_deferred_arrive(h, true);  // fused: stays pending for the next move kernel
         h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof, dev_total(h), dev_owned(h));
     }

@@ -154,15 +154,36 @@ __device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t
     }
 }
 
+// ---- fused pass B (opt-in, MSIM_FLAG_FUSED_ARRIVE) -----------------------------------------------------------
+// The arrival bits of the PREVIOUS move pass are consumed by the warp that streams the same entities in THIS pass: bit
+// `lane` of the two mask words of a 64-entity chunk belongs to the lane that loads that entity's position and target, so
+// nothing has to change lanes.  A lane takes one of its (up to four) pending arrivals per round; one round serves up to
+// 32 arrivals of the warp with their gather chains side by side, a second round is rare (two arrivals in one lane).
+// The streaming loads of the iteration are already in flight while the chains run, and the mask words are read before
+// this iteration's arrival bits overwrite them (same warp, program order).
+struct FusedArrive {
+    float2* target;  // read-write alias of the move kernel's `target` (which is therefore not read through __restrict__)
+    uint32_t* road;
+    uint4* rng;
+    const uint4* roads;
+    const uint32_t* conn;
+    unsigned long long conn_count;
+    uint32_t consume;  // 0: no pass B is pending (first move after an upload / after a stand-alone pass B)
+};
+
 // EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
 // sort's digit histograms for all passes in shared memory (flushed once per CTA), so the neighbour
 // rebuild needs no separate histogram read of the keys.
 // SHARD (multi-GPU bands) additionally does the shard pack for the entities it has just moved (see above).
-template <bool EMIT_KEYS, bool SHARD>
-__global__ void __launch_bounds__(MOVE_THREADS)
+// MINB = minimum resident CTAs per SM asked of the compiler (register cap 65536 / (256 MINB)).  0 = no cap: 40 / 52 / 58
+// registers without / with keys / sharded, i.e. 6 / 4 / 4 resident CTAs; the variants with keys wait on L2 atomics, so
+// more resident warps may pay for a few spilled registers (MSIM_MOVE_MIN_BLOCKS = 5 or 6, see tuning() in api.cu).
+template <bool EMIT_KEYS, bool SHARD, bool FUSE, int MINB>
+__global__ void __launch_bounds__(MOVE_THREADS, MINB)
 move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
             uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
-            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh) {
+            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh, FusedArrive fa) {
+    static_assert(!FUSE || MOVE_ITEMS == 2, "the fused pass B selects among 2 x 2 entity slots per lane");
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
     if (EMIT_KEYS) {
         for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
@@ -177,13 +198,42 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
     for (uint32_t base = blockIdx.x * PER_BLOCK; base < pairs_pad; base += gridDim.x * PER_BLOCK) {
         float4 P[MOVE_ITEMS], T[MOVE_ITEMS];
         bool live[MOVE_ITEMS];
+        uint32_t pend = 0;  // FUSE: bit 2k + s = entity slot s of item k arrived in the previous pass and has no new waypoint yet
 #pragma unroll
         for (int k = 0; k < MOVE_ITEMS; k++) {
             const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
             live[k] = pi < pairs_pad;
             if (live[k]) {
                 P[k] = __ldcs(pos_in + pi);
-                T[k] = __ldcs(target + pi);
+                if (FUSE) {
+                    T[k] = __ldcs(reinterpret_cast<const float4*>(fa.target) + pi);
+                    if (fa.consume) {
+                        const uint2 pm = *reinterpret_cast<const uint2*>(arrived_mask + (pi >> 5) * 2u);  // one address per warp
+                        const uint32_t e0 = pi * 2u;
+                        if (((pm.x >> lane) & 1u) && e0 < n) pend |= 1u << (2 * k);
+                        if (((pm.y >> lane) & 1u) && e0 + 1u < n) pend |= 2u << (2 * k);
+                    }
+                } else {
+                    T[k] = __ldcs(target + pi);
+                }
+            }
+        }
+        if (FUSE) {
+            while (__any_sync(0xffffffffu, pend != 0u)) {
+                if (pend) {
+                    const uint32_t slot = static_cast<uint32_t>(__ffs(static_cast<int>(pend))) - 1u;
+                    pend &= pend - 1u;
+                    const uint32_t pi = base + (slot >> 1) * MOVE_THREADS + threadIdx.x;
+                    const uint32_t e = pi * 2u + (slot & 1u);
+                    const float4 t4 = (slot >> 1) ? T[1] : T[0];
+                    const float2 reached = (slot & 1u) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+                    const float2 nt = new_target(e, reached, fa.road, fa.rng, fa.roads, fa.conn, fa.conn_count);
+                    fa.target[e] = nt;
+                    if (slot == 0u) { T[0].x = nt.x; T[0].y = nt.y; }
+                    if (slot == 1u) { T[0].z = nt.x; T[0].w = nt.y; }
+                    if (slot == 2u) { T[1].x = nt.x; T[1].y = nt.y; }
+                    if (slot == 3u) { T[1].z = nt.x; T[1].w = nt.y; }
+                }
             }
         }
         RunRank R0[MOVE_ITEMS], R1[MOVE_ITEMS];
@@ -297,30 +347,70 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
     }
 }
 
+// one launch of the chosen variant; the grid is a whole number of resident CTAs per SM (grid-stride loop inside)
+template <bool EMIT_KEYS, bool SHARD, bool FUSE, int MINB, typename... Args>
+void launch_move_variant(cudaStream_t s, int sm_count, uint32_t blocks_needed, Args... args) {
+    uint32_t per_sm = 8u;  // 8 x 256 threads = 2048 threads per SM (what the register budget of MINB = 0 allows is less: see above)
+    if (tuning().move_grid_by_occupancy) {
+        static int occupancy = 0;  // per instantiation
+        if (occupancy == 0 &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, move_kernel<EMIT_KEYS, SHARD, FUSE, MINB>, MOVE_THREADS, 0) != cudaSuccess)
+            occupancy = 8;
+        per_sm = static_cast<uint32_t>(occupancy > 0 ? occupancy : 8);
+    }
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * per_sm;
+    const uint32_t blocks = blocks_needed > resident ? resident : blocks_needed;
+    move_kernel<EMIT_KEYS, SHARD, FUSE, MINB><<<blocks, MOVE_THREADS, 0, s>>>(args...);
+}
+template <bool EMIT_KEYS, bool SHARD, bool FUSE, typename... Args>
+void launch_move_minb(cudaStream_t s, int sm_count, uint32_t blocks_needed, Args... args) {
+    switch (tuning().move_min_blocks) {
+        case 5: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 5>(s, sm_count, blocks_needed, args...); break;
+        case 6: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 6>(s, sm_count, blocks_needed, args...); break;
+        default: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 0>(s, sm_count, blocks_needed, args...); break;
+    }
+}
+
 }  // namespace
 
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev, const ShardMoveArgs* shard) {
+                const uint32_t* n_dev, const ShardMoveArgs* shard, const FusedArriveArgs* fuse) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
-    uint32_t blocks = (pairs + per_block - 1) / per_block;
-    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;  // 8 x 256 threads = 2048 threads per SM
-    if (blocks > resident) blocks = resident;  // grid-stride: a whole number of CTAs per SM
+    const uint32_t blocks = (pairs + per_block - 1) / per_block;
     const float4* pin = reinterpret_cast<const float4*>(pos_in);
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
+    uint2* keys2 = reinterpret_cast<uint2*>(keys);
+    uint2* rank2 = reinterpret_cast<uint2*>(rank);
+    const int passes = hist ? hist_passes : 0;
+    const float4* no_target = nullptr;  // the fused variants read the waypoints through FusedArrive::target (read-write alias)
+    uint2* no_keys = nullptr;
+    uint32_t* no_table = nullptr;
     prof->begin(s, K_MOVE);
     const ShardMoveArgs none{};
-    if (keys && shard)
-        move_kernel<true, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
-                                                                cell_count, reinterpret_cast<uint2*>(rank), *shard);
+    FusedArrive fa{};
+    if (fuse) {
+        fa.target = fuse->target;
+        fa.road = fuse->road;
+        fa.rng = fuse->rng;
+        fa.roads = reinterpret_cast<const uint4*>(fuse->roads);
+        fa.conn = fuse->connections;
+        fa.conn_count = fuse->connection_count;
+        fa.consume = fuse->consume ? 1u : 0u;
+    }
+    if (keys && shard)  // sharded handles keep the stand-alone pass B: migrants travel with their pre-arrival state
+        launch_move_minb<true, true, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, *shard, fa);
+    else if (keys && fuse)
+        launch_move_minb<true, false, true>(s, sm_count, blocks, n, n_dev, pin, pout, no_target, arrived, keys2, grid, hist, passes, cell_count, rank2, none, fa);
     else if (keys)
-        move_kernel<true, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, reinterpret_cast<uint2*>(keys), grid, hist, hist ? hist_passes : 0,
-                                                                 cell_count, reinterpret_cast<uint2*>(rank), none);
+        launch_move_minb<true, false, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, none, fa);
+    else if (fuse)
+        launch_move_minb<false, false, true>(s, sm_count, blocks, n, n_dev, pin, pout, no_target, arrived, no_keys, grid, no_table, 0, no_table, no_keys, none, fa);
     else
-        move_kernel<false, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr, none);
+        launch_move_minb<false, false, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, no_keys, grid, no_table, 0, no_table, no_keys, none, fa);
     prof->end(s);
     return 1;
 }

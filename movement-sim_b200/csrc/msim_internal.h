@@ -117,16 +117,33 @@ struct Profiler {
     }
 };
 
+// ---- launch tuning read once from the environment (api.cu); defaults = the configuration every committed number was measured with
+struct Tuning {
+    int move_min_blocks;          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
+    bool move_grid_by_occupancy;  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
+};
+const Tuning& tuning();
+
 // ---- kernel launchers (each returns the number of kernels it launched) ------------------------
 // move.cu
 // pass A (streaming) and pass B (next waypoint of the arrived entities) of one move dispatch
 // Device-resident counts (asynchronous sharded ticks): when `n_dev` is non-NULL a kernel takes its element
 // count from *n_dev (written by an earlier kernel on the stream) and the host-side `n` is only an upper
 // bound used to size the grid.
+// MSIM_FLAG_FUSED_ARRIVE: pass B of the PREVIOUS move pass runs inside this move kernel (move.cu); `consume` says whether one is pending
+struct FusedArriveArgs {
+    float2* target;
+    uint32_t* road;
+    uint4* rng;
+    const msim_road* roads;
+    const uint32_t* connections;
+    uint64_t connection_count;
+    bool consume;
+};
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
                 int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr);
+                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr, const FusedArriveArgs* fuse = nullptr);
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
