@@ -160,6 +160,18 @@ int msim_set_stream(msim_handle* h, void* cuda_stream);
 /* OpTensorSyncLocal({tensorEntities}) + tensor->vector<Entity>() (Simulator.cpp:197,250,262):
  * packs SoA -> 64-byte AoS on the device and copies `count` entities to dst (host memory). */
 int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count);
+/* Asynchronous readback: what replaces the reference's blocking per-tick evalAsync/evalAwait +
+ * tensor->vector<Entity>() copy (Simulator.cpp:250-262) for consumers that can take a pointer.
+ *   begin  packs the CURRENT state (everything enqueued so far) SoA -> AoS into a device image on the handle's stream and
+ *          starts its copy into library-owned PINNED host memory on a separate copy stream; returns at once, ticks enqueued
+ *          afterwards run while the copy engine drains the image;
+ *   poll   *ready = 1 once the copy has landed (never blocks);
+ *   end    waits for it and hands out the pinned buffer: valid until the begin AFTER the next one (two host buffers
+ *          alternate, so a consumer may keep reading one snapshot while the next is being filled) or msim_destroy.
+ * One snapshot may be in flight per handle: begin while one is pending first waits (on the device) for its copy. */
+int msim_snapshot_begin(msim_handle* h);
+int msim_snapshot_poll(msim_handle* h, int* ready);
+int msim_snapshot_end(msim_handle* h, const msim_entity** entities, uint64_t* count);
 /* Rendering fast path: positions only (8 B per entity) and collision flags (1 B per entity). */
 int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count);
 int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count);

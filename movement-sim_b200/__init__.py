@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "msim_create", "msim_destroy", "msim_last_error", "msim_status_string", "msim_upload_entities",
     "msim_dispatch", "msim_enqueue_move", "msim_enqueue_collide", "msim_enqueue_ticks", "msim_sync",
     "msim_set_stream", "msim_read_entities", "msim_read_positions", "msim_read_collision_flags",
-    "msim_read_quadtree_nodes", "msim_read_debug", "msim_get_stats", "msim_get_device_view",
+    "msim_read_quadtree_nodes", "msim_read_debug", "msim_snapshot_begin", "msim_snapshot_poll", "msim_snapshot_end", "msim_get_stats", "msim_get_device_view",
     "msim_profile_begin", "msim_profile_end",
     "msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid",
     "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
@@ -213,6 +213,9 @@ def lib():
         "msim_read_collision_flags": (i32, [vp, vp, u64]),
         "msim_read_quadtree_nodes": (i32, [vp, vp, u64, C.POINTER(u64)]),
         "msim_read_debug": (i32, [vp, vp]),
+        "msim_snapshot_begin": (i32, [vp]),
+        "msim_snapshot_poll": (i32, [vp, C.POINTER(i32)]),
+        "msim_snapshot_end": (i32, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "msim_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "msim_get_device_view": (i32, [vp, C.POINTER(DeviceView)]),
         "msim_profile_begin": (i32, [vp]),
@@ -481,6 +484,25 @@ class Simulation:
 
     def read_entities_ptr(self, ptr: int, count: int):
         self._check(lib().msim_read_entities(self._h, ptr, count))
+
+    def snapshot_begin(self):
+        """Asynchronous readback: image of the current state, copied to pinned host memory while later ticks run."""
+        self._check(lib().msim_snapshot_begin(self._h))
+
+    def snapshot_ready(self) -> bool:
+        ready = C.c_int(0)
+        self._check(lib().msim_snapshot_poll(self._h, C.byref(ready)))
+        return bool(ready.value)
+
+    def snapshot_end(self, copy: bool = True) -> np.ndarray:
+        """Entities of the last snapshot_begin.  copy=False returns a view of the library's pinned buffer (valid until the
+        begin after the next one)."""
+        ptr, count = C.c_void_p(), C.c_uint64()
+        self._check(lib().msim_snapshot_end(self._h, C.byref(ptr), C.byref(count)))
+        if count.value == 0:
+            return np.empty(0, dtype=ENTITY_DTYPE)
+        view = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count.value * 64,)).view(ENTITY_DTYPE)
+        return view.copy() if copy else view
 
     def read_positions(self) -> np.ndarray:
         out = np.empty((self.count, 2), dtype=np.float32)

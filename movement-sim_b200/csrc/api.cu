@@ -151,6 +151,16 @@ struct msim_handle {
     uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
     bool async_counts{false};       // host-side n / n_ghost are stale (upper bound = capacity) until the next refresh
 
+    // asynchronous readback (msim_snapshot_*): device image of the AoS state, two pinned host buffers used alternately
+    msim_entity* snap_dev{nullptr};
+    msim_entity* snap_host[2]{nullptr, nullptr};
+    size_t snap_cap{0};
+    uint64_t snap_count{0};
+    int snap_slot{0};
+    bool snap_pending{false};
+    cudaStream_t copy_stream{nullptr};
+    cudaEvent_t ev_packed{nullptr}, ev_copied{nullptr};
+
     Profiler prof;
     std::string error;
 };
@@ -251,6 +261,15 @@ void free_all(msim_handle* h) {
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    cudaFree(h->snap_dev);
+    for (msim_entity* p : h->snap_host)
+        if (p) cudaFreeHost(p);
+    if (h->ev_packed) cudaEventDestroy(h->ev_packed);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
@@ -659,6 +678,27 @@ int materialise_flags(msim_handle* h) {
     return MSIM_OK;
 }
 
+// arguments of the SoA -> AoS pack for a readback of the current state; completes a pending pass B and the lazy flag scatter first
+PackArgs pack_args(msim_handle* h) {
+    materialise_flags(h);
+    join_side(h);
+    PackArgs a{};
+    a.pos_cur = h->pos[h->cur];
+    a.pos_prev = h->pos[h->cur ^ 1];
+    a.target = h->target;
+    a.road = h->road;
+    a.rng = h->rng;
+    a.color0 = h->color0;
+    a.dir0 = h->dir0;
+    a.arrived = h->arrived;
+    a.flag_entity = h->collided ? h->flag_entity : nullptr;
+    a.init_mask = nullptr;
+    a.slot_of = h->perm_active ? h->slot_of : nullptr;
+    a.initialized_all = h->uninitialised ? 0u : 1u;
+    a.has_moved = h->has_moved ? 1u : 0u;
+    return a;
+}
+
 }  // namespace
 
 extern "C" {
@@ -880,28 +920,77 @@ int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
     if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
     if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_move_pack and msim_shard_integrate");
     if (h->flags_stale) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_integrate and the collision pass");
-    materialise_flags(h);
-    join_side(h);
-    PackArgs a{};
-    a.pos_cur = h->pos[h->cur];
-    a.pos_prev = h->pos[h->cur ^ 1];
-    a.target = h->target;
-    a.road = h->road;
-    a.rng = h->rng;
-    a.color0 = h->color0;
-    a.dir0 = h->dir0;
-    a.arrived = h->arrived;
-    a.flag_entity = h->collided ? h->flag_entity : nullptr;
-    a.init_mask = nullptr;
-    a.slot_of = h->perm_active ? h->slot_of : nullptr;
-    a.initialized_all = h->uninitialised ? 0u : 1u;
-    a.has_moved = h->has_moved ? 1u : 0u;
+    const PackArgs a = pack_args(h);
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
         const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
         h->launches += launch_pack(h->stream, static_cast<uint32_t>(off), chunk, a, h->stage, &h->prof);
         MSIM_CUDA(h, cudaMemcpyAsync(dst + off, h->stage, static_cast<size_t>(chunk) * sizeof(msim_entity), cudaMemcpyDeviceToHost, h->stream));
     }
     return check_device_errors(h);
+}
+
+/* ---- asynchronous readback: snapshot now, copy while later ticks run (include/msim.h) -------------------------- */
+int msim_snapshot_begin(msim_handle* h) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    rc = refresh_counts(h);
+    if (rc != MSIM_OK) return rc;
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_begin: sharded handle is between msim_shard_move_pack and msim_shard_integrate");
+    if (h->flags_stale) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_begin: sharded handle is between msim_shard_integrate and the collision pass");
+    if (h->snap_cap < h->n || !h->snap_dev) {  // (re)allocate for the resident population: device image + two pinned host buffers
+        if (h->snap_pending) MSIM_CUDA(h, cudaEventSynchronize(h->ev_copied));
+        h->snap_pending = false;
+        cudaFree(h->snap_dev);
+        h->snap_dev = nullptr;
+        for (msim_entity*& p : h->snap_host) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+        }
+        h->snap_cap = 0;
+        const size_t cap = std::max<size_t>(h->n, 1);
+        MSIM_CUDA(h, dev_alloc(&h->snap_dev, cap));
+        for (msim_entity*& p : h->snap_host) MSIM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&p), cap * sizeof(msim_entity), cudaHostAllocDefault));
+        h->snap_cap = cap;
+        if (!h->copy_stream) MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->ev_packed) MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming));
+        if (!h->ev_copied) MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    }
+    // the device image is reused: the previous copy must have left it before it is packed again
+    if (h->snap_pending) MSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
+    const PackArgs a = pack_args(h);
+    h->launches += launch_pack(h->stream, 0u, h->n, a, h->snap_dev, &h->prof);
+    MSIM_CUDA(h, cudaEventRecord(h->ev_packed, h->stream));
+    // from here on the main stream is free for the next ticks; the copy engine drains the image on its own stream
+    h->snap_slot ^= 1;
+    MSIM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_packed, 0));
+    if (h->n) MSIM_CUDA(h, cudaMemcpyAsync(h->snap_host[h->snap_slot], h->snap_dev, static_cast<size_t>(h->n) * sizeof(msim_entity), cudaMemcpyDeviceToHost, h->copy_stream));
+    MSIM_CUDA(h, cudaEventRecord(h->ev_copied, h->copy_stream));
+    h->snap_count = h->n;
+    h->snap_pending = true;
+    return MSIM_OK;
+}
+
+int msim_snapshot_poll(msim_handle* h, int* ready) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!ready) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_poll: ready is null");
+    if (!h->snap_pending) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_poll: no snapshot has been started");
+    const cudaError_t q = cudaEventQuery(h->ev_copied);
+    if (q != cudaSuccess && q != cudaErrorNotReady) MSIM_CUDA(h, q);
+    *ready = q == cudaSuccess ? 1 : 0;
+    return MSIM_OK;
+}
+
+int msim_snapshot_end(msim_handle* h, const msim_entity** entities, uint64_t* count) {
+    int rc = bind(h);
+    if (rc != MSIM_OK) return rc;
+    if (!entities || !count) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_end: null argument");
+    if (!h->snap_pending) return fail(h, MSIM_ERR_INVALID, "msim_snapshot_end: no snapshot has been started");
+    MSIM_CUDA(h, cudaEventSynchronize(h->ev_copied));
+    h->snap_pending = false;
+    *entities = h->snap_host[h->snap_slot];
+    *count = h->snap_count;
+    return MSIM_OK;
 }
 
 int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count) {

@@ -99,3 +99,51 @@ def test_move_tuning_variants_in_subprocess(env):
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+# ---- msim_snapshot_*: asynchronous readback into pinned double buffers ----------------------------------------------
+def test_snapshot_is_the_state_at_begin(msim, orc, small_city):
+    """A snapshot holds the state as of msim_snapshot_begin even though more ticks are enqueued before it is collected; two
+    snapshots alternate between two pinned buffers, so the first stays intact while the second is filled."""
+    n = 30_000
+    ents = small_city.init_entities(n, seed=21)
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+        sim.dispatch(2)
+        oracle_dispatch(orc, want, omap, 10.0, 2)
+        tick = 3
+
+        def advance(k):
+            nonlocal tick
+            sim.enqueue_ticks(k, True)
+            for _ in range(k):
+                oracle_dispatch(orc, want, omap, 10.0, tick + 1)
+                oracle_dispatch(orc, want, omap, 10.0, tick + 2)
+                tick += 2
+
+        advance(5)
+        sim.snapshot_begin()
+        want_a = want.copy()
+        advance(7)  # runs while the copy engine drains the image
+        snap_a = sim.snapshot_end(copy=False)
+        assert_entities_equal(snap_a, want_a, what="snapshot A = state at begin")
+        sim.snapshot_begin()
+        want_b = want.copy()
+        advance(2)
+        while not sim.snapshot_ready():
+            pass
+        snap_b = sim.snapshot_end(copy=False)
+        assert_entities_equal(snap_b, want_b, what="snapshot B")
+        assert_entities_equal(snap_a, want_a, what="snapshot A after B was taken (other pinned buffer)")
+        assert_entities_equal(sim.read_entities(), want, what="blocking readback afterwards")
+
+
+def test_snapshot_argument_errors(msim, test_map):
+    with msim.Simulation(test_map, test_map.init_entities(100), flags=msim.FLAG_NO_COLLISIONS) as sim:
+        with pytest.raises(msim.MsimError) as ei:
+            sim.snapshot_end()
+        assert ei.value.status == msim.MSIM_ERR_INVALID and "no snapshot" in ei.value.message
+        sim.snapshot_begin()
+        got = sim.snapshot_end()
+        assert got.shape[0] == 100 and np.array_equal(got["road_index"], sim.read_entities()["road_index"])
