@@ -1,0 +1,24 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~12 min of box time):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash profiles/run_r2_first.sh'
+# 1. the required suite (must stay green), 2. the gated tests of the paths written without a GPU, 3. one bench line per
+# experiment knob (short runs: 100 steps, no CPU baseline), 4. collisions-off at 10 M with and without the fused pass B.
+# Everything lands in gpurun_out/r2a_*.  Nothing here is a result until it has been read and copied to profiles/.
+set -x
+mkdir -p gpurun_out
+B="python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2a_pytest_gpu.log
+MSIM_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_zz_gpu_unverified.py -m gpu -q > gpurun_out/r2a_pytest_unverified.log 2>&1; tail -15 gpurun_out/r2a_pytest_unverified.log
+
+$B > gpurun_out/r2a_bench_default.json 2> gpurun_out/r2a_bench_default.err
+$B --fused-arrive > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fused.err
+MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_bench_minb5.err
+MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
+MSIM_MOVE_GRID=occupancy $B > gpurun_out/r2a_bench_occgrid.json 2> gpurun_out/r2a_bench_occgrid.err
+MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy $B --fused-arrive > gpurun_out/r2a_bench_fused_minb6_occ.json 2> gpurun_out/r2a_bench_fused_minb6_occ.err
+# collisions off: BASELINE configs[1] (1 M, L2 flushed between steps) and the same at 10 M (HBM-bound)
+$B --workload munich_1m_nocollisions > gpurun_out/r2a_bench_1m_off.json 2> gpurun_out/r2a_bench_1m_off.err
+$B --workload munich_1m_nocollisions --fused-arrive > gpurun_out/r2a_bench_1m_off_fused.json 2> gpurun_out/r2a_bench_1m_off_fused.err
+$B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off.json 2> gpurun_out/r2a_bench_10m_off.err
+$B --workload munich_1m_nocollisions --entities 10000000 --fused-arrive > gpurun_out/r2a_bench_10m_off_fused.json 2> gpurun_out/r2a_bench_10m_off_fused.err
+for f in gpurun_out/r2a_bench_*.json; do echo "== $f"; python profiles/show_bench.py "$f" 2>/dev/null | head -12; done
