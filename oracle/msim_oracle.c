@@ -5,8 +5,9 @@
  * compute shader /root/reference/src/sim/shader/random_move.comp.  Every function cites the lines
  * it follows.  Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
  *
- * Parity pin: movement/RNG "unpinned" by the reference's own tests (none exist); collision flags
- * pinned against the reference's CPU quadtree (oracle/_ref) — see msim_oracle.h.
+ * Parity pin: both halves are pinned against the reference's own code compiled into oracle/_ref — movement / RNG / road
+ * choice against the shader's own text (libref_shader_move.so), collision flags against the reference's CPU quadtree
+ * (libref_quadtree.so) — see msim_oracle.h.
  */
 #include "msim_oracle.h"
 

@@ -16,8 +16,14 @@
  * -ffp-contract=off), correctly rounded sqrt and divide.
  *
  * PARITY PIN STATUS.  The reference holds no golden vector for movement / road choice / RNG
- * (SURVEY.md §8c): for those functions this oracle is authored from the shader text and parity is
- * "unpinned" by the reference's own tests.  The collision half IS pinned: the reference's CPU
+ * (SURVEY.md §8c), so the pin is the reference's own source: oracle/Makefile compiles the movement
+ * functions of random_move.comp (:5-24, :725-750, :778-852) as C++ into oracle/_ref/libref_shader_move.so
+ * (GLSL prelude + driver of ours around the streamed shader text) and this oracle must equal it bit for
+ * bit on every field after every pass (tests/test_oracle_vs_ref_shader.py: config 1 in full, a street
+ * graph population, RNG known answers, degenerate distances); digests the compiled shader produced are
+ * committed for boxes without oracle/_ref (tests/golden/ref_shader_digests.json).  What stays open is
+ * the float freedom of a real Vulkan driver: both sides use IEEE RNE without FMA.
+ * The collision half is pinned as well: the reference's CPU
  * restatement (shader_validation/src/main.cpp) is compiled into oracle/_ref and (a) its disabled
  * known-answer test run_collision_detection_test_1 passes, (b) its flagged set equals this oracle's
  * on seeded point clouds (tests/test_oracle_vs_ref.py).  calc_node_count(1,2,3,4,8) = 1,5,21,85,21845

@@ -254,6 +254,46 @@ class RefQuadTree:
         return rects[:n], types[:n], counts[:n]
 
 
+# --------------------------------------------------------------------------------------------
+# The movement half of the reference's compute shader, compiled from its own text (oracle/Makefile,
+# oracle/ref_shader_prelude.inc + random_move.comp:5-24,725-750,778-852 + oracle/ref_shader_driver.inc)
+# --------------------------------------------------------------------------------------------
+REF_SHADER_LIB = os.path.join(HERE, "_ref", "libref_shader_move.so")
+_ref_shader = None
+
+
+def ref_shader_available() -> bool:
+    return os.path.exists(REF_SHADER_LIB)
+
+
+def ref_shader():
+    global _ref_shader
+    if _ref_shader is None:
+        R = C.CDLL(REF_SHADER_LIB)
+        R.ref_shader_move_pass.restype = None
+        R.ref_shader_move_pass.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        for name in ("ref_shader_next", "ref_shader_next_range"):
+            getattr(R, name).restype = C.c_uint32
+        R.ref_shader_next.argtypes = [C.c_void_p]
+        R.ref_shader_next_range.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        R.ref_shader_next_float.restype = C.c_float
+        R.ref_shader_next_float.argtypes = [C.c_void_p]
+        R.ref_shader_speed.restype = C.c_float
+        _ref_shader = R
+    return _ref_shader
+
+
+def ref_shader_move_pass(e: np.ndarray, m: OracleMap) -> None:
+    """One even-tick dispatch of the shader's main() (random_move.comp:860-873) over all entities, executed by the
+    shader's own update_direction / move / new_target / next compiled for the CPU."""
+    _check_entities(e)
+    padded = getattr(m, "_padded_connections", None)
+    if padded is None:  # App. B1: the shader reads one entry past the table; canonical value 0
+        padded = np.concatenate([m.connections, np.zeros(1, dtype=np.uint32)])
+        m._padded_connections = padded
+    ref_shader().ref_shader_move_pass(e.ctypes.data, 0, e.shape[0], m.roads.ctypes.data, padded.ctypes.data)
+
+
 def run_ref_kat() -> subprocess.CompletedProcess:
     """Runs the reference's own (disabled) known-answer test in a subprocess (it asserts)."""
     return subprocess.run([REF_KAT], capture_output=True, text=True, timeout=120)

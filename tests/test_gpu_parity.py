@@ -50,6 +50,22 @@ def test_config1_test_map_10k_1000_moves(msim, orc, test_map):
         assert st["move_passes"] == 1000 and st["collide_passes"] == 0
 
 
+def test_cuda_path_matches_compiled_shader(msim, orc, small_city):
+    """The CUDA move path against the reference's OWN movement code: random_move.comp compiled for the CPU
+    (oracle/_ref/libref_shader_move.so, see tests/test_oracle_vs_ref_shader.py) instead of the oracle's restatement."""
+    if not orc.ref_shader_available():
+        pytest.skip("oracle/_ref/libref_shader_move.so not built (needs /root/reference at build time)")
+    ents = small_city.init_entities(30_000, seed=17)
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+    with msim.Simulation(small_city, ents, flags=msim.FLAG_NO_COLLISIONS) as sim:
+        for step in range(1 + 250):
+            sim.dispatch(2 + 2 * step)
+            orc.ref_shader_move_pass(want, omap)
+            if step in (0, 1, 2, 30, 100, 250):
+                assert_entities_equal(sim.read_entities(), want, what=f"dispatch {step} vs compiled shader")
+
+
 def test_enqueue_ticks_matches_dispatch(msim, orc, test_map):
     ents = test_map.init_entities(4097, seed=3)
     omap = oracle_map(orc, test_map)

@@ -1,0 +1,127 @@
+"""Pins the oracle's MOVEMENT half (RNG, road choice, update_direction, move) against the reference's own shader text:
+oracle/Makefile compiles /root/reference/src/sim/shader/random_move.comp:5-24,725-750,778-852 as C++ between a GLSL
+prelude and a C driver into oracle/_ref/libref_shader_move.so (nothing of the shader is copied into the repository).
+The C restatement oracle/msim_oracle.c must agree with it bit for bit on every field, every tick.
+
+Where oracle/_ref is not available (a clone without the reference checkout) the same pin is held by digests the
+compiled shader produced here: tests/golden/ref_shader_digests.json (script: tests/golden/make_ref_shader_golden.py).
+
+Residual freedom this cannot close: a real Vulkan driver may round sqrt / division less precisely
+or contract a*b+c; the compiled shader, like the oracle, is evaluated with IEEE-754 RNE and no contraction."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, oracle_map, to_oracle_entities
+
+
+@pytest.fixture(scope="module")
+def shader(orc):
+    if not orc.ref_shader_available():
+        pytest.skip("oracle/_ref/libref_shader_move.so not built (needs /root/reference at build time)")
+    return orc
+
+
+def bytes_equal(a, b, what):
+    if a.tobytes() != b.tobytes():
+        bad = np.nonzero((a.view(np.uint32).reshape(-1, 16) != b.view(np.uint32).reshape(-1, 16)).any(axis=1))[0]
+        raise AssertionError(f"{what}: {bad.size} of {a.shape[0]} entities differ; first {int(bad[0])}: oracle {a[bad[0]]} shader {b[bad[0]]}")
+
+
+def test_rng_functions_match_shader(shader):
+    """xorshift128 / next_float / next(state, min, max) (random_move.comp:725-746): oracle C, oracle numpy helper and the
+    compiled shader on the same states, including the states that give the extreme outputs."""
+    R = shader.ref_shader()
+    assert R.ref_shader_speed() == np.float32(1.4)
+    rnd = np.random.default_rng(5)
+    states = [rnd.integers(0, 2**32, size=4, dtype=np.uint32) for _ in range(2000)]
+    states += [np.array(s, dtype=np.uint32) for s in ([0, 0, 0, 0], [1, 0, 0, 0], [0, 0, 0, 1], [0xFFFFFFFF] * 4, [0, 0, 0, 0x80000000])]
+    for st in states:
+        for lo, hi in ((1, 3), (1, 4), (1, 5), (1, 7), (0, 0), (3, 9)):
+            a, b = st.copy(), st.copy()
+            want = R.ref_shader_next_range(b.ctypes.data, lo, hi)
+            assert shader.next_range(a, lo, hi) == want and (a == b).all()
+        a, b = st.copy(), st.copy()
+        assert shader.xorshift128(a) == R.ref_shader_next(b.ctypes.data) and (a == b).all()
+        a, b = st.copy(), st.copy()
+        got, want = np.float32(shader.next_float(a)), np.float32(R.ref_shader_next_float(b.ctypes.data))
+        assert got.tobytes() == want.tobytes() and (a == b).all()
+
+
+def test_config1_matches_shader_every_tick(shader, msim, test_map):
+    """BASELINE config 1 (test_map.json, 10 k entities, seed 42, 1000 move passes): oracle == compiled shader after every pass.
+    test_map has 4-way junctions (RNG draws) and the past-the-end connection read of App. B1."""
+    ents = test_map.init_entities(10_000, seed=42)
+    omap = oracle_map(shader, test_map)
+    a = to_oracle_entities(shader, ents)
+    b = a.copy()
+    stats = {"arrivals": 0, "rng_draws": 0, "oob_reads": 0}
+    for tick in range(1001):
+        st = shader.move_pass(a, omap)
+        shader.ref_shader_move_pass(b, omap)
+        for k in stats:
+            stats[k] += st[k]
+        bytes_equal(a, b, f"pass {tick}")
+    assert stats["arrivals"] > 200_000 and stats["rng_draws"] > 100_000 and stats["oob_reads"] > 1_000, stats
+
+
+def test_city_population_matches_shader(shader, small_city):
+    """Munich-style street graph (dead ends, 2-way continuations, 3-5-way junctions): 60 k entities, 400 move passes."""
+    ents = small_city.init_entities(60_000, seed=9)
+    omap = oracle_map(shader, small_city)
+    a = to_oracle_entities(shader, ents)
+    b = a.copy()
+    uturns = 0
+    for tick in range(401):
+        st = shader.move_pass(a, omap, threads=4)
+        shader.ref_shader_move_pass(b, omap)
+        uturns += st["uturns"]
+        if tick % 20 == 0 or tick > 390:
+            bytes_equal(a, b, f"pass {tick}")
+    bytes_equal(a, b, "final")
+    assert uturns > 1000
+
+
+def test_degenerate_inputs_match_shader(shader, test_map):
+    """Entities that start ON their waypoint (len == 0 -> direction (0,0), :832-835), exactly SPEED away (dist > SPEED is
+    false -> arrival, :844), and one ULP further (walks)."""
+    omap = oracle_map(shader, test_map)
+    e = to_oracle_entities(shader, test_map.init_entities(6, seed=1))
+    e["initialized"] = 1
+    tgt = e["target"].copy()
+    e["pos"][0] = tgt[0]
+    e["pos"][1] = tgt[1] - np.array([1.4, 0.0], dtype=np.float32)
+    e["pos"][2] = tgt[2] - np.array([np.nextafter(np.float32(1.4), np.float32(2.0)), 0.0], dtype=np.float32)
+    e["pos"][3] = tgt[3] - np.array([0.0, 1.4], dtype=np.float32)
+    a, b = e.copy(), e.copy()
+    for tick in range(60):
+        shader.move_pass(a, omap)
+        shader.ref_shader_move_pass(b, omap)
+        bytes_equal(a, b, f"pass {tick}")
+
+
+# ---- the same pin without oracle/_ref: digests produced by the compiled shader ------------------------------------
+def digest_run(O, step, m, ents, passes, every):
+    omap = oracle_map(O, m)
+    e = to_oracle_entities(O, ents)
+    out = []
+    for t in range(passes):
+        step(e, omap)
+        if (t + 1) % every == 0:
+            out.append(hashlib.sha256(e.tobytes()).hexdigest())
+    return out
+
+
+def test_oracle_matches_committed_shader_digests(orc, msim, test_map, small_city):
+    path = os.path.join(GOLDEN, "ref_shader_digests.json")
+    with open(path) as f:
+        gold = json.load(f)
+    cases = {"test_map_10k_seed42": (test_map, test_map.init_entities(10_000, seed=42)),
+             "small_city_20k_seed9": (small_city, small_city.init_entities(20_000, seed=9))}
+    for name, (m, ents) in cases.items():
+        g = gold[name]
+        got = digest_run(orc, lambda e, omap: orc.move_pass(e, omap), m, ents, g["passes"], g["every"])
+        assert got == g["sha256"], f"{name}: oracle state diverges from the compiled shader's at digest {[i for i, (x, y) in enumerate(zip(got, g['sha256'])) if x != y][:1]}"
