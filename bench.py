@@ -174,17 +174,21 @@ def build_workload(M, name: str, entities_override: int | None, seed: int = 42):
 # --------------------------------------------------------------------------------------------------
 # CPU: the reference's own CPU path (oracle/_ref quadtree) + the oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_step(O, e, omap, radius, threads, collisions, use_ref):
-    """One sim tick on the host.  Movement always comes from the oracle port (the reference's CPU
-    harness has no road-graph movement, shader_validation/src/main.cpp:923-957); the neighbour
-    structure is the reference's own quadtree when oracle/_ref is available: rebuilt by
-    quad_tree_insert (single-threaded: its multi-threaded insert and its incremental
-    quad_tree_update trip the harness's own lock assertions) and queried by
-    quad_tree_check_collisions on all host threads."""
-    O.move_pass(e, omap, threads=threads)
+def cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree):
+    """One sim tick on the host with as much of the reference's OWN code as compiles here (oracle/_ref):
+    movement = the shader's update_direction / move / new_target / next compiled for the CPU (random_move.comp:725-852,
+    libref_shader_move.so) on all host threads by static entity ranges, else the oracle port;
+    neighbour structure = the reference's CPU quadtree (shader_validation/src/main.cpp, libref_quadtree.so): rebuilt by
+    quad_tree_insert (single-threaded: its multi-threaded insert and its incremental quad_tree_update trip the harness's
+    own lock assertions) and queried by quad_tree_check_collisions on all host threads, else the oracle's
+    cell grid."""
+    if ref_move:
+        O.ref_shader_move_pass(e, omap, threads=threads)
+    else:
+        O.move_pass(e, omap, threads=threads)
     if not collisions:
         return
-    if use_ref:
+    if ref_tree:
         q = O.RefQuadTree(omap.world_w, omap.world_h, radius, 10)
         q.insert(e["pos"], 1)
         q.collide(threads)
@@ -192,16 +196,27 @@ def cpu_step(O, e, omap, radius, threads, collisions, use_ref):
         O.collide_pass(e, omap.world_w, omap.world_h, radius, threads=threads)
 
 
-def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, use_ref, threads):
+def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, ref_move, ref_tree, threads):
     e = np.ascontiguousarray(ents_aos).view(O.ENTITY_DTYPE).copy()
     e["initialized"] = 1
     for _ in range(warmup):
-        cpu_step(O, e, omap, radius, threads, collisions, use_ref)
+        cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(O, e, omap, radius, threads, collisions, use_ref)
+        cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree)
     dt = time.perf_counter() - t0
     return e.shape[0] * steps / dt, dt / steps
+
+
+def cpu_arm_description(ref_move, ref_tree, collisions):
+    """kind + wording of the CPU arm: "reference" only when every part of the step is the reference's own code."""
+    move = ("movement = the reference shader's own move / new_target / RNG code compiled for the CPU (oracle/_ref/libref_shader_move.so), all threads"
+            if ref_move else "movement = oracle port, all threads")
+    if not collisions:
+        return ("reference" if ref_move else "port"), move
+    tree = ("neighbour structure = reference quadtree (oracle/_ref/libref_quadtree.so): insert on 1 thread, collision walk on all threads"
+            if ref_tree else "neighbour structure = oracle cell grid, all threads")
+    return ("reference" if (ref_move and ref_tree) else "port"), move + "; " + tree
 
 
 def run_reference(args):
@@ -214,8 +229,9 @@ def run_reference(args):
 
     w, m = build_workload(M, args.workload, args.entities)
     threads = os.cpu_count() or 1
-    use_ref = O.ref_available() and w["collisions"]
-    sample = min(w["entities"], args.ref_sample, int(O.ref().ref_capacity()) if use_ref else 1 << 62)
+    ref_move = O.ref_shader_available()
+    ref_tree = O.ref_available() and w["collisions"]
+    sample = min(w["entities"], args.ref_sample, int(O.ref().ref_capacity()) if ref_tree else 1 << 62)
     omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
     ents = m.init_entities(sample, seed=42, box=w["box"])
     e = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()
@@ -224,11 +240,9 @@ def run_reference(args):
         O.move_pass(e, omap, threads=threads)
     steps = max(1, min(args.steps, args.ref_max_steps))
     warmup = max(1, min(args.warmup, 2))
-    value, sec = time_cpu(O, e, omap, 10.0, w["collisions"], steps, warmup, use_ref, threads)
-    kind = "reference" if use_ref else "port"
-    sample_desc = (f"{sample} of {w['entities']} entities of the same workload, {steps} sim ticks after {args.preroll} pre-roll move passes; "
-                   + ("movement = oracle port on all threads, neighbour structure = reference quadtree (oracle/_ref): insert on 1 thread, collision walk on all threads"
-                      if use_ref else "oracle port (move + cell-grid collisions) on all threads"))
+    value, sec = time_cpu(O, e, omap, 10.0, w["collisions"], steps, warmup, ref_move, ref_tree, threads)
+    kind, how = cpu_arm_description(ref_move, ref_tree, w["collisions"])
+    sample_desc = f"{sample} of {w['entities']} entities of the same workload, {steps} sim ticks after {args.preroll} pre-roll move passes; {how}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32",
@@ -407,16 +421,16 @@ def run_b200(args):
         from oracle import oracle as O
 
         threads = os.cpu_count() or 1
-        use_ref = O.ref_available() and collisions
-        sample = min(n, args.cpu_sample, int(O.ref().ref_capacity()) if use_ref else 1 << 62)
+        ref_move = O.ref_shader_available()
+        ref_tree = O.ref_available() and collisions
+        sample = min(n, args.cpu_sample, int(O.ref().ref_capacity()) if ref_tree else 1 << 62)
         host = np.frombuffer(pinned.numpy(), dtype=M.ENTITY_DTYPE)[:sample]
         omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
-        v, sec = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, use_ref, threads)
-        v_port, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, False, threads)
-        cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": "reference" if use_ref else "port",
-               "sample": f"first {sample} entities of the resident population, {args.cpu_steps} sim ticks, {sec:.3f} s per tick; "
-                         + ("movement = oracle port (all threads), neighbour structure = reference quadtree from oracle/_ref (insert 1 thread, collision walk all threads)"
-                            if use_ref else "oracle port on all threads"),
+        v, sec = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, ref_move, ref_tree, threads)
+        v_port, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, False, False, threads)
+        kind, how = cpu_arm_description(ref_move, ref_tree, collisions)
+        cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": kind,
+               "sample": f"first {sample} entities of the resident population, {args.cpu_steps} sim ticks, {sec:.3f} s per tick; {how}",
                "port_value": v_port}
 
     line = {

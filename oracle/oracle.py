@@ -279,11 +279,13 @@ def ref_shader():
         R.ref_shader_next_float.restype = C.c_float
         R.ref_shader_next_float.argtypes = [C.c_void_p]
         R.ref_shader_speed.restype = C.c_float
+        R.ref_shader_move_pass_mt.restype = None
+        R.ref_shader_move_pass_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         _ref_shader = R
     return _ref_shader
 
 
-def ref_shader_move_pass(e: np.ndarray, m: OracleMap) -> None:
+def ref_shader_move_pass(e: np.ndarray, m: OracleMap, threads: int = 1) -> None:
     """One even-tick dispatch of the shader's main() (random_move.comp:860-873) over all entities, executed by the
     shader's own update_direction / move / new_target / next compiled for the CPU."""
     _check_entities(e)
@@ -291,7 +293,10 @@ def ref_shader_move_pass(e: np.ndarray, m: OracleMap) -> None:
     if padded is None:  # App. B1: the shader reads one entry past the table; canonical value 0
         padded = np.concatenate([m.connections, np.zeros(1, dtype=np.uint32)])
         m._padded_connections = padded
-    ref_shader().ref_shader_move_pass(e.ctypes.data, 0, e.shape[0], m.roads.ctypes.data, padded.ctypes.data)
+    if threads > 1:
+        ref_shader().ref_shader_move_pass_mt(e.ctypes.data, e.shape[0], m.roads.ctypes.data, padded.ctypes.data, threads)
+    else:
+        ref_shader().ref_shader_move_pass(e.ctypes.data, 0, e.shape[0], m.roads.ctypes.data, padded.ctypes.data)
 
 
 def run_ref_kat() -> subprocess.CompletedProcess:

@@ -37,7 +37,11 @@ def test_reference_arm_config1():
     line = run_bench("--impl", "reference", "--workload", "test_map_10k_nocollisions", "--steps", "3", "--warmup", "1", "--preroll", "4")
     check_reference_line(line, "test_map_10k_nocollisions")
     assert line["config"]["collisions"] is False and line["config"]["entities_sampled"] == 10_000
-    assert line["cpu_baseline"]["kind"] == "port"  # the reference's CPU harness has no road-graph movement
+    from oracle import oracle as O
+
+    # movement is the reference shader's own code compiled for the CPU when oracle/_ref was built, else the oracle port
+    assert line["cpu_baseline"]["kind"] == ("reference" if O.ref_shader_available() else "port")
+    assert ("libref_shader_move.so" in line["cpu_baseline"]["sample"]) == O.ref_shader_available()
 
 
 def test_reference_arm_dense_crowd_sample():
