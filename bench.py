@@ -414,6 +414,28 @@ def run_b200(args):
     e2e = {"value": n * e2e_steps / (e2e_ms * 1e-3), "unit": "entity-updates/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 64,
            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
            "what": "msim_upload_entities(pinned AoS) + msim_dispatch(move)" + (" + msim_dispatch(collide)" if collisions else "") + " + msim_read_entities(pinned AoS), blocking calls"}
+    if args.e2e_pipelined:
+        # experiment (msim_snapshot_* has not run on hardware yet): the readback of step i leaves through the copy stream while
+        # step i+1 uploads and computes - PCIe is full duplex, so the two 64 B x N transfers overlap instead of adding up
+        def piped_step(first):
+            nonlocal tick
+            sim.upload_ptr(ptr, n)
+            sim.dispatch(tick)
+            if collisions:
+                sim.dispatch(tick + 1)
+            tick += 2
+            if not first:
+                sim.snapshot_end(copy=False)  # result of the previous step (library-owned pinned memory)
+            sim.snapshot_begin()
+
+        piped_step(True)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            piped_step(False)
+        sim.snapshot_end(copy=False)
+        wall = time.perf_counter() - t0
+        e2e["pipelined"] = {"value": n * e2e_steps / wall, "ms_per_step": wall * 1e3 / e2e_steps,
+                            "what": "same bytes per step; msim_snapshot_begin/end instead of msim_read_entities (D2H of step i overlaps H2D + compute of step i+1), wall clock"}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
     cpu = None
@@ -480,6 +502,7 @@ def main():
     ap.add_argument("--counting-sort", action="store_true", help="force the single-digit counting sort")
     ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")
     ap.add_argument("--no-reorder", action="store_true", help="keep the state in upload order (onesweep rebuild)")
+    ap.add_argument("--e2e-pipelined", action="store_true", help="experiment (not yet run on hardware): adds e2e.pipelined, readback through msim_snapshot_*")
     ap.add_argument("--fused-arrive", action="store_true",
                     help="experiment (not yet run on hardware): MSIM_FLAG_FUSED_ARRIVE, the next-waypoint pass rides inside the next move kernel")
     args = ap.parse_args()

@@ -28,7 +28,8 @@ thread_local std::string g_create_error;
 constexpr uint64_t MAX_ENTITIES_PER_HANDLE = 1ull << 30;  // look-back words carry 30-bit counts
 constexpr uint32_t MAX_GRID_CELLS = 1u << 27;
 constexpr uint32_t STAGE_ENTITIES = 1u << 20;  // 64 MiB AoS staging chunk
-constexpr uint32_t CSORT_MAX_CELLS = 1u << 25;  // counter + prefix tables of 2 x 128 MiB at most; beyond that: onesweep
+// counting sort: counter + prefix tables of 2 x 128 MiB at most by default (2^25 cells); beyond that: onesweep
+inline uint32_t csort_max_cells() { return 1u << msim::tuning().csort_max_cells_log2; }
 }  // namespace
 
 struct msim_handle {
@@ -168,7 +169,11 @@ struct msim_handle {
 namespace msim {
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v{0, false};
+        Tuning v{0, false, 25};
+        if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
+            const int k = std::atoi(e);
+            if (k >= 25 && k <= 27) v.csort_max_cells_log2 = k;
+        }
         if (const char* e = std::getenv("MSIM_MOVE_MIN_BLOCKS")) {
             const int k = std::atoi(e);
             if (k == 5 || k == 6) v.move_min_blocks = k;
@@ -351,8 +356,7 @@ void prepare_counts(msim_handle* h) {
 int ensure_cells(msim_handle* h) {
     // counting sort: on request, or by default whenever the storage is kept in cell order
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
-    h->use_csort = want_counting && h->grid.ncells <= CSORT_MAX_CELLS;
-    if ((h->flags & MSIM_FLAG_SORT_COUNTING) && h->grid.ncells <= CSORT_MAX_CELLS) h->use_csort = true;
+    h->use_csort = want_counting && h->grid.ncells <= csort_max_cells();
     if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
     cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums);
     h->cell_range = nullptr; h->cell_count = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;

@@ -96,6 +96,7 @@ SimulatorConfig SimulatorConfig::from_environment() {
     if (const char* v = env_or_null("MSIM_COLLISIONS")) c.collisions = std::strcmp(v, "0") != 0;
     if (const char* v = env_or_null("MSIM_DEVICE")) c.device = std::atoi(v);
     if (const char* v = env_or_null("MSIM_CSV")) c.csvPath = v;
+    if (const char* v = env_or_null("MSIM_ASYNC_READBACK")) c.asyncReadback = std::strcmp(v, "0") != 0;
     return c;
 }
 
@@ -271,7 +272,28 @@ void Simulator::sim_tick() {  // Simulator.cpp:213-279
         wantEntities = !entities;
         wantNodes = !quadTreeNodes;
     }
-    if (wantEntities) {
+    if (config.asyncReadback) {
+        // the reference overlaps nothing here (evalAsync + evalAwait back to back, :250-253); with a snapshot the 64 B x N copy
+        // leaves through the copy engine while the next ticks run, and is handed over once it has landed
+        if (snapshotPending && wantEntities) {
+            int ready = 0;
+            check(msim_snapshot_poll(handle, &ready), "entity readback (poll)");
+            if (ready) {
+                const msim_entity* src = nullptr;
+                uint64_t n = 0;
+                check(msim_snapshot_end(handle, &src, &n), "entity readback (collect)");
+                snapshotPending = false;
+                const Entity* first = reinterpret_cast<const Entity*>(src);
+                auto fresh = std::make_shared<std::vector<Entity>>(first, first + n);
+                std::lock_guard<std::mutex> guard(handoffMutex);
+                entities = std::move(fresh);
+            }
+        }
+        if (!snapshotPending && wantEntities) {
+            check(msim_snapshot_begin(handle), "entity readback (begin)");
+            snapshotPending = true;
+        }
+    } else if (wantEntities) {
         auto fresh = std::make_shared<std::vector<Entity>>(config.entities);
         check(msim_read_entities(handle, reinterpret_cast<msim_entity*>(fresh->data()), fresh->size()), "entity readback");
         std::lock_guard<std::mutex> guard(handoffMutex);

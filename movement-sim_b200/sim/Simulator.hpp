@@ -44,6 +44,8 @@ struct SimulatorConfig {
     float collisionRadius{COLLISION_RADIUS};
     std::filesystem::path csvPath{};               // empty = "<entities>.csv" (Simulator.cpp:337-340)
     bool quiet{false};                             // do not echo CSV rows to stderr
+    bool asyncReadback{false};                     // env MSIM_ASYNC_READBACK=1: entity readback through msim_snapshot_* (the copy overlaps
+                                                   // the following ticks; get_entities() then lags the simulation by a few ticks)
 
     static SimulatorConfig from_environment();
 };
@@ -113,6 +115,7 @@ class Simulator {
     msim_handle* handle{nullptr};  // replaces kp::Manager / kp::Tensor / kp::Algorithm / kp::Sequence
     PushConsts pushConsts{};
     uint64_t completedTicks{0};
+    bool snapshotPending{false};  // asyncReadback: a msim_snapshot_begin has not been collected yet
 
     std::mutex handoffMutex{};  // the reference hands these two pointers over unsynchronised
     std::shared_ptr<std::vector<Entity>> entities{std::make_shared<std::vector<Entity>>()};

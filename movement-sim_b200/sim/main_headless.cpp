@@ -15,13 +15,15 @@
 namespace {
 void usage() {
     std::cerr << "usage: msim_headless [--headless] [--map PATH|synthetic:city|synthetic:grid:NXxNY] [--entities N] [--seed S]\n"
-                 "                     [--ticks T] [--no-collisions] [--device D] [--csv PATH] [--dump PATH] [--quiet]\n";
+                 "                     [--ticks T] [--no-collisions] [--device D] [--csv PATH] [--dump PATH] [--quiet]\n"
+                 "                     [--consume-entities] [--async-readback]\n";
 }
 }  // namespace
 
 int main(int argc, char** argv) {
     sim::SimulatorConfig cfg = sim::SimulatorConfig::from_environment();
     std::string dumpPath;
+    bool consumeEntities = false;  // take the entity buffer like the UI does every frame (EntityGlObject.cpp:17,22): exercises the readback path
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* {
@@ -41,6 +43,8 @@ int main(int argc, char** argv) {
         else if (a == "--csv") cfg.csvPath = next();
         else if (a == "--dump") dumpPath = next();
         else if (a == "--quiet") cfg.quiet = true;
+        else if (a == "--consume-entities") consumeEntities = true;
+        else if (a == "--async-readback") cfg.asyncReadback = true;
         else {
             usage();
             return 2;
@@ -52,14 +56,18 @@ int main(int argc, char** argv) {
         simulator.start_worker();
         simulator.continue_simulation();
         const auto begin = std::chrono::steady_clock::now();
-        while (!simulator.reached_tick_limit()) std::this_thread::sleep_for(std::chrono::milliseconds(cfg.tickLimit ? 2 : 100));
+        uint64_t frames = 0;
+        while (!simulator.reached_tick_limit()) {
+            if (consumeEntities && simulator.get_entities()) frames++;  // the worker refills the buffer after a later tick
+            std::this_thread::sleep_for(std::chrono::milliseconds(cfg.tickLimit ? 2 : 100));
+        }
         const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
         simulator.pause_simulation();
         simulator.stop_worker();
         const double updates = static_cast<double>(cfg.entities) * static_cast<double>(simulator.get_completed_ticks());
         std::cout << "ticks=" << simulator.get_completed_ticks() << " entities=" << cfg.entities << " seconds=" << seconds
                   << " entity_updates_per_s=" << (seconds > 0 ? updates / seconds : 0.0) << " avg_update=" << simulator.get_update_tick_history().get_avg_time_str()
-                  << " avg_collision=" << simulator.get_collision_detection_tick_history().get_avg_time_str() << '\n';
+                  << " avg_collision=" << simulator.get_collision_detection_tick_history().get_avg_time_str() << " entity_frames=" << frames << '\n';
         if (!dumpPath.empty()) {
             std::vector<sim::Entity> out;
             simulator.read_entities_now(out);

@@ -22,3 +22,4 @@ $B --workload munich_1m_nocollisions --fused-arrive > gpurun_out/r2a_bench_1m_of
 $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off.json 2> gpurun_out/r2a_bench_10m_off.err
 $B --workload munich_1m_nocollisions --entities 10000000 --fused-arrive > gpurun_out/r2a_bench_10m_off_fused.json 2> gpurun_out/r2a_bench_10m_off_fused.err
 for f in gpurun_out/r2a_bench_*.json; do echo "== $f"; python profiles/show_bench.py "$f" 2>/dev/null | head -12; done
+$B --e2e-pipelined --e2e-steps 5 > gpurun_out/r2a_bench_e2e_pipelined.json 2> gpurun_out/r2a_bench_e2e_pipelined.err; python -c "import json; print(json.load(open(\"gpurun_out/r2a_bench_e2e_pipelined.json\"))[\"e2e\"])"

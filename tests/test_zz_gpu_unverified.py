@@ -147,3 +147,31 @@ def test_snapshot_argument_errors(msim, test_map):
         sim.snapshot_begin()
         got = sim.snapshot_end()
         assert got.shape[0] == 100 and np.array_equal(got["road_index"], sim.read_entities()["road_index"])
+
+
+# ---- the drop-in Simulator with the asynchronous readback (MSIM_ASYNC_READBACK / --async-readback) -------------------
+@pytest.mark.parametrize("mode", ["blocking", "async"])
+def test_cpp_simulator_with_a_consumer(msim, orc, small_city, tmp_path, mode):
+    """A consumer takes the entity buffer every 2 ms, like the UI does per frame; the simulation result must not depend on
+    how the readback is done, and frames must actually flow."""
+    import re
+    import subprocess
+
+    from conftest import ROOT
+
+    runner = os.path.join(ROOT, "movement-sim_b200", "msim_headless")
+    path = str(tmp_path / "city.msimmap")
+    small_city.save_binary(path)
+    dump = str(tmp_path / "entities.bin")
+    cmd = [runner, "--headless", "--quiet", "--map", path, "--entities", "40000", "--seed", "7", "--ticks", "400", "--consume-entities", "--dump", dump,
+           "--csv", str(tmp_path / "t.csv")] + (["--async-readback"] if mode == "async" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    frames = int(re.search(r"entity_frames=(\d+)", r.stdout).group(1))
+    assert frames >= 2, r.stdout
+    got = np.fromfile(dump, dtype=msim.ENTITY_DTYPE)
+    want = to_oracle_entities(orc, small_city.init_entities(40_000, seed=7))
+    om = oracle_map(orc, small_city)
+    for tick in range(2, 2 + 2 * 400):
+        oracle_dispatch(orc, want, om, 10.0, tick)
+    assert_entities_equal(got, want, what=f"C++ Simulator with a consumer, {mode} readback")
