@@ -169,7 +169,9 @@ struct msim_handle {
 namespace msim {
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v{0, false, 25};
+        Tuning v{0, false, false, 0, 25};
+        if (const char* e = std::getenv("MSIM_ARRIVE_GRID")) v.arrive_persistent = std::strcmp(e, "persistent") == 0;
+        if (const char* e = std::getenv("MSIM_SCAN_MIN_BLOCKS")) v.scan_min_blocks = std::atoi(e) == 8 ? 8 : 0;
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
             const int k = std::atoi(e);
             if (k >= 25 && k <= 27) v.csort_max_cells_log2 = k;

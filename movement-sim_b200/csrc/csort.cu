@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint
 }
 
 // phase 2: exclusive scan inside each tile + the sum of the earlier tiles' totals.  Thread t owns SCAN_ITEMS consecutive cells.
-__global__ void __launch_bounds__(SCAN_THREADS)
+// MINB = 8 caps the kernel at 32 registers (31 used, nothing spilled) so that 8 CTAs fit one SM: Munich's 1165 tiles are then ONE
+// resident wave; with the 34 registers of MINB = 0 (the measured default) 6 CTAs fit and 277 tiles wait for a second wave.
+template <int MINB>
+__global__ void __launch_bounds__(SCAN_THREADS, MINB)
 scan_tiles_kernel(uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets /* per-tile TOTALS */,
                   uint32_t* __restrict__ starts) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_before[SCAN_THREADS / 32];
@@ -197,7 +200,10 @@ int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint3
     const uint32_t tiles = csort_tiles(cells);
     prof->begin(s, K_CELL_SCAN);
     scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums);
-    scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
+    if (tuning().scan_min_blocks == 8)
+        scan_tiles_kernel<8><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
+    else
+        scan_tiles_kernel<0><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
     prof->end(s);
     return 2;
 }

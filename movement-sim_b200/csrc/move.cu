@@ -298,6 +298,9 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
 // and hands exactly one arrival to each lane per round: the gather chains run 32-wide and balanced.
 constexpr int ARRIVE_THREADS = 256;
 
+// STRIDE = false (default): the grid covers every mask word, one pass.  STRIDE = true (MSIM_ARRIVE_GRID=persistent): the grid is capped
+// at the resident CTAs and strides over the words (10 M entities need 1221 CTAs where 1184 are resident: no left-over wave).
+template <bool STRIDE>
 __global__ void __launch_bounds__(ARRIVE_THREADS)
 arrive_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ arrived_mask, float2* __restrict__ target,
               uint32_t* __restrict__ road, uint4* __restrict__ rng, const uint4* __restrict__ roads,
@@ -305,37 +308,41 @@ arrive_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_
     const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t words = ((n + 63u) >> 6) << 1;  // two mask words per 64-entity chunk
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t w = blockIdx.x * ARRIVE_THREADS + threadIdx.x;  // one mask word per lane
-    const uint32_t mask = (w < words) ? __ldcs(arrived_mask + w) : 0u;
-    const uint32_t cnt = __popc(mask);
-    uint32_t incl = cnt;
+    uint32_t w = blockIdx.x * ARRIVE_THREADS + threadIdx.x;  // one mask word per lane
+    do {
+        const uint32_t mask = (w < words) ? __ldcs(arrived_mask + w) : 0u;
+        const uint32_t cnt = __popc(mask);
+        uint32_t incl = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += up;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    for (uint32_t base = 0; base < total; base += 32u) {
-        const uint32_t r = base + lane;  // rank of the arrival this lane handles
-        // owner = first lane whose inclusive count exceeds r (binary search over the warp's counts)
-        uint32_t lo = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t r = base + lane;  // rank of the arrival this lane handles
+            // owner = first lane whose inclusive count exceeds r (binary search over the warp's counts)
+            uint32_t lo = 0;
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t probe = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31u);
-            if (probe <= r) lo += step;
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t probe = __shfl_sync(0xffffffffu, incl, (lo + step - 1) & 31u);
+                if (probe <= r) lo += step;
+            }
+            const uint32_t owner = min(lo, 31u);
+            const uint32_t owner_mask = __shfl_sync(0xffffffffu, mask, owner);
+            const uint32_t owner_incl = __shfl_sync(0xffffffffu, incl, owner);
+            const uint32_t owner_cnt = __shfl_sync(0xffffffffu, cnt, owner);
+            if (r < total) {
+                const uint32_t nth = r - (owner_incl - owner_cnt);          // 0-based among the owner's set bits
+                const uint32_t bit = __fns(owner_mask, 0, static_cast<int>(nth) + 1);
+                const uint32_t ow = (w - lane) + owner;                     // the owner's mask word index
+                const uint32_t e = (ow >> 1) * 64u + bit * 2u + (ow & 1u);  // inverse of arrived_word/arrived_bit
+                if (e < n) target[e] = new_target(e, target[e], road, rng, roads, conn, conn_count);
+            }
         }
-        const uint32_t owner = min(lo, 31u);
-        const uint32_t owner_mask = __shfl_sync(0xffffffffu, mask, owner);
-        const uint32_t owner_incl = __shfl_sync(0xffffffffu, incl, owner);
-        const uint32_t owner_cnt = __shfl_sync(0xffffffffu, cnt, owner);
-        if (r < total) {
-            const uint32_t nth = r - (owner_incl - owner_cnt);          // 0-based among the owner's set bits
-            const uint32_t bit = __fns(owner_mask, 0, static_cast<int>(nth) + 1);
-            const uint32_t ow = (w - lane) + owner;                     // the owner's mask word index
-            const uint32_t e = (ow >> 1) * 64u + bit * 2u + (ow & 1u);  // inverse of arrived_word/arrived_bit
-            if (e < n) target[e] = new_target(e, target[e], road, rng, roads, conn, conn_count);
-        }
-    }
+        if (!STRIDE) break;
+        w += gridDim.x * ARRIVE_THREADS;
+    } while (w - threadIdx.x < words);  // CTA-uniform: whole warps stay together for the shuffles
 }
 
 __global__ void __launch_bounds__(256)
@@ -419,9 +426,15 @@ int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, ui
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
     const uint32_t words = ((n + 63u) >> 6) << 1;  // grid size (n is an upper bound when n_dev is given)
+    uint32_t blocks = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
+    // 10 M entities need 1221 CTAs where 1184 are resident (31 registers, 8 per SM): the 37 left over start when the first finish.
+    // MSIM_ARRIVE_GRID=persistent: one resident wave that strides over the words instead
+    const bool stride = tuning().arrive_persistent && blocks > 148u * 8u;
     prof->begin(s, K_ARRIVE);
-    arrive_kernel<<<(words + ARRIVE_THREADS - 1) / ARRIVE_THREADS, ARRIVE_THREADS, 0, s>>>(
-        n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
+    if (stride)
+        arrive_kernel<true><<<148u * 8u, ARRIVE_THREADS, 0, s>>>(n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
+    else
+        arrive_kernel<false><<<blocks, ARRIVE_THREADS, 0, s>>>(n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
     prof->end(s);
     return 1;
 }

@@ -121,6 +121,8 @@ struct Profiler {
 struct Tuning {
     int move_min_blocks;          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
     bool move_grid_by_occupancy;  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
+    bool arrive_persistent;       // MSIM_ARRIVE_GRID=persistent: pass B as one resident wave with a stride loop
+    int scan_min_blocks;          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
     int csort_max_cells_log2;     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
 };

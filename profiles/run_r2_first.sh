@@ -15,11 +15,14 @@ $B --fused-arrive > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fuse
 MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_bench_minb5.err
 MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
 MSIM_MOVE_GRID=occupancy $B > gpurun_out/r2a_bench_occgrid.json 2> gpurun_out/r2a_bench_occgrid.err
+MSIM_SCAN_MIN_BLOCKS=8 $B > gpurun_out/r2a_bench_scan8.json 2> gpurun_out/r2a_bench_scan8.err
+MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy MSIM_SCAN_MIN_BLOCKS=8 $B --fused-arrive > gpurun_out/r2a_bench_all.json 2> gpurun_out/r2a_bench_all.err
 MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy $B --fused-arrive > gpurun_out/r2a_bench_fused_minb6_occ.json 2> gpurun_out/r2a_bench_fused_minb6_occ.err
 # collisions off: BASELINE configs[1] (1 M, L2 flushed between steps) and the same at 10 M (HBM-bound)
 $B --workload munich_1m_nocollisions > gpurun_out/r2a_bench_1m_off.json 2> gpurun_out/r2a_bench_1m_off.err
 $B --workload munich_1m_nocollisions --fused-arrive > gpurun_out/r2a_bench_1m_off_fused.json 2> gpurun_out/r2a_bench_1m_off_fused.err
 $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off.json 2> gpurun_out/r2a_bench_10m_off.err
+MSIM_ARRIVE_GRID=persistent $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off_persistent.json 2> gpurun_out/r2a_bench_10m_off_persistent.err
 $B --workload munich_1m_nocollisions --entities 10000000 --fused-arrive > gpurun_out/r2a_bench_10m_off_fused.json 2> gpurun_out/r2a_bench_10m_off_fused.err
 for f in gpurun_out/r2a_bench_*.json; do echo "== $f"; python profiles/show_bench.py "$f" 2>/dev/null | head -12; done
 $B --e2e-pipelined --e2e-steps 5 > gpurun_out/r2a_bench_e2e_pipelined.json 2> gpurun_out/r2a_bench_e2e_pipelined.err; python -c "import json; print(json.load(open(\"gpurun_out/r2a_bench_e2e_pipelined.json\"))[\"e2e\"])"

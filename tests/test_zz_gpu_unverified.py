@@ -87,7 +87,8 @@ def test_fused_arrive_blocking_dispatch_is_unchanged(msim, orc, small_city):
 
 # ---- launch tuning from the environment (read once per process: run each value in its own process) ---------------
 @pytest.mark.parametrize("env", [{"MSIM_MOVE_MIN_BLOCKS": "5"}, {"MSIM_MOVE_MIN_BLOCKS": "6"}, {"MSIM_MOVE_GRID": "occupancy"},
-                                 {"MSIM_MOVE_MIN_BLOCKS": "6", "MSIM_MOVE_GRID": "occupancy"}])
+                                 {"MSIM_MOVE_MIN_BLOCKS": "6", "MSIM_MOVE_GRID": "occupancy"}, {"MSIM_SCAN_MIN_BLOCKS": "8"},
+                                 {"MSIM_ARRIVE_GRID": "persistent"}, {"MSIM_CSORT_MAX_CELLS_LOG2": "27"}])
 def test_move_tuning_variants_in_subprocess(env):
     """The register-capped instantiations of the move kernel and the occupancy-sized grid: smoke() (bit-exact against the
     oracle over 8 sim ticks) in a fresh process per setting."""
@@ -99,6 +100,31 @@ def test_move_tuning_variants_in_subprocess(env):
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=dict(os.environ, **env), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+def test_persistent_arrive_grid_at_a_size_that_strides():
+    """MSIM_ARRIVE_GRID=persistent only changes the launch above 1184 CTAs x 8192 entities: 10.5 M entities on the test map, 60 move
+    passes against the oracle, in a fresh process (the knob is read once)."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    code = (
+        "import numpy as np, movement_sim_b200 as M\n"
+        "from oracle import oracle as O\n"
+        "m = M.Map.load_json('tests/golden/test_map.json')\n"
+        "ents = m.init_entities(10_500_000, seed=3)\n"
+        "om = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)\n"
+        "want = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()\n"
+        "for _ in range(61): O.move_pass(want, om, threads=16)\n"
+        "with M.Simulation(m, ents, flags=M.FLAG_NO_COLLISIONS) as sim:\n"
+        "    sim.dispatch(2); sim.enqueue_ticks(60, False); got = sim.read_entities()\n"
+        "assert got.tobytes() == want.tobytes(), 'mismatch'\n"
+        "print('persistent arrive ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, MSIM_ARRIVE_GRID="persistent"), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "persistent arrive ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
 # ---- msim_snapshot_*: asynchronous readback into pinned double buffers ----------------------------------------------
