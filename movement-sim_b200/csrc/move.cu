@@ -56,9 +56,15 @@ __device__ __forceinline__ uint32_t read_connection(const uint32_t* __restrict__
 }
 
 // random_move.comp:778-828.  `tgt` is the waypoint just reached; returns the new waypoint.
+// PREFETCH_RNG (fused pass B only): the RNG state is requested together with the road index instead of after the road record has
+// told us that more than two roads meet here — one DRAM latency less on the dependent chain road -> record -> connection -> record,
+// for 16 bytes read in vain at dead ends and two-way points.  Same results: the state is only written back when it was drawn from.
+template <bool PREFETCH_RNG = false>
 __device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* __restrict__ road, uint4* __restrict__ rng,
                                              const uint4* __restrict__ roads, const uint32_t* __restrict__ conn,
                                              uint64_t conn_count) {
+    uint4 early = make_uint4(0u, 0u, 0u, 0u);
+    if (PREFETCH_RNG) early = rng[e];
     const uint32_t cur = road[e];
     const uint4 a = __ldg(roads + 2ull * cur);      // start: pos.x pos.y connectedIndex connectedCount
     const uint4 b = __ldg(roads + 2ull * cur + 1);  // end
@@ -72,7 +78,7 @@ __device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* _
     if (here.w == 2u) {  // :802-804
         next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + 1ull);
     } else {  // :805-810
-        uint4 s = rng[e];
+        uint4 s = PREFETCH_RNG ? early : rng[e];
         const uint32_t off = next_range(s, 1u, here.w);
         rng[e] = s;
         next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + off);
@@ -227,7 +233,7 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                     const uint32_t e = pi * 2u + (slot & 1u);
                     const float4 t4 = (slot >> 1) ? T[1] : T[0];
                     const float2 reached = (slot & 1u) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
-                    const float2 nt = new_target(e, reached, fa.road, fa.rng, fa.roads, fa.conn, fa.conn_count);
+                    const float2 nt = new_target<true>(e, reached, fa.road, fa.rng, fa.roads, fa.conn, fa.conn_count);
                     fa.target[e] = nt;
                     if (slot == 0u) { T[0].x = nt.x; T[0].y = nt.y; }
                     if (slot == 1u) { T[0].z = nt.x; T[0].w = nt.y; }
