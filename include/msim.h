@@ -178,9 +178,10 @@ int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count);
 /* OpTensorSyncLocal({tensorQuadTreeNodes}) (Simulator.cpp:198,255,267): display quadtree rebuilt from
  * the current positions. *count receives the number of nodes written (<= cap). */
 int msim_read_quadtree_nodes(msim_handle* h, msim_quadtree_node* dst, uint64_t cap, uint64_t* count);
-/* tensorDebugData (Simulator.cpp:86-89,273): [0] = cumulative initialisations (quad_tree_insert
- * calls of the first dispatch, shader :311), [1] = cumulative UNIQUE in-range pairs (documented
- * deviation from the reference's over-count), [2..9] = 0. */
+/* tensorDebugData (Simulator.cpp:86-89,273): [0] = cumulative initialisations (the quad_tree_insert
+ * calls of the first dispatch, shader :311; the shader also counts the re-inserts of quad_tree_update
+ * there, which depend on the tree's shape and are not reproduced), [1] = cumulative UNIQUE in-range
+ * pairs (documented deviation from the reference's over-count), [2..9] = 0. */
 int msim_read_debug(msim_handle* h, uint32_t dst[10]);
 
 typedef struct msim_stats {

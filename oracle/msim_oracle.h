@@ -23,7 +23,10 @@
  * graph population, RNG known answers, degenerate distances); digests the compiled shader produced are
  * committed for boxes without oracle/_ref (tests/golden/ref_shader_digests.json).  What stays open is
  * the float freedom of a real Vulkan driver: both sides use IEEE RNE without FMA.
- * The collision half is pinned as well: the reference's CPU
+ * The whole shader - main() and the lock-based quadtree included - is compiled the same way into
+ * oracle/_ref/libref_shader_full.so; run dispatch by dispatch on one host thread it equals this oracle on all
+ * 64 bytes of every entity, colours included (same test file).
+ * The collision half is pinned a second time against the author's C++ harness: the reference's CPU
  * restatement (shader_validation/src/main.cpp) is compiled into oracle/_ref and (a) its disabled
  * known-answer test run_collision_detection_test_1 passes, (b) its flagged set equals this oracle's
  * on seeded point clouds (tests/test_oracle_vs_ref.py).  calc_node_count(1,2,3,4,8) = 1,5,21,85,21845

@@ -299,6 +299,65 @@ def ref_shader_move_pass(e: np.ndarray, m: OracleMap, threads: int = 1) -> None:
         ref_shader().ref_shader_move_pass(e.ctypes.data, 0, e.shape[0], m.roads.ctypes.data, padded.ctypes.data)
 
 
+# --------------------------------------------------------------------------------------------
+# The WHOLE shader compiled from its own text (oracle/Makefile: libref_shader_full.so): main() with its three branches -
+# initialise + quad_tree_insert, even tick move + quad_tree_update, odd tick colour + quad_tree_check_collisions -
+# executed invocation by invocation on one host thread.
+# --------------------------------------------------------------------------------------------
+REF_SHADER_FULL_LIB = os.path.join(HERE, "_ref", "libref_shader_full.so")
+NODE_DTYPE = np.dtype([("acquireLock", "<i4"), ("writeLock", "<i4"), ("readerLock", "<i4"), ("offsetX", "<f4"), ("offsetY", "<f4"), ("width", "<f4"),
+                       ("height", "<f4"), ("contentType", "<u4"), ("entityCount", "<u4"), ("first", "<u4"), ("prevNodeIndex", "<u4"), ("nextTL", "<u4"),
+                       ("nextTR", "<u4"), ("nextBL", "<u4"), ("nextBR", "<u4"), ("padding", "<u4")])
+TREE_ENTITY_DTYPE = np.dtype([("nodeIndex", "<u4"), ("typeNext", "<u4"), ("next", "<u4"), ("typePrev", "<u4"), ("prev", "<u4")])
+assert NODE_DTYPE.itemsize == 64 and TREE_ENTITY_DTYPE.itemsize == 20
+_ref_shader_full = None
+
+
+def ref_shader_full_available() -> bool:
+    return os.path.exists(REF_SHADER_FULL_LIB)
+
+
+class RefShaderDeadlock(RuntimeError):
+    """The shader's lock protocol left a lock behind (a reference bug in quad_tree_update's remove / merge path, also tripped by
+    the author's own CPU harness: DESIGN.md)."""
+
+
+class RefShaderSim:
+    """The reference's Simulator::init + sim_tick around the compiled shader: buffers as Simulator.cpp:58-89 creates them, push
+    constants as :94-101, one ref_shader_full_dispatch per tick number (:220-235).  Single-threaded; a handful of thousand
+    entities per second of patience (every insert / update walks the tree from the root under its lock protocol)."""
+
+    def __init__(self, e: np.ndarray, m: OracleMap, radius: float = 10.0, max_depth: int = 8, node_cap: int = 10):
+        global _ref_shader_full
+        if _ref_shader_full is None:
+            R = C.CDLL(REF_SHADER_FULL_LIB)
+            R.ref_shader_full_bind.restype = None
+            R.ref_shader_full_bind.argtypes = [C.c_void_p] * 7
+            R.ref_shader_full_push_consts.restype = None
+            R.ref_shader_full_push_consts.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32]
+            R.ref_shader_full_dispatch.restype = C.c_int64
+            R.ref_shader_full_dispatch.argtypes = [C.c_uint64]
+            _ref_shader_full = R
+        self.R = _ref_shader_full
+        _check_entities(e)
+        self.e, self.m, self.radius, self.max_depth, self.node_cap = e, m, float(radius), int(max_depth), int(node_cap)
+        self.connections = np.concatenate([m.connections, np.zeros(1, dtype=np.uint32)])  # App. B1
+        self.nodes = np.zeros(calc_node_count(max_depth), dtype=NODE_DTYPE)
+        self.nodes[0]["width"], self.nodes[0]["height"], self.nodes[0]["contentType"] = m.world_w, m.world_h, 2  # init_node_zero
+        self.tree_entities = np.zeros(max(1, e.shape[0]), dtype=TREE_ENTITY_DTYPE)
+        self.used = np.zeros(self.nodes.shape[0] + 2, dtype=np.uint32)
+        self.used[1] = 2  # Simulator.cpp:81
+        self.debug = np.zeros(10, dtype=np.uint32)
+
+    def dispatch(self, tick: int) -> None:
+        self.R.ref_shader_full_bind(self.e.ctypes.data, self.connections.ctypes.data, self.m.roads.ctypes.data, self.nodes.ctypes.data,
+                                    self.tree_entities.ctypes.data, self.used.ctypes.data, self.debug.ctypes.data)
+        self.R.ref_shader_full_push_consts(self.m.world_w, self.m.world_h, self.nodes.shape[0], self.max_depth, self.node_cap, self.radius, tick)
+        stuck = int(self.R.ref_shader_full_dispatch(self.e.shape[0]))
+        if stuck >= 0:
+            raise RefShaderDeadlock(f"tick {tick}: invocation {stuck} found a quadtree lock that no running invocation holds")
+
+
 def run_ref_kat() -> subprocess.CompletedProcess:
     """Runs the reference's own (disabled) known-answer test in a subprocess (it asserts)."""
     return subprocess.run([REF_KAT], capture_output=True, text=True, timeout=120)

@@ -31,6 +31,22 @@ def main():
     for name, (m, ents, passes, every) in cases.items():
         out[name] = {"passes": passes, "every": every, "sha256": digest_run(O, O.ref_shader_move_pass, m, ents, passes, every)}
         print(name, len(out[name]["sha256"]), "digests")
+    # the whole shader (main() with quadtree insert / update / collision walk): dispatch ticks 2, 3, 4, ... on a world one metre larger
+    # than the map (the shader never terminates for an entity on the map's maximum coordinate)
+    import hashlib
+
+    assert O.ref_shader_full_available()
+    om = O.OracleMap(small_city.width + 1.0, small_city.height + 1.0, small_city.roads.view(O.ROAD_DTYPE), small_city.connections)
+    e = O.np.ascontiguousarray(small_city.init_entities(6000, seed=5)).view(O.ENTITY_DTYPE).copy()
+    sim = O.RefShaderSim(e, om, radius=10.0)
+    digests = []
+    for tick in range(2, 2 + 80):
+        sim.dispatch(tick)
+        if tick % 8 == 1:
+            digests.append(hashlib.sha256(e.tobytes()).hexdigest())
+    out["small_city_6k_seed5_full_shader"] = {"dispatches": 80, "every": 8, "radius": 10.0, "world_pad": 1.0, "sha256": digests,
+                                              "debug_data": sim.debug.tolist()}
+    print("small_city_6k_seed5_full_shader", len(digests), "digests, debugData", sim.debug[:2].tolist())
     with open(os.path.join(HERE, "ref_shader_digests.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -66,6 +66,29 @@ def test_cuda_path_matches_compiled_shader(msim, orc, small_city):
                 assert_entities_equal(sim.read_entities(), want, what=f"dispatch {step} vs compiled shader")
 
 
+def test_cuda_path_matches_the_whole_compiled_shader(msim, orc, small_city):
+    """Full sim ticks of the CUDA path against the reference's ENTIRE shader compiled for the CPU (oracle/_ref/libref_shader_full.so:
+    main() with the lock-based quadtree's insert / update / collision walk): every field incl. the colours, dispatch by dispatch.
+    The world handed to both is one metre larger than the map (the shader never terminates for an entity on the map's maximum
+    coordinate, tests/test_oracle_vs_ref_shader.py)."""
+    if not orc.ref_shader_full_available():
+        pytest.skip("oracle/_ref/libref_shader_full.so not built (needs /root/reference at build time)")
+    padded = msim.Map(small_city.width + 1.0, small_city.height + 1.0, small_city.roads, small_city.connections)
+    ents = padded.init_entities(20_000, seed=23)
+    om = oracle_map(orc, padded)
+    want = to_oracle_entities(orc, ents)
+    ref = orc.RefShaderSim(want, om, radius=10.0)
+    with msim.Simulation(padded, ents, radius=10.0) as sim:
+        for tick in range(2, 2 + 2 * 40):
+            sim.dispatch(tick)
+            ref.dispatch(tick)
+            if tick in (2, 3, 4, 5, 40, 41, 80, 81):
+                assert_entities_equal(sim.read_entities(), want, what=f"dispatch {tick} vs the whole compiled shader")
+        assert (sim.read_collision_flags() == orc.collision_flags(want)).all()
+        # debugData[1]: the shader over-counts (App. B5); the CUDA path reports the unique pairs, never more
+        assert sim.read_debug()[1] <= ref.debug[1]
+
+
 def test_enqueue_ticks_matches_dispatch(msim, orc, test_map):
     ents = test_map.init_entities(4097, seed=3)
     omap = oracle_map(orc, test_map)

@@ -125,3 +125,105 @@ def test_oracle_matches_committed_shader_digests(orc, msim, test_map, small_city
         g = gold[name]
         got = digest_run(orc, lambda e, omap: orc.move_pass(e, omap), m, ents, g["passes"], g["every"])
         assert got == g["sha256"], f"{name}: oracle state diverges from the compiled shader's at digest {[i for i, (x, y) in enumerate(zip(got, g['sha256'])) if x != y][:1]}"
+
+
+def test_oracle_matches_committed_full_shader_digests(orc, small_city):
+    """Full sim ticks (move + collision colours) against digests the WHOLE compiled shader produced (quadtree code included)."""
+    with open(os.path.join(GOLDEN, "ref_shader_digests.json")) as f:
+        g = json.load(f)["small_city_6k_seed5_full_shader"]
+    om = orc.OracleMap(small_city.width + g["world_pad"], small_city.height + g["world_pad"], small_city.roads.view(orc.ROAD_DTYPE), small_city.connections)
+    e = to_oracle_entities(orc, small_city.init_entities(6000, seed=5))
+    got, unique_pairs = [], 0
+    for tick in range(2, 2 + g["dispatches"]):
+        pairs, _ = orc.dispatch(e, om, g["radius"], tick)
+        unique_pairs += pairs
+        if tick % g["every"] == 1:
+            got.append(hashlib.sha256(e.tobytes()).hexdigest())
+    assert got == g["sha256"]
+    assert g["debug_data"][1] >= unique_pairs  # the shader's counter over-counts (App. B5)
+
+
+# ---- the WHOLE shader (quadtree half and main() included): oracle/_ref/libref_shader_full.so ------------------------------
+@pytest.fixture(scope="module")
+def full(orc):
+    if not orc.ref_shader_full_available():
+        pytest.skip("oracle/_ref/libref_shader_full.so not built (needs /root/reference at build time)")
+    return orc
+
+
+def padded_map(O, m, pad=1.0):
+    """World one metre larger than the map: the shader never terminates for an entity that stands exactly on the map's maximum
+    coordinate (test_full_shader_endless_walk_on_the_max_coordinate); nothing else depends on the world size."""
+    return O.OracleMap(m.width + pad, m.height + pad, m.roads.view(O.ROAD_DTYPE), m.connections)
+
+
+@pytest.mark.timeout(600)
+def test_full_shader_sim_ticks_match_oracle(full, small_city):
+    """Simulator::sim_tick as the reference runs it - dispatch ticks 2, 3, 4, ... through main() of the compiled shader: initialise
+    + quad_tree_insert, move + quad_tree_update, colour + quad_tree_check_collisions (lock-based quadtree, cap 10, depth 8) - against
+    the oracle (cell grid): all 64 bytes of every entity after every dispatch, colours included."""
+    om = padded_map(full, small_city)
+    a = to_oracle_entities(full, small_city.init_entities(4000, seed=3))
+    b = a.copy()
+    sim = full.RefShaderSim(b, om, radius=10.0)
+    unique_pairs = 0
+    for tick in range(2, 2 + 160):
+        pairs, _ = full.dispatch(a, om, 10.0, tick)
+        unique_pairs += pairs
+        sim.dispatch(tick)
+        bytes_equal(a, b, f"dispatch {tick}")
+    # debugData (App. B5): [1] counts a pair once per direction the walk meets it - never less than the unique pairs; [0] counts every
+    # quad_tree_insert call, i.e. the first dispatch's initialisations plus every re-insert of quad_tree_update
+    assert sim.debug[1] >= unique_pairs > 10_000
+    assert sim.debug[0] > 4000
+
+
+@pytest.mark.timeout(600)
+def test_full_shader_at_200k_on_the_munich_stand_in(full, msim):
+    """The bench's map and population (dispersed by 64 move passes), 200 k entities: insert, collide, move + update, collide."""
+    m = msim.Map.city()
+    om = padded_map(full, m)
+    a = to_oracle_entities(full, m.init_entities(200_000, seed=42))
+    for _ in range(65):
+        full.move_pass(a, om, threads=8)
+    a["initialized"] = 0
+    b = a.copy()
+    sim = full.RefShaderSim(b, om, radius=10.0)
+    for tick in (2, 3, 4, 5):
+        full.dispatch(a, om, 10.0, tick)
+        sim.dispatch(tick)
+        bytes_equal(a, b, f"dispatch {tick}")
+    assert int(full.collision_flags(a).sum()) > 50_000
+
+
+@pytest.mark.timeout(600)
+def test_full_shader_stacked_start_and_other_radii(full, small_city):
+    """App. B10: every entity starts on its road's first point, thousands share a position (quad_tree_same_pos_as_fist keeps them on one
+    leaf beyond its capacity); radii 2 m and 25 m exercise the sibling-node walk differently."""
+    for radius in (2.0, 10.0, 25.0):
+        om = padded_map(full, small_city)
+        a = to_oracle_entities(full, small_city.init_entities(15_000, seed=8))
+        b = a.copy()
+        sim = full.RefShaderSim(b, om, radius=radius)
+        for tick in range(2, 12):
+            full.dispatch(a, om, radius, tick)
+            sim.dispatch(tick)
+            bytes_equal(a, b, f"radius {radius}, dispatch {tick}")
+
+
+@pytest.mark.timeout(120)
+def test_full_shader_endless_walk_on_the_max_coordinate(full, small_city):
+    """A finding about the reference: quad_tree_is_entity_on_node tests `pos < offset + width` strictly (random_move.comp:373-376)
+    while the world size IS the largest coordinate of the map (Map.cpp:45-52), so an entity standing exactly on the map's maximum x or
+    y is on no node, not even the root, and the climb of quad_tree_update (:529-534) never ends once such an entity has to leave its
+    leaf.  small_city has junctions on its upper edge; with the unpadded world the compiled shader reports the endless walk."""
+    om = oracle_map(full, small_city)
+    a = to_oracle_entities(full, small_city.init_entities(2000, seed=3))
+    on_edge = (a["pos"][:, 0] == np.float32(small_city.width)) | (a["pos"][:, 1] == np.float32(small_city.height))
+    assert on_edge.any()
+    sim = full.RefShaderSim(a, om, radius=10.0)
+    sim.dispatch(2)
+    sim.dispatch(3)
+    with pytest.raises(full.RefShaderDeadlock):
+        for tick in range(4, 40):
+            sim.dispatch(tick)
