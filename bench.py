@@ -208,6 +208,30 @@ def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, ref_move, ref
     return e.shape[0] * steps / dt, dt / steps
 
 
+def time_whole_shader(O, ents_aos, m, radius, collisions, sample=100_000, ticks=2):
+    """The reference's ENTIRE shader compiled for the CPU (oracle/_ref/libref_shader_full.so), one host thread, dispatch by dispatch:
+    reported beside the multi-threaded arm.  The world is one metre larger than the map (the shader never terminates for an
+    entity on the map's maximum coordinate)."""
+    if not (collisions and O.ref_shader_full_available()):
+        return None
+    e = np.ascontiguousarray(ents_aos[:sample]).view(O.ENTITY_DTYPE).copy()
+    e["initialized"] = 0
+    om = O.OracleMap(m.width + 1.0, m.height + 1.0, m.roads.view(O.ROAD_DTYPE), m.connections)
+    sim = O.RefShaderSim(e, om, radius=radius)
+    try:
+        sim.dispatch(2)  # initialise + quad_tree_insert (untimed, like the GPU arm's first dispatch)
+        sim.dispatch(3)
+        t0 = time.perf_counter()
+        for k in range(ticks):
+            sim.dispatch(4 + 2 * k)
+            sim.dispatch(5 + 2 * k)
+        dt = time.perf_counter() - t0
+    except O.RefShaderDeadlock as ex:
+        return {"error": str(ex)}
+    return {"value": e.shape[0] * ticks / dt, "unit": "entity-updates/s", "cores": 1, "sample": f"{e.shape[0]} entities, {ticks} sim ticks",
+            "what": "random_move.comp compiled as C++: main() with quad_tree_update + quad_tree_check_collisions, invocations in index order"}
+
+
 def cpu_arm_description(ref_move, ref_tree, collisions):
     """kind + wording of the CPU arm: "reference" only when every part of the step is the reference's own code."""
     move = ("movement = the reference shader's own move / new_target / RNG code compiled for the CPU (oracle/_ref/libref_shader_move.so), all threads"
@@ -243,11 +267,12 @@ def run_reference(args):
     value, sec = time_cpu(O, e, omap, 10.0, w["collisions"], steps, warmup, ref_move, ref_tree, threads)
     kind, how = cpu_arm_description(ref_move, ref_tree, w["collisions"])
     sample_desc = f"{sample} of {w['entities']} entities of the same workload, {steps} sim ticks after {args.preroll} pre-roll move passes; {how}"
+    whole = time_whole_shader(O, e, m, 10.0, w["collisions"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32",
         "data": "synthetic", "config": {"workload": args.workload, "entities_sampled": sample, "collisions": w["collisions"], "map": w["map_desc"]},
-        "cpu_baseline": {"value": value, "unit": "entity-updates/s", "cores": threads, "kind": kind, "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "entity-updates/s", "cores": threads, "kind": kind, "sample": sample_desc, "whole_shader_1_thread": whole},
         "e2e": {"value": value, "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -453,7 +478,7 @@ def run_b200(args):
         kind, how = cpu_arm_description(ref_move, ref_tree, collisions)
         cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": kind,
                "sample": f"first {sample} entities of the resident population, {args.cpu_steps} sim ticks, {sec:.3f} s per tick; {how}",
-               "port_value": v_port}
+               "port_value": v_port, "whole_shader_1_thread": time_whole_shader(O, host, m, 10.0, collisions)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),

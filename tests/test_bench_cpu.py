@@ -49,6 +49,11 @@ def test_reference_arm_dense_crowd_sample():
     check_reference_line(line, "munich_50m_dense")
     assert line["config"]["collisions"] is True and line["config"]["entities_sampled"] == 3000
     assert "central box" in line["config"]["map"]
+    from oracle import oracle as O
+
+    if O.ref_shader_full_available():  # the whole compiled shader, one thread, beside the multi-threaded arm
+        whole = line["cpu_baseline"]["whole_shader_1_thread"]
+        assert whole["cores"] == 1 and whole["value"] > 0
 
 
 def test_reference_arm_other_ranks_print_nothing():
