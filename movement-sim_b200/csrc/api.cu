@@ -169,7 +169,11 @@ struct msim_handle {
 namespace msim {
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v{0, false, false, 0, 25};
+        Tuning v{0, false, false, 0, 0, 25};
+        if (const char* e = std::getenv("MSIM_ARRIVE_BESIDE_CTAS")) {
+            const int k = std::atoi(e);
+            if (k >= 1 && k <= 8) v.arrive_beside_ctas_per_sm = k;
+        }
         if (const char* e = std::getenv("MSIM_ARRIVE_GRID")) v.arrive_persistent = std::strcmp(e, "persistent") == 0;
         if (const char* e = std::getenv("MSIM_SCAN_MIN_BLOCKS")) v.scan_min_blocks = std::atoi(e) == 8 ? 8 : 0;
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
@@ -302,7 +306,7 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
         cudaEventRecord(h->ev_moved, h->stream);
         cudaStreamWaitEvent(h->side, h->ev_moved, 0);
         h->launches += launch_arrive(h->side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
-                                     dev_owned(h));
+                                     dev_owned(h), /*beside=*/true);
         cudaEventRecord(h->ev_arrived, h->side);
         h->side_pending = true;
     } else {

@@ -429,16 +429,18 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
 }
 
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev) {
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev, bool beside) {
     if (n == 0) return 0;
     const uint32_t words = ((n + 63u) >> 6) << 1;  // grid size (n is an upper bound when n_dev is given)
     uint32_t blocks = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
     // 10 M entities need 1221 CTAs where 1184 are resident (31 registers, 8 per SM): the 37 left over start when the first finish.
     // MSIM_ARRIVE_GRID=persistent: one resident wave that strides over the words instead
-    const bool stride = tuning().arrive_persistent && blocks > 148u * 8u;
+    uint32_t cap = tuning().arrive_persistent ? 148u * 8u : 0u;
+    if (beside && tuning().arrive_beside_ctas_per_sm) cap = 148u * static_cast<uint32_t>(tuning().arrive_beside_ctas_per_sm);
+    const bool stride = cap != 0u && blocks > cap;
     prof->begin(s, K_ARRIVE);
     if (stride)
-        arrive_kernel<true><<<148u * 8u, ARRIVE_THREADS, 0, s>>>(n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
+        arrive_kernel<true><<<cap, ARRIVE_THREADS, 0, s>>>(n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
     else
         arrive_kernel<false><<<blocks, ARRIVE_THREADS, 0, s>>>(n, n_dev, arrived, target, road, rng, reinterpret_cast<const uint4*>(roads), connections, connection_count);
     prof->end(s);

@@ -122,6 +122,9 @@ struct Tuning {
     int move_min_blocks;          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
     bool move_grid_by_occupancy;  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
     bool arrive_persistent;       // MSIM_ARRIVE_GRID=persistent: pass B as one resident wave with a stride loop
+    int arrive_beside_ctas_per_sm;  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
+                                  // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots instead of taking
+                                  // them all for 45-70 us (it is latency-bound and only has to finish before the next move); 0 = full grid (default)
     int scan_min_blocks;          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
     int csort_max_cells_log2;     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
@@ -148,8 +151,9 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
                 int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
                 const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr, const FusedArriveArgs* fuse = nullptr);
+// `beside`: the pass runs on the side stream next to the issue-bound query (see Tuning::arrive_beside_ctas_per_sm)
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr);
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr, bool beside = false);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
 
 // sort.cu

@@ -15,6 +15,7 @@ $B --fused-arrive > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fuse
 MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_bench_minb5.err
 MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
 MSIM_MOVE_GRID=occupancy $B > gpurun_out/r2a_bench_occgrid.json 2> gpurun_out/r2a_bench_occgrid.err
+for k in 1 2 4; do MSIM_ARRIVE_BESIDE_CTAS=$k $B > gpurun_out/r2a_bench_besidectas$k.json 2> gpurun_out/r2a_bench_besidectas$k.err; done
 MSIM_SCAN_MIN_BLOCKS=8 $B > gpurun_out/r2a_bench_scan8.json 2> gpurun_out/r2a_bench_scan8.err
 MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy MSIM_SCAN_MIN_BLOCKS=8 $B --fused-arrive > gpurun_out/r2a_bench_all.json 2> gpurun_out/r2a_bench_all.err
 MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy $B --fused-arrive > gpurun_out/r2a_bench_fused_minb6_occ.json 2> gpurun_out/r2a_bench_fused_minb6_occ.err

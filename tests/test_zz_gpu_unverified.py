@@ -201,3 +201,33 @@ def test_cpp_simulator_with_a_consumer(msim, orc, small_city, tmp_path, mode):
     for tick in range(2, 2 + 2 * 400):
         oracle_dispatch(orc, want, om, 10.0, tick)
     assert_entities_equal(got, want, what=f"C++ Simulator with a consumer, {mode} readback")
+
+
+def test_background_pass_b_beside_the_query():
+    """MSIM_ARRIVE_BESIDE_CTAS=1: pass B rides beside the query as a strided grid of one CTA per SM (148 x 8192 entities per stride, so
+    1.5 M entities make it stride).  Six sim ticks on the bench's map against the oracle, in a fresh process (the knob is read once)."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    code = (
+        "import numpy as np, movement_sim_b200 as M\n"
+        "from oracle import oracle as O\n"
+        "m = M.Map.city()\n"
+        "ents = m.init_entities(1_500_000, seed=4)\n"
+        "om = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)\n"
+        "want = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()\n"
+        "pairs = 0\n"
+        "for t in range(2, 2 + 2 * 7):\n"
+        "    if t % 2 == 0: O.move_pass(want, om, threads=16)\n"
+        "    else: pairs = O.collide_pass(want, om.world_w, om.world_h, 10.0, threads=16)\n"
+        "with M.Simulation(m, ents, radius=10.0) as sim:\n"
+        "    sim.dispatch(2); sim.dispatch(3); sim.enqueue_ticks(6, True); sim.sync()\n"
+        "    assert sim.stats()['last_pair_count'] == pairs, (sim.stats()['last_pair_count'], pairs)\n"
+        "    got = sim.read_entities()\n"
+        "assert got.tobytes() == want.tobytes(), 'mismatch'\n"
+        "print('background pass B ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, MSIM_ARRIVE_BESIDE_CTAS="1"), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "background pass B ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
