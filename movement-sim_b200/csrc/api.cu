@@ -169,7 +169,8 @@ struct msim_handle {
 namespace msim {
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v{0, false, false, 0, 0, 25};
+        Tuning v{0, false, false, 0, false, 0, 25};
+        if (const char* e = std::getenv("MSIM_QUERY_PAIRED")) v.query_paired = std::atoi(e) == 1;
         if (const char* e = std::getenv("MSIM_ARRIVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
             if (k >= 1 && k <= 8) v.arrive_beside_ctas_per_sm = k;

@@ -125,6 +125,7 @@ struct Tuning {
     int arrive_beside_ctas_per_sm;  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
                                   // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots instead of taking
                                   // them all for 45-70 us (it is latency-bound and only has to finish before the next move); 0 = full grid (default)
+    bool query_paired;            // MSIM_QUERY_PAIRED=1: query with two adjacent slots per thread (collide.cu, query_paired_kernel)
     int scan_min_blocks;          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
     int csort_max_cells_log2;     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)

@@ -16,8 +16,9 @@ MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_be
 MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
 MSIM_MOVE_GRID=occupancy $B > gpurun_out/r2a_bench_occgrid.json 2> gpurun_out/r2a_bench_occgrid.err
 for k in 1 2 4; do MSIM_ARRIVE_BESIDE_CTAS=$k $B > gpurun_out/r2a_bench_besidectas$k.json 2> gpurun_out/r2a_bench_besidectas$k.err; done
+MSIM_QUERY_PAIRED=1 $B > gpurun_out/r2a_bench_paired.json 2> gpurun_out/r2a_bench_paired.err
 MSIM_SCAN_MIN_BLOCKS=8 $B > gpurun_out/r2a_bench_scan8.json 2> gpurun_out/r2a_bench_scan8.err
-MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy MSIM_SCAN_MIN_BLOCKS=8 $B --fused-arrive > gpurun_out/r2a_bench_all.json 2> gpurun_out/r2a_bench_all.err
+MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy MSIM_SCAN_MIN_BLOCKS=8 MSIM_QUERY_PAIRED=1 $B --fused-arrive > gpurun_out/r2a_bench_all.json 2> gpurun_out/r2a_bench_all.err
 MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy $B --fused-arrive > gpurun_out/r2a_bench_fused_minb6_occ.json 2> gpurun_out/r2a_bench_fused_minb6_occ.err
 # collisions off: BASELINE configs[1] (1 M, L2 flushed between steps) and the same at 10 M (HBM-bound)
 $B --workload munich_1m_nocollisions > gpurun_out/r2a_bench_1m_off.json 2> gpurun_out/r2a_bench_1m_off.err

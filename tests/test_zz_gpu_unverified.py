@@ -88,7 +88,7 @@ def test_fused_arrive_blocking_dispatch_is_unchanged(msim, orc, small_city):
 # ---- launch tuning from the environment (read once per process: run each value in its own process) ---------------
 @pytest.mark.parametrize("env", [{"MSIM_MOVE_MIN_BLOCKS": "5"}, {"MSIM_MOVE_MIN_BLOCKS": "6"}, {"MSIM_MOVE_GRID": "occupancy"},
                                  {"MSIM_MOVE_MIN_BLOCKS": "6", "MSIM_MOVE_GRID": "occupancy"}, {"MSIM_SCAN_MIN_BLOCKS": "8"},
-                                 {"MSIM_ARRIVE_GRID": "persistent"}, {"MSIM_CSORT_MAX_CELLS_LOG2": "27"}])
+                                 {"MSIM_ARRIVE_GRID": "persistent"}, {"MSIM_CSORT_MAX_CELLS_LOG2": "27"}, {"MSIM_QUERY_PAIRED": "1"}])
 def test_move_tuning_variants_in_subprocess(env):
     """The register-capped instantiations of the move kernel and the occupancy-sized grid: smoke() (bit-exact against the
     oracle over 8 sim ticks) in a fresh process per setting."""
@@ -231,3 +231,19 @@ def test_background_pass_b_beside_the_query():
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, MSIM_ARRIVE_BESIDE_CTAS="1"), capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0 and "background pass B ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env", [{"MSIM_QUERY_PAIRED": "1"},
+                                 {"MSIM_MOVE_MIN_BLOCKS": "6", "MSIM_MOVE_GRID": "occupancy", "MSIM_SCAN_MIN_BLOCKS": "8", "MSIM_ARRIVE_GRID": "persistent",
+                                  "MSIM_ARRIVE_BESIDE_CTAS": "2", "MSIM_QUERY_PAIRED": "1"}])
+def test_whole_parity_file_under_the_knobs(env):
+    """Every test of tests/test_gpu_parity.py (ragged sizes, city population tick by tick with pair counts, point clouds with duplicates and
+    exact-radius pairs, stacked start, all rebuild modes) in a fresh process with the launch knobs set."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-x", "-q"], cwd=ROOT, env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-3000:]
