@@ -1,0 +1,125 @@
+// collide_common.cuh - device helpers of the collision query shared by collide.cu (query_kernel) and collide_paired.cu (the opt-in
+// two-slots-per-thread variant): distance test, candidate scans over global / shared memory, cell-run look-up, 1-D TMA bulk copy.
+// Included inside namespace msim { namespace { ... } } of the including translation unit.
+#pragma once
+
+// squared distance with individually rounded operations, as the oracle computes it.  The x and y
+// lanes go through Blackwell's packed binary32 pipes (FADD2 / FMUL2, sm_100+): same IEEE round-to-nearest
+// result per lane as two scalar instructions, half the issue slots — the query kernel is issue-bound.
+__device__ __forceinline__ float dist2(float2 a, float2 b) {
+    unsigned long long ua, ub, d, sq;
+    ua = (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+    ub = (static_cast<unsigned long long>(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(ua), "l"(ub));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(sq) : "l"(d), "l"(d));
+    return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
+}
+
+// number of slots k in [a, b) with dist2(sorted_pos[k], p) < threshold; four loads in flight
+__device__ __forceinline__ uint32_t count_in_range(const float2* __restrict__ sorted_pos, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t c = 0;
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = __ldg(sorted_pos + k), q1 = __ldg(sorted_pos + k + 1), q2 = __ldg(sorted_pos + k + 2), q3 = __ldg(sorted_pos + k + 3);
+        c += (dist2(q0, p) < threshold) ? 1u : 0u;
+        c += (dist2(q1, p) < threshold) ? 1u : 0u;
+        c += (dist2(q2, p) < threshold) ? 1u : 0u;
+        c += (dist2(q3, p) < threshold) ? 1u : 0u;
+    }
+    for (; k < b; k++) c += (dist2(__ldg(sorted_pos + k), p) < threshold) ? 1u : 0u;
+    return c;
+}
+
+// true iff some slot k in [a, b) is within range; four independent loads per step, so the scan costs
+// one memory latency per four candidates instead of one per candidate
+__device__ __forceinline__ bool any_in_range(const float2* __restrict__ sorted_pos, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = __ldg(sorted_pos + k), q1 = __ldg(sorted_pos + k + 1), q2 = __ldg(sorted_pos + k + 2), q3 = __ldg(sorted_pos + k + 3);
+        const bool h = (dist2(q0, p) < threshold) | (dist2(q1, p) < threshold) | (dist2(q2, p) < threshold) | (dist2(q3, p) < threshold);
+        if (h) return true;
+    }
+    for (; k < b; k++)
+        if (dist2(__ldg(sorted_pos + k), p) < threshold) return true;
+    return false;
+}
+
+// the three cells x0..x1 of one grid row are adjacent keys = one contiguous run [lo, hi) of the sorted order
+template <bool PREFIX>
+__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, int ncx, int yy, int x0, int x1,
+                                        uint32_t& lo, uint32_t& hi) {
+    if (PREFIX) {  // counting-sort path: exclusive prefix table, run = [start[first cell], start[last cell + 1])
+        const uint32_t* row = cell_start + static_cast<size_t>(yy) * ncx;
+        lo = __ldg(row + x0);
+        hi = __ldg(row + x1 + 1);
+        return;
+    }
+    const uint2* row = cell_range + static_cast<size_t>(yy) * ncx;
+    lo = 0xffffffffu;
+    hi = 0u;
+    for (int xx = x0; xx <= x1; xx++) {
+        const uint2 r = __ldg(row + xx);  // empty cell = {0xffffffff, ~0xffffffff = 0}: neutral for min/max
+        lo = min(lo, r.x);
+        hi = max(hi, ~r.y);
+    }
+    if (lo > hi) lo = hi;  // all three empty
+}
+
+// ---- shared-memory variants of the scans (same arithmetic, candidates already staged) -----------
+__device__ __forceinline__ uint32_t count_in_tile(const float2* __restrict__ tile, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t c = 0;
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = tile[k], q1 = tile[k + 1], q2 = tile[k + 2], q3 = tile[k + 3];
+        c += (dist2(q0, p) < threshold) ? 1u : 0u;
+        c += (dist2(q1, p) < threshold) ? 1u : 0u;
+        c += (dist2(q2, p) < threshold) ? 1u : 0u;
+        c += (dist2(q3, p) < threshold) ? 1u : 0u;
+    }
+    for (; k < b; k++) c += (dist2(tile[k], p) < threshold) ? 1u : 0u;
+    return c;
+}
+
+__device__ __forceinline__ bool any_in_tile(const float2* __restrict__ tile, uint32_t a, uint32_t b, float2 p, float threshold) {
+    uint32_t k = a;
+    for (; k + 4 <= b; k += 4) {
+        const float2 q0 = tile[k], q1 = tile[k + 1], q2 = tile[k + 2], q3 = tile[k + 3];
+        if ((dist2(q0, p) < threshold) | (dist2(q1, p) < threshold) | (dist2(q2, p) < threshold) | (dist2(q3, p) < threshold)) return true;
+    }
+    for (; k < b; k++)
+        if (dist2(tile[k], p) < threshold) return true;
+    return false;
+}
+
+// ---- bulk asynchronous copy (TMA, 1-D) of a contiguous window of sorted_pos into shared memory ----------------
+// One elected thread arms an mbarrier with the byte count and issues cp.async.bulk; the copy engine fills the window while
+// no thread spends issue slots on LDG + STS (the query kernel is issue-bound: the two staging loops were ~10 % of its
+// instructions).  Source, destination and size must be multiples of 16 bytes: windows are widened to even slot indices.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_global, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_global),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+constexpr int QUERY_THREADS = 256;
+constexpr int COUNTER_STRIPES = 64;
+constexpr int COUNTER_STRIDE = 16;  // in u64 words: 128 bytes between stripes
+constexpr uint32_t QUERY_WINDOW = 1728;  // candidates staged per window: 2 x 13.5 KB, so that 8 CTAs (64 warps) fit one SM with the 1 KB per-CTA reserve
+

@@ -185,6 +185,9 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
                  const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
                  const uint32_t* n_dev = nullptr, const uint32_t* n_owned_dev = nullptr);
 size_t query_stripe_bytes();
+// collide_paired.cu (opt-in, Tuning::query_paired): the query kernel only; the caller folds the striped counters
+void launch_query_paired(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid,
+                         unsigned long long* stripes);
 int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu
