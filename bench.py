@@ -208,28 +208,63 @@ def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, ref_move, ref
     return e.shape[0] * steps / dt, dt / steps
 
 
-def time_whole_shader(O, ents_aos, m, radius, collisions, sample=100_000, ticks=2):
+def time_whole_shader(O, ents_aos, m, radius, collisions, sample=100_000, ticks=2, limit_s=90.0):
     """The reference's ENTIRE shader compiled for the CPU (oracle/_ref/libref_shader_full.so), one host thread, dispatch by dispatch:
     reported beside the multi-threaded arm.  The world is one metre larger than the map (the shader never terminates for an
-    entity on the map's maximum coordinate)."""
+    entity on the map's maximum coordinate).  Runs in a forked child under a time limit: the reference's lock protocol is known to leave
+    locks behind, and a bench must never hang on the code it is being compared with (the child touches no CUDA state)."""
     if not (collisions and O.ref_shader_full_available()):
         return None
+    import select
+
+    # copied BEFORE the fork: the caller's buffer may be CUDA-pinned memory, which a forked child does not inherit
     e = np.ascontiguousarray(ents_aos[:sample]).view(O.ENTITY_DTYPE).copy()
     e["initialized"] = 0
-    om = O.OracleMap(m.width + 1.0, m.height + 1.0, m.roads.view(O.ROAD_DTYPE), m.connections)
-    sim = O.RefShaderSim(e, om, radius=radius)
-    try:
-        sim.dispatch(2)  # initialise + quad_tree_insert (untimed, like the GPU arm's first dispatch)
-        sim.dispatch(3)
-        t0 = time.perf_counter()
-        for k in range(ticks):
-            sim.dispatch(4 + 2 * k)
-            sim.dispatch(5 + 2 * k)
-        dt = time.perf_counter() - t0
-    except O.RefShaderDeadlock as ex:
-        return {"error": str(ex)}
-    return {"value": e.shape[0] * ticks / dt, "unit": "entity-updates/s", "cores": 1, "sample": f"{e.shape[0]} entities, {ticks} sim ticks",
-            "what": "random_move.comp compiled as C++: main() with quad_tree_update + quad_tree_check_collisions, invocations in index order"}
+
+    def work():
+        om = O.OracleMap(m.width + 1.0, m.height + 1.0, m.roads.view(O.ROAD_DTYPE), m.connections)
+        sim = O.RefShaderSim(e, om, radius=radius)
+        try:
+            sim.dispatch(2)  # initialise + quad_tree_insert (untimed, like the GPU arm's first dispatch)
+            sim.dispatch(3)
+            t0 = time.perf_counter()
+            for k in range(ticks):
+                sim.dispatch(4 + 2 * k)
+                sim.dispatch(5 + 2 * k)
+            dt = time.perf_counter() - t0
+        except O.RefShaderDeadlock as ex:
+            return {"error": str(ex)}
+        return {"value": e.shape[0] * ticks / dt, "unit": "entity-updates/s", "cores": 1, "sample": f"{e.shape[0]} entities, {ticks} sim ticks",
+                "what": "random_move.comp compiled as C++: main() with quad_tree_update + quad_tree_check_collisions, invocations in index order"}
+
+    rd, wr = os.pipe()
+    pid = os.fork()
+    if pid == 0:  # child
+        code = 1
+        try:
+            os.close(rd)
+            os.write(wr, json.dumps(work()).encode())
+            code = 0
+        finally:
+            os._exit(code)
+    os.close(wr)
+    out = b""
+    deadline = time.monotonic() + limit_s
+    while True:
+        left = deadline - time.monotonic()
+        ready, _, _ = select.select([rd], [], [], max(0.0, left))
+        if not ready:
+            os.kill(pid, 9)
+            result = {"error": f"no result within {limit_s:.0f} s"}
+            break
+        chunk = os.read(rd, 65536)
+        if not chunk:
+            result = json.loads(out.decode()) if out else {"error": "the child exited without a result"}
+            break
+        out += chunk
+    os.close(rd)
+    os.waitpid(pid, 0)
+    return result
 
 
 def cpu_arm_description(ref_move, ref_tree, collisions):
