@@ -119,16 +119,17 @@ struct Profiler {
 
 // ---- launch tuning read once from the environment (api.cu); defaults = the configuration every committed number was measured with
 struct Tuning {
-    int move_min_blocks;          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
-    bool move_grid_by_occupancy;  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
-    bool arrive_persistent;       // MSIM_ARRIVE_GRID=persistent: pass B as one resident wave with a stride loop
-    int arrive_beside_ctas_per_sm;  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
+    int move_min_blocks{0};          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
+    bool move_grid_by_occupancy{false};  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
+    bool arrive_persistent{false};       // MSIM_ARRIVE_GRID=persistent: pass B as one resident wave with a stride loop
+    int arrive_beside_ctas_per_sm{0};  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
                                   // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots instead of taking
                                   // them all for 45-70 us (it is latency-bound and only has to finish before the next move); 0 = full grid (default)
-    bool query_paired;            // MSIM_QUERY_PAIRED=1: query with two adjacent slots per thread (collide.cu, query_paired_kernel)
-    int scan_min_blocks;          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
-    int csort_max_cells_log2;     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
+    bool query_paired{false};            // MSIM_QUERY_PAIRED=1: query with two adjacent slots per thread (collide.cu, query_paired_kernel)
+    int scan_min_blocks{0};          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
+    int csort_max_cells_log2{25};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
+    bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
 };
 const Tuning& tuning();
 

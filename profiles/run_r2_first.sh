@@ -16,6 +16,7 @@ MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_be
 MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
 MSIM_MOVE_GRID=occupancy $B > gpurun_out/r2a_bench_occgrid.json 2> gpurun_out/r2a_bench_occgrid.err
 for k in 1 2 4; do MSIM_ARRIVE_BESIDE_CTAS=$k $B > gpurun_out/r2a_bench_besidectas$k.json 2> gpurun_out/r2a_bench_besidectas$k.err; done
+MSIM_L2_PERSIST_ROADS=1 $B > gpurun_out/r2a_bench_l2roads.json 2> gpurun_out/r2a_bench_l2roads.err
 MSIM_QUERY_PAIRED=1 $B > gpurun_out/r2a_bench_paired.json 2> gpurun_out/r2a_bench_paired.err
 MSIM_SCAN_MIN_BLOCKS=8 $B > gpurun_out/r2a_bench_scan8.json 2> gpurun_out/r2a_bench_scan8.err
 MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy MSIM_SCAN_MIN_BLOCKS=8 MSIM_QUERY_PAIRED=1 $B --fused-arrive > gpurun_out/r2a_bench_all.json 2> gpurun_out/r2a_bench_all.err
@@ -24,6 +25,7 @@ MSIM_MOVE_MIN_BLOCKS=6 MSIM_MOVE_GRID=occupancy $B --fused-arrive > gpurun_out/r
 $B --workload munich_1m_nocollisions > gpurun_out/r2a_bench_1m_off.json 2> gpurun_out/r2a_bench_1m_off.err
 $B --workload munich_1m_nocollisions --fused-arrive > gpurun_out/r2a_bench_1m_off_fused.json 2> gpurun_out/r2a_bench_1m_off_fused.err
 $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off.json 2> gpurun_out/r2a_bench_10m_off.err
+MSIM_L2_PERSIST_ROADS=1 $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off_l2roads.json 2> gpurun_out/r2a_bench_10m_off_l2roads.err
 MSIM_ARRIVE_GRID=persistent $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off_persistent.json 2> gpurun_out/r2a_bench_10m_off_persistent.err
 $B --workload munich_1m_nocollisions --entities 10000000 --fused-arrive > gpurun_out/r2a_bench_10m_off_fused.json 2> gpurun_out/r2a_bench_10m_off_fused.err
 for f in gpurun_out/r2a_bench_*.json; do echo "== $f"; python profiles/show_bench.py "$f" 2>/dev/null | head -12; done

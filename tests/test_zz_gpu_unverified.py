@@ -88,7 +88,7 @@ def test_fused_arrive_blocking_dispatch_is_unchanged(msim, orc, small_city):
 # ---- launch tuning from the environment (read once per process: run each value in its own process) ---------------
 @pytest.mark.parametrize("env", [{"MSIM_MOVE_MIN_BLOCKS": "5"}, {"MSIM_MOVE_MIN_BLOCKS": "6"}, {"MSIM_MOVE_GRID": "occupancy"},
                                  {"MSIM_MOVE_MIN_BLOCKS": "6", "MSIM_MOVE_GRID": "occupancy"}, {"MSIM_SCAN_MIN_BLOCKS": "8"},
-                                 {"MSIM_ARRIVE_GRID": "persistent"}, {"MSIM_CSORT_MAX_CELLS_LOG2": "27"}, {"MSIM_QUERY_PAIRED": "1"}])
+                                 {"MSIM_ARRIVE_GRID": "persistent"}, {"MSIM_CSORT_MAX_CELLS_LOG2": "27"}, {"MSIM_QUERY_PAIRED": "1"}, {"MSIM_L2_PERSIST_ROADS": "1"}])
 def test_move_tuning_variants_in_subprocess(env):
     """The register-capped instantiations of the move kernel and the occupancy-sized grid: smoke() (bit-exact against the
     oracle over 8 sim ticks) in a fresh process per setting."""
