@@ -438,6 +438,28 @@ def run_b200(args):
         move_only = {"what": "move pass only (pass A streaming + pass B arrivals), 24 B per entity-update", "ms_per_step": mo_ms,
                      "value": n / (mo_ms * 1e-3), "achieved_gbs": mo_gbs, "frac_of_measured_peak": mo_gbs / peak}
 
+    # the same tick with MSIM_FLAG_NO_PAIR_COUNT: colours only, the query stops at an entity's first neighbour.  The colours are all the
+    # reference's host ever looks at (it discards debugData, Simulator.cpp:273); `value` above keeps the exact unique-pair count switched on
+    flags_only = None
+    if collisions and not args.no_flags_only:
+        try:
+            sim2 = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=flags | M.FLAG_NO_PAIR_COUNT, stream=stream.cuda_stream)
+            sim2.dispatch(2)
+            sim2.enqueue_ticks(args.preroll, False)
+            sim2.enqueue_ticks(5, True)
+            sim2.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sim2.enqueue_ticks(args.steps, True)
+            e1.record(stream)
+            e1.synchronize()
+            fo_ms = e0.elapsed_time(e1) / args.steps
+            flags_only = {"what": "sim tick with MSIM_FLAG_NO_PAIR_COUNT (collision colours exact, no pair count)", "ms_per_step": fo_ms,
+                          "value": n / (fo_ms * 1e-3), "flagged_last_tick": sim2.stats()["last_flagged_count"]}
+            sim2.close()
+        except Exception as ex:  # an extra, never the headline: report and go on
+            flags_only = {"error": repr(ex)}
+
     # keep the GPU under the same load long enough for nvidia-smi to sample it (untimed)
     t_end = time.time() + 1.2
     while time.time() < t_end:
@@ -529,6 +551,7 @@ def run_b200(args):
                  "frac_of_nominal_8tbs": tick_gbs / 8000.0, "kernel_time_ms_per_step": total_kernel_ms / args.steps},
         "kernels": kernels,
         "move_only": move_only,
+        "flags_only": flags_only,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -554,6 +577,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1_000_000)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flags-only", action="store_true", help="skip the extra colours-only measurement")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="N > 1: strong = the workload's population split over N GPUs (BASELINE config 3), weak = that population per GPU")
     ap.add_argument("--exchange", choices=["p2p", "collective"], default="p2p",
