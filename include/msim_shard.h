@@ -94,6 +94,11 @@ int msim_shard_row_histogram(msim_handle* h, uint32_t* dst, uint32_t rows);
 int msim_grid_rows(float world_w, float world_h, float radius, const float* xy, uint64_t count, uint32_t* rows_out,
                    uint32_t* cells_x, uint32_t* cells_y);
 
+/* Host helper, no GPU: the neighbour grid the device builds for this world and radius - 1 / cell edge (the edge lies slightly above the
+ * radius so that two points closer than the radius always fall into adjacent cells in spite of the binary32 rounding of pos * inv_cell) and
+ * the exact binary32 threshold T with (d2 < T) <=> (sqrtf(d2) < radius), which lets the query skip the square root.  Any pointer may be NULL. */
+int msim_grid_params(float world_w, float world_h, float radius, float* inv_cell, float* hit_threshold, uint32_t* cells_x, uint32_t* cells_y);
+
 #ifdef __cplusplus
 }
 #endif

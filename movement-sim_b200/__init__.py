@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_p2p_create", "msim_shard_p2p_connect",
     "msim_shard_p2p_connect_local", "msim_shard_p2p_move_pack", "msim_shard_p2p_integrate", "msim_shard_integrate", "msim_shard_integrate_async",
     "msim_shard_counts", "msim_shard_read_gids",
-    "msim_shard_row_histogram", "msim_grid_rows",
+    "msim_shard_row_histogram", "msim_grid_rows", "msim_grid_params",
     # include/msim_mapgen.h
     "msim_map_from_geojson", "msim_map_save_binary", "msim_map_load_binary", "msim_map_load", "msim_map_from_arrays", "msim_haversine_m",
 ]
@@ -235,6 +235,7 @@ def lib():
         "msim_shard_read_gids": (i32, [vp, vp, u64]),
         "msim_shard_row_histogram": (i32, [vp, vp, u32]),
         "msim_grid_rows": (i32, [f32, f32, f32, vp, u64, vp, C.POINTER(u32), C.POINTER(u32)]),
+        "msim_grid_params": (i32, [f32, f32, f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(u32), C.POINTER(u32)]),
         "msim_map_load_json": (i32, [C.c_char_p, C.POINTER(vp)]),
         "msim_map_save_json": (i32, [vp, C.c_char_p]),
         "msim_map_generate_city": (i32, [f32, f32, f32, f32, f32, u64, C.POINTER(vp)]),
@@ -383,6 +384,15 @@ def grid_rows(world_w: float, world_h: float, radius: float, xy: np.ndarray):
     if rc != MSIM_OK:
         raise MsimError(rc, "msim_grid_rows")
     return rows, cx.value, cy.value
+
+
+def grid_params(world_w: float, world_h: float, radius: float) -> dict:
+    """The device's neighbour grid for this world and radius: inv_cell, hit_threshold (binary32), cells_x, cells_y."""
+    inv, thr, cx, cy = C.c_float(), C.c_float(), C.c_uint32(), C.c_uint32()
+    rc = lib().msim_grid_params(world_w, world_h, radius, C.byref(inv), C.byref(thr), C.byref(cx), C.byref(cy))
+    if rc != MSIM_OK:
+        raise MsimError(rc, "msim_grid_params")
+    return {"inv_cell": np.float32(inv.value), "hit_threshold": np.float32(thr.value), "cells_x": cx.value, "cells_y": cy.value}
 
 
 def shard_buffer_bytes(migrant_capacity: int, halo_capacity: int) -> int:

@@ -1679,4 +1679,15 @@ int msim_grid_rows(float world_w, float world_h, float radius, const float* xy, 
     return MSIM_OK;
 }
 
+int msim_grid_params(float world_w, float world_h, float radius, float* inv_cell, float* hit_threshold, uint32_t* cells_x, uint32_t* cells_y) {
+    GridParams g{};
+    int bits = 0;
+    compute_grid(world_w, world_h, radius, g, bits);
+    if (inv_cell) *inv_cell = g.inv_cell;
+    if (hit_threshold) *hit_threshold = g.hit_threshold;
+    if (cells_x) *cells_x = static_cast<uint32_t>(g.ncx);
+    if (cells_y) *cells_y = static_cast<uint32_t>(g.ncy);
+    return MSIM_OK;
+}
+
 }  // extern "C"

