@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Differential fuzzing of the oracle against the reference's WHOLE shader compiled for the CPU (oracle/_ref/libref_shader_full.so).
-TEST INFRASTRUCTURE.    python oracle/fuzz_vs_ref_shader.py <seed> <configurations>
+TEST INFRASTRUCTURE.    python tests/fuzz_vs_ref_shader.py <seed> <configurations>
 Random map / population / radius / quadtree depth and capacity / world padding / number of dispatches; every dispatch compares all 64
 bytes of every entity.  Seeds 1-5 (920 configurations) ran clean when this was written: no mismatch, no lock left behind."""
 import sys, time
 import os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repository root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import movement_sim_b200 as M
