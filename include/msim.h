@@ -249,6 +249,11 @@ const char* msim_map_last_error(void);
 int msim_entities_init(const msim_road* roads, uint64_t road_count, uint64_t count, uint64_t seed,
                        const float* box, msim_entity* out);
 
+/* Host-only twin of msim_read_quadtree_nodes (no GPU): the display quadtree of caller-owned positions (xy = count x {x, y}), built by the
+ * same code from a leaf histogram taken on the host. */
+int msim_quadtree_from_positions(const float* xy, uint64_t count_in, float world_w, float world_h, uint32_t max_depth, uint32_t node_cap,
+                                 msim_quadtree_node* dst, uint64_t cap, uint64_t* count);
+
 /* gpu_quad_tree::calc_node_count (src/sim/GpuQuadTree.cpp:11-17) */
 uint64_t msim_calc_node_count(uint32_t max_depth);
 uint32_t msim_abi_version(void);

@@ -83,7 +83,7 @@ ABI_SYMBOLS = [
     "msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid",
     "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
-    "msim_entities_init", "msim_calc_node_count", "msim_abi_version",
+    "msim_entities_init", "msim_calc_node_count", "msim_abi_version", "msim_quadtree_from_positions",
     # include/msim_shard.h
     "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_p2p_create", "msim_shard_p2p_connect",
     "msim_shard_p2p_connect_local", "msim_shard_p2p_move_pack", "msim_shard_p2p_integrate", "msim_shard_integrate", "msim_shard_integrate_async",
@@ -250,6 +250,7 @@ def lib():
         "msim_map_last_error": (C.c_char_p, []),
         "msim_entities_init": (i32, [vp, u64, u64, u64, vp, vp]),
         "msim_calc_node_count": (u64, [u32]),
+        "msim_quadtree_from_positions": (i32, [vp, u64, f32, f32, u32, u32, vp, u64, C.POINTER(u64)]),
         "msim_abi_version": (u32, []),
         "msim_map_from_geojson": (i32, [C.c_char_p, u32, C.POINTER(vp), C.POINTER(MapgenStats)]),
         "msim_map_save_binary": (i32, [vp, C.c_char_p]),
@@ -384,6 +385,18 @@ def grid_rows(world_w: float, world_h: float, radius: float, xy: np.ndarray):
     if rc != MSIM_OK:
         raise MsimError(rc, "msim_grid_rows")
     return rows, cx.value, cy.value
+
+
+def quadtree_from_positions(xy: np.ndarray, world_w: float, world_h: float, max_depth: int = 8, node_cap: int = 10) -> np.ndarray:
+    """Display quadtree of the given positions, built on the host by the code behind msim_read_quadtree_nodes."""
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+    cap = calc_node_count(max_depth)
+    out = np.zeros(cap, dtype=QUADTREE_NODE_DTYPE)
+    n = C.c_uint64()
+    rc = lib().msim_quadtree_from_positions(xy.ctypes.data, xy.shape[0], world_w, world_h, max_depth, node_cap, out.ctypes.data, cap, C.byref(n))
+    if rc != MSIM_OK:
+        raise MsimError(rc, "msim_quadtree_from_positions")
+    return out[: n.value]
 
 
 def grid_params(world_w: float, world_h: float, radius: float) -> dict:

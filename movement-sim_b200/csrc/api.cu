@@ -1690,4 +1690,51 @@ int msim_grid_params(float world_w, float world_h, float radius, float* inv_cell
     return MSIM_OK;
 }
 
+// Host-only twin of msim_read_quadtree_nodes: the same tree from caller-owned positions, the leaf histogram taken on the host with the
+// descent quadtree.cu uses on the device (compare with offset + width / 2 in binary32, halve, repeat: random_move.comp:319-341).  Lets the
+// display quadtree be checked without a GPU (tests/test_quadtree_host.py: against the tree the reference's own shader code builds).
+int msim_quadtree_from_positions(const float* xy, uint64_t count_in, float world_w, float world_h, uint32_t max_depth, uint32_t node_cap,
+                                 msim_quadtree_node* dst, uint64_t cap, uint64_t* count) {
+    if (!dst || cap == 0 || !count || (count_in && !xy)) return MSIM_ERR_INVALID;
+    const int depth = static_cast<int>(std::min<uint32_t>(std::max<uint32_t>(max_depth ? max_depth : 8u, 1u), 8u));
+    const int levels = depth - 1;
+    const bool root_only = count_in == 0 || levels == 0;
+    std::vector<std::vector<uint32_t>> sums(levels + 1);
+    if (!root_only) {
+        const uint32_t side0 = 1u << levels;
+        sums[0].assign(static_cast<size_t>(side0) * side0, 0u);
+        auto descend = [levels](float x, float extent) {
+            float off = 0.0f, width = extent;
+            uint32_t index = 0;
+            for (int l = 0; l < levels; l++) {
+                width = width * 0.5f;
+                const float mid = off + width;
+                index <<= 1;
+                if (!(x < mid)) {
+                    off = mid;
+                    index |= 1u;
+                }
+            }
+            return index;
+        };
+        for (uint64_t i = 0; i < count_in; i++) sums[0][static_cast<size_t>(descend(xy[2 * i + 1], world_h)) * side0 + descend(xy[2 * i], world_w)]++;
+        for (int l = 1; l <= levels; l++) {
+            const uint32_t side = 1u << (levels - l);
+            sums[l].resize(static_cast<size_t>(side) * side);
+            const std::vector<uint32_t>& f = sums[l - 1];
+            const size_t fs = static_cast<size_t>(side) * 2;
+            for (uint32_t y = 0; y < side; y++)
+                for (uint32_t x = 0; x < side; x++)
+                    sums[l][static_cast<size_t>(y) * side + x] = f[(2 * y) * fs + 2 * x] + f[(2 * y) * fs + 2 * x + 1] + f[(2 * y + 1) * fs + 2 * x] + f[(2 * y + 1) * fs + 2 * x + 1];
+        }
+    } else {
+        sums.assign(1, std::vector<uint32_t>(1, static_cast<uint32_t>(count_in)));
+    }
+    QuadBuilder b{&sums, root_only ? 0 : levels, node_cap ? node_cap : 10u, dst, cap, 0, false};
+    b.emit(root_only ? 0 : levels, 0, 0, 0.0f, 0.0f, world_w, world_h, 0);
+    if (b.overflow) return MSIM_ERR_CAPACITY;
+    *count = b.used;
+    return MSIM_OK;
+}
+
 }  // extern "C"
