@@ -249,6 +249,11 @@ const char* msim_map_last_error(void);
 int msim_entities_init(const msim_road* roads, uint64_t road_count, uint64_t count, uint64_t seed,
                        const float* box, msim_entity* out);
 
+/* The road-index stream of msim_entities_init alone: road_index_out[i] = the road entity i of that seeded population starts on (its position
+ * is that road's start point).  Lets a sharded host find out where a population lives without building it. */
+int msim_entities_init_roads(const msim_road* roads, uint64_t road_count, uint64_t count, uint64_t seed, const float* box,
+                             uint32_t* road_index_out);
+
 /* Host-only twin of msim_read_quadtree_nodes (no GPU): the display quadtree of caller-owned positions (xy = count x {x, y}), built by the
  * same code from a leaf histogram taken on the host. */
 int msim_quadtree_from_positions(const float* xy, uint64_t count_in, float world_w, float world_h, uint32_t max_depth, uint32_t node_cap,

@@ -83,7 +83,7 @@ ABI_SYMBOLS = [
     "msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid",
     "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count",
     "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error",
-    "msim_entities_init", "msim_calc_node_count", "msim_abi_version", "msim_quadtree_from_positions",
+    "msim_entities_init", "msim_calc_node_count", "msim_abi_version", "msim_quadtree_from_positions", "msim_entities_init_roads",
     # include/msim_shard.h
     "msim_shard_buffer_bytes", "msim_shard_enable", "msim_shard_pack", "msim_shard_move_pack", "msim_shard_p2p_create", "msim_shard_p2p_connect",
     "msim_shard_p2p_connect_local", "msim_shard_p2p_move_pack", "msim_shard_p2p_integrate", "msim_shard_integrate", "msim_shard_integrate_async",
@@ -249,6 +249,7 @@ def lib():
         "msim_map_connections": (vp, [vp]),
         "msim_map_last_error": (C.c_char_p, []),
         "msim_entities_init": (i32, [vp, u64, u64, u64, vp, vp]),
+        "msim_entities_init_roads": (i32, [vp, u64, u64, u64, vp, vp]),
         "msim_calc_node_count": (u64, [u32]),
         "msim_quadtree_from_positions": (i32, [vp, u64, f32, f32, u32, u32, vp, u64, C.POINTER(u64)]),
         "msim_abi_version": (u32, []),
@@ -374,6 +375,23 @@ class Map:
         if rc != MSIM_OK:
             raise MsimError(rc, L.msim_map_last_error().decode())
         return out
+
+
+def _init_road_indices(self, count: int, seed: int = 42, box=None) -> np.ndarray:
+    """road_index of every entity init_entities(count, seed, box) would create, without creating them (msim_entities_init_roads)."""
+    out = np.zeros(count, dtype=np.uint32)
+    boxp = None
+    if box is not None:
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        assert box.shape == (4,)
+        boxp = box.ctypes.data
+    rc = lib().msim_entities_init_roads(self.roads.ctypes.data, self.roads.shape[0], count, seed, boxp, out.ctypes.data)
+    if rc != MSIM_OK:
+        raise MsimError(rc, lib().msim_map_last_error().decode())
+    return out
+
+
+Map.init_road_indices = _init_road_indices
 
 
 def grid_rows(world_w: float, world_h: float, radius: float, xy: np.ndarray):

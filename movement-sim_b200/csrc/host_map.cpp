@@ -417,6 +417,28 @@ int msim_entities_init(const msim_road* roads, uint64_t road_count, uint64_t cou
     return MSIM_OK;
 }
 
+// the road-index stream of msim_entities_init alone (same generator, same distribution, same box rule): where every entity of a seeded
+// population starts, without materialising the population
+int msim_entities_init_roads(const msim_road* roads, uint64_t road_count, uint64_t count, uint64_t seed, const float* box, uint32_t* road_index_out) {
+    if (!roads || road_count == 0 || (!road_index_out && count)) return map_fail(MSIM_ERR_INVALID, "msim_entities_init_roads: bad arguments");
+    std::vector<uint32_t> pool;
+    if (box) {
+        for (uint64_t r = 0; r < road_count; r++) {
+            auto inside = [&](const float* p) { return p[0] >= box[0] && p[0] <= box[2] && p[1] >= box[1] && p[1] <= box[3]; };
+            if (inside(roads[r].start.pos) && inside(roads[r].end.pos)) pool.push_back(static_cast<uint32_t>(r));
+        }
+        if (pool.empty()) return map_fail(MSIM_ERR_INVALID, "msim_entities_init_roads: no road inside the box");
+    }
+    const uint64_t choices = box ? pool.size() : road_count;
+    std::mt19937 genRoad(static_cast<uint32_t>(seed));
+    std::uniform_int_distribution<unsigned int> pick(0, static_cast<unsigned int>(choices - 1));
+    for (uint64_t i = 0; i < count; i++) {
+        const unsigned int chosen = pick(genRoad);
+        road_index_out[i] = box ? pool[chosen] : chosen;
+    }
+    return MSIM_OK;
+}
+
 uint64_t msim_calc_node_count(uint32_t max_depth) {
     uint64_t total = 0, level = 1;
     for (uint32_t d = 0; d < max_depth; d++) {

@@ -143,3 +143,26 @@ def test_entity_init_box_restriction(msim, small_city):
         assert (pos[:, 0] >= box[0]).all() and (pos[:, 0] <= box[2]).all() and (pos[:, 1] >= box[1]).all() and (pos[:, 1] <= box[3]).all()
     with pytest.raises(msim.MsimError):
         small_city.init_entities(10, seed=5, box=[-5, -5, -1, -1])
+
+
+def test_road_index_stream_alone_matches_entity_init(msim, small_city):
+    """msim_entities_init_roads = the road-index generator of msim_entities_init on its own (the sharded host's partition histogram)."""
+    box = np.array([0.2 * small_city.width, 0.2 * small_city.height, 0.8 * small_city.width, 0.8 * small_city.height], dtype=np.float32)
+    for count, seed, bx in ((0, 1, None), (1, 2, None), (50_000, 42, None), (33_333, 7, box)):
+        want = small_city.init_entities(count, seed=seed, box=bx)["road_index"]
+        assert np.array_equal(small_city.init_road_indices(count, seed=seed, box=bx), want)
+    with pytest.raises(msim.MsimError):
+        small_city.init_road_indices(10, seed=1, box=np.array([-5.0, -5.0, -4.0, -4.0], dtype=np.float32))
+
+
+def test_partition_histogram_equals_the_full_population(msim, small_city):
+    from movement_sim_b200 import sharding as S
+
+    total, seed = 2 * S.CHUNK + 12_345, 42  # three seeded chunks
+    want = None
+    for _, ents in S.generate_population(msim, small_city, total, seed):
+        rows, ncx, ncy = msim.grid_rows(small_city.width, small_city.height, 10.0, ents["pos"])
+        h = np.bincount(rows, minlength=ncy).astype(np.int64)
+        want = h if want is None else want + h
+    hist, gx, gy = S.global_row_histogram(msim, small_city, total, seed, 10.0)
+    assert (gx, gy) == (ncx, ncy) and np.array_equal(hist, want) and int(hist.sum()) == total
