@@ -28,5 +28,5 @@ $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_
 MSIM_L2_PERSIST_ROADS=1 $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off_l2roads.json 2> gpurun_out/r2a_bench_10m_off_l2roads.err
 MSIM_ARRIVE_GRID=persistent $B --workload munich_1m_nocollisions --entities 10000000 > gpurun_out/r2a_bench_10m_off_persistent.json 2> gpurun_out/r2a_bench_10m_off_persistent.err
 $B --workload munich_1m_nocollisions --entities 10000000 --fused-arrive > gpurun_out/r2a_bench_10m_off_fused.json 2> gpurun_out/r2a_bench_10m_off_fused.err
-for f in gpurun_out/r2a_bench_*.json; do echo "== $f"; python profiles/show_bench.py "$f" 2>/dev/null | head -12; done
+python profiles/compare_bench.py gpurun_out/r2a_bench_default.json gpurun_out/r2a_bench_[!d]*.json
 $B --e2e-pipelined --e2e-steps 5 > gpurun_out/r2a_bench_e2e_pipelined.json 2> gpurun_out/r2a_bench_e2e_pipelined.err; python -c "import json; print(json.load(open(\"gpurun_out/r2a_bench_e2e_pipelined.json\"))[\"e2e\"])"
