@@ -6,11 +6,11 @@
 # Everything lands in gpurun_out/r2a_*.  Nothing here is a result until it has been read and copied to profiles/.
 set -x
 mkdir -p gpurun_out
-B="python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1"
+B="python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 --no-flags-only"
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2a_pytest_gpu.log
 MSIM_TEST_UNVERIFIED=1 timeout 1500 python -m pytest tests/test_zz_gpu_unverified.py -m gpu -q > gpurun_out/r2a_pytest_unverified.log 2>&1; tail -15 gpurun_out/r2a_pytest_unverified.log
 
-$B > gpurun_out/r2a_bench_default.json 2> gpurun_out/r2a_bench_default.err
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 > gpurun_out/r2a_bench_default.json 2> gpurun_out/r2a_bench_default.err  # with the colours-only extra
 $B --fused-arrive > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fused.err
 MSIM_MOVE_MIN_BLOCKS=5 $B > gpurun_out/r2a_bench_minb5.json 2> gpurun_out/r2a_bench_minb5.err
 MSIM_MOVE_MIN_BLOCKS=6 $B > gpurun_out/r2a_bench_minb6.json 2> gpurun_out/r2a_bench_minb6.err
