@@ -166,3 +166,16 @@ def test_partition_histogram_equals_the_full_population(msim, small_city):
         want = h if want is None else want + h
     hist, gx, gy = S.global_row_histogram(msim, small_city, total, seed, 10.0)
     assert (gx, gy) == (ncx, ncy) and np.array_equal(hist, want) and int(hist.sum()) == total
+
+
+def test_population_build_is_independent_of_the_thread_count(msim, small_city):
+    from movement_sim_b200 import sharding as S
+
+    total, seed = 3 * S.CHUNK + 777, 5
+    h1 = S.global_row_histogram(msim, small_city, total, seed, 10.0, threads=1)
+    h3 = S.global_row_histogram(msim, small_city, total, seed, 10.0, threads=3)
+    assert np.array_equal(h1[0], h3[0]) and h1[1:] == h3[1:]
+    e1, g1 = S.collect_band(msim, small_city, total, seed, 10.0, 20, 90, threads=1)
+    e3, g3 = S.collect_band(msim, small_city, total, seed, 10.0, 20, 90, threads=3)
+    assert e1.tobytes() == e3.tobytes() and np.array_equal(g1, g3) and g1.shape[0] == e1.shape[0] > 0
+    assert S.host_threads(1) >= 1 and S.host_threads(10_000) == 1
