@@ -1,0 +1,176 @@
+"""Dry run of bench.py's GPU arm (run_b200) on the CPU: torch.cuda and the library's Simulation are replaced by stand-ins (the
+Simulation computes with the oracle, events return a made-up clock), so that every statement that assembles the JSON line - including the
+blocks added after the last GPU run (colours-only extra, experiment flags, CPU baseline with the compiled shader, forked whole-shader
+timing, optional pipelined e2e) - executes once before a GPU box has to.  The numbers mean nothing; the keys and the control flow do."""
+import ctypes
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, oracle_map, to_oracle_entities
+
+sys.path.insert(0, ROOT)
+
+
+class FakeEvent:
+    clock = 0.0
+
+    def __init__(self, enable_timing=True):
+        self.t = None
+
+    def record(self, stream=None):
+        FakeEvent.clock += 0.37
+        self.t = FakeEvent.clock
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+class FakeTensor:
+    def __init__(self, n):
+        self.a = np.zeros(n, dtype=np.uint8)
+
+    def data_ptr(self):
+        return self.a.ctypes.data
+
+    def numpy(self):
+        return self.a
+
+    def fill_(self, v):
+        return self
+
+
+def fake_torch():
+    t = types.ModuleType("torch")
+    t.uint8 = "uint8"
+    t.empty = lambda n, dtype=None, pin_memory=False, device=None: FakeTensor(n)
+    cuda = types.SimpleNamespace()
+    cuda.set_device = lambda d: None
+    cuda.Stream = lambda: types.SimpleNamespace(cuda_stream=0)
+    cuda.Event = FakeEvent
+    cuda.synchronize = lambda: None
+    cuda.get_device_properties = lambda d: types.SimpleNamespace(uuid=None)
+
+    class stream_ctx:
+        def __init__(self, s):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    cuda.stream = stream_ctx
+    t.cuda = cuda
+    return t
+
+
+def make_fake_simulation(M, O):
+    class Sim:
+        def __init__(self, m, entities, radius=10.0, device=0, flags=0, stream=None, **_):
+            self.om = oracle_map(O, m)
+            self.e = to_oracle_entities(O, entities)
+            self.radius, self.flags, self.count = float(radius), flags, self.e.shape[0]
+            self.launches, self.pairs, self.profile = 0, 0, None
+            self.snap = None
+
+        def _tick(self, collide):
+            O.move_pass(self.e, self.om, threads=4)
+            self.launches += 2
+            if self.profile is not None:
+                for k in ("move", "arrive"):
+                    c, ms = self.profile.get(k, (0, 0.0))
+                    self.profile[k] = (c + 1, ms + 0.05)
+            if collide:
+                self.pairs = O.collide_pass(self.e, self.om.world_w, self.om.world_h, self.radius, threads=4)
+                self.launches += 5
+                if self.profile is not None:
+                    for k, cost in (("cell_scan", 0.03), ("cell_scatter", 0.1), ("query", 0.25)):
+                        c, ms = self.profile.get(k, (0, 0.0))
+                        self.profile[k] = (c + 1, ms + cost)
+
+        def dispatch(self, tick):
+            if not self.e["initialized"].all() or tick % 2 == 0:
+                O.move_pass(self.e, self.om, threads=4)
+            else:
+                self.pairs = O.collide_pass(self.e, self.om.world_w, self.om.world_h, self.radius, threads=4)
+
+        def enqueue_ticks(self, k, collide):
+            for _ in range(k):
+                self._tick(collide)
+
+        def sync(self):
+            pass
+
+        def stats(self):
+            return {"kernel_launches": self.launches, "last_pair_count": self.pairs, "last_flagged_count": int(O.collision_flags(self.e).sum()),
+                    "entity_count": self.count, "grid_cells_x": 1, "grid_cells_y": 1}
+
+        def profile_begin(self):
+            self.profile = {}
+
+        def profile_end(self):
+            out, self.profile = self.profile, None
+            return out
+
+        def read_entities_ptr(self, ptr, n):
+            ctypes.memmove(ptr, self.e.ctypes.data, n * 64)
+
+        def upload_ptr(self, ptr, n):
+            ctypes.memmove(self.e.ctypes.data, ptr, n * 64)
+
+        def snapshot_begin(self):
+            self.snap = self.e.copy()
+
+        def snapshot_end(self, copy=True):
+            return self.snap
+
+        def close(self):
+            pass
+
+    return Sim
+
+
+@pytest.mark.parametrize("argv", [["--workload", "munich_10m_collisions", "--entities", "6000"],
+                                  ["--workload", "munich_1m_nocollisions", "--entities", "5000"],
+                                  ["--workload", "munich_10m_collisions", "--entities", "4000", "--fused-arrive", "--e2e-pipelined", "--no-flags-only"]])
+def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv):
+    import bench
+
+    monkeypatch.setitem(sys.modules, "torch", fake_torch())
+    monkeypatch.setattr(msim, "Simulation", make_fake_simulation(msim, orc))
+    monkeypatch.setattr(bench, "ClockSampler", lambda uuid: types.SimpleNamespace(stop=lambda: {"sm_mhz": None, "reasons": ["dry run"]}))
+    monkeypatch.setattr(bench, "_RESULT_FD", None)
+    monkeypatch.delenv("MSIM_BENCH_RESULT_FD", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "3", "--warmup", "3", "--preroll", "4", "--cpu-sample", "3000", "--cpu-steps", "1", *argv])
+    monkeypatch.setattr(bench, "quiet_stdout", lambda: None)
+    monkeypatch.setattr(bench.time, "time", iter(range(10_000)).__next__)  # the "keep the GPU busy for 1.2 s" loop ends at once
+    assert bench.main() == 0
+    out = capfd.readouterr().out.strip().splitlines()
+    line = json.loads(out[-1])
+    collisions = "nocollisions" not in argv[1]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "roofline", "tick", "kernels", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["metric"] == "entity-updates/sec" and line["n_gpus"] == 1 and line["steps"] == 3 and line["vs_baseline"] is None
+    assert line["config"]["workload"] == argv[1] and line["config"]["experiments"]["fused_arrive"] == ("--fused-arrive" in argv)
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["kernel"] == ("query" if collisions else "move")
+    assert line["e2e"]["h2d_bytes_per_step"] == line["config"]["entities"] * 64 == line["e2e"]["d2h_bytes_per_step"]
+    assert ("pipelined" in line["e2e"]) == ("--e2e-pipelined" in argv)
+    assert (line["move_only"] is not None) == collisions
+    if collisions and "--no-flags-only" not in argv:
+        assert line["flags_only"]["ms_per_step"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["port_value"] > 0
+    if collisions and orc.ref_shader_full_available():
+        assert cb["whole_shader_1_thread"]["value"] > 0
