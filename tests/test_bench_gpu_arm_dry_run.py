@@ -174,3 +174,43 @@ def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv):
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["port_value"] > 0
     if collisions and orc.ref_shader_full_available():
         assert cb["whole_shader_1_thread"]["value"] > 0
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("argv", [["--workload", "munich_10m_collisions", "--entities", "5000"],
+                                  ["--workload", "munich_50m_dense", "--entities", "3000"],
+                                  ["--workload", "munich_1m_nocollisions", "--entities", "4000"]])
+def test_multi_gpu_arm_assembles_its_json_line(tmp_path, argv):
+    """bench.py --gpus 2 (sharding.bench_main) as two gloo ranks on the CPU: stand-ins for torch.cuda and the CUDA engine (the
+    oracle-backed engine of the sharding tests), everything else - workload builder, partition histogram, population build on the rank's
+    host threads, orchestration, collectives, JSON assembly - is the code the GPU run executes (tests/bench_shard_dry_worker.py)."""
+    import socket
+    import subprocess
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    full = ["--steps", "3", "--warmup", "3", "--preroll", "3", "--e2e-steps", "1", *argv]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_shard_dry_worker.py"), str(r), "2", str(port),
+                               str(tmp_path / f"out{r}.json"), json.dumps(full)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=500) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    r0 = json.load(open(tmp_path / "out0.json"))
+    r1 = json.load(open(tmp_path / "out1.json"))
+    assert r0["rc"] == 0 and r1["rc"] == 0 and len(r0["lines"]) == 1 and r1["lines"] == []  # rank 0 alone prints
+    line = r0["lines"][0]
+    collisions = "nocollisions" not in argv[1]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "roofline", "tick", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["config"]["workload"] == argv[1]
+    assert sum(line["config"]["owned_per_rank"]) == line["config"]["entities_total"] == int(argv[3])
+    assert line["tick"]["survey_bytes_per_entity_update"] == (124.0 if collisions else 24.0)
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    if collisions:
+        assert line["config"]["exchange"] == "collective" and line["config"]["global_pairs_last_tick"] is not None
+        assert line["roofline"]["kernel"] == "query"
+    if "dense" in argv[1]:
+        assert "central box" in line["config"]["map"]
