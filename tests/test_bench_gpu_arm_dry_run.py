@@ -179,7 +179,8 @@ def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv):
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("argv", [["--workload", "munich_10m_collisions", "--entities", "5000"],
                                   ["--workload", "munich_50m_dense", "--entities", "3000"],
-                                  ["--workload", "munich_1m_nocollisions", "--entities", "4000"]])
+                                  ["--workload", "munich_1m_nocollisions", "--entities", "4000"],
+                                  ["--workload", "munich_10m_collisions", "--entities", "2500", "--scaling", "weak"]])
 def test_multi_gpu_arm_assembles_its_json_line(tmp_path, argv):
     """bench.py --gpus 2 (sharding.bench_main) as two gloo ranks on the CPU: stand-ins for torch.cuda and the CUDA engine (the
     oracle-backed engine of the sharding tests), everything else - workload builder, partition histogram, population build on the rank's
@@ -205,8 +206,9 @@ def test_multi_gpu_arm_assembles_its_json_line(tmp_path, argv):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
                 "config", "roofline", "tick", "e2e", "gpu_launches", "clocks"):
         assert key in line, key
-    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["config"]["workload"] == argv[1]
-    assert sum(line["config"]["owned_per_rank"]) == line["config"]["entities_total"] == int(argv[3])
+    weak = "weak" in argv
+    assert line["n_gpus"] == 2 and line["scaling"] == ("weak" if weak else "strong") and line["config"]["workload"] == argv[1]
+    assert sum(line["config"]["owned_per_rank"]) == line["config"]["entities_total"] == int(argv[3]) * (2 if weak else 1)
     assert line["tick"]["survey_bytes_per_entity_update"] == (124.0 if collisions else 24.0)
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     if collisions:
