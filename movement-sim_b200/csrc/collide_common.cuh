@@ -6,6 +6,12 @@
 // squared distance with individually rounded operations, as the oracle computes it.  The x and y
 // lanes go through Blackwell's packed binary32 pipes (FADD2 / FMUL2, sm_100+): same IEEE round-to-nearest
 // result per lane as two scalar instructions, half the issue slots — the query kernel is issue-bound.
+#ifdef MSIM_HOST_EMU  // tests/cuda_emu: the same individually rounded operations without the packed PTX forms
+__device__ __forceinline__ float dist2(float2 a, float2 b) {
+    const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+#else
 __device__ __forceinline__ float dist2(float2 a, float2 b) {
     unsigned long long ua, ub, d, sq;
     ua = (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
@@ -14,6 +20,7 @@ __device__ __forceinline__ float dist2(float2 a, float2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(sq) : "l"(d), "l"(d));
     return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
 }
+#endif
 
 // number of slots k in [a, b) with dist2(sorted_pos[k], p) < threshold; four loads in flight
 __device__ __forceinline__ uint32_t count_in_range(const float2* __restrict__ sorted_pos, uint32_t a, uint32_t b, float2 p, float threshold) {
@@ -95,6 +102,12 @@ __device__ __forceinline__ bool any_in_tile(const float2* __restrict__ tile, uin
 // One elected thread arms an mbarrier with the byte count and issues cp.async.bulk; the copy engine fills the window while
 // no thread spends issue slots on LDG + STS (the query kernel is issue-bound: the two staging loops were ~10 % of its
 // instructions).  Source, destination and size must be multiples of 16 bytes: windows are widened to even slot indices.
+#ifdef MSIM_HOST_EMU  // tests/cuda_emu: the elected thread copies at once; waiting on the barrier is a barrier over the block
+__device__ __forceinline__ void mbar_init(unsigned long long*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, uint32_t) {}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_global, uint32_t bytes, unsigned long long*) { memcpy(dst_smem, src_global, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, uint32_t) { __syncthreads(); }
+#else
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t arrivals) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
@@ -117,6 +130,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
                      : "memory");
     } while (!done);
 }
+#endif
 
 constexpr int QUERY_THREADS = 256;
 constexpr int COUNTER_STRIPES = 64;

@@ -303,7 +303,8 @@ int launch_shard_append_ghosts(cudaStream_t s, const ShardArrays& a, uint32_t fi
 int launch_shard_row_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, int ncx, uint32_t* rows, uint32_t nrows, Profiler* prof);
 
 // ---- device helpers shared by several translation units ---------------------------------------
-#ifdef __CUDACC__
+// (MSIM_HOST_EMU: tests/cuda_emu compiles the kernels for a host SIMT emulator; it has twins for the few inline-PTX helpers)
+#if defined(__CUDACC__) || defined(MSIM_HOST_EMU)
 __device__ __forceinline__ uint32_t cell_key_of(float2 p, const GridParams& g) {
     // single multiply per axis (no FMA involved), floor, clamp: monotone in each coordinate
     int cx = __float2int_rd(__fmul_rn(p.x, g.inv_cell));
@@ -332,12 +333,14 @@ __device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
 }
 
 // system-scope flag accesses of the peer-memory exchange (the flag lives in another GPU's memory or is written by one)
+#ifndef MSIM_HOST_EMU
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 // bit position of entity e inside the `arrived` mask written by the move kernel: entities are
 // processed as float4 pairs (2*lane, 2*lane+1) of a 64-entity warp chunk; each parity has its own word.

@@ -1,0 +1,82 @@
+// tests/cuda_emu/emu_kernels.cpp - TEST INFRASTRUCTURE: the kernels of movement-sim_b200/csrc compiled for the host SIMT emulator
+// (tests/cuda_emu/cuda_runtime.h) with C entry points for tests/test_kernels_under_emulator.py.  Built by tests/cuda_emu/Makefile:
+//   g++ -std=c++17 -O1 -ffp-contract=off -DMSIM_HOST_EMU -I tests/cuda_emu (first!) ... -shared
+// The kernel sources are included as they are; only their <<<...>>> launchers are compiled out (MSIM_HOST_EMU).
+#include "cuda_runtime.h"
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+namespace cuda_emu {
+thread_local Block* block = nullptr;
+thread_local unsigned lane = 0, warp = 0;
+}  // namespace cuda_emu
+
+#include "../../movement-sim_b200/csrc/move.cu"
+#include "../../movement-sim_b200/csrc/collide_paired.cu"
+
+namespace msim {
+const Tuning& tuning() {
+    static const Tuning t;
+    return t;
+}
+}  // namespace msim
+
+using namespace msim;
+
+extern "C" {
+
+// move_kernel<keys = false, shard = false, FUSE = fuse>: one move pass over n entities (SoA), `blocks` CTAs of 256 threads
+void emu_move(uint32_t n, const float* pos_in, float* pos_out, float* target, uint32_t* arrived, uint32_t* road, uint32_t* rng,
+              const void* roads, const uint32_t* conn, uint64_t conn_count, int fuse, int consume, uint32_t blocks) {
+    const ShardMoveArgs none{};
+    FusedArrive fa{};
+    fa.target = reinterpret_cast<float2*>(target);
+    fa.road = road;
+    fa.rng = reinterpret_cast<uint4*>(rng);
+    fa.roads = static_cast<const uint4*>(roads);
+    fa.conn = conn;
+    fa.conn_count = conn_count;
+    fa.consume = consume ? 1u : 0u;
+    GridParams grid{};
+    const float4* pin = reinterpret_cast<const float4*>(pos_in);
+    float4* pout = reinterpret_cast<float4*>(pos_out);
+    const float4* tgt = reinterpret_cast<const float4*>(target);
+    if (fuse)
+        cuda_emu::launch(move_kernel<false, false, true, 0>, blocks, MOVE_THREADS, n, static_cast<const uint32_t*>(nullptr), pin, pout, static_cast<const float4*>(nullptr),
+                         arrived, static_cast<uint2*>(nullptr), grid, static_cast<uint32_t*>(nullptr), 0, static_cast<uint32_t*>(nullptr), static_cast<uint2*>(nullptr), none, fa);
+    else
+        cuda_emu::launch(move_kernel<false, false, false, 0>, blocks, MOVE_THREADS, n, static_cast<const uint32_t*>(nullptr), pin, pout, tgt, arrived,
+                         static_cast<uint2*>(nullptr), grid, static_cast<uint32_t*>(nullptr), 0, static_cast<uint32_t*>(nullptr), static_cast<uint2*>(nullptr), none, fa);
+}
+
+// arrive_kernel<stride>: pass B; blocks = 0 means "as many as the words need"
+void emu_arrive(uint32_t n, const uint32_t* arrived, float* target, uint32_t* road, uint32_t* rng, const void* roads, const uint32_t* conn,
+                uint64_t conn_count, int stride, uint32_t blocks) {
+    const uint32_t words = ((n + 63u) >> 6) << 1;
+    const uint32_t need = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
+    if (stride)
+        cuda_emu::launch(arrive_kernel<true>, blocks ? blocks : need, ARRIVE_THREADS, n, static_cast<const uint32_t*>(nullptr), arrived, reinterpret_cast<float2*>(target), road,
+                         reinterpret_cast<uint4*>(rng), static_cast<const uint4*>(roads), conn, conn_count);
+    else
+        cuda_emu::launch(arrive_kernel<false>, need, ARRIVE_THREADS, n, static_cast<const uint32_t*>(nullptr), arrived, reinterpret_cast<float2*>(target), road,
+                         reinterpret_cast<uint4*>(rng), static_cast<const uint4*>(roads), conn, conn_count);
+}
+
+// query_paired_kernel over n sorted slots; stripes = 64 x 16 u64 (hits at [s * 16], pairs at [s * 16 + 1])
+void emu_query_paired(uint32_t n, const float* sorted_pos, const uint32_t* cell_start, uint8_t* flag_sorted, float inv_cell, float hit_threshold,
+                      float radius, int ncx, int ncy, unsigned long long* stripes) {
+    GridParams grid{};
+    grid.inv_cell = inv_cell;
+    grid.hit_threshold = hit_threshold;
+    grid.radius = radius;
+    grid.ncx = ncx;
+    grid.ncy = ncy;
+    grid.ncells = static_cast<uint32_t>(ncx) * static_cast<uint32_t>(ncy);
+    if (n == 0) return;
+    cuda_emu::launch(query_paired_kernel, (n + 2 * PAIRED_THREADS - 1) / (2 * PAIRED_THREADS), PAIRED_THREADS, n, reinterpret_cast<const float2*>(sorted_pos), cell_start,
+                     flag_sorted, grid, stripes);
+}
+
+uint32_t emu_query_window(void) { return QUERY_WINDOW; }
+
+}  // extern "C"
