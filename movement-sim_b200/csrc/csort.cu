@@ -167,6 +167,8 @@ cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const u
 
 uint32_t csort_tiles(uint32_t cells) { return (cells + 1u + SCAN_TILE - 1) / SCAN_TILE; }
 
+#ifndef MSIM_HOST_EMU  // (tests/cuda_emu launches the kernels itself)
+
 void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler* prof) {
     prof->begin(s, K_MEMSET);
     cudaMemsetAsync(cell_count, 0, (static_cast<size_t>(cells) + 1) * sizeof(uint32_t), s);
@@ -220,5 +222,7 @@ int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const 
     prof->end(s);
     return 1;
 }
+
+#endif  // MSIM_HOST_EMU
 
 }  // namespace msim

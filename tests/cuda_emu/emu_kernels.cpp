@@ -13,6 +13,7 @@ thread_local unsigned lane = 0, warp = 0;
 
 #include "../../movement-sim_b200/csrc/move.cu"
 #include "../../movement-sim_b200/csrc/collide_paired.cu"
+#include "../../movement-sim_b200/csrc/csort.cu"
 
 namespace msim {
 const Tuning& tuning() {
@@ -78,5 +79,49 @@ void emu_query_paired(uint32_t n, const float* sorted_pos, const uint32_t* cell_
 }
 
 uint32_t emu_query_window(void) { return QUERY_WINDOW; }
+
+// move_kernel<keys = true, shard = false, FUSE = fuse> with the counting sort's rank fused in (cell keys, per-cell counters, rank per entity)
+void emu_move_keys(uint32_t n, const float* pos_in, float* pos_out, float* target, uint32_t* arrived, uint32_t* road, uint32_t* rng, const void* roads,
+                   const uint32_t* conn, uint64_t conn_count, int fuse, int consume, uint32_t blocks, uint32_t* keys, uint32_t* cell_count, uint32_t* rank,
+                   float inv_cell, int ncx, int ncy) {
+    const ShardMoveArgs none{};
+    FusedArrive fa{};
+    fa.target = reinterpret_cast<float2*>(target);
+    fa.road = road;
+    fa.rng = reinterpret_cast<uint4*>(rng);
+    fa.roads = static_cast<const uint4*>(roads);
+    fa.conn = conn;
+    fa.conn_count = conn_count;
+    fa.consume = consume ? 1u : 0u;
+    GridParams grid{};
+    grid.inv_cell = inv_cell;
+    grid.ncx = ncx;
+    grid.ncy = ncy;
+    grid.ncells = static_cast<uint32_t>(ncx) * static_cast<uint32_t>(ncy);
+    const float4* pin = reinterpret_cast<const float4*>(pos_in);
+    float4* pout = reinterpret_cast<float4*>(pos_out);
+    uint2* keys2 = reinterpret_cast<uint2*>(keys);
+    uint2* rank2 = reinterpret_cast<uint2*>(rank);
+    if (fuse)
+        cuda_emu::launch(move_kernel<true, false, true, 0>, blocks, MOVE_THREADS, n, static_cast<const uint32_t*>(nullptr), pin, pout, static_cast<const float4*>(nullptr),
+                         arrived, keys2, grid, static_cast<uint32_t*>(nullptr), 0, cell_count, rank2, none, fa);
+    else
+        cuda_emu::launch(move_kernel<true, false, false, 0>, blocks, MOVE_THREADS, n, static_cast<const uint32_t*>(nullptr), pin, pout,
+                         reinterpret_cast<const float4*>(target), arrived, keys2, grid, static_cast<uint32_t*>(nullptr), 0, cell_count, rank2, none, fa);
+}
+
+// scan_tile_sums + scan_tiles<MINB> (the counters are zeroed as they are consumed) and cell_scatter: the counting sort behind the cell directory
+void emu_scan_scatter(uint32_t n, uint32_t cells, uint32_t* cell_count, uint32_t* tile_sums, uint32_t* cell_start, const uint32_t* keys, const uint32_t* rank,
+                      const float* pos, float* sorted_pos, uint32_t* sorted_idx, int scan_min_blocks_8, uint32_t scatter_blocks) {
+    const uint32_t tiles = csort_tiles(cells);
+    cuda_emu::launch(scan_tile_sums_kernel, tiles, SCAN_THREADS, static_cast<const uint32_t*>(cell_count), cells, tile_sums);
+    if (scan_min_blocks_8)
+        cuda_emu::launch(scan_tiles_kernel<8>, tiles, SCAN_THREADS, cell_count, cells, static_cast<const uint32_t*>(tile_sums), cell_start);
+    else
+        cuda_emu::launch(scan_tiles_kernel<0>, tiles, SCAN_THREADS, cell_count, cells, static_cast<const uint32_t*>(tile_sums), cell_start);
+    cuda_emu::launch(cell_scatter_kernel, scatter_blocks, 256u, n, static_cast<const uint32_t*>(nullptr), reinterpret_cast<const uint2*>(keys),
+                     reinterpret_cast<const uint2*>(rank), reinterpret_cast<const float4*>(pos), static_cast<const uint32_t*>(cell_start),
+                     reinterpret_cast<float2*>(sorted_pos), sorted_idx);
+}
 
 }  // extern "C"

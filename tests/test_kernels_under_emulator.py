@@ -149,3 +149,59 @@ def test_paired_query_kernel_under_the_emulator(emu, msim, orc, small_city, test
     assert np.array_equal(got_flags, want_flags)
     if case == "dense_untiled":  # 6000 entities on four roads: the 3-cell runs exceed the shared-memory window, the CTAs take the global-memory scans
         assert np.diff(cell_start.astype(np.int64)).max() * 2 > emu.emu_query_window()
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_whole_collision_tick_under_the_emulator(emu, msim, orc, small_city, fuse):
+    """A complete sim tick of the counting-sort path, kernel by kernel as api.cu enqueues it: move_kernel<keys> with the rank atomics fused in
+    (with and without the fused pass B) -> scan_tile_sums -> scan_tiles (both register variants, alternating) -> cell_scatter ->
+    query_paired_kernel, every tick against the oracle's move and collision passes: positions, waypoints, roads, RNG states, colour flags and
+    the unique-pair count."""
+    vp, u32, u64, i32, f = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
+    emu.emu_move_keys.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, u32, vp, vp, vp, f, i32, i32]
+    emu.emu_move_keys.restype = None
+    emu.emu_scan_scatter.argtypes = [u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32]
+    emu.emu_scan_scatter.restype = None
+    n, radius = 9000, 10.0
+    e, om = initialised(orc, small_city, n, 77)
+    for _ in range(60):  # leave the stacked start behind
+        orc.move_pass(e, om, threads=4)
+    s = SoA(e, small_city)
+    g = msim.grid_params(small_city.width, small_city.height, radius)
+    ncx, ncy = g["cells_x"], g["cells_y"]
+    cells = ncx * ncy
+    cap = s.pos[0].shape[0]
+    keys, rank = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    cell_count, cell_start = np.zeros(cells + 1, np.uint32), np.zeros(cells + 1, np.uint32)
+    tile_sums = np.zeros(cells // 4096 + 2, np.uint32)
+    sorted_pos, sorted_idx = np.zeros((cap, 2), f32), np.zeros(cap, np.uint32)
+    for t in range(12):
+        emu.emu_move_keys(n, s.pos[s.cur].ctypes.data, s.pos[s.cur ^ 1].ctypes.data, s.target.ctypes.data, s.arrived.ctypes.data, s.road.ctypes.data,
+                          s.rng.ctypes.data, s.roads.ctypes.data, s.conn.ctypes.data, s.conn.shape[0], fuse, 1 if (fuse and t) else 0, 2,
+                          keys.ctypes.data, cell_count.ctypes.data, rank.ctypes.data, g["inv_cell"], ncx, ncy)
+        s.cur ^= 1
+        if not fuse:
+            s.arrive(emu)
+        orc.move_pass(e, om, threads=4)
+        want_pairs = orc.collide_pass(e, om.world_w, om.world_h, radius, threads=4)
+        emu.emu_scan_scatter(n, cells, cell_count.ctypes.data, tile_sums.ctypes.data, cell_start.ctypes.data, keys.ctypes.data, rank.ctypes.data,
+                             s.pos[s.cur].ctypes.data, sorted_pos.ctypes.data, sorted_idx.ctypes.data, t % 2, 3)
+        assert not cell_count[:cells].any(), "the scan leaves the counters zeroed for the next tick"
+        assert int(cell_start[cells]) == n and np.all(np.diff(cell_start.astype(np.int64)) >= 0)
+        assert np.array_equal(np.sort(sorted_idx[:n]), np.arange(n, dtype=np.uint32))  # a permutation
+        assert np.array_equal(sorted_pos[:n], s.pos[s.cur][sorted_idx[:n]])
+        assert np.all(np.diff(keys[sorted_idx[:n]].astype(np.int64)) >= 0), "slots are in cell order"
+        flags_sorted = np.full(cap, 9, np.uint8)
+        stripes = np.zeros(64 * 16, np.uint64)
+        emu.emu_query_paired(n, sorted_pos.ctypes.data, cell_start.ctypes.data, flags_sorted.ctypes.data, g["inv_cell"], g["hit_threshold"], f32(radius), ncx,
+                             ncy, stripes.ctypes.data)
+        got_flags = np.zeros(n, np.uint8)
+        got_flags[sorted_idx[:n]] = flags_sorted[:n]
+        assert int(stripes[1::16].sum()) == want_pairs, f"tick {t}"
+        assert np.array_equal(got_flags, orc.collision_flags(e)), f"tick {t}"
+        if not fuse:
+            s.check(e, f"tick {t}")
+    if fuse:
+        s.arrive(emu)  # complete the pending pass before looking
+    s.check(e, "after 12 ticks")
