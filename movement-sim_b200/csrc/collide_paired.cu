@@ -171,12 +171,9 @@ query_paired_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uin
 
 }  // namespace
 
-#ifndef MSIM_HOST_EMU  // (tests/cuda_emu launches the kernel itself)
 void launch_query_paired(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid,
                          unsigned long long* stripes) {
     query_paired_kernel<<<(n + 2 * PAIRED_THREADS - 1) / (2 * PAIRED_THREADS), PAIRED_THREADS, 0, s>>>(n, sorted_pos, cell_start, flag_sorted, grid, stripes);
 }
-
-#endif
 
 }  // namespace msim

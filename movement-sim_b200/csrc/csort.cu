@@ -167,7 +167,6 @@ cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const u
 
 uint32_t csort_tiles(uint32_t cells) { return (cells + 1u + SCAN_TILE - 1) / SCAN_TILE; }
 
-#ifndef MSIM_HOST_EMU  // (tests/cuda_emu launches the kernels itself)
 
 void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler* prof) {
     prof->begin(s, K_MEMSET);
@@ -222,7 +221,5 @@ int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const 
     prof->end(s);
     return 1;
 }
-
-#endif  // MSIM_HOST_EMU
 
 }  // namespace msim

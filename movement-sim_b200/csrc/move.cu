@@ -360,7 +360,6 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
     }
 }
 
-#ifndef MSIM_HOST_EMU  // (tests/cuda_emu launches the kernels itself)
 // one launch of the chosen variant; the grid is a whole number of resident CTAs per SM (grid-stride loop inside)
 template <bool EMIT_KEYS, bool SHARD, bool FUSE, int MINB, typename... Args>
 void launch_move_variant(cudaStream_t s, int sm_count, uint32_t blocks_needed, Args... args) {
@@ -458,9 +457,5 @@ int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys,
     prof->end(s);
     return 1;
 }
-
-#else
-}  // namespace
-#endif  // MSIM_HOST_EMU
 
 }  // namespace msim

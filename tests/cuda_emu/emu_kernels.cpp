@@ -1,7 +1,6 @@
 // tests/cuda_emu/emu_kernels.cpp - TEST INFRASTRUCTURE: the kernels of movement-sim_b200/csrc compiled for the host SIMT emulator
-// (tests/cuda_emu/cuda_runtime.h) with C entry points for tests/test_kernels_under_emulator.py.  Built by tests/cuda_emu/Makefile:
-//   g++ -std=c++17 -O1 -ffp-contract=off -DMSIM_HOST_EMU -I tests/cuda_emu (first!) ... -shared
-// The kernel sources are included as they are; only their <<<...>>> launchers are compiled out (MSIM_HOST_EMU).
+// (tests/cuda_emu/cuda_runtime.h) with C entry points that launch single kernels, for tests/test_kernels_under_emulator.py.  Built by
+// tests/cuda_emu/build_emu_lib.py next to the whole-library build (libmsim_emu.so).
 #include "cuda_runtime.h"
 
 thread_local uint3 threadIdx, blockIdx;
@@ -9,11 +8,13 @@ thread_local dim3 blockDim, gridDim;
 namespace cuda_emu {
 thread_local Block* block = nullptr;
 thread_local unsigned lane = 0, warp = 0;
+thread_local void* dynamic_smem_ptr = nullptr;
 }  // namespace cuda_emu
 
-#include "../../movement-sim_b200/csrc/move.cu"
-#include "../../movement-sim_b200/csrc/collide_paired.cu"
-#include "../../movement-sim_b200/csrc/csort.cu"
+// the scratch copies build_emu_lib.py writes: the sources with <<<...>>> rewritten to cuda_emu::cfg(...)(...)
+#include "_gen/movement-sim_b200/csrc/move.cpp"
+#include "_gen/movement-sim_b200/csrc/collide_paired.cpp"
+#include "_gen/movement-sim_b200/csrc/csort.cpp"
 
 namespace msim {
 const Tuning& tuning() {

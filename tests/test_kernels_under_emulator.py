@@ -22,7 +22,9 @@ f32 = np.float32
 
 @pytest.fixture(scope="module")
 def emu():
-    r = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True)
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "build_emu_lib.py")], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.fail("the emulator build failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
     L = C.CDLL(os.path.join(EMU_DIR, "libemu_kernels.so"))

@@ -1,0 +1,169 @@
+"""The WHOLE library on the CPU: api.cu (handle state machine, readback, re-sort, snapshots), every kernel file and the host map code are
+compiled for the host SIMT emulator (tests/cuda_emu/build_emu_lib.py -> libmsim_emu.so, same C ABI) and driven through the ordinary ctypes
+binding, loaded as a second copy of the package so that the product module and its real library are not touched.
+
+What runs here: the gated tests of the paths written without a GPU (tests/test_zz_gpu_unverified.py: fused pass B through the real handle
+state machine, asynchronous snapshots) and a sample of the required GPU parity tests at emulator-friendly sizes.  Same bar: bit-exact against
+the oracle.  This is a development loop and a logic check; it is not hardware and proves nothing about speed, timing-dependent behaviour or
+the real memory system.  TEST INFRASTRUCTURE ONLY: the product never loads this library (its binding has no switch for it)."""
+import importlib.util
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import test_gpu_parity as parity
+import test_zz_gpu_unverified as gated
+from conftest import ROOT, assert_entities_equal, oracle_dispatch, oracle_map, to_oracle_entities
+
+EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
+
+
+@pytest.fixture(scope="module")
+def emu_msim():
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "build_emu_lib.py")], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.fail("the emulator build of the library failed:\n" + r.stdout[-4000:] + r.stderr[-2000:])
+    pkg = os.path.join(ROOT, "movement-sim_b200")
+    spec = importlib.util.spec_from_file_location("movement_sim_b200_under_emulator", os.path.join(pkg, "__init__.py"), submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    mod.LIB_PATH = os.path.join(EMU_DIR, "libmsim_emu.so")
+    mod.lib()
+    return mod
+
+
+@pytest.fixture(scope="module")
+def emu_city(emu_msim):
+    return emu_msim.Map.city(2200.0, 1600.0, 35.0, 0.3, 0.12, 7)  # tests/conftest.py::small_city, as the emulated copy's own Map type
+
+
+@pytest.fixture(scope="module")
+def emu_test_map(emu_msim):
+    return emu_msim.Map.load_json(os.path.join(ROOT, "tests", "golden", "test_map.json"))
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("flag_names", [(), ("FLAG_NO_REORDER",), ("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), ("FLAG_SORT_ONESWEEP",), ("FLAG_FUSED_ARRIVE",),
+                                        ("FLAG_NO_PAIR_COUNT",)])
+def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkeypatch):
+    """Blocking dispatches, every rebuild mode of the neighbour structure, a cell re-sort every 3 collision passes, readback at several points."""
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
+    flags = 0
+    for name in flag_names:
+        flags |= getattr(emu_msim, name)
+    n = 2500
+    ents = emu_city.init_entities(n, seed=12)
+    om = oracle_map(orc, emu_city)
+    want = to_oracle_entities(orc, ents)
+    with emu_msim.Simulation(emu_city, ents, radius=10.0, flags=flags) as sim:
+        for tick in range(2, 2 + 2 * 9):
+            sim.dispatch(tick)
+            pairs = oracle_dispatch(orc, want, om, 10.0, tick)
+            if tick % 2 == 1 and "FLAG_NO_PAIR_COUNT" not in flag_names:
+                assert sim.stats()["last_pair_count"] == pairs, f"tick {tick}"
+            if tick in (3, 8, 9, 19):
+                assert_entities_equal(sim.read_entities(), want, what=f"{flag_names}: tick {tick}")
+        assert (sim.read_collision_flags() == orc.collision_flags(want)).all()
+        assert (sim.read_positions() == want["pos"]).all()
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("n", [1, 65, 1023])
+def test_gated_fused_arrive_collisions_off(emu_msim, orc, emu_test_map, n):
+    gated.test_fused_arrive_collisions_off(emu_msim, orc, emu_test_map, n)
+
+
+@pytest.mark.timeout(1800)
+def test_gated_fused_arrive_with_collisions(emu_msim, orc, emu_city, monkeypatch):
+    """The gated test itself, at a population the emulator finishes in a minute."""
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "5")
+    n = 2000
+    ents = emu_city.init_entities(n, seed=11)
+    om = oracle_map(orc, emu_city)
+    want = to_oracle_entities(orc, ents)
+    with emu_msim.Simulation(emu_city, ents, radius=10.0, flags=emu_msim.FLAG_FUSED_ARRIVE) as sim:
+        sim.dispatch(2)
+        oracle_dispatch(orc, want, om, 10.0, 2)
+        tick = 3
+        for chunk in (1, 3, 8):
+            sim.enqueue_ticks(chunk, True)
+            sim.sync()
+            pairs = 0
+            for _ in range(chunk):
+                oracle_dispatch(orc, want, om, 10.0, tick + 1)
+                pairs = oracle_dispatch(orc, want, om, 10.0, tick + 2)
+                tick += 2
+            assert sim.stats()["last_pair_count"] == pairs
+            assert_entities_equal(sim.read_entities(), want, what=f"fused, tick {tick}")
+        assert sim.stats()["reorders"] >= 2  # the re-sort completes the pending pass B with the stand-alone kernel first
+
+
+@pytest.mark.timeout(1800)
+def test_gated_snapshots(emu_msim, orc, emu_city, emu_test_map):
+    """msim_snapshot_begin / poll / end through the real handle code (the emulated runtime copies synchronously: buffer rotation, state-at-begin
+    semantics and the error paths are what is checked)."""
+    n = 1500
+    ents = emu_city.init_entities(n, seed=21)
+    om = oracle_map(orc, emu_city)
+    want = to_oracle_entities(orc, ents)
+    with emu_msim.Simulation(emu_city, ents, radius=10.0) as sim:
+        sim.dispatch(2)
+        oracle_dispatch(orc, want, om, 10.0, 2)
+        tick = 3
+
+        def advance(k):
+            nonlocal tick
+            sim.enqueue_ticks(k, True)
+            for _ in range(k):
+                oracle_dispatch(orc, want, om, 10.0, tick + 1)
+                oracle_dispatch(orc, want, om, 10.0, tick + 2)
+                tick += 2
+
+        advance(3)
+        sim.snapshot_begin()
+        want_a = want.copy()
+        advance(4)
+        snap_a = sim.snapshot_end(copy=False)
+        assert_entities_equal(snap_a, want_a, what="snapshot A = state at begin")
+        sim.snapshot_begin()
+        want_b = want.copy()
+        advance(1)
+        assert sim.snapshot_ready()
+        snap_b = sim.snapshot_end(copy=False)
+        assert_entities_equal(snap_b, want_b, what="snapshot B")
+        assert_entities_equal(snap_a, want_a, what="snapshot A is still intact (other pinned buffer)")
+        assert_entities_equal(sim.read_entities(), want, what="blocking readback afterwards")
+    gated.test_snapshot_argument_errors(emu_msim, emu_test_map)
+
+
+@pytest.mark.timeout(1800)
+def test_required_parity_tests_at_emulator_size(emu_msim, orc, emu_test_map, emu_city):
+    """Two of the required GPU tests as they are (they are small enough): 300 enqueued move passes, and the CUDA path against the reference's
+    compiled shader (250 dispatches of 30 k entities would take too long here: the same test body at 2 k)."""
+    parity.test_enqueue_ticks_matches_dispatch(emu_msim, orc, emu_test_map)
+    if orc.ref_shader_available():
+        ents = emu_city.init_entities(2000, seed=17)
+        om = oracle_map(orc, emu_city)
+        want = to_oracle_entities(orc, ents)
+        with emu_msim.Simulation(emu_city, ents, flags=emu_msim.FLAG_NO_COLLISIONS) as sim:
+            for step in range(1 + 60):
+                sim.dispatch(2 + 2 * step)
+                orc.ref_shader_move_pass(want, om)
+            assert_entities_equal(sim.read_entities(), want, what="emulated library vs compiled shader")
+
+
+@pytest.mark.timeout(1800)
+def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
+    """msim_read_quadtree_nodes (device histogram with dynamic shared memory + host builder) equals its host twin."""
+    ents = emu_city.init_entities(3000, seed=3)
+    with emu_msim.Simulation(emu_city, ents, radius=10.0) as sim:
+        for tick in range(2, 40):
+            sim.dispatch(tick)
+        got = sim.read_quadtree_nodes()
+        pos = sim.read_positions()
+    want = emu_msim.quadtree_from_positions(pos, emu_city.width, emu_city.height, 8, 10)
+    assert got.shape == want.shape and got.tobytes() == want.tobytes()
