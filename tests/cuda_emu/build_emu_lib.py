@@ -36,7 +36,20 @@ def transform(text):
     return text
 
 
+def up_to_date():
+    outs = [OUT, os.path.join(HERE, "libemu_kernels.so")]
+    if not all(os.path.exists(o) for o in outs):
+        return False
+    deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    deps += [os.path.join(HERE, n) for n in ("cuda_runtime.h", "emu_kernels.cpp", "build_emu_lib.py")]
+    deps += [os.path.join(ROOT, "include", n) for n in os.listdir(os.path.join(ROOT, "include"))]
+    return min(os.path.getmtime(o) for o in outs) > max(os.path.getmtime(d) for d in deps)
+
+
 def main():
+    if "--force" not in sys.argv and up_to_date():
+        print("up to date")
+        return 0
     cxx = os.environ.get("CXX", "g++")
     dst = os.path.join(GEN, "movement-sim_b200", "csrc")
     shutil.rmtree(GEN, ignore_errors=True)

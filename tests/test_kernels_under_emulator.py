@@ -102,13 +102,13 @@ def test_fused_move_kernel_under_the_emulator(emu, orc, test_map, n, blocks):
 @pytest.mark.timeout(900)
 def test_unfused_kernels_and_strided_pass_b_under_the_emulator(emu, orc, small_city):
     """The verified pair (move_kernel, arrive_kernel) as the control, and arrive_kernel<STRIDE> with a grid far smaller than the mask."""
-    e, om = initialised(orc, small_city, 20_000, 5)
+    e, om = initialised(orc, small_city, 12_000, 5)
     plain, strided = SoA(e, small_city), SoA(e, small_city)
-    for t in range(40):
+    for t in range(24):
         plain.move(emu, 0, 0, 3)
         plain.arrive(emu)
         strided.move(emu, 0, 0, 3)
-        strided.arrive(emu, stride=1, blocks=1 + t % 2)  # 20 000 entities = 626 mask words = 3 CTAs' worth: 1 or 2 CTAs stride over them
+        strided.arrive(emu, stride=1, blocks=1)  # 12 000 entities = 376 mask words = 2 CTAs' worth: one CTA strides over them
         orc.move_pass(e, om, threads=4)
     plain.check(e, "move + arrive")
     strided.check(e, "move + strided arrive")
@@ -165,7 +165,7 @@ def test_whole_collision_tick_under_the_emulator(emu, msim, orc, small_city, fus
     emu.emu_move_keys.restype = None
     emu.emu_scan_scatter.argtypes = [u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32]
     emu.emu_scan_scatter.restype = None
-    n, radius = 9000, 10.0
+    n, radius = 6000, 10.0
     e, om = initialised(orc, small_city, n, 77)
     for _ in range(60):  # leave the stacked start behind
         orc.move_pass(e, om, threads=4)
@@ -178,7 +178,7 @@ def test_whole_collision_tick_under_the_emulator(emu, msim, orc, small_city, fus
     cell_count, cell_start = np.zeros(cells + 1, np.uint32), np.zeros(cells + 1, np.uint32)
     tile_sums = np.zeros(cells // 4096 + 2, np.uint32)
     sorted_pos, sorted_idx = np.zeros((cap, 2), f32), np.zeros(cap, np.uint32)
-    for t in range(12):
+    for t in range(8):
         emu.emu_move_keys(n, s.pos[s.cur].ctypes.data, s.pos[s.cur ^ 1].ctypes.data, s.target.ctypes.data, s.arrived.ctypes.data, s.road.ctypes.data,
                           s.rng.ctypes.data, s.roads.ctypes.data, s.conn.ctypes.data, s.conn.shape[0], fuse, 1 if (fuse and t) else 0, 2,
                           keys.ctypes.data, cell_count.ctypes.data, rank.ctypes.data, g["inv_cell"], ncx, ncy)
@@ -206,4 +206,4 @@ def test_whole_collision_tick_under_the_emulator(emu, msim, orc, small_city, fus
             s.check(e, f"tick {t}")
     if fuse:
         s.arrive(emu)  # complete the pending pass before looking
-    s.check(e, "after 12 ticks")
+    s.check(e, "after 8 ticks")
