@@ -15,8 +15,35 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
+def load_library_under_emulator():
+    """A second copy of the binding whose library is tests/cuda_emu/libmsim_emu.so: the whole library (api.cu, kernels) compiled for the host
+    SIMT emulator.  Test infrastructure: the product binding itself has no switch for it."""
+    import importlib.util
+    import subprocess
+
+    emu_dir = os.path.join(ROOT, "tests", "cuda_emu")
+    r = subprocess.run([sys.executable, os.path.join(emu_dir, "build_emu_lib.py")], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.fail("the emulator build of the library failed:\n" + r.stdout[-4000:] + r.stderr[-2000:])
+    name = "movement_sim_b200_under_emulator"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = os.path.join(ROOT, "movement-sim_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(pkg, "__init__.py"), submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    mod.LIB_PATH = os.path.join(emu_dir, "libmsim_emu.so")
+    mod.lib()
+    return mod
+
+
 @pytest.fixture(scope="session")
 def msim():
+    """The product binding.  MSIM_TEST_EMULATOR=1 hands the tests the emulated copy instead, which lets `-m gpu` tests run on a box without a
+    GPU (a development loop: slow, sizes permitting; it is never what the required GPU run uses)."""
+    if os.environ.get("MSIM_TEST_EMULATOR") == "1":
+        return load_library_under_emulator()
     import movement_sim_b200 as M
 
     M.lib()  # fail loudly if the library was not built

@@ -6,10 +6,7 @@ What runs here: the gated tests of the paths written without a GPU (tests/test_z
 state machine, asynchronous snapshots) and a sample of the required GPU parity tests at emulator-friendly sizes.  Same bar: bit-exact against
 the oracle.  This is a development loop and a logic check; it is not hardware and proves nothing about speed, timing-dependent behaviour or
 the real memory system.  TEST INFRASTRUCTURE ONLY: the product never loads this library (its binding has no switch for it)."""
-import importlib.util
 import os
-import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -23,17 +20,9 @@ EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
 
 @pytest.fixture(scope="module")
 def emu_msim():
-    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "build_emu_lib.py")], capture_output=True, text=True)
-    if r.returncode != 0:
-        pytest.fail("the emulator build of the library failed:\n" + r.stdout[-4000:] + r.stderr[-2000:])
-    pkg = os.path.join(ROOT, "movement-sim_b200")
-    spec = importlib.util.spec_from_file_location("movement_sim_b200_under_emulator", os.path.join(pkg, "__init__.py"), submodule_search_locations=[pkg])
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[spec.name] = mod
-    spec.loader.exec_module(mod)
-    mod.LIB_PATH = os.path.join(EMU_DIR, "libmsim_emu.so")
-    mod.lib()
-    return mod
+    from conftest import load_library_under_emulator
+
+    return load_library_under_emulator()
 
 
 @pytest.fixture(scope="module")
