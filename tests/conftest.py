@@ -38,11 +38,40 @@ def load_library_under_emulator():
     return mod
 
 
+def emulate_torch_cuda():
+    """MSIM_TEST_EMULATOR=1: the few torch.cuda pieces the single-process GPU tests use become host stand-ins ("device" memory of the emulated
+    library is host memory): streams do nothing, device="cuda" tensors live on the CPU."""
+    import contextlib
+    import types
+
+    import torch
+
+    if getattr(torch, "_msim_emulated", False):
+        return
+    torch._msim_emulated = True
+    torch.cuda.Stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=1, synchronize=lambda: None)
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.is_available = lambda: True
+    torch.cuda.device_count = lambda: 1
+    for name in ("zeros", "empty", "ones", "tensor"):
+        real = getattr(torch, name)
+
+        def on_host(*a, _real=real, **k):
+            if str(k.get("device", "cpu")).startswith("cuda"):
+                k["device"] = "cpu"
+            k.pop("pin_memory", None)
+            return _real(*a, **k)
+
+        setattr(torch, name, on_host)
+
+
 @pytest.fixture(scope="session")
 def msim():
     """The product binding.  MSIM_TEST_EMULATOR=1 hands the tests the emulated copy instead, which lets `-m gpu` tests run on a box without a
     GPU (a development loop: slow, sizes permitting; it is never what the required GPU run uses)."""
     if os.environ.get("MSIM_TEST_EMULATOR") == "1":
+        emulate_torch_cuda()
         return load_library_under_emulator()
     import movement_sim_b200 as M
 
