@@ -156,3 +156,17 @@ def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
         pos = sim.read_positions()
     want = emu_msim.quadtree_from_positions(pos, emu_city.width, emu_city.height, 8, 10)
     assert got.shape == want.shape and got.tobytes() == want.tobytes()
+
+
+@pytest.mark.timeout(1800)
+def test_launch_knobs_in_a_fresh_process():
+    """The environment knobs are read once per process: the sim-tick tests above again, in a child process with the paired query, the
+    register-capped scan and move variants, the occupancy-sized grid and the L2 window switched on (the query then goes through
+    launch_query_paired and the striped counters' fold, the scan through scan_tiles_kernel<8>)."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, MSIM_QUERY_PAIRED="1", MSIM_SCAN_MIN_BLOCKS="8", MSIM_MOVE_MIN_BLOCKS="6", MSIM_MOVE_GRID="occupancy", MSIM_L2_PERSIST_ROADS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_library_under_emulator.py"), "-q", "-x", "-k",
+                        "sim_ticks or fused_arrive_with"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1700)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:]
