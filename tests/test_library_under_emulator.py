@@ -170,3 +170,34 @@ def test_launch_knobs_in_a_fresh_process():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_library_under_emulator.py"), "-q", "-x", "-k",
                         "sim_ticks or fused_arrive_with"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1700)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("mode", ["blocking", "async"])
+def test_cpp_simulator_and_headless_runner_on_the_emulated_library(emu_msim, orc, emu_city, tmp_path, mode):
+    """The drop-in sim::Simulator (worker thread, hand-off protocol, CSV) and the headless runner, linked against libmsim_emu.so: a consumer takes
+    the entity buffer every 2 ms like the UI does per frame; blocking readback and the asynchronous snapshot path must give the same simulation."""
+    import re
+    import subprocess
+
+    runner = os.path.join(EMU_DIR, "msim_headless_emu")
+    sim_dir = os.path.join(ROOT, "movement-sim_b200", "sim")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", runner, os.path.join(sim_dir, "main_headless.cpp"), os.path.join(sim_dir, "Simulator.cpp"),
+                        "-L" + EMU_DIR, "-lmsim_emu", "-Wl,-rpath," + EMU_DIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    path = str(tmp_path / "city.msimmap")
+    emu_city.save_binary(path)
+    n, ticks = 2000, 60
+    dump = str(tmp_path / "entities.bin")
+    cmd = [runner, "--headless", "--quiet", "--map", path, "--entities", str(n), "--seed", "7", "--ticks", str(ticks), "--consume-entities", "--dump", dump,
+           "--csv", str(tmp_path / "t.csv")] + (["--async-readback"] if mode == "async" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert int(re.search(r"entity_frames=(\d+)", r.stdout).group(1)) >= 2
+    want = to_oracle_entities(orc, emu_city.init_entities(n, seed=7))
+    om = oracle_map(orc, emu_city)
+    for tick in range(2, 2 + 2 * ticks):
+        oracle_dispatch(orc, want, om, 10.0, tick)
+    assert_entities_equal(np.fromfile(dump, dtype=emu_msim.ENTITY_DTYPE), want, what=f"C++ Simulator on the emulated library, {mode} readback")
+    rows = open(tmp_path / "t.csv").read().strip().splitlines()
+    assert len(rows) == ticks and rows[-1].split(";")[1] == str(ticks)
