@@ -50,17 +50,23 @@ def main():
             if f.endswith((".cu", ".h")):
                 with open(os.path.join(tmp, f), "w") as out:
                     out.write(subprocess.run(["git", "-C", ROOT, "show", f"{rev}:{f}"], capture_output=True, text=True, check=True).stdout)
-        for f in sorted(files):
-            if not f.endswith(".cu"):
-                continue
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(f):
             name = os.path.basename(f)[:-3]
             new_obj = os.path.join(CSRC, name + ".o")
             if not os.path.exists(new_obj):
-                print(f"{name}: no current object (build first)")
-                continue
+                return name, None, None
             old_obj = os.path.join(tmp, name + ".o")
             subprocess.run(["nvcc", *FLAGS, "-c", os.path.join(tmp, f), "-o", old_obj], check=True, capture_output=True)
-            old, new = sass(old_obj), sass(new_obj)
+            return name, sass(old_obj), sass(new_obj)
+
+        with ThreadPoolExecutor(max_workers=8) as pool:  # nvcc and cuobjdump are subprocesses: the files compile side by side
+            results = list(pool.map(one, sorted(f for f in files if f.endswith(".cu"))))
+        for name, old, new in results:
+            if old is None:
+                print(f"{name}: no current object (build first)")
+                continue
             new_by_base = {}
             for k, v in new.items():
                 new_by_base.setdefault(base_name(k), []).append(v)
