@@ -353,7 +353,7 @@ def run_b200(args):
         order = np.lexsort((ents["pos"][:, 0], rows))
         ents = np.ascontiguousarray(ents[order])
     flags = (0 if collisions else M.FLAG_NO_COLLISIONS) | (M.FLAG_SORT_COUNTING if args.counting_sort else 0) | (M.FLAG_NO_REORDER if args.no_reorder else 0) | (
-        M.FLAG_SORT_ONESWEEP if args.onesweep else 0) | (M.FLAG_FUSED_ARRIVE if args.fused_arrive else 0)
+        M.FLAG_SORT_ONESWEEP if args.onesweep else 0)
     sim = M.Simulation(m, ents, radius=10.0, device=local_rank, flags=flags, stream=stream.cuda_stream)
     sim.dispatch(2)  # the reference's first dispatch: initialise only
     sim.enqueue_ticks(args.preroll, False)  # disperse the population along the roads (untimed)
@@ -550,8 +550,7 @@ def run_b200(args):
         "config": {"workload": args.workload, "entities": n, "collisions": collisions, "collision_radius_m": 10.0, "map": w["map_desc"],
                    "entity_seed": 42, "preroll_move_passes": args.preroll, "pair_count": collisions,
                    "l2": ("flushed between timed steps (512 MiB fill)" if small else "inputs larger than L2 (no flush)"),
-                   "experiments": {"fused_arrive": bool(args.fused_arrive), "MSIM_MOVE_MIN_BLOCKS": os.environ.get("MSIM_MOVE_MIN_BLOCKS"),
-                                   "MSIM_MOVE_GRID": os.environ.get("MSIM_MOVE_GRID")},
+                   "experiments": {k: v for k, v in os.environ.items() if k.startswith("MSIM_") and k != "MSIM_BENCH_RESULT_FD"},
                    "grid": sim.stats()},
         "roofline": roofline,
         "tick": {"survey_bytes_per_entity_update": w["survey_bytes"], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / peak,
@@ -594,8 +593,6 @@ def main():
     ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")
     ap.add_argument("--no-reorder", action="store_true", help="keep the state in upload order (onesweep rebuild)")
     ap.add_argument("--e2e-pipelined", action="store_true", help="experiment (not yet run on hardware): adds e2e.pipelined, readback through msim_snapshot_*")
-    ap.add_argument("--fused-arrive", action="store_true",
-                    help="experiment (not yet run on hardware): MSIM_FLAG_FUSED_ARRIVE, the next-waypoint pass rides inside the next move kernel")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

@@ -100,10 +100,7 @@ enum {
     MSIM_FLAG_SORT_COUNTING = 1u << 3, /* always rebuild the neighbour structure with the single-digit (counting) radix sort */
     MSIM_FLAG_NO_REORDER    = 1u << 4, /* keep the resident state in upload order (default: re-sorted into cell order every
                                           32 collision passes, with the counting sort as the rebuild) */
-    MSIM_FLAG_SORT_ONESWEEP = 1u << 5, /* always rebuild with the multi-pass onesweep radix sort */
-    MSIM_FLAG_FUSED_ARRIVE  = 1u << 6  /* opt-in: the next-waypoint pass of a move is served by the NEXT move kernel instead of a
-                                          kernel of its own (asynchronous msim_enqueue_* sequences on unsharded handles; every
-                                          synchronising call completes a pending pass first, results are identical) */
+    MSIM_FLAG_SORT_ONESWEEP = 1u << 5  /* always rebuild with the multi-pass onesweep radix sort */
 };
 
 typedef struct msim_config {

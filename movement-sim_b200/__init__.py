@@ -71,7 +71,6 @@ FLAG_NO_QUADTREE = 1 << 2
 FLAG_SORT_COUNTING = 1 << 3
 FLAG_NO_REORDER = 1 << 4
 FLAG_SORT_ONESWEEP = 1 << 5
-FLAG_FUSED_ARRIVE = 1 << 6
 
 # every symbol include/msim.h declares (tests/test_abi.py checks the library exports exactly these)
 ABI_SYMBOLS = [

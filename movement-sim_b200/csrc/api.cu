@@ -70,6 +70,7 @@ struct msim_handle {
     uint2* cell_range{nullptr};   // onesweep path: {first, ~end} per cell
     uint32_t cell_capacity{0};
     uint32_t* cell_count{nullptr};  // counting-sort path: per-cell counters, prefix table, scan scratch, ranks
+    uint32_t* cell_table{nullptr};  // allocation behind cell_start: cell_start = cell_table + 4, and cell_table[3] is a permanent 0
     uint32_t* cell_start{nullptr};
     uint32_t* tile_sums{nullptr};
     uint32_t* rank{nullptr};
@@ -85,7 +86,8 @@ struct msim_handle {
     int key_bits{1};
 
     Counters* counters{nullptr};
-    unsigned long long* stripes{nullptr};  // striped per-query counters (collide.cu)
+    unsigned long long* stripes{nullptr};  // striped per-query counters (collide.cu), followed by the query's completion ticket
+    bool slots_valid{false};               // h->rank holds entity -> sorted slot of the last collision pass (tiles path)
     unsigned int* scratch{nullptr};  // [0] uninitialised count, [1] max road index
     uint32_t* leaf_hist{nullptr};    // display quadtree: entities per finest cell
     msim_entity* stage{nullptr};
@@ -171,22 +173,14 @@ const Tuning& tuning() {
     static const Tuning t = [] {
         Tuning v;
         if (const char* e = std::getenv("MSIM_L2_PERSIST_ROADS")) v.l2_persist_roads = std::atoi(e) == 1;
-        if (const char* e = std::getenv("MSIM_QUERY_PAIRED")) v.query_paired = std::atoi(e) == 1;
         if (const char* e = std::getenv("MSIM_ARRIVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
             if (k >= 1 && k <= 8) v.arrive_beside_ctas_per_sm = k;
         }
-        if (const char* e = std::getenv("MSIM_ARRIVE_GRID")) v.arrive_persistent = std::strcmp(e, "persistent") == 0;
-        if (const char* e = std::getenv("MSIM_SCAN_MIN_BLOCKS")) v.scan_min_blocks = std::atoi(e) == 8 ? 8 : 0;
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
             const int k = std::atoi(e);
             if (k >= 25 && k <= 27) v.csort_max_cells_log2 = k;
         }
-        if (const char* e = std::getenv("MSIM_MOVE_MIN_BLOCKS")) {
-            const int k = std::atoi(e);
-            if (k == 5 || k == 6) v.move_min_blocks = k;
-        }
-        if (const char* e = std::getenv("MSIM_MOVE_GRID")) v.move_grid_by_occupancy = std::strcmp(e, "occupancy") == 0;
         return v;
     }();
     return t;
@@ -262,7 +256,7 @@ void free_all(msim_handle* h) {
     cudaFree(h->pos[0]); cudaFree(h->pos[1]); cudaFree(h->target); cudaFree(h->road); cudaFree(h->rng);
     cudaFree(h->color0); cudaFree(h->dir0); cudaFree(h->arrived); cudaFree(h->roads); cudaFree(h->conn);
     cudaFree(h->keys); cudaFree(h->sort_a); cudaFree(h->sort_b); cudaFree(h->sorted_pos); cudaFree(h->cell_range);
-    cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums); cudaFree(h->rank); cudaFree(h->sorted_idx);
+    cudaFree(h->cell_count); cudaFree(h->cell_table); cudaFree(h->tile_sums); cudaFree(h->rank); cudaFree(h->sorted_idx);
     cudaFree(h->flag_sorted); cudaFree(h->flag_entity); cudaFree(h->sort_mem); cudaFree(h->counters);
     cudaFree(h->scratch); cudaFree(h->stage); cudaFree(h->stripes); cudaFree(h->leaf_hist);
     cudaFree(h->pos_spare); cudaFree(h->target_alt); cudaFree(h->road_alt); cudaFree(h->rng_alt); cudaFree(h->arrived_alt);
@@ -317,7 +311,10 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
     }
 }
 
-inline bool fused_arrive(const msim_handle* h) { return (h->flags & MSIM_FLAG_FUSED_ARRIVE) && !h->sharded; }
+// Single-GPU default rebuild + query (csort.cu cell_scatter_slots, collide_tiles.cu): the move pass only counts the cells, the scatter
+// takes the slots, the query reads aligned groups.  Sharded handles (ghost slots, ranks maintained through the exchange), the
+// colours-only mode and the onesweep rebuild keep the kernels with per-entity keys and ranks.
+inline bool tiles_path(const msim_handle* h) { return h->use_csort && !h->sharded && !(h->flags & MSIM_FLAG_NO_PAIR_COUNT); }
 
 // MSIM_L2_PERSIST_ROADS=1 (opt-in, not yet run on hardware): the road table (32 B per road, 22 MB for the Munich stand-in) is declared a
 // persisting L2 access-policy window on both streams, so that pass B's dependent gathers (two 16-byte loads of the current road, two of the
@@ -383,7 +380,7 @@ int refresh_counts(msim_handle* h) {
 // all zero and the next count needs no memset.  Only a count that was never scanned (a move pass that fused the count and
 // was not followed by a collision pass, an upload in between, ...) leaves it dirty: then the whole table is cleared.
 void prepare_counts(msim_handle* h) {
-    if (h->counts_dirty) csort_clear(h->stream, h->cell_count, h->grid.ncells, &h->prof);
+    if (h->counts_dirty) csort_clear(h->stream, h->cell_count, h->cell_capacity, &h->prof);  // the whole allocation: an earlier, larger grid may have counted beyond ncells
     h->counts_dirty = true;  // about to be counted into
 }
 
@@ -392,13 +389,16 @@ int ensure_cells(msim_handle* h) {
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
     h->use_csort = want_counting && h->grid.ncells <= csort_max_cells();
     if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
-    cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->tile_sums);
-    h->cell_range = nullptr; h->cell_count = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;
+    cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_table); cudaFree(h->tile_sums);
+    h->cell_range = nullptr; h->cell_count = nullptr; h->cell_table = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;
     h->cell_capacity = 0;
     if (h->use_csort) {
         MSIM_CUDA(h, dev_alloc(&h->cell_count, static_cast<size_t>(h->grid.ncells) + 1));
         h->counts_dirty = true;
-        MSIM_CUDA(h, dev_alloc(&h->cell_start, static_cast<size_t>(h->grid.ncells) + 1));
+        // four words in front of the table: the tiles path reads the table one word earlier (csort.cu), that word stays 0
+        MSIM_CUDA(h, dev_alloc(&h->cell_table, static_cast<size_t>(h->grid.ncells) + 8));
+        MSIM_CUDA(h, cudaMemsetAsync(h->cell_table, 0, 4 * sizeof(uint32_t), h->stream));
+        h->cell_start = h->cell_table + 4;
         MSIM_CUDA(h, dev_alloc(&h->tile_sums, static_cast<size_t>(csort_tiles(h->grid.ncells))));
     } else {
         MSIM_CUDA(h, dev_alloc(&h->cell_range, h->grid.ncells));
@@ -420,8 +420,8 @@ int alloc_collision_buffers(msim_handle* h) {
     MSIM_CUDA(h, dev_alloc(&h->flag_entity, h->cap));
     MSIM_CUDA(h, cudaMemsetAsync(h->flag_entity, 0, h->cap, h->stream));
     const size_t ws_bytes = sort_workspace_bytes(h->cap);
-    MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->stripes), query_stripe_bytes()));
-    MSIM_CUDA(h, cudaMemsetAsync(h->stripes, 0, query_stripe_bytes(), h->stream));
+    MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->stripes), query_stripe_bytes() + 128));
+    MSIM_CUDA(h, cudaMemsetAsync(h->stripes, 0, query_stripe_bytes() + 128, h->stream));
     MSIM_CUDA(h, cudaMalloc(&h->sort_mem, ws_bytes));
     sort_workspace_bind(h->ws, h->sort_mem, h->cap);
     h->ws.error_flag = &h->counters->error_flag;
@@ -453,6 +453,7 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->counts_valid = false;
     h->collided = false;
     h->flags_scattered = false;
+    h->slots_valid = false;
     h->n_ghost = 0;
     h->flags_stale = false;
     h->async_counts = false;
@@ -519,30 +520,21 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     // onesweep digit histograms.  Sharded handles change their key set in the exchange that follows.
     const bool fuse_count = emit && h->use_csort && (!h->sharded || shard);
     const bool fuse_hist = emit && !h->use_csort && !h->sharded;
+    const bool tiles = emit && tiles_path(h);  // count only: no keys, no ranks (the scatter recomputes the key and takes the slot)
     h->n_ghost = 0;
     h->count_fused = fuse_count && h->sharded;
     if (fuse_count) {
         prepare_counts(h);
     }
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
-    // MSIM_FLAG_FUSED_ARRIVE (unsharded handles): pass B of a move is left pending and served by the NEXT move kernel itself;
-    // anything else that reads target / road / rng joins it first (join_side launches the stand-alone kernel)
-    const bool fused = fused_arrive(h);
-    FusedArriveArgs fa{h->target, h->road, h->rng, h->roads, h->conn, h->conn_count, false};
-    if (fused && h->arrive_deferred && !h->side_pending) {
-        fa.consume = true;
-        h->arrive_deferred = false;
-    }
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
-                               emit ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
+                               emit && !tiles ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof,
-                               dev_owned(h), shard, fused ? &fa : nullptr);
+                               dev_owned(h), shard);
     h->counts_valid = fuse_count;
-    if (fused) {
-        h->arrive_deferred = true;
-    } else if (emit && h->side && (!h->sharded || shard)) {
-        h->arrive_deferred = true;  // a collision pass follows and needs only positions and keys: pass B is launched beside its query
+    if (emit && h->side && (!h->sharded || shard)) {
+        h->arrive_deferred = true;  // a collision pass follows and needs only positions: pass B is launched beside its query
     } else {
         h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
                                      dev_owned(h));
@@ -550,8 +542,9 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     h->cur ^= 1;
     h->has_moved = true;
     h->band_valid = false;  // entities may have crossed the band's rows until the next pack + integrate
-    h->keys_valid = emit;
+    h->keys_valid = emit && !tiles;
     h->hist_valid = fuse_hist;
+    if (emit && !tiles) h->slots_valid = false;  // a pass with keys overwrites h->rank; the counting pass leaves the slot map of the last collision pass alone
     h->move_passes++;
     return MSIM_OK;
 }
@@ -617,7 +610,9 @@ int reorder_storage(msim_handle* h) {
     a.slot_of = h->slot_of;
     a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
     a.flag_entity = h->flag_entity;
+    if (h->slots_valid) h->launches += launch_invert_slots(h->stream, h->n, h->rank, h->sorted_idx, &h->prof);  // tiles path: slot -> entity on demand
     h->launches += launch_reorder(h->stream, h->n, h->sorted_idx, h->flag_sorted, a, &h->prof);
+    h->slots_valid = false;
     // the sorted positions ARE the new current positions: swap buffers instead of copying
     float2* old_cur = h->pos[h->cur];
     float2* old_prev = h->pos[h->cur ^ 1];
@@ -645,7 +640,21 @@ int enqueue_collide(msim_handle* h) {
     if (consume_init_dispatch(h)) return MSIM_OK;
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
-    if (!h->keys_valid) {
+    const bool tiles = tiles_path(h);
+    if (tiles) {
+        if (!h->counts_valid) {  // no counting move pass in front of this dispatch (first dispatch after an upload, grid change)
+            prepare_counts(h);
+            h->launches += launch_cell_count_pos(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_count, h->grid, &h->prof);
+        }
+        h->counts_valid = false;
+        h->launches += launch_cell_scan(h->stream, h->cell_count, h->grid.ncells, h->tile_sums, h->cell_start, &h->prof);
+        h->counts_dirty = false;
+        h->launches += launch_cell_scatter_slots(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_start, h->sorted_pos, h->rank, h->grid, &h->prof);
+        launch_deferred_arrive(h, true);
+        h->launches += launch_query_tiles(h->stream, h->n, h->sorted_pos, h->cell_start - 1, h->flag_sorted, h->grid, h->counters, h->stripes, &h->prof);
+        h->slots_valid = true;
+        h->keys_valid = false;
+    } else if (!h->keys_valid) {
         rc = refresh_counts(h);  // (asynchronous sharded ticks) keygen is sized by the exact owned count
         if (rc != MSIM_OK) return rc;
         h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
@@ -654,7 +663,9 @@ int enqueue_collide(msim_handle* h) {
     }
     const uint32_t total = launch_total(h);  // ghosts (multi-GPU halo) sit behind the owned entities
     const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
-    if (h->use_csort) {
+    if (tiles) {
+        // done above
+    } else if (h->use_csort) {
         // sharded handles: the counter table is cleared / scanned over the band's cell range only, keys outside it
         // (a leaver that jumped two rows while the boundary moved: out of everybody's reach) are left out of the
         // order, and the number of sorted slots is the scan's grand total, read by the query from the table itself
@@ -670,7 +681,7 @@ int enqueue_collide(msim_handle* h) {
         h->counts_dirty = false;  // the scan zeroed every counter it read, and nothing was counted outside [c0, c1)
         h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
                                            dev_total(h));
-        if (!fused_arrive(h)) launch_deferred_arrive(h, true);  // fused: stays pending for the next move kernel
+        launch_deferred_arrive(h, true);
         h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof, h->sharded ? h->cell_start + c1 : nullptr, dev_owned(h));
     } else {
@@ -679,7 +690,7 @@ int enqueue_collide(msim_handle* h) {
         h->hist_valid = false;  // the sort consumed the tickets and look-back words
         h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
                                           &h->prof, dev_total(h));
-        if (!fused_arrive(h)) launch_deferred_arrive(h, true);  // fused: stays pending for the next move kernel
+        launch_deferred_arrive(h, true);
         h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof, dev_total(h), dev_owned(h));
     }
@@ -710,7 +721,10 @@ int materialise_flags(msim_handle* h) {
             h->collide_owned = h->n;
             h->collide_total = h->n + h->n_ghost;
         }
-        h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted_idx, h->flag_sorted, h->flag_entity, &h->prof);
+        if (h->slots_valid)
+            h->launches += launch_gather_flags(h->stream, h->collide_owned, h->rank, h->flag_sorted, h->flag_entity, &h->prof);
+        else
+            h->launches += launch_scatter_flags(h->stream, h->collide_total, h->collide_owned, h->sorted_idx, h->flag_sorted, h->flag_entity, &h->prof);
         h->flags_scattered = true;
     }
     return MSIM_OK;
@@ -941,6 +955,7 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
         h->keys_valid = false;
         h->hist_valid = false;
         h->counts_valid = false;
+        h->counts_dirty = true;  // a count under the old grid may have left counters anywhere in the allocation
         if (h->keys) {
             rc = ensure_cells(h);
             if (rc != MSIM_OK) return rc;

@@ -266,12 +266,6 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
     const uint32_t blocks = (n + QUERY_THREADS - 1) / QUERY_THREADS;
     const bool ghosts = n_owned < n || n_owned_dev != nullptr, prefix = cell_start != nullptr;
     prof->begin(s, K_QUERY);
-    if (tuning().query_paired && count_pairs && !ghosts && prefix && !n_dev) {  // opt-in: two adjacent slots per thread (collide_paired.cu)
-        launch_query_paired(s, n, sorted_pos, cell_start, flag_sorted, grid, stripes);
-        fold_counters_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
-        prof->end(s);
-        return 2;
-    }
 #define MSIM_QUERY(CP, GH, PF) \
     query_kernel<CP, GH, PF><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, n_dev, n_owned_dev, sorted_idx, sorted_pos, cell_range, cell_start, flag_sorted, grid, stripes)
     if (count_pairs) {

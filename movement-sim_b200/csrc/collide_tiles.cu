@@ -1,0 +1,189 @@
+// collide_tiles.cu — the odd-tick dispatch on one GPU (default path): who has a neighbour within the collision radius,
+// and how many unordered pairs are in range.
+//
+// Observable contract (reference shader /root/reference/src/sim/shader/random_move.comp):
+//   :875-877  every entity turns green, then  :545-547  both members of every in-range pair turn blue;
+//   :551-562  in_range(a,b,r): sqrt(dx*dx+dy*dy) < r (strict), evaluated here as d2 < T with the exact binary32 bound T
+//             (api.cu exact_hit_threshold), individually rounded operations, no FMA.
+//
+// Input: positions in cell order (sorted_pos) and the prefix table tab[c] = first slot of cell c (csort.cu).  One thread
+// per sorted slot j; every unordered pair is examined from its HIGHER slot: thread j tests the slots below it — the three
+// cells (cx-1..cx+1) of the grid row above, one contiguous run [ab_lo, ab_hi), and its own row from cell cx-1 up to j,
+// the run [own_lo, j).
+//
+// What this kernel is built around (ncu of its predecessors, profiles/r2_query_history.md): with ~15 tests per entity the
+// query is not bound by the distance tests but by everything around them — the round-1 kernel spent 613 warp instructions
+// per 32 entities on 488 useful tests, its main loops ran at 13-15 of 32 lanes, and a third of its stall samples sat at
+// CTA-wide barriers.  So:
+//   * candidates are read in ALIGNED GROUPS OF FOUR slots (two 128-bit loads), without per-candidate range checks.  Slots
+//     just outside a run belong to cells at least two columns away (their distance test fails by itself) as long as the
+//     above run and the own run are at least three slots apart; warps where some lane's runs are closer (tiny or nearly
+//     empty maps) take an exact scalar path instead.  Only the group that contains slot j itself is masked (k < j);
+//   * a hit costs 1.5 instructions: one packed subtract (d2 - T) per two candidates and one LEA.HI that adds the sign bit;
+//   * no shared memory and no barrier: lanes of one cell read the same addresses, the 32 slots of a warp and the run above
+//     them are a few hundred contiguous bytes that stay in L1 (75 % hit rate); staging them per CTA or per warp with TMA
+//     bulk copies was measured slower (mbarrier set-up, hull exchange and waits cost more issue slots than the loads save:
+//     191 / 212 us against 156 us), so every warp is independent from its first instruction;
+//   * totals leave as one reduction per warp and counter (RED, nothing waits) into striped counters; a one-CTA kernel folds them.
+#include "msim_internal.h"
+
+namespace msim {
+namespace {
+
+#include "collide_common.cuh"
+
+// ---- the inner loop: four candidates per step ------------------------------------------------------------------------------
+// A group is 32 bytes {x0 y0 x1 y1}{x2 y2 x3 y3}: two LDG.128 through the read-only path.  Per candidate: FADD2 (dx, dy), FMUL2 (dx^2, dy^2), FADD (d2) —
+// individually rounded, as the oracle computes them — then per PAIR of candidates one FADD2 (d2 - T) and per candidate one
+// LEA.HI that adds the sign bit of the difference to the count: d2 >= +0 and T > 0 are never NaN (positions are finite), so
+// the difference is negative exactly when d2 < T.
+#ifdef MSIM_HOST_EMU
+__device__ __forceinline__ uint32_t below(float d2, float thr) { return d2 < thr ? 1u : 0u; }
+__device__ __forceinline__ uint32_t hits_in_pair(float4 a, float2 p, float thr) {
+    return below(dist2(make_float2(a.x, a.y), p), thr) + below(dist2(make_float2(a.z, a.w), p), thr);
+}
+#else
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint32_t below(float d2, float thr) { return __float_as_uint(__fsub_rn(d2, thr)) >> 31; }
+__device__ __forceinline__ uint32_t hits_in_pair(float4 a, float2 p, float thr) {
+    const unsigned long long pp = pack2(p.x, p.y), tt = pack2(thr, thr);
+    unsigned long long d0, d1, t;
+    float x0, y0, x1, y1, t0, t1;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(pack2(a.x, a.y)), "l"(pp));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(pack2(a.z, a.w)), "l"(pp));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d0) : "l"(d0));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d1) : "l"(d1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(y0) : "l"(d0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x1), "=f"(y1) : "l"(d1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pack2(__fadd_rn(x0, y0), __fadd_rn(x1, y1))), "l"(tt));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+    return (__float_as_uint(t0) >> 31) + (__float_as_uint(t1) >> 31);
+}
+#endif
+
+struct Group { float4 a, b; };
+__device__ __forceinline__ Group load_group(const float4* g) { return Group{__ldg(g), __ldg(g + 1)}; }
+
+// groups [g0, g1) of sorted_pos, no masks
+__device__ __forceinline__ uint32_t count_groups(const float4* __restrict__ base, uint32_t g0, uint32_t g1, float2 p, float thr) {
+    uint32_t c = 0;
+#pragma unroll 1
+    for (uint32_t g = g0; g < g1; g++) {
+        const Group q = load_group(base + 2u * g);
+        c += hits_in_pair(q.a, p, thr) + hits_in_pair(q.b, p, thr);
+    }
+    return c;
+}
+
+// the group that holds slot j itself: only its first `below_j` (0..3) candidates count
+__device__ __forceinline__ uint32_t count_last_group(const float4* __restrict__ g, uint32_t below_j, float2 p, float thr) {
+    const Group q = load_group(g);
+    const uint32_t c0 = below(dist2(make_float2(q.a.x, q.a.y), p), thr), c1 = below(dist2(make_float2(q.a.z, q.a.w), p), thr),
+                   c2 = below(dist2(make_float2(q.b.x, q.b.y), p), thr);
+    return (below_j > 0u ? c0 : 0u) + (below_j > 1u ? c1 : 0u) + (below_j > 2u ? c2 : 0u);
+}
+
+constexpr int TILES_THREADS = 128;
+
+__global__ void __launch_bounds__(TILES_THREADS)
+query_tiles_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint32_t* __restrict__ tab, uint8_t* __restrict__ flag_sorted, GridParams grid,
+                   unsigned long long* __restrict__ stripes) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_base = (blockIdx.x * TILES_THREADS + threadIdx.x) & ~31u;
+    if (warp_base >= n) return;
+    const uint32_t j_raw = warp_base + lane;
+    const bool mine = j_raw < n;
+    const uint32_t j = mine ? j_raw : n - 1u;  // the lanes behind the last slot repeat it (and keep their results to themselves)
+
+    // ---- this lane's runs: three loads from the prefix table ---------------------------------------------------------------
+    const float2 p = __ldg(sorted_pos + j);
+    int cx = __float2int_rd(__fmul_rn(p.x, grid.inv_cell));
+    int cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
+    cx = min(max(cx, 0), grid.ncx - 1);
+    cy = min(max(cy, 0), grid.ncy - 1);
+    const uint32_t ncx = static_cast<uint32_t>(grid.ncx);
+    const uint32_t r = static_cast<uint32_t>(cy) * ncx;                               // < 2^27 cells: 32-bit indices throughout
+    const uint32_t x0 = static_cast<uint32_t>(max(cx - 1, 0)), x1e = min(static_cast<uint32_t>(cx) + 2u, ncx);
+    const uint32_t own_lo = __ldg(tab + (r + x0));
+    uint32_t ab_lo = 0u, ab_hi = 0u;
+    if (cy > 0) {
+        ab_lo = __ldg(tab + (r - ncx + x0));
+        ab_hi = __ldg(tab + (r - ncx + x1e));
+    }
+
+    uint32_t pairs = 0;
+    const float thr = grid.hit_threshold;
+    // aligned groups are only safe when the slots around a run are far-away cells: above run and own run >= 3 slots apart
+    const bool close_runs = ab_hi != ab_lo && own_lo - ab_hi < 3u;
+    if (__any_sync(0xffffffffu, close_runs)) {  // exact scalar scans (tiny or nearly empty maps)
+        pairs = count_in_range(sorted_pos, ab_lo, ab_hi, p, thr) + count_in_range(sorted_pos, own_lo, j, p, thr);
+    } else {
+        const float4* G = reinterpret_cast<const float4*>(sorted_pos);
+        const uint32_t ga0 = ab_lo >> 2, ga1 = ab_hi != ab_lo ? (ab_hi + 3u) >> 2 : ga0;
+        pairs = count_groups(G, ga0, ga1, p, thr) + count_groups(G, own_lo >> 2, j >> 2, p, thr) + count_last_group(G + 2u * (j >> 2), j & 3u, p, thr);
+    }
+    bool hit = pairs != 0u;
+    // nothing below: look at the slots above (rest of the own row, then the row below), where the first hit is enough
+    if (!hit) {
+        hit = any_in_range(sorted_pos, j + 1u, __ldg(tab + (r + x1e)), p, thr);
+        if (!hit && cy + 1 < grid.ncy) hit = any_in_range(sorted_pos, __ldg(tab + (r + ncx + x0)), __ldg(tab + (r + ncx + x1e)), p, thr);
+    }
+    if (mine) flag_sorted[j] = hit ? 1 : 0;
+
+    // ---- totals: one reduction (no return value, nothing waits) per counter and warp into a striped counter; a one-CTA kernel folds the stripes
+    const uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit && mine));
+    pairs = __reduce_add_sync(0xffffffffu, mine ? pairs : 0u);
+    if (lane == 0) {
+        unsigned long long* stripe = stripes + ((warp_base >> 5) % COUNTER_STRIPES) * COUNTER_STRIDE;
+        if (hits) atomicAdd(stripe, static_cast<unsigned long long>(hits));
+        if (pairs) atomicAdd(stripe + 1, static_cast<unsigned long long>(pairs));
+    }
+}
+
+// folds the striped counters of one query into Counters and clears them for the next pass
+__global__ void __launch_bounds__(COUNTER_STRIPES) fold_stripes_kernel(unsigned long long* __restrict__ stripes, Counters* __restrict__ counters) {
+    __shared__ unsigned long long s_h[COUNTER_STRIPES / 32], s_p[COUNTER_STRIPES / 32];
+    unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
+    unsigned long long h = stripe[0], pr = stripe[1];
+    stripe[0] = 0;
+    stripe[1] = 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        h += __shfl_down_sync(0xffffffffu, h, d);
+        pr += __shfl_down_sync(0xffffffffu, pr, d);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        s_h[threadIdx.x >> 5] = h;
+        s_p[threadIdx.x >> 5] = pr;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        h = pr = 0;
+        for (int w = 0; w < COUNTER_STRIPES / 32; w++) {
+            h += s_h[w];
+            pr += s_p[w];
+        }
+        counters->flagged_last = h;
+        counters->pairs_last = pr;
+        counters->pairs_total += pr;
+    }
+}
+
+}  // namespace
+
+int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, Counters* counters,
+                       unsigned long long* stripes, Profiler* prof) {
+    if (n == 0) return 0;
+    const uint32_t blocks = (n + TILES_THREADS - 1) / TILES_THREADS;
+    prof->begin(s, K_QUERY);
+    query_tiles_kernel<<<blocks, TILES_THREADS, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
+    fold_stripes_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
+    prof->end(s);
+    return 2;
+}
+
+}  // namespace msim

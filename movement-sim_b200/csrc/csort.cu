@@ -163,6 +163,91 @@ cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const u
     }
 }
 
+
+// ---- slot-returning scatter (single-GPU default) ------------------------------------------------------------------
+// The move pass only COUNTED the cells (one RED per run, move.cu); here the run heads take their slots from the scanned
+// table itself: base = atomicAdd(&cursor[key], run length), where cursor[c] starts out as start(c).  When the kernel is
+// done cursor[c] = start(c) + count(c) = start(c + 1), so the same table, read one word earlier (the word in front of it is
+// a permanent 0), is the prefix table the query needs: tab[c] = start(c), tab[ncells] = n.
+// Per entity: position R8 (the key is recomputed: 6 instructions instead of 8 bytes), sorted position W8, slot W4
+// (coalesced, entity order: the flag readback and the periodic re-sort find an entity's slot there; nothing scattered but
+// the positions themselves).  One entity per lane per load: a warp's 32 consecutive entities form a few runs whose slots are
+// consecutive, so the 8-byte stores of a run coalesce into whole sectors; four independent chunks per warp iteration keep
+// four atomic round trips in flight per lane.
+constexpr int SCATTER_CHUNKS = 4;
+
+struct RunSlot {
+    uint32_t base;     // head lanes: first slot of the run
+    uint32_t my_head;  // lane of the head of this lane's run
+};
+__device__ __forceinline__ RunSlot run_slot_issue(uint32_t* __restrict__ cursor, uint32_t key, bool valid, uint32_t lane) {
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != prev;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+    RunSlot r;
+    r.my_head = 31u - __clz(heads & ((2u << lane) - 1u));
+    r.base = 0;
+    if (head && valid) {  // valid lanes precede invalid ones (tail of the array), so a run with a valid member has a valid head
+        const uint32_t above = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
+        const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
+        const uint32_t run = (next_head == 32u ? 0xffffffffu : ((1u << next_head) - 1u)) & ~((1u << lane) - 1u);
+        r.base = atomicAdd(&cursor[key], static_cast<uint32_t>(__popc(run & valid_mask)));
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+cell_scatter_slots_kernel(uint32_t n, const float2* __restrict__ pos, uint32_t* __restrict__ cursor, float2* __restrict__ sorted_pos,
+                          uint32_t* __restrict__ slot_of_entity, GridParams grid) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps_total = (gridDim.x * blockDim.x) >> 5;
+    constexpr uint32_t PER_WARP = 32u * SCATTER_CHUNKS;
+    for (uint32_t base = warp_global * PER_WARP; base < n; base += warps_total * PER_WARP) {
+        float2 p[SCATTER_CHUNKS];
+        RunSlot r[SCATTER_CHUNKS];
+#pragma unroll
+        for (int k = 0; k < SCATTER_CHUNKS; k++) {
+            const uint32_t e = base + k * 32u + lane;
+            p[k] = e < n ? __ldcs(pos + e) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < SCATTER_CHUNKS; k++) {
+            const uint32_t e = base + k * 32u + lane;
+            r[k] = run_slot_issue(cursor, cell_key_of(p[k], grid), e < n, lane);
+        }
+#pragma unroll
+        for (int k = 0; k < SCATTER_CHUNKS; k++) {
+            const uint32_t e = base + k * 32u + lane;
+            const uint32_t slot = __shfl_sync(0xffffffffu, r[k].base, r[k].my_head) + (lane - r[k].my_head);
+            if (e < n) {
+                sorted_pos[slot] = p[k];
+                __stcs(slot_of_entity + e, slot);
+            }
+        }
+    }
+}
+
+// count pass for a collision dispatch that was not preceded by a counting move pass (first dispatch after an upload, grid change)
+__global__ void __launch_bounds__(256)
+cell_count_pos_kernel(uint32_t n, const float2* __restrict__ pos, uint32_t* __restrict__ cell_count, GridParams grid) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        atomicAdd(&cell_count[cell_key_of(__ldcs(pos + e), grid)], 1u);
+}
+
+// sorted slot -> entity, from the entity -> slot map the scatter wrote (only the periodic re-sort wants this direction)
+__global__ void __launch_bounds__(256) invert_slots_kernel(uint32_t n, const uint32_t* __restrict__ slot_of_entity, uint32_t* __restrict__ sorted_idx) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) sorted_idx[__ldcs(slot_of_entity + e)] = e;
+}
+
+// collision flag per entity = flag of its sorted slot (+1: 1 = green, 2 = blue, 0 = "no collision pass yet")
+__global__ void __launch_bounds__(256)
+gather_flags_kernel(uint32_t n, const uint32_t* __restrict__ slot_of_entity, const uint8_t* __restrict__ flag_sorted, uint8_t* __restrict__ flag_entity) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) flag_entity[e] = flag_sorted[__ldcs(slot_of_entity + e)] + 1;
+}
+
 }  // namespace
 
 uint32_t csort_tiles(uint32_t cells) { return (cells + 1u + SCAN_TILE - 1) / SCAN_TILE; }
@@ -201,10 +286,7 @@ int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint3
     const uint32_t tiles = csort_tiles(cells);
     prof->begin(s, K_CELL_SCAN);
     scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums);
-    if (tuning().scan_min_blocks == 8)
-        scan_tiles_kernel<8><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
-    else
-        scan_tiles_kernel<0><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
+    scan_tiles_kernel<0><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
     prof->end(s);
     return 2;
 }
@@ -218,6 +300,49 @@ int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const 
     prof->begin(s, K_CELL_SCATTER);
     cell_scatter_kernel<<<blocks, 256, 0, s>>>(n, n_dev, reinterpret_cast<const uint2*>(keys), reinterpret_cast<const uint2*>(rank),
                                                reinterpret_cast<const float4*>(pos), cell_start, sorted_pos, sorted_idx);
+    prof->end(s);
+    return 1;
+}
+
+}  // namespace msim
+
+namespace msim {
+
+int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cursor, float2* sorted_pos, uint32_t* slot_of_entity,
+                              const GridParams& grid, Profiler* prof) {
+    if (n == 0) return 0;
+    uint32_t blocks = (n + 256u * SCATTER_CHUNKS - 1u) / (256u * SCATTER_CHUNKS);
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
+    if (blocks > resident) blocks = resident;
+    prof->begin(s, K_CELL_SCATTER);
+    cell_scatter_slots_kernel<<<blocks, 256, 0, s>>>(n, pos, cursor, sorted_pos, slot_of_entity, grid);
+    prof->end(s);
+    return 1;
+}
+
+int launch_cell_count_pos(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cell_count, const GridParams& grid, Profiler* prof) {
+    if (n == 0) return 0;
+    uint32_t blocks = (n + 255u) / 256u;
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
+    if (blocks > resident) blocks = resident;
+    prof->begin(s, K_CELL_COUNT);
+    cell_count_pos_kernel<<<blocks, 256, 0, s>>>(n, pos, cell_count, grid);
+    prof->end(s);
+    return 1;
+}
+
+int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof) {
+    if (n == 0) return 0;
+    prof->begin(s, K_MISC);
+    invert_slots_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, slot_of_entity, sorted_idx);
+    prof->end(s);
+    return 1;
+}
+
+int launch_gather_flags(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof) {
+    if (n == 0) return 0;
+    prof->begin(s, K_SCATTER_FLAGS);
+    gather_flags_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, slot_of_entity, flag_sorted, flag_entity);
     prof->end(s);
     return 1;
 }

@@ -56,15 +56,9 @@ __device__ __forceinline__ uint32_t read_connection(const uint32_t* __restrict__
 }
 
 // random_move.comp:778-828.  `tgt` is the waypoint just reached; returns the new waypoint.
-// PREFETCH_RNG (fused pass B only): the RNG state is requested together with the road index instead of after the road record has
-// told us that more than two roads meet here — one DRAM latency less on the dependent chain road -> record -> connection -> record,
-// for 16 bytes read in vain at dead ends and two-way points.  Same results: the state is only written back when it was drawn from.
-template <bool PREFETCH_RNG = false>
 __device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* __restrict__ road, uint4* __restrict__ rng,
                                              const uint4* __restrict__ roads, const uint32_t* __restrict__ conn,
                                              uint64_t conn_count) {
-    uint4 early = make_uint4(0u, 0u, 0u, 0u);
-    if (PREFETCH_RNG) early = rng[e];
     const uint32_t cur = road[e];
     const uint4 a = __ldg(roads + 2ull * cur);      // start: pos.x pos.y connectedIndex connectedCount
     const uint4 b = __ldg(roads + 2ull * cur + 1);  // end
@@ -78,7 +72,7 @@ __device__ __forceinline__ float2 new_target(uint32_t e, float2 tgt, uint32_t* _
     if (here.w == 2u) {  // :802-804
         next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + 1ull);
     } else {  // :805-810
-        uint4 s = PREFETCH_RNG ? early : rng[e];
+        uint4 s = rng[e];
         const uint32_t off = next_range(s, 1u, here.w);
         rng[e] = s;
         next_road = read_connection(conn, conn_count, static_cast<uint64_t>(here.z) + off);
@@ -133,6 +127,22 @@ __device__ __forceinline__ uint32_t run_rank_finish(const RunRank& r, uint32_t l
     return __shfl_sync(0xffffffffu, r.base, r.my_head) + (lane - r.my_head);
 }
 
+// Count-only variant (single-GPU counting sort, csort.cu): the run heads add their run length to the cell's counter with a
+// reduction that returns nothing (RED): no L2 round trip to wait for, the streaming loop never stalls on it.  The rank
+// inside the cell is taken later by the scatter kernel, whose atomics return the slot directly.
+__device__ __forceinline__ void run_count(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, uint32_t lane) {
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != prev;  // invalid lanes only exist in the padded tail: they may extend a run, never start a counted one
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+    if (head && valid) {
+        const uint32_t above = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
+        const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
+        const uint32_t run = (next_head == 32u ? 0xffffffffu : ((1u << next_head) - 1u)) & ~((1u << lane) - 1u);
+        atomicAdd(&cell_count[key], static_cast<uint32_t>(__popc(run & valid_mask)));
+    }
+}
+
 // ---- fused shard pack (multi-GPU bands, shard.cu) ------------------------------------------------
 // Whole warp calls this once per entity slot.  Storage is in cell order, so only the warps at either end of
 // the slot range ever see a boundary row: everybody else leaves after one vote.
@@ -160,36 +170,22 @@ __device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t
     }
 }
 
-// ---- fused pass B (opt-in, MSIM_FLAG_FUSED_ARRIVE) -----------------------------------------------------------
-// The arrival bits of the PREVIOUS move pass are consumed by the warp that streams the same entities in THIS pass: bit
-// `lane` of the two mask words of a 64-entity chunk belongs to the lane that loads that entity's position and target, so
-// nothing has to change lanes.  A lane takes one of its (up to four) pending arrivals per round; one round serves up to
-// 32 arrivals of the warp with their gather chains side by side, a second round is rare (two arrivals in one lane).
-// The streaming loads of the iteration are already in flight while the chains run, and the mask words are read before
-// this iteration's arrival bits overwrite them (same warp, program order).
-struct FusedArrive {
-    float2* target;  // read-write alias of the move kernel's `target` (which is therefore not read through __restrict__)
-    uint32_t* road;
-    uint4* rng;
-    const uint4* roads;
-    const uint32_t* conn;
-    unsigned long long conn_count;
-    uint32_t consume;  // 0: no pass B is pending (first move after an upload / after a stand-alone pass B)
-};
-
-// EMIT_KEYS additionally writes the cell key of the new position (4 B) and accumulates the radix
-// sort's digit histograms for all passes in shared memory (flushed once per CTA), so the neighbour
-// rebuild needs no separate histogram read of the keys.
-// SHARD (multi-GPU bands) additionally does the shard pack for the entities it has just moved (see above).
-// MINB = minimum resident CTAs per SM asked of the compiler (register cap 65536 / (256 MINB)).  0 = no cap: 40 / 52 / 58
-// registers without / with keys / sharded, i.e. 6 / 4 / 4 resident CTAs; the variants with keys wait on L2 atomics, so
-// more resident warps may pay for a few spilled registers (MSIM_MOVE_MIN_BLOCKS = 5 or 6, see tuning() in api.cu).
-template <bool EMIT_KEYS, bool SHARD, bool FUSE, int MINB>
-__global__ void __launch_bounds__(MOVE_THREADS, MINB)
+// MODE selects what the pass hands to the neighbour rebuild that follows it:
+//   MOVE_PLAIN  nothing (collisions off): the 24 B per entity minimum
+//   MOVE_COUNT  the per-cell population (csort.cu, single-GPU default): cell key of the new position -> one RED per run of
+//               equal keys in adjacent lanes.  No key or rank is written: the scatter kernel recomputes the key from the
+//               position it has to read anyway and takes the slot from an atomic on the scanned table
+//   MOVE_KEYS   cell key (4 B) + rank inside the cell (4 B, counting sort with ranks: sharded handles) and / or the radix
+//               sort's digit histograms for all passes, accumulated in shared memory and flushed once per CTA (onesweep)
+// SHARD (multi-GPU bands, MOVE_KEYS only) additionally does the shard pack for the entities it has just moved (see above).
+enum { MOVE_PLAIN = 0, MOVE_COUNT = 1, MOVE_KEYS = 2 };
+template <int MODE, bool SHARD>
+__global__ void __launch_bounds__(MOVE_THREADS)
 move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
             uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
-            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh, FusedArrive fa) {
-    static_assert(!FUSE || MOVE_ITEMS == 2, "the fused pass B selects among 2 x 2 entity slots per lane");
+            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh) {
+    static_assert(!SHARD || MODE == MOVE_KEYS, "the shard pack classifies by key");
+    constexpr bool EMIT_KEYS = MODE == MOVE_KEYS;
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
     if (EMIT_KEYS) {
         for (int i = threadIdx.x; i < MAX_SORT_PASSES * RADIX; i += MOVE_THREADS) s_hist[i] = 0;
@@ -204,42 +200,13 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
     for (uint32_t base = blockIdx.x * PER_BLOCK; base < pairs_pad; base += gridDim.x * PER_BLOCK) {
         float4 P[MOVE_ITEMS], T[MOVE_ITEMS];
         bool live[MOVE_ITEMS];
-        uint32_t pend = 0;  // FUSE: bit 2k + s = entity slot s of item k arrived in the previous pass and has no new waypoint yet
 #pragma unroll
         for (int k = 0; k < MOVE_ITEMS; k++) {
             const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
             live[k] = pi < pairs_pad;
             if (live[k]) {
                 P[k] = __ldcs(pos_in + pi);
-                if (FUSE) {
-                    T[k] = __ldcs(reinterpret_cast<const float4*>(fa.target) + pi);
-                    if (fa.consume) {
-                        const uint2 pm = *reinterpret_cast<const uint2*>(arrived_mask + (pi >> 5) * 2u);  // one address per warp
-                        const uint32_t e0 = pi * 2u;
-                        if (((pm.x >> lane) & 1u) && e0 < n) pend |= 1u << (2 * k);
-                        if (((pm.y >> lane) & 1u) && e0 + 1u < n) pend |= 2u << (2 * k);
-                    }
-                } else {
-                    T[k] = __ldcs(target + pi);
-                }
-            }
-        }
-        if (FUSE) {
-            while (__any_sync(0xffffffffu, pend != 0u)) {
-                if (pend) {
-                    const uint32_t slot = static_cast<uint32_t>(__ffs(static_cast<int>(pend))) - 1u;
-                    pend &= pend - 1u;
-                    const uint32_t pi = base + (slot >> 1) * MOVE_THREADS + threadIdx.x;
-                    const uint32_t e = pi * 2u + (slot & 1u);
-                    const float4 t4 = (slot >> 1) ? T[1] : T[0];
-                    const float2 reached = (slot & 1u) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
-                    const float2 nt = new_target<true>(e, reached, fa.road, fa.rng, fa.roads, fa.conn, fa.conn_count);
-                    fa.target[e] = nt;
-                    if (slot == 0u) { T[0].x = nt.x; T[0].y = nt.y; }
-                    if (slot == 1u) { T[0].z = nt.x; T[0].w = nt.y; }
-                    if (slot == 2u) { T[1].x = nt.x; T[1].y = nt.y; }
-                    if (slot == 3u) { T[1].z = nt.x; T[1].w = nt.y; }
-                }
+                T[k] = __ldcs(target + pi);
             }
         }
         RunRank R0[MOVE_ITEMS], R1[MOVE_ITEMS];
@@ -258,6 +225,10 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
             if (lane == 0) {
                 const uint32_t w = (pi >> 5) * 2u;
                 *reinterpret_cast<uint2*>(arrived_mask + w) = make_uint2(m0, m1);
+            }
+            if (MODE == MOVE_COUNT) {
+                run_count(cell_count, cell_key_of(q0, grid), e0 < n, lane);
+                run_count(cell_count, cell_key_of(q1, grid), e1 < n, lane);
             }
             if (EMIT_KEYS) {
                 const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);
@@ -360,70 +331,35 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
     }
 }
 
-// one launch of the chosen variant; the grid is a whole number of resident CTAs per SM (grid-stride loop inside)
-template <bool EMIT_KEYS, bool SHARD, bool FUSE, int MINB, typename... Args>
-void launch_move_variant(cudaStream_t s, int sm_count, uint32_t blocks_needed, Args... args) {
-    uint32_t per_sm = 8u;  // 8 x 256 threads = 2048 threads per SM (what the register budget of MINB = 0 allows is less: see above)
-    if (tuning().move_grid_by_occupancy) {
-        static int occupancy = 0;  // per instantiation
-        if (occupancy == 0 &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, move_kernel<EMIT_KEYS, SHARD, FUSE, MINB>, MOVE_THREADS, 0) != cudaSuccess)
-            occupancy = 8;
-        per_sm = static_cast<uint32_t>(occupancy > 0 ? occupancy : 8);
-    }
-    const uint32_t resident = static_cast<uint32_t>(sm_count) * per_sm;
-    const uint32_t blocks = blocks_needed > resident ? resident : blocks_needed;
-    move_kernel<EMIT_KEYS, SHARD, FUSE, MINB><<<blocks, MOVE_THREADS, 0, s>>>(args...);
-}
-template <bool EMIT_KEYS, bool SHARD, bool FUSE, typename... Args>
-void launch_move_minb(cudaStream_t s, int sm_count, uint32_t blocks_needed, Args... args) {
-    switch (tuning().move_min_blocks) {
-        case 5: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 5>(s, sm_count, blocks_needed, args...); break;
-        case 6: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 6>(s, sm_count, blocks_needed, args...); break;
-        default: launch_move_variant<EMIT_KEYS, SHARD, FUSE, 0>(s, sm_count, blocks_needed, args...); break;
-    }
-}
-
 }  // namespace
 
+// `keys` non-NULL: MOVE_KEYS (key + rank / digit histograms, optionally the shard pack); `keys` NULL and `cell_count` non-NULL:
+// MOVE_COUNT; neither: MOVE_PLAIN.  The grid is 8 CTAs per SM (2048 threads) with a grid-stride loop inside.
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev, const ShardMoveArgs* shard, const FusedArriveArgs* fuse) {
+                const uint32_t* n_dev, const ShardMoveArgs* shard) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
-    const uint32_t blocks = (pairs + per_block - 1) / per_block;
+    uint32_t blocks = (pairs + per_block - 1) / per_block;
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
+    if (blocks > resident) blocks = resident;
     const float4* pin = reinterpret_cast<const float4*>(pos_in);
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
     uint2* keys2 = reinterpret_cast<uint2*>(keys);
     uint2* rank2 = reinterpret_cast<uint2*>(rank);
     const int passes = hist ? hist_passes : 0;
-    const float4* no_target = nullptr;  // the fused variants read the waypoints through FusedArrive::target (read-write alias)
-    uint2* no_keys = nullptr;
-    uint32_t* no_table = nullptr;
-    prof->begin(s, K_MOVE);
     const ShardMoveArgs none{};
-    FusedArrive fa{};
-    if (fuse) {
-        fa.target = fuse->target;
-        fa.road = fuse->road;
-        fa.rng = fuse->rng;
-        fa.roads = reinterpret_cast<const uint4*>(fuse->roads);
-        fa.conn = fuse->connections;
-        fa.conn_count = fuse->connection_count;
-        fa.consume = fuse->consume ? 1u : 0u;
-    }
-    if (keys && shard)  // sharded handles keep the stand-alone pass B: migrants travel with their pre-arrival state
-        launch_move_minb<true, true, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, *shard, fa);
-    else if (keys && fuse)
-        launch_move_minb<true, false, true>(s, sm_count, blocks, n, n_dev, pin, pout, no_target, arrived, keys2, grid, hist, passes, cell_count, rank2, none, fa);
+    prof->begin(s, K_MOVE);
+    if (keys && shard)
+        move_kernel<MOVE_KEYS, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, *shard);
     else if (keys)
-        launch_move_minb<true, false, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, none, fa);
-    else if (fuse)
-        launch_move_minb<false, false, true>(s, sm_count, blocks, n, n_dev, pin, pout, no_target, arrived, no_keys, grid, no_table, 0, no_table, no_keys, none, fa);
+        move_kernel<MOVE_KEYS, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, none);
+    else if (cell_count)
+        move_kernel<MOVE_COUNT, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, cell_count, nullptr, none);
     else
-        launch_move_minb<false, false, false>(s, sm_count, blocks, n, n_dev, pin, pout, tgt, arrived, no_keys, grid, no_table, 0, no_table, no_keys, none, fa);
+        move_kernel<MOVE_PLAIN, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr, none);
     prof->end(s);
     return 1;
 }
@@ -435,7 +371,7 @@ int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, ui
     uint32_t blocks = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
     // 10 M entities need 1221 CTAs where 1184 are resident (31 registers, 8 per SM): the 37 left over start when the first finish.
     // MSIM_ARRIVE_GRID=persistent: one resident wave that strides over the words instead
-    uint32_t cap = tuning().arrive_persistent ? 148u * 8u : 0u;
+    uint32_t cap = 0u;
     if (beside && tuning().arrive_beside_ctas_per_sm) cap = 148u * static_cast<uint32_t>(tuning().arrive_beside_ctas_per_sm);
     const bool stride = cap != 0u && blocks > cap;
     prof->begin(s, K_ARRIVE);

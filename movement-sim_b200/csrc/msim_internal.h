@@ -117,16 +117,11 @@ struct Profiler {
     }
 };
 
-// ---- launch tuning read once from the environment (api.cu); defaults = the configuration every committed number was measured with
+// ---- launch tuning read once from the environment (api.cu)
 struct Tuning {
-    int move_min_blocks{0};          // MSIM_MOVE_MIN_BLOCKS: 0 (default, no register cap), 5 or 6 resident CTAs per SM asked of the compiler
-    bool move_grid_by_occupancy{false};  // MSIM_MOVE_GRID=occupancy: grid = SMs x resident CTAs of the variant instead of SMs x 8
-    bool arrive_persistent{false};       // MSIM_ARRIVE_GRID=persistent: pass B as one resident wave with a stride loop
     int arrive_beside_ctas_per_sm{0};  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
-                                  // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots instead of taking
-                                  // them all for 45-70 us (it is latency-bound and only has to finish before the next move); 0 = full grid (default)
-    bool query_paired{false};            // MSIM_QUERY_PAIRED=1: query with two adjacent slots per thread (collide.cu, query_paired_kernel)
-    int scan_min_blocks{0};          // MSIM_SCAN_MIN_BLOCKS=8: scan_tiles capped at 32 registers (8 CTAs per SM, one wave for Munich's table)
+                                  // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots (it is latency-bound and
+                                  // only has to finish before the next move); 0 = full grid
     int csort_max_cells_log2{25};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
@@ -139,20 +134,10 @@ const Tuning& tuning();
 // Device-resident counts (asynchronous sharded ticks): when `n_dev` is non-NULL a kernel takes its element
 // count from *n_dev (written by an earlier kernel on the stream) and the host-side `n` is only an upper
 // bound used to size the grid.
-// MSIM_FLAG_FUSED_ARRIVE: pass B of the PREVIOUS move pass runs inside this move kernel (move.cu); `consume` says whether one is pending
-struct FusedArriveArgs {
-    float2* target;
-    uint32_t* road;
-    uint4* rng;
-    const msim_road* roads;
-    const uint32_t* connections;
-    uint64_t connection_count;
-    bool consume;
-};
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
                 int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
-                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr, const FusedArriveArgs* fuse = nullptr);
+                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr);
 // `beside`: the pass runs on the side stream next to the issue-bound query (see Tuning::arrive_beside_ctas_per_sm)
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr, bool beside = false);
@@ -176,6 +161,12 @@ int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t
 int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
                         float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
+// single-GPU default (count-only move pass): slots come from atomics on the scanned table `cursor`, which ends up shifted by one cell
+int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cursor, float2* sorted_pos, uint32_t* slot_of_entity,
+                              const GridParams& grid, Profiler* prof);
+int launch_cell_count_pos(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cell_count, const GridParams& grid, Profiler* prof);
+int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof);
+int launch_gather_flags(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
@@ -186,9 +177,9 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
                  const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
                  const uint32_t* n_dev = nullptr, const uint32_t* n_owned_dev = nullptr);
 size_t query_stripe_bytes();
-// collide_paired.cu (opt-in, Tuning::query_paired): the query kernel only; the caller folds the striped counters
-void launch_query_paired(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid,
-                         unsigned long long* stripes);
+// collide_tiles.cu — single-GPU default query: aligned candidate groups, striped counters folded by a one-CTA kernel behind it
+int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, Counters* counters,
+                       unsigned long long* stripes, Profiler* prof);
 int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu

@@ -37,11 +37,11 @@ def transform(text):
 
 
 def up_to_date():
-    outs = [OUT, os.path.join(HERE, "libemu_kernels.so")]
+    outs = [OUT]
     if not all(os.path.exists(o) for o in outs):
         return False
     deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
-    deps += [os.path.join(HERE, n) for n in ("cuda_runtime.h", "emu_kernels.cpp", "build_emu_lib.py")]
+    deps += [os.path.join(HERE, n) for n in ("cuda_runtime.h", "build_emu_lib.py")]
     deps += [os.path.join(ROOT, "include", n) for n in os.listdir(os.path.join(ROOT, "include"))]
     return min(os.path.getmtime(o) for o in outs) > max(os.path.getmtime(d) for d in deps)
 
@@ -91,10 +91,6 @@ def main():
                 "namespace cuda_emu {\nthread_local Block* block = nullptr;\nthread_local unsigned lane = 0, warp = 0;\nthread_local void* dynamic_smem_ptr = nullptr;\n}\n")
     subprocess.check_call([cxx, *flags, "-shared", "-o", OUT, emu_globals, *objs])
     print(OUT)
-    # single-kernel entry points (tests/test_kernels_under_emulator.py) from the same scratch copies
-    kernels = os.path.join(HERE, "libemu_kernels.so")
-    subprocess.check_call([cxx, *flags, "-I", dst, "-shared", "-o", kernels, os.path.join(HERE, "emu_kernels.cpp")])
-    print(kernels)
     return 0
 
 

@@ -143,10 +143,10 @@ def make_fake_simulation(M, O):
 @pytest.mark.parametrize("backend,argv", [
     ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "6000"]),
     ("stand-in", ["--workload", "munich_1m_nocollisions", "--entities", "5000"]),
-    ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "4000", "--fused-arrive", "--e2e-pipelined", "--no-flags-only"]),
+    ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "4000", "--e2e-pipelined", "--no-flags-only"]),
     # against the real api.cu + kernels under the emulator: the bench's map has 4.8 M grid cells, i.e. 2 x 1165 scan CTAs per tick, which costs
     # the emulator minutes - all three configurations passed that way by hand; in the suite only with MSIM_TEST_SLOW=1
-    pytest.param("emulated library", ["--workload", "munich_10m_collisions", "--entities", "1200", "--fused-arrive", "--e2e-pipelined"],
+    pytest.param("emulated library", ["--workload", "munich_10m_collisions", "--entities", "1200", "--e2e-pipelined"],
                  marks=pytest.mark.skipif(os.environ.get("MSIM_TEST_SLOW") != "1", reason="minutes under the emulator: set MSIM_TEST_SLOW=1")),
 ])
 def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv, backend):
@@ -175,7 +175,7 @@ def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv, ba
                 "config", "roofline", "tick", "kernels", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in line, key
     assert line["metric"] == "entity-updates/sec" and line["n_gpus"] == 1 and line["steps"] == 3 and line["vs_baseline"] is None
-    assert line["config"]["workload"] == argv[1] and line["config"]["experiments"]["fused_arrive"] == ("--fused-arrive" in argv)
+    assert line["config"]["workload"] == argv[1]
     assert line["roofline"]["bound"] == "hbm"
     if backend == "stand-in":
         assert line["roofline"]["kernel"] == ("query" if collisions else "move")

@@ -246,6 +246,24 @@ def test_collide_without_prior_move_and_radius_change(msim, orc, small_city):
         assert_entities_equal(sim.read_entities(), want, what="after radius change")
 
 
+@pytest.mark.parametrize("mode", ["default", "counting"])
+def test_radius_back_and_forth_reuses_the_counter_table(msim, orc, small_city, mode):
+    """A move pass counts the cells of grid A, the radius grows (smaller grid B, same allocation), shrinks back to A: the counters
+    the first grid left beyond B's cells must not survive into A's next count (round-1 advisor finding: out-of-bounds ranks)."""
+    ents = small_city.init_entities(15_000, seed=29)
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+    plan = [(2, 10.0), (3, 10.0), (4, 10.0), (5, 25.0), (6, 25.0), (7, 10.0), (8, 10.0), (9, 4.0), (10, 4.0), (11, 10.0), (13, 25.0), (15, 10.0)]
+    with msim.Simulation(small_city, ents, radius=10.0, flags=MODES(msim)[mode]) as sim:
+        for tick, radius in plan:
+            sim.radius = radius
+            sim.dispatch(tick)
+            pairs = oracle_dispatch(orc, want, omap, radius, tick)
+            if tick % 2 == 1 and tick > 2:
+                assert sim.stats()["last_pair_count"] == pairs, f"tick {tick} r={radius}"
+        assert_entities_equal(sim.read_entities(), want, what="radius back and forth")
+
+
 def test_invalid_inputs(msim, small_city):
     ents = small_city.init_entities(100, seed=1)
     bad = ents.copy()

@@ -2,8 +2,8 @@
 compiled for the host SIMT emulator (tests/cuda_emu/build_emu_lib.py -> libmsim_emu.so, same C ABI) and driven through the ordinary ctypes
 binding, loaded as a second copy of the package so that the product module and its real library are not touched.
 
-What runs here: the gated tests of the paths written without a GPU (tests/test_zz_gpu_unverified.py: fused pass B through the real handle
-state machine, asynchronous snapshots) and a sample of the required GPU parity tests at emulator-friendly sizes.  Same bar: bit-exact against
+What runs here: sim ticks in every rebuild / flag mode, the asynchronous snapshots, the display quadtree, the C++ drop-in with its headless
+runner, and a sample of the required GPU parity tests at emulator-friendly sizes.  Same bar: bit-exact against
 the oracle.  This is a development loop and a logic check; it is not hardware and proves nothing about speed, timing-dependent behaviour or
 the real memory system.  TEST INFRASTRUCTURE ONLY: the product never loads this library (its binding has no switch for it)."""
 import os
@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import test_gpu_parity as parity
-import test_zz_gpu_unverified as gated
+import test_gpu_readback as readback
 from conftest import ROOT, assert_entities_equal, oracle_dispatch, oracle_map, to_oracle_entities
 
 EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
@@ -36,7 +36,7 @@ def emu_test_map(emu_msim):
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("flag_names", [(), ("FLAG_NO_REORDER",), ("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), ("FLAG_SORT_ONESWEEP",), ("FLAG_FUSED_ARRIVE",),
+@pytest.mark.parametrize("flag_names", [(), ("FLAG_NO_REORDER",), ("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), ("FLAG_SORT_ONESWEEP",),
                                         ("FLAG_NO_PAIR_COUNT",)])
 def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkeypatch):
     """Blocking dispatches, every rebuild mode of the neighbour structure, a cell re-sort every 3 collision passes, readback at several points."""
@@ -61,38 +61,15 @@ def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkey
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("n", [1, 65, 1023])
-def test_gated_fused_arrive_collisions_off(emu_msim, orc, emu_test_map, n):
-    gated.test_fused_arrive_collisions_off(emu_msim, orc, emu_test_map, n)
+@pytest.mark.parametrize("mode", ["default", "counting"])
+def test_radius_back_and_forth(emu_msim, orc, emu_city, mode):
+    """tests/test_gpu_parity.py::test_radius_back_and_forth_reuses_the_counter_table through the emulated library (the sequence the round-1
+    advisor reproduced a crash with)."""
+    parity.test_radius_back_and_forth_reuses_the_counter_table(emu_msim, orc, emu_city, mode)
 
 
 @pytest.mark.timeout(1800)
-def test_gated_fused_arrive_with_collisions(emu_msim, orc, emu_city, monkeypatch):
-    """The gated test itself, at a population the emulator finishes in a minute."""
-    monkeypatch.setenv("MSIM_REORDER_EVERY", "5")
-    n = 2000
-    ents = emu_city.init_entities(n, seed=11)
-    om = oracle_map(orc, emu_city)
-    want = to_oracle_entities(orc, ents)
-    with emu_msim.Simulation(emu_city, ents, radius=10.0, flags=emu_msim.FLAG_FUSED_ARRIVE) as sim:
-        sim.dispatch(2)
-        oracle_dispatch(orc, want, om, 10.0, 2)
-        tick = 3
-        for chunk in (1, 3, 8):
-            sim.enqueue_ticks(chunk, True)
-            sim.sync()
-            pairs = 0
-            for _ in range(chunk):
-                oracle_dispatch(orc, want, om, 10.0, tick + 1)
-                pairs = oracle_dispatch(orc, want, om, 10.0, tick + 2)
-                tick += 2
-            assert sim.stats()["last_pair_count"] == pairs
-            assert_entities_equal(sim.read_entities(), want, what=f"fused, tick {tick}")
-        assert sim.stats()["reorders"] >= 2  # the re-sort completes the pending pass B with the stand-alone kernel first
-
-
-@pytest.mark.timeout(1800)
-def test_gated_snapshots(emu_msim, orc, emu_city, emu_test_map):
+def test_snapshots(emu_msim, orc, emu_city, emu_test_map):
     """msim_snapshot_begin / poll / end through the real handle code (the emulated runtime copies synchronously: buffer rotation, state-at-begin
     semantics and the error paths are what is checked)."""
     n = 1500
@@ -126,7 +103,7 @@ def test_gated_snapshots(emu_msim, orc, emu_city, emu_test_map):
         assert_entities_equal(snap_b, want_b, what="snapshot B")
         assert_entities_equal(snap_a, want_a, what="snapshot A is still intact (other pinned buffer)")
         assert_entities_equal(sim.read_entities(), want, what="blocking readback afterwards")
-    gated.test_snapshot_argument_errors(emu_msim, emu_test_map)
+    readback.test_snapshot_argument_errors(emu_msim, emu_test_map)
 
 
 @pytest.mark.timeout(1800)
@@ -156,20 +133,6 @@ def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
         pos = sim.read_positions()
     want = emu_msim.quadtree_from_positions(pos, emu_city.width, emu_city.height, 8, 10)
     assert got.shape == want.shape and got.tobytes() == want.tobytes()
-
-
-@pytest.mark.timeout(1800)
-def test_launch_knobs_in_a_fresh_process():
-    """The environment knobs are read once per process: the sim-tick tests above again, in a child process with the paired query, the
-    register-capped scan and move variants, the occupancy-sized grid and the L2 window switched on (the query then goes through
-    launch_query_paired and the striped counters' fold, the scan through scan_tiles_kernel<8>)."""
-    import subprocess
-    import sys
-
-    env = dict(os.environ, MSIM_QUERY_PAIRED="1", MSIM_SCAN_MIN_BLOCKS="8", MSIM_MOVE_MIN_BLOCKS="6", MSIM_MOVE_GRID="occupancy", MSIM_L2_PERSIST_ROADS="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_library_under_emulator.py"), "-q", "-x", "-k",
-                        "sim_ticks or fused_arrive_with"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1700)
-    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:]
 
 
 @pytest.mark.timeout(1800)
