@@ -72,7 +72,9 @@ struct msim_handle {
     uint32_t* cell_count{nullptr};  // counting-sort path: per-cell counters, prefix table, scan scratch, ranks
     uint32_t* cell_table{nullptr};  // allocation behind cell_start: cell_start = cell_table + 4, and cell_table[3] is a permanent 0
     uint32_t* cell_start{nullptr};
-    uint32_t* tile_sums{nullptr};
+    uint32_t* tile_sums{nullptr};   // scratch of the single-pass scan (csort.cu ScanState)
+    uint32_t scan_tiles_cap{0};
+    uint32_t scan_epoch{0};
     uint32_t* rank{nullptr};
     uint32_t* sorted_idx{nullptr};
     bool use_csort{false};
@@ -175,7 +177,7 @@ const Tuning& tuning() {
         if (const char* e = std::getenv("MSIM_L2_PERSIST_ROADS")) v.l2_persist_roads = std::atoi(e) == 1;
         if (const char* e = std::getenv("MSIM_ARRIVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
-            if (k >= 1 && k <= 8) v.arrive_beside_ctas_per_sm = k;
+            if (k >= 0 && k <= 8) v.arrive_beside_ctas_per_sm = k;
         }
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
             const int k = std::atoi(e);
@@ -384,6 +386,13 @@ void prepare_counts(msim_handle* h) {
     h->counts_dirty = true;  // about to be counted into
 }
 
+// exclusive prefix sum of the per-cell counters over cells [c0, c1) into cell_start (one kernel, csort.cu)
+int scan_cells(msim_handle* h, uint32_t c0, uint32_t c1) {
+    if (++h->scan_epoch == 0u) ++h->scan_epoch;
+    return launch_cell_scan(h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->scan_tiles_cap, h->scan_epoch, h->cell_start + c0, &h->counters->error_flag,
+                            &h->prof);
+}
+
 int ensure_cells(msim_handle* h) {
     // counting sort: on request, or by default whenever the storage is kept in cell order
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
@@ -399,7 +408,9 @@ int ensure_cells(msim_handle* h) {
         MSIM_CUDA(h, dev_alloc(&h->cell_table, static_cast<size_t>(h->grid.ncells) + 8));
         MSIM_CUDA(h, cudaMemsetAsync(h->cell_table, 0, 4 * sizeof(uint32_t), h->stream));
         h->cell_start = h->cell_table + 4;
-        MSIM_CUDA(h, dev_alloc(&h->tile_sums, static_cast<size_t>(csort_tiles(h->grid.ncells))));
+        h->scan_tiles_cap = csort_tiles(h->grid.ncells);
+        MSIM_CUDA(h, dev_alloc(&h->tile_sums, csort_scan_scratch_words(h->grid.ncells)));
+        MSIM_CUDA(h, cudaMemsetAsync(h->tile_sums, 0, csort_scan_scratch_words(h->grid.ncells) * sizeof(uint32_t), h->stream));
     } else {
         MSIM_CUDA(h, dev_alloc(&h->cell_range, h->grid.ncells));
     }
@@ -494,7 +505,7 @@ int check_device_errors(msim_handle* h) {
     h->last_pairs = h->n ? c.pairs_last : 0;
     h->total_pairs = c.pairs_total;
     h->last_flagged = h->n ? c.flagged_last : 0;
-    if (c.error_flag) return fail(h, MSIM_ERR_INTERNAL, "radix sort look-back watchdog tripped");
+    if (c.error_flag) return fail(h, MSIM_ERR_INTERNAL, "look-back watchdog tripped (radix sort / cell scan): a tile never published its total");
     return MSIM_OK;
 }
 
@@ -647,7 +658,7 @@ int enqueue_collide(msim_handle* h) {
             h->launches += launch_cell_count_pos(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_count, h->grid, &h->prof);
         }
         h->counts_valid = false;
-        h->launches += launch_cell_scan(h->stream, h->cell_count, h->grid.ncells, h->tile_sums, h->cell_start, &h->prof);
+        h->launches += scan_cells(h, 0, h->grid.ncells);
         h->counts_dirty = false;
         h->launches += launch_cell_scatter_slots(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_start, h->sorted_pos, h->rank, h->grid, &h->prof);
         launch_deferred_arrive(h, true);
@@ -677,7 +688,7 @@ int enqueue_collide(msim_handle* h) {
             h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, c0, c1, &h->prof, dev_total(h));
         }
         h->counts_valid = false;
-        h->launches += launch_cell_scan(h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->cell_start + c0, &h->prof);
+        h->launches += scan_cells(h, c0, c1);
         h->counts_dirty = false;  // the scan zeroed every counter it read, and nothing was counted outside [c0, c1)
         h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
                                            dev_total(h));

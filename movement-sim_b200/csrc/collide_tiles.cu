@@ -25,6 +25,8 @@
 //     bulk copies was measured slower (mbarrier set-up, hull exchange and waits cost more issue slots than the loads save:
 //     191 / 212 us against 156 us), so every warp is independent from its first instruction;
 //   * totals leave as one reduction per warp and counter (RED, nothing waits) into striped counters; a one-CTA kernel folds them.
+#include <cstdlib>
+
 #include "msim_internal.h"
 
 namespace msim {
@@ -87,8 +89,7 @@ __device__ __forceinline__ uint32_t count_last_group(const float4* __restrict__ 
     return (below_j > 0u ? c0 : 0u) + (below_j > 1u ? c1 : 0u) + (below_j > 2u ? c2 : 0u);
 }
 
-constexpr int TILES_THREADS = 128;
-
+template <int TILES_THREADS>
 __global__ void __launch_bounds__(TILES_THREADS)
 query_tiles_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint32_t* __restrict__ tab, uint8_t* __restrict__ flag_sorted, GridParams grid,
                    unsigned long long* __restrict__ stripes) {
@@ -178,9 +179,12 @@ __global__ void __launch_bounds__(COUNTER_STRIPES) fold_stripes_kernel(unsigned 
 int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, Counters* counters,
                        unsigned long long* stripes, Profiler* prof) {
     if (n == 0) return 0;
-    const uint32_t blocks = (n + TILES_THREADS - 1) / TILES_THREADS;
+    static const int threads = [] { const char* e = getenv("MSIM_TILES_THREADS"); const int v = e ? atoi(e) : 128; return v == 64 || v == 256 ? v : 128; }();
+    const uint32_t blocks = (n + threads - 1) / threads;
     prof->begin(s, K_QUERY);
-    query_tiles_kernel<<<blocks, TILES_THREADS, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
+    if (threads == 64) query_tiles_kernel<64><<<blocks, 64, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
+    else if (threads == 256) query_tiles_kernel<256><<<blocks, 256, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
+    else query_tiles_kernel<128><<<blocks, 128, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
     fold_stripes_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
     prof->end(s);
     return 2;

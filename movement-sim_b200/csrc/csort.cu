@@ -7,7 +7,7 @@
 // key and one pass suffices:
 //   count    rank[e] = atomicAdd(&cell_count[key[e]], 1)   — fused into the move kernel (move.cu), or
 //            cell_count_kernel below when the keys did not come from a move pass (sharded / keygen)
-//   scan     cell_start = exclusive prefix sum of cell_count (two small kernels over the table)
+//   scan     cell_start = exclusive prefix sum of cell_count (one kernel, one pass over the table)
 //   scatter  slot = cell_start[key] + rank: sorted_pos[slot] = pos[e], sorted_idx[slot] = e
 // Per entity that is key W4 + rank W4 in the move pass and key R4 + rank R4 + pos R8 + pos W8 + idx W4
 // in the scatter = 36 B, against 44 B + 24 B for three onesweep passes plus the gather — and far fewer
@@ -18,6 +18,8 @@
 // Measured (profiles/r1_sort_paths.md): with entities in random index order the 20 M scattered 4/8-byte
 // stores cost 484 us at 10 M entities against 3 x 90 us for the staged onesweep scatter, so onesweep
 // (sort.cu) stays the default; with cell-ordered storage the scatter drops to 92 us and this path wins.
+#include <cstdlib>
+
 #include "msim_internal.h"
 
 namespace msim {
@@ -38,102 +40,149 @@ cell_count_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uin
     }
 }
 
-__device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* s_warp) {
-    v = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint32_t total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) total += s_warp[w];
-    __syncthreads();
-    return total;
+// ---- single-pass scan ---------------------------------------------------------------------------------------------------------
+// One kernel, one pass over the table: 19 MB in, 19 MB out, counters zeroed on the way.  A tile (4096 cells) publishes its total
+// as soon as it has read its cells, and needs the sum of the totals before it.  Two things were measured and discarded first:
+//   * the classic look-back (wait for a predecessor's inclusive prefix) degenerates when the whole table is one resident wave -
+//     every tile walks all the way back (32-40 us);
+//   * every tile summing ALL earlier totals (also what the round-1 two-kernel scan did) is 680 k relaxed loads on the same 73 L2
+//     lines: the hot lines serialise and the kernel takes 25-37 us however its own accesses are laid out.
+// So the totals are summed in two levels: tiles form groups of SCAN_GROUP; the last tile of a group to arrive (found with one
+// 64-bit atomic that carries {arrivals, sum}) publishes the group's sum, and a tile reads the totals before it in its own group
+// plus the sums of the groups before its own: at most 31 + T / 32 words instead of T.  Nothing waits for anything but totals.
+// A status word is {epoch : 32 | value : 32}: words of an earlier launch (other epoch) read as "not there yet", so the arrays are
+// never cleared.  Tiles take their index from a ticket, so a tile only ever waits for tiles that are already running.
+#ifdef MSIM_HOST_EMU
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#endif
 
-// phase 1: per-tile totals
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint32_t* __restrict__ counts, uint32_t cells, uint32_t* __restrict__ tile_sums) {
+constexpr int SCAN_STEPS = SCAN_ITEMS / 4;                 // uint4 loads per thread
+constexpr int SCAN_WARP_CELLS = 32 * SCAN_ITEMS;           // 512 consecutive cells per warp
+
+struct ScanState {
+    unsigned long long* tile_total;   // [tiles]   {epoch, total of the tile}
+    unsigned long long* group_total;  // [groups]  {epoch, sum of the group's tiles}
+    unsigned long long* group_acc;    // [groups]  {arrivals, running sum}; left at 0 by the last arrival
+    uint32_t* ticket;
+    uint32_t group;                   // tiles per group
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_cells_kernel(uint32_t* __restrict__ counts, uint32_t cells, uint32_t* __restrict__ starts, ScanState st, uint32_t epoch, uint32_t* __restrict__ error_flag) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    const uint32_t base = blockIdx.x * SCAN_TILE;
-    uint32_t v = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint32_t c = base + i * SCAN_THREADS + threadIdx.x;
-        if (c < cells) v += __ldcs(counts + c);
-    }
-    const uint32_t total = block_reduce_sum(v, s_warp);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// phase 2: exclusive scan inside each tile + the sum of the earlier tiles' totals.  Thread t owns SCAN_ITEMS consecutive cells.
-// MINB = 8 caps the kernel at 32 registers (31 used, nothing spilled) so that 8 CTAs fit one SM: Munich's 1165 tiles are then ONE
-// resident wave; with the 34 registers of MINB = 0 (the measured default) 6 CTAs fit and 277 tiles wait for a second wave.
-template <int MINB>
-__global__ void __launch_bounds__(SCAN_THREADS, MINB)
-scan_tiles_kernel(uint32_t* __restrict__ counts, uint32_t cells, const uint32_t* __restrict__ tile_offsets /* per-tile TOTALS */,
-                  uint32_t* __restrict__ starts) {
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_before[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    uint32_t sum = 0;
-    // the counters are consumed here: they are zeroed on the way, so the next tick's count needs no memset of the table
-    if (first + SCAN_ITEMS <= cells) {
-        uint4* src = reinterpret_cast<uint4*>(counts + first);  // first is a multiple of 16 and the base 16-byte aligned
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
-            const uint4 c = __ldcs(src + q);
-            v[4 * q] = c.x; v[4 * q + 1] = c.y; v[4 * q + 2] = c.z; v[4 * q + 3] = c.w;
-            src[q] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            v[i] = 0u;
-            if (first + i < cells) {
-                v[i] = counts[first + i];
-                counts[first + i] = 0u;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) sum += v[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += up;
-    }
-    // offset of this tile = sum of the totals of the tiles before it (at most ~1.2 k words, L2-resident): cheaper than
-    // a third kernel that scans the totals with one CTA between the two passes over the table
-    uint32_t before = 0;
-    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) before += __ldcg(tile_offsets + t);
-    before = __reduce_add_sync(0xffffffffu, before);
-    if (lane == 31) s_warp[warp] = incl;
-    if (lane == 0) s_before[warp] = before;
+    if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
     __syncthreads();
-    uint32_t run = incl - sum;
+    const uint32_t tile = s_tile;
+    const uint32_t warp_first = tile * SCAN_TILE + warp * SCAN_WARP_CELLS;
+    uint4 c[SCAN_STEPS];
+    // the counters are consumed here; they are zeroed when the tile writes its results (below), so the next tick's count needs no memset.
+    // NOT right behind the load: a store to the address a load has just been issued for waits for that load in the LSU and holds up
+    // the loads behind it - measured 36 us with the zeroing here against 20 us with it at the end
+#pragma unroll
+    for (int q = 0; q < SCAN_STEPS; q++) {
+        const uint32_t first = warp_first + q * 128u + lane * 4u;  // multiple of 4: 16-byte aligned (the base is)
+        if (first + 4u <= cells) {
+            uint4* src = reinterpret_cast<uint4*>(counts + first);
+            c[q] = __ldcs(src);
+        } else {
+            uint32_t t[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (first + i < cells) {
+                    t[i] = counts[first + i];
+                    counts[first + i] = 0u;  // (tail of the table: a handful of cells)
+                }
+            }
+            c[q] = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+    }
+    // exclusive offset of this lane's four cells inside its step, and the step totals
+    uint32_t excl[SCAN_STEPS], step_base[SCAN_STEPS];
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_STEPS; q++) {
+        const uint32_t mine = c[q].x + c[q].y + c[q].z + c[q].w;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += up;
+        }
+        excl[q] = incl - mine;
+        step_base[q] = warp_total;
+        warp_total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_warp[warp] = warp_total;
+    __syncthreads();
+    uint32_t warp_before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; w++) {
-        run += s_before[w];
-        if (static_cast<uint32_t>(w) < warp) run += s_warp[w];
+        if (static_cast<uint32_t>(w) < warp) warp_before += s_warp[w];
+        total += s_warp[w];
     }
-    // starts has cells + 1 entries: entry `cells` receives the grand total
-    if (first + SCAN_ITEMS <= cells) {
-        uint4* dst = reinterpret_cast<uint4*>(starts + first);
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
-            uint4 o;
-            o.x = run; run += v[4 * q];
-            o.y = run; run += v[4 * q + 1];
-            o.z = run; run += v[4 * q + 2];
-            o.w = run; run += v[4 * q + 3];
-            dst[q] = o;
+    // publish the tile's total (and, as the group's last arrival, the group's sum); sum what lies before this tile
+    const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
+    const uint32_t g = tile / st.group, in_group = tile - g * st.group;
+    if (threadIdx.x == 0) {
+        st_relaxed_u64(st.tile_total + tile, tag | total);
+        const uint32_t members = min(st.group, gridDim.x - g * st.group);
+        const unsigned long long old = atomicAdd(st.group_acc + g, (1ull << 32) | total);
+        if (static_cast<uint32_t>(old >> 32) + 1u == members) {
+            st_relaxed_u64(st.group_total + g, tag | (static_cast<uint32_t>(old) + total));
+            st.group_acc[g] = 0ull;  // nobody touches it again in this launch
         }
-        if (first + SCAN_ITEMS == cells) starts[cells] = run;
-    } else {
+    }
+    uint32_t acc = 0, spins = 0;
+    for (uint32_t i = threadIdx.x; i < in_group + g; i += SCAN_THREADS) {
+        const unsigned long long* word = i < in_group ? st.tile_total + (g * st.group + i) : st.group_total + (i - in_group);
+        unsigned long long w = ld_relaxed_u64(word);
+        while ((w >> 32) != epoch) {
+            if (++spins > (1u << 22)) {  // never a hang: a tile that does not show up is reported
+                atomicExch(error_flag, 1u);
+                break;
+            }
+            w = ld_relaxed_u64(word);
+        }
+        acc += static_cast<uint32_t>(w);
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    __syncthreads();  // s_warp has been read by everybody
+    if (lane == 0) s_warp[warp] = acc;
+    if (threadIdx.x == 0 && tile == gridDim.x - 1u) *st.ticket = 0u;  // every ticket has been handed out: ready for the next launch
+    __syncthreads();
+    uint32_t before = warp_before;
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            if (first + i <= cells) starts[first + i] = run;
-            run += v[i];
+    for (int w = 0; w < SCAN_THREADS / 32; w++) before += s_warp[w];
+    // starts has cells + 1 entries: entry `cells` receives the grand total
+#pragma unroll
+    for (int q = 0; q < SCAN_STEPS; q++) {
+        const uint32_t first = warp_first + q * 128u + lane * 4u;
+        uint4 o;
+        o.x = before + step_base[q] + excl[q];
+        o.y = o.x + c[q].x;
+        o.z = o.y + c[q].y;
+        o.w = o.z + c[q].z;
+        if (first + 4u <= cells) {
+            *reinterpret_cast<uint4*>(starts + first) = o;
+            *reinterpret_cast<uint4*>(counts + first) = make_uint4(0u, 0u, 0u, 0u);
+            if (first + 4u == cells) starts[cells] = o.w + c[q].w;
+        } else {
+            const uint32_t t[5] = {o.x, o.y, o.z, o.w, o.w + c[q].w};
+#pragma unroll
+            for (int i = 0; i < 5; i++)
+                if (first + i <= cells && (i < 4 || first + 4u > cells)) starts[first + i] = t[i];
         }
     }
 }
@@ -172,9 +221,8 @@ cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const u
 // Per entity: position R8 (the key is recomputed: 6 instructions instead of 8 bytes), sorted position W8, slot W4
 // (coalesced, entity order: the flag readback and the periodic re-sort find an entity's slot there; nothing scattered but
 // the positions themselves).  One entity per lane per load: a warp's 32 consecutive entities form a few runs whose slots are
-// consecutive, so the 8-byte stores of a run coalesce into whole sectors; four independent chunks per warp iteration keep
-// four atomic round trips in flight per lane.
-constexpr int SCATTER_CHUNKS = 4;
+// consecutive, so the 8-byte stores of a run coalesce into whole sectors; eight independent chunks per warp iteration keep
+// eight atomic round trips in flight per lane (the kernel is bound by those round trips: 79 % long-scoreboard stalls).
 
 struct RunSlot {
     uint32_t base;     // head lanes: first slot of the run
@@ -189,14 +237,15 @@ __device__ __forceinline__ RunSlot run_slot_issue(uint32_t* __restrict__ cursor,
     r.my_head = 31u - __clz(heads & ((2u << lane) - 1u));
     r.base = 0;
     if (head && valid) {  // valid lanes precede invalid ones (tail of the array), so a run with a valid member has a valid head
-        const uint32_t above = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
-        const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
-        const uint32_t run = (next_head == 32u ? 0xffffffffu : ((1u << next_head) - 1u)) & ~((1u << lane) - 1u);
+        const uint32_t above = (heads >> lane) >> 1;  // heads behind this lane, shifted down to bit 0
+        const uint32_t len = above ? static_cast<uint32_t>(__ffs(above)) : 32u - lane;  // lanes up to the next head
+        const uint32_t run = (len == 32u ? 0xffffffffu : ((1u << len) - 1u)) << lane;
         r.base = atomicAdd(&cursor[key], static_cast<uint32_t>(__popc(run & valid_mask)));
     }
     return r;
 }
 
+template <int SCATTER_CHUNKS>
 __global__ void __launch_bounds__(256)
 cell_scatter_slots_kernel(uint32_t n, const float2* __restrict__ pos, uint32_t* __restrict__ cursor, float2* __restrict__ sorted_pos,
                           uint32_t* __restrict__ slot_of_entity, GridParams grid) {
@@ -282,13 +331,25 @@ int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t
     return 1;
 }
 
-int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof) {
-    const uint32_t tiles = csort_tiles(cells);
+// scan scratch: zero-initialised device memory of csort_scan_scratch_words(cells) 32-bit words; `epoch` differs from launch to launch, never 0
+size_t csort_scan_scratch_words(uint32_t cells) {
+    const size_t tiles = csort_tiles(cells);
+    return 2 * tiles + 4 * (tiles / 32 + 2) + 4;
+}
+
+int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* scratch, uint32_t scratch_tiles, uint32_t epoch, uint32_t* cell_start,
+                     uint32_t* error_flag, Profiler* prof) {
+    const uint32_t tiles = csort_tiles(cells);  // <= scratch_tiles (a band of a sharded handle scans fewer cells than the table has)
+    ScanState st;
+    st.group = scratch_tiles > 4096u ? 256u : 32u;
+    st.tile_total = reinterpret_cast<unsigned long long*>(scratch);
+    st.group_total = st.tile_total + scratch_tiles;
+    st.group_acc = st.group_total + (scratch_tiles / 32u + 2u);
+    st.ticket = reinterpret_cast<uint32_t*>(st.group_acc + (scratch_tiles / 32u + 2u));
     prof->begin(s, K_CELL_SCAN);
-    scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums);
-    scan_tiles_kernel<0><<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, tile_sums, cell_start);
+    scan_cells_kernel<<<tiles, SCAN_THREADS, 0, s>>>(cell_count, cells, cell_start, st, epoch, error_flag);
     prof->end(s);
-    return 2;
+    return 1;
 }
 
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
@@ -311,11 +372,12 @@ namespace msim {
 int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cursor, float2* sorted_pos, uint32_t* slot_of_entity,
                               const GridParams& grid, Profiler* prof) {
     if (n == 0) return 0;
-    uint32_t blocks = (n + 256u * SCATTER_CHUNKS - 1u) / (256u * SCATTER_CHUNKS);
+    constexpr uint32_t chunks = 8u;  // measured: 2 / 4 / 8 chunks in flight per warp = 85 / 82.6 / 76.3 us at 10 M entities
+    uint32_t blocks = (n + 256u * chunks - 1u) / (256u * chunks);
     const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
     if (blocks > resident) blocks = resident;
     prof->begin(s, K_CELL_SCATTER);
-    cell_scatter_slots_kernel<<<blocks, 256, 0, s>>>(n, pos, cursor, sorted_pos, slot_of_entity, grid);
+    cell_scatter_slots_kernel<chunks><<<blocks, 256, 0, s>>>(n, pos, cursor, sorted_pos, slot_of_entity, grid);
     prof->end(s);
     return 1;
 }

@@ -130,16 +130,17 @@ __device__ __forceinline__ uint32_t run_rank_finish(const RunRank& r, uint32_t l
 // Count-only variant (single-GPU counting sort, csort.cu): the run heads add their run length to the cell's counter with a
 // reduction that returns nothing (RED): no L2 round trip to wait for, the streaming loop never stalls on it.  The rank
 // inside the cell is taken later by the scatter kernel, whose atomics return the slot directly.
-__device__ __forceinline__ void run_count(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, uint32_t lane) {
+// `full`: every lane of the warp holds a live entity (warp-uniform; true everywhere but in the last warp of the array).
+__device__ __forceinline__ void run_count(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, bool full, uint32_t lane) {
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || key != prev;  // invalid lanes only exist in the padded tail: they may extend a run, never start a counted one
+    const bool head = lane == 0 || key != prev;  // dead lanes only exist in the padded tail: they may extend a run, never start a counted one
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-    if (head && valid) {
-        const uint32_t above = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
-        const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
-        const uint32_t run = (next_head == 32u ? 0xffffffffu : ((1u << next_head) - 1u)) & ~((1u << lane) - 1u);
-        atomicAdd(&cell_count[key], static_cast<uint32_t>(__popc(run & valid_mask)));
+    const uint32_t valid_mask = full ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+    if (head && (full || valid)) {
+        const uint32_t above = (heads >> lane) >> 1;  // heads behind this lane, shifted down to bit 0
+        const uint32_t len = above ? static_cast<uint32_t>(__ffs(above)) : 32u - lane;  // lanes up to the next head
+        const uint32_t run = (len == 32u ? 0xffffffffu : ((1u << len) - 1u)) << lane;
+        atomicAdd(&cell_count[key], full ? len : static_cast<uint32_t>(__popc(run & valid_mask)));
     }
 }
 
@@ -227,8 +228,9 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                 *reinterpret_cast<uint2*>(arrived_mask + w) = make_uint2(m0, m1);
             }
             if (MODE == MOVE_COUNT) {
-                run_count(cell_count, cell_key_of(q0, grid), e0 < n, lane);
-                run_count(cell_count, cell_key_of(q1, grid), e1 < n, lane);
+                const bool full = ((pi | 31u) * 2u + 1u) < n;  // warp-uniform
+                run_count(cell_count, cell_key_of(q0, grid), e0 < n, full, lane);
+                run_count(cell_count, cell_key_of(q1, grid), e1 < n, full, lane);
             }
             if (EMIT_KEYS) {
                 const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);

@@ -119,9 +119,9 @@ struct Profiler {
 
 // ---- launch tuning read once from the environment (api.cu)
 struct Tuning {
-    int arrive_beside_ctas_per_sm{0};  // MSIM_ARRIVE_BESIDE_CTAS=1..8: when pass B rides beside the query it is launched as a strided grid of that many
+    int arrive_beside_ctas_per_sm{1};  // MSIM_ARRIVE_BESIDE_CTAS=0..8: when pass B rides beside the query it is launched as a strided grid of that many
                                   // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots (it is latency-bound and
-                                  // only has to finish before the next move); 0 = full grid
+                                  // only has to finish before the next move); 0 = full grid.  Measured at 10 M entities: tick 361 / 334 / 339 us for 0 / 1 / 2
     int csort_max_cells_log2{25};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
                                   // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
@@ -158,7 +158,9 @@ void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler*
 void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int ncy, uint32_t* c0, uint32_t* c1);
 int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
                       const uint32_t* n_dev = nullptr);
-int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* tile_sums, uint32_t* cell_start, Profiler* prof);
+size_t csort_scan_scratch_words(uint32_t cells);
+int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* scratch, uint32_t scratch_tiles, uint32_t epoch, uint32_t* cell_start,
+                     uint32_t* error_flag, Profiler* prof);
 int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
                         float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
 // single-GPU default (count-only move pass): slots come from atomics on the scanned table `cursor`, which ends up shifted by one cell
