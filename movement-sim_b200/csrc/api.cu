@@ -313,10 +313,6 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
     }
 }
 
-// Single-GPU default rebuild + query (csort.cu cell_scatter_slots, collide_tiles.cu): the move pass only counts the cells, the scatter
-// takes the slots, the query reads aligned groups.  Sharded handles (ghost slots, ranks maintained through the exchange), the
-// colours-only mode and the onesweep rebuild keep the kernels with per-entity keys and ranks.
-inline bool tiles_path(const msim_handle* h) { return h->use_csort && !h->sharded && !(h->flags & MSIM_FLAG_NO_PAIR_COUNT); }
 
 // MSIM_L2_PERSIST_ROADS=1 (opt-in, not yet run on hardware): the road table (32 B per road, 22 MB for the Munich stand-in) is declared a
 // persisting L2 access-policy window on both streams, so that pass B's dependent gathers (two 16-byte loads of the current road, two of the
@@ -527,11 +523,11 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
         if (rc != MSIM_OK) return rc;
     }
     const int passes = (h->key_bits + RADIX_BITS - 1) / RADIX_BITS;
-    // what the neighbour rebuild can take over from this pass: the counting sort's per-cell ranks, or the
+    // what the neighbour rebuild can take over from this pass: the counting sort's per-cell population, or the
     // onesweep digit histograms.  Sharded handles change their key set in the exchange that follows.
     const bool fuse_count = emit && h->use_csort && (!h->sharded || shard);
     const bool fuse_hist = emit && !h->use_csort && !h->sharded;
-    const bool tiles = emit && tiles_path(h);  // count only: no keys, no ranks (the scatter recomputes the key and takes the slot)
+    const bool count_only = fuse_count && !h->sharded;  // no keys written: the scatter recomputes the key and takes the slot
     h->n_ghost = 0;
     h->count_fused = fuse_count && h->sharded;
     if (fuse_count) {
@@ -540,9 +536,8 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
     join_side(h);  // the previous pass B must have rewritten the targets before they are read again
     h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
-                               emit && !tiles ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
-                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, h->rank, &h->prof,
-                               dev_owned(h), shard);
+                               emit && !count_only ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
+                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, &h->prof, dev_owned(h), shard);
     h->counts_valid = fuse_count;
     if (emit && h->side && (!h->sharded || shard)) {
         h->arrive_deferred = true;  // a collision pass follows and needs only positions: pass B is launched beside its query
@@ -553,9 +548,8 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     h->cur ^= 1;
     h->has_moved = true;
     h->band_valid = false;  // entities may have crossed the band's rows until the next pack + integrate
-    h->keys_valid = emit && !tiles;
+    h->keys_valid = emit && !count_only;
     h->hist_valid = fuse_hist;
-    if (emit && !tiles) h->slots_valid = false;  // a pass with keys overwrites h->rank; the counting pass leaves the slot map of the last collision pass alone
     h->move_passes++;
     return MSIM_OK;
 }
@@ -588,12 +582,14 @@ int reorder_storage(msim_handle* h) {
         a.slot_of = nullptr;
         a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
         a.flag_entity = h->flag_entity;
-        a.first_owned = h->cell_start + static_cast<size_t>(h->band_lo) * static_cast<size_t>(h->grid.ncx);
+        a.first_owned = h->cell_start - 1 + static_cast<size_t>(h->band_lo) * static_cast<size_t>(h->grid.ncx);  // the shifted table: run starts
         a.n_owned_dev = h->dev_counts + DEV_N_OWNED;
         a.sorted_pos = h->sorted_pos;
         a.pos_cur_new = h->pos[h->cur];  // not read by the kernel: sorted_pos holds the same positions in the new order
         a.error_word = h->dev_counts + DEV_SHARD_ERROR;
+        h->launches += launch_invert_slots(h->stream, launch_total(h), h->rank, h->sorted_idx, &h->prof, dev_total(h));  // slot -> entity on demand
         h->launches += launch_reorder_sharded(h->stream, launch_owned(h), h->cap / 32 + 2, h->sorted_idx, h->flag_sorted, a, &h->prof);
+        h->slots_valid = false;
         float2* old_prev = h->pos[h->cur ^ 1];
         h->pos[h->cur ^ 1] = h->pos_spare;
         h->pos_spare = old_prev;
@@ -621,7 +617,7 @@ int reorder_storage(msim_handle* h) {
     a.slot_of = h->slot_of;
     a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
     a.flag_entity = h->flag_entity;
-    if (h->slots_valid) h->launches += launch_invert_slots(h->stream, h->n, h->rank, h->sorted_idx, &h->prof);  // tiles path: slot -> entity on demand
+    if (h->slots_valid) h->launches += launch_invert_slots(h->stream, h->n, h->rank, h->sorted_idx, &h->prof);  // counting sort: slot -> entity on demand
     h->launches += launch_reorder(h->stream, h->n, h->sorted_idx, h->flag_sorted, a, &h->prof);
     h->slots_valid = false;
     // the sorted positions ARE the new current positions: swap buffers instead of copying
@@ -651,21 +647,7 @@ int enqueue_collide(msim_handle* h) {
     if (consume_init_dispatch(h)) return MSIM_OK;
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
-    const bool tiles = tiles_path(h);
-    if (tiles) {
-        if (!h->counts_valid) {  // no counting move pass in front of this dispatch (first dispatch after an upload, grid change)
-            prepare_counts(h);
-            h->launches += launch_cell_count_pos(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_count, h->grid, &h->prof);
-        }
-        h->counts_valid = false;
-        h->launches += scan_cells(h, 0, h->grid.ncells);
-        h->counts_dirty = false;
-        h->launches += launch_cell_scatter_slots(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_start, h->sorted_pos, h->rank, h->grid, &h->prof);
-        launch_deferred_arrive(h, true);
-        h->launches += launch_query_tiles(h->stream, h->n, h->sorted_pos, h->cell_start - 1, h->flag_sorted, h->grid, h->counters, h->stripes, &h->prof);
-        h->slots_valid = true;
-        h->keys_valid = false;
-    } else if (!h->keys_valid) {
+    if (!h->keys_valid && (h->sharded || !h->use_csort)) {  // (the unsharded counting sort works on positions: no keys)
         rc = refresh_counts(h);  // (asynchronous sharded ticks) keygen is sized by the exact owned count
         if (rc != MSIM_OK) return rc;
         h->launches += launch_keygen(h->stream, h->n, h->pos[h->cur], h->keys, h->grid, &h->prof);
@@ -674,27 +656,29 @@ int enqueue_collide(msim_handle* h) {
     }
     const uint32_t total = launch_total(h);  // ghosts (multi-GPU halo) sit behind the owned entities
     const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
-    if (tiles) {
-        // done above
-    } else if (h->use_csort) {
+    if (h->use_csort) {
         // sharded handles: the counter table is cleared / scanned over the band's cell range only, keys outside it
         // (a leaver that jumped two rows while the boundary moved: out of everybody's reach) are left out of the
         // order, and the number of sorted slots is the scan's grand total, read by the query from the table itself
         uint32_t c0 = 0, c1 = h->grid.ncells;
         const bool band = h->sharded && h->band_valid;
         if (band) csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &c0, &c1);
-        if (!h->counts_valid) {  // keys came from keygen or changed in a shard exchange: count them now
+        if (!h->counts_valid) {  // no counting move pass in front of this dispatch, or the keys changed in a shard exchange: count now
             prepare_counts(h);
-            h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, h->rank, c0, c1, &h->prof, dev_total(h));
+            if (h->sharded) h->launches += launch_cell_count(h->stream, total, h->keys, h->cell_count, c0, c1, &h->prof, dev_total(h));
+            else h->launches += launch_cell_count_pos(h->stream, h->sm_count, h->n, h->pos[h->cur], h->cell_count, h->grid, &h->prof);
         }
         h->counts_valid = false;
         h->launches += scan_cells(h, c0, c1);
         h->counts_dirty = false;  // the scan zeroed every counter it read, and nothing was counted outside [c0, c1)
-        h->launches += launch_cell_scatter(h->stream, total, h->keys, h->rank, h->pos[h->cur], h->cell_start, h->sorted_pos, h->sorted_idx, &h->prof,
-                                           dev_total(h));
+        // the scatter's atomics turn cell_start into the table of run ENDS; read one word earlier it is the table of run starts
+        h->launches += launch_cell_scatter_slots(h->stream, h->sm_count, total, h->pos[h->cur], h->sharded ? h->keys : nullptr, h->cell_start, h->sorted_pos,
+                                                 h->rank, h->grid, c0, c1, &h->prof, dev_total(h));
         launch_deferred_arrive(h, true);
-        h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, nullptr, h->cell_start, h->flag_sorted, h->grid, count_pairs,
-                                    h->counters, h->stripes, &h->prof, h->sharded ? h->cell_start + c1 : nullptr, dev_owned(h));
+        const uint32_t* tab = h->cell_start - 1;
+        h->launches += launch_query_tiles(h->stream, total, h->sorted_pos, tab, h->flag_sorted, h->grid, count_pairs, h->counters, h->stripes, &h->prof,
+                                          h->sharded ? tab + c1 : nullptr, band, h->band_lo, h->band_hi);
+        h->slots_valid = true;
     } else {
         h->launches += launch_sort(h->stream, total, h->keys, h->sort_a, h->sort_b, h->key_bits, h->ws, &h->sorted,
                                    h->hist_valid && h->n_ghost == 0 && !h->async_counts, &h->prof, dev_total(h));
@@ -702,8 +686,9 @@ int enqueue_collide(msim_handle* h) {
         h->launches += launch_build_cells(h->stream, total, h->sorted, h->pos[h->cur], h->sorted_pos, h->sorted_idx, h->cell_range, h->grid, h->counters,
                                           &h->prof, dev_total(h));
         launch_deferred_arrive(h, true);
-        h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, h->cell_range, nullptr, h->flag_sorted, h->grid, count_pairs,
+        h->launches += launch_query(h->stream, total, launch_owned(h), h->sorted_idx, h->sorted_pos, h->cell_range, h->flag_sorted, h->grid, count_pairs,
                                     h->counters, h->stripes, &h->prof, dev_total(h), dev_owned(h));
+        h->slots_valid = false;
     }
     h->collide_total = total;
     h->collide_owned = launch_owned(h);
@@ -1281,7 +1266,6 @@ ShardArrays shard_arrays(msim_handle* h) {
     a.arrived = h->arrived;
     if (h->count_fused) {
         a.cell_count = h->cell_count;
-        a.rank = h->rank;
         csort_band(h->grid.ncells, h->grid.ncx, h->band_lo, h->band_hi, h->grid.ncy, &a.c0, &a.c1);
     }
     return a;

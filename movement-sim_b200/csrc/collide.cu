@@ -56,11 +56,11 @@ build_cells_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const un
 //
 // GHOSTS: slots whose entity index is >= n_owned belong to a neighbouring GPU (halo): they are
 // candidates for everybody else but get no flag and count no pairs here — their owner does that.
-template <bool COUNT_PAIRS, bool GHOSTS, bool PREFIX>
+template <bool COUNT_PAIRS, bool GHOSTS>
 __global__ void __launch_bounds__(QUERY_THREADS)
 query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ n_owned_dev,
              const uint32_t* __restrict__ sorted_idx, const float2* __restrict__ sorted_pos,
-             const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, uint8_t* __restrict__ flag_sorted, GridParams grid,
+             const uint2* __restrict__ cell_range, uint8_t* __restrict__ flag_sorted, GridParams grid,
              unsigned long long* __restrict__ stripes) {
     __shared__ __align__(16) float2 s_above[QUERY_WINDOW];
     __shared__ __align__(16) float2 s_own[QUERY_WINDOW];
@@ -93,28 +93,15 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
         cy = min(max(cy, 0), grid.ncy - 1);
         x0 = max(cx - 1, 0);
         x1 = min(cx + 1, grid.ncx - 1);
-        row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy, x0, x1, own_lo, own_hi);
-        if (cy > 0) row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy - 1, x0, x1, ab_lo, ab_hi);
+        row_run(cell_range, grid.ncx, cy, x0, x1, own_lo, own_hi);
+        if (cy > 0) row_run(cell_range, grid.ncx, cy - 1, x0, x1, ab_lo, ab_hi);
         else ab_lo = ab_hi = 0;
     }
 
     // CTA-wide hull of the windows: min of the run starts, max of the run ends
     const bool has_above = mine && ab_lo < ab_hi;
     uint32_t w_own_lo = 0xffffffffu, w_ab_lo = 0xffffffffu, w_ab_hi = 0;
-    if (PREFIX && !GHOSTS) {
-        // every slot is a querying entity and the run bounds come from ONE prefix table: they are non-decreasing in the
-        // slot index, so the hull is [bound of the CTA's first slot, bound of its last slot] - no reduction needed.
-        // (Row 0 has no row above: bound 0, which keeps the hull a superset; such a CTA may fall back to the global scan.)
-        if (threadIdx.x == 0) {
-            s_red[0][0] = own_lo;
-            s_red[1][0] = cy > 0 ? ab_lo : 0u;
-        }
-        if (j == min(block_base + QUERY_THREADS, n) - 1u) s_red[2][0] = cy > 0 ? ab_hi : 0u;
-        __syncthreads();
-        w_own_lo = s_red[0][0];
-        w_ab_lo = s_red[1][0];
-        w_ab_hi = s_red[2][0];
-    } else {
+    {
         uint32_t r0 = __reduce_min_sync(0xffffffffu, mine ? own_lo : 0xffffffffu);
         uint32_t r1 = __reduce_min_sync(0xffffffffu, has_above ? ab_lo : 0xffffffffu);
         uint32_t r2 = __reduce_max_sync(0xffffffffu, has_above ? ab_hi : 0u);
@@ -176,7 +163,7 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
         if (!hit) hit = any_in_range(sorted_pos, max(j + 1, own_lo), own_hi, p, thr);
         if (!hit && cy + 1 < grid.ncy) {
             uint32_t lo, hi;
-            row_run<PREFIX>(cell_range, cell_start, grid.ncx, cy + 1, x0, x1, lo, hi);
+            row_run(cell_range, grid.ncx, cy + 1, x0, x1, lo, hi);
             hit = any_in_range(sorted_pos, lo, hi, p, thr);
         }
         flag_sorted[j] = hit ? 1 : 0;
@@ -260,20 +247,18 @@ int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const
 }
 
 int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
-                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters,
-                 unsigned long long* stripes, Profiler* prof, const uint32_t* n_dev, const uint32_t* n_owned_dev) {
+                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
+                 const uint32_t* n_dev, const uint32_t* n_owned_dev) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + QUERY_THREADS - 1) / QUERY_THREADS;
-    const bool ghosts = n_owned < n || n_owned_dev != nullptr, prefix = cell_start != nullptr;
+    const bool ghosts = n_owned < n || n_owned_dev != nullptr;
     prof->begin(s, K_QUERY);
-#define MSIM_QUERY(CP, GH, PF) \
-    query_kernel<CP, GH, PF><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, n_dev, n_owned_dev, sorted_idx, sorted_pos, cell_range, cell_start, flag_sorted, grid, stripes)
+#define MSIM_QUERY(CP, GH) \
+    query_kernel<CP, GH><<<blocks, QUERY_THREADS, 0, s>>>(n, n_owned, n_dev, n_owned_dev, sorted_idx, sorted_pos, cell_range, flag_sorted, grid, stripes)
     if (count_pairs) {
-        if (ghosts) { if (prefix) MSIM_QUERY(true, true, true); else MSIM_QUERY(true, true, false); }
-        else { if (prefix) MSIM_QUERY(true, false, true); else MSIM_QUERY(true, false, false); }
+        if (ghosts) MSIM_QUERY(true, true); else MSIM_QUERY(true, false);
     } else {
-        if (ghosts) { if (prefix) MSIM_QUERY(false, true, true); else MSIM_QUERY(false, true, false); }
-        else { if (prefix) MSIM_QUERY(false, false, true); else MSIM_QUERY(false, false, false); }
+        if (ghosts) MSIM_QUERY(false, true); else MSIM_QUERY(false, false);
     }
 #undef MSIM_QUERY
     fold_counters_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);

@@ -1,5 +1,4 @@
-// collide_common.cuh - device helpers of the collision query shared by collide.cu (query_kernel) and collide_paired.cu (the opt-in
-// two-slots-per-thread variant): distance test, candidate scans over global / shared memory, cell-run look-up, 1-D TMA bulk copy.
+// collide_common.cuh - device helpers of the collision query shared by collide.cu (query_kernel) and collide_tiles.cu (query_tiles_kernel): distance test, candidate scans over global / shared memory, cell-run look-up, 1-D TMA bulk copy.
 // Included inside namespace msim { namespace { ... } } of the including translation unit.
 #pragma once
 
@@ -52,15 +51,7 @@ __device__ __forceinline__ bool any_in_range(const float2* __restrict__ sorted_p
 }
 
 // the three cells x0..x1 of one grid row are adjacent keys = one contiguous run [lo, hi) of the sorted order
-template <bool PREFIX>
-__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, const uint32_t* __restrict__ cell_start, int ncx, int yy, int x0, int x1,
-                                        uint32_t& lo, uint32_t& hi) {
-    if (PREFIX) {  // counting-sort path: exclusive prefix table, run = [start[first cell], start[last cell + 1])
-        const uint32_t* row = cell_start + static_cast<size_t>(yy) * ncx;
-        lo = __ldg(row + x0);
-        hi = __ldg(row + x1 + 1);
-        return;
-    }
+__device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, int ncx, int yy, int x0, int x1, uint32_t& lo, uint32_t& hi) {
     const uint2* row = cell_range + static_cast<size_t>(yy) * ncx;
     lo = 0xffffffffu;
     hi = 0u;

@@ -89,16 +89,34 @@ __device__ __forceinline__ uint32_t count_last_group(const float4* __restrict__ 
     return (below_j > 0u ? c0 : 0u) + (below_j > 1u ? c1 : 0u) + (below_j > 2u ? c2 : 0u);
 }
 
-template <int TILES_THREADS>
+// true iff some candidate of groups [g0, g1) is in range (colours-only mode: the first hit ends the scan)
+__device__ __forceinline__ bool any_in_groups(const float4* __restrict__ base, uint32_t g0, uint32_t g1, float2 p, float thr) {
+#pragma unroll 1
+    for (uint32_t g = g0; g < g1; g++) {
+        const Group q = load_group(base + 2u * g);
+        if (hits_in_pair(q.a, p, thr) + hits_in_pair(q.b, p, thr)) return true;
+    }
+    return false;
+}
+
+constexpr int TILES_THREADS = 128;  // measured: 64 / 128 / 256 threads per CTA = 170.7 / 169.4 / 173.6 us in the tick
+
+// COUNT_PAIRS = false (MSIM_FLAG_NO_PAIR_COUNT): colours only, a thread stops at its first neighbour.
+// GHOSTS (sharded handles): the sorted order also holds the neighbours' boundary rows and this tick's leavers, whose cell rows lie
+// outside the band [row_lo, row_hi): candidates for everybody else, but they get no flag and count no pairs here - their owner does
+// that.  Every pair is counted by the GPU that owns its higher slot, so the all-reduced sum equals the single-GPU count.  The
+// number of sorted slots is the scan's grand total, read from the table itself (n_dev); `n` then only sizes the grid.
+template <bool COUNT_PAIRS, bool GHOSTS>
 __global__ void __launch_bounds__(TILES_THREADS)
-query_tiles_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint32_t* __restrict__ tab, uint8_t* __restrict__ flag_sorted, GridParams grid,
-                   unsigned long long* __restrict__ stripes) {
+query_tiles_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float2* __restrict__ sorted_pos, const uint32_t* __restrict__ tab,
+                   uint8_t* __restrict__ flag_sorted, GridParams grid, unsigned long long* __restrict__ stripes, int row_lo, int row_hi) {
+    const uint32_t n = GHOSTS && n_dev ? *n_dev : n_host;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp_base = (blockIdx.x * TILES_THREADS + threadIdx.x) & ~31u;
     if (warp_base >= n) return;
     const uint32_t j_raw = warp_base + lane;
-    const bool mine = j_raw < n;
-    const uint32_t j = mine ? j_raw : n - 1u;  // the lanes behind the last slot repeat it (and keep their results to themselves)
+    const bool in_range = j_raw < n;
+    const uint32_t j = in_range ? j_raw : n - 1u;  // the lanes behind the last slot repeat it (and keep their results to themselves)
 
     // ---- this lane's runs: three loads from the prefix table ---------------------------------------------------------------
     const float2 p = __ldg(sorted_pos + j);
@@ -106,10 +124,15 @@ query_tiles_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint
     int cy = __float2int_rd(__fmul_rn(p.y, grid.inv_cell));
     cx = min(max(cx, 0), grid.ncx - 1);
     cy = min(max(cy, 0), grid.ncy - 1);
+    const bool mine = in_range && (!GHOSTS || (cy >= row_lo && cy < row_hi));
+    if (GHOSTS && !__any_sync(0xffffffffu, mine)) {  // a warp of ghosts (the halo rows): nothing to find out here
+        if (in_range) flag_sorted[j] = 0;
+        return;
+    }
     const uint32_t ncx = static_cast<uint32_t>(grid.ncx);
     const uint32_t r = static_cast<uint32_t>(cy) * ncx;                               // < 2^27 cells: 32-bit indices throughout
     const uint32_t x0 = static_cast<uint32_t>(max(cx - 1, 0)), x1e = min(static_cast<uint32_t>(cx) + 2u, ncx);
-    const uint32_t own_lo = __ldg(tab + (r + x0));
+    uint32_t own_lo = __ldg(tab + (r + x0));
     uint32_t ab_lo = 0u, ab_hi = 0u;
     if (cy > 0) {
         ab_lo = __ldg(tab + (r - ncx + x0));
@@ -118,22 +141,37 @@ query_tiles_kernel(uint32_t n, const float2* __restrict__ sorted_pos, const uint
 
     uint32_t pairs = 0;
     const float thr = grid.hit_threshold;
+    uint32_t scan_hi = j;  // own run [own_lo, scan_hi)
+    if (GHOSTS && !mine) {  // a ghost among owned slots: empty runs, nothing counted
+        ab_lo = ab_hi = 0u;
+        own_lo = scan_hi = j & ~3u;
+    }
     // aligned groups are only safe when the slots around a run are far-away cells: above run and own run >= 3 slots apart
     const bool close_runs = ab_hi != ab_lo && own_lo - ab_hi < 3u;
+    const float4* G = reinterpret_cast<const float4*>(sorted_pos);
+    const uint32_t ga0 = ab_lo >> 2, ga1 = ab_hi != ab_lo ? (ab_hi + 3u) >> 2 : ga0;
+    bool hit;
     if (__any_sync(0xffffffffu, close_runs)) {  // exact scalar scans (tiny or nearly empty maps)
-        pairs = count_in_range(sorted_pos, ab_lo, ab_hi, p, thr) + count_in_range(sorted_pos, own_lo, j, p, thr);
+        if (COUNT_PAIRS) {
+            pairs = count_in_range(sorted_pos, ab_lo, ab_hi, p, thr) + count_in_range(sorted_pos, own_lo, scan_hi, p, thr);
+            hit = pairs != 0u;
+        } else {
+            hit = any_in_range(sorted_pos, own_lo, scan_hi, p, thr) || any_in_range(sorted_pos, ab_lo, ab_hi, p, thr);
+        }
+    } else if (COUNT_PAIRS) {
+        pairs = count_groups(G, ga0, ga1, p, thr) + count_groups(G, own_lo >> 2, scan_hi >> 2, p, thr) +
+                count_last_group(G + 2u * (scan_hi >> 2), scan_hi & 3u, p, thr);
+        hit = pairs != 0u;
     } else {
-        const float4* G = reinterpret_cast<const float4*>(sorted_pos);
-        const uint32_t ga0 = ab_lo >> 2, ga1 = ab_hi != ab_lo ? (ab_hi + 3u) >> 2 : ga0;
-        pairs = count_groups(G, ga0, ga1, p, thr) + count_groups(G, own_lo >> 2, j >> 2, p, thr) + count_last_group(G + 2u * (j >> 2), j & 3u, p, thr);
+        hit = count_last_group(G + 2u * (scan_hi >> 2), scan_hi & 3u, p, thr) != 0u || any_in_groups(G, own_lo >> 2, scan_hi >> 2, p, thr) ||
+              any_in_groups(G, ga0, ga1, p, thr);
     }
-    bool hit = pairs != 0u;
     // nothing below: look at the slots above (rest of the own row, then the row below), where the first hit is enough
-    if (!hit) {
+    if (!hit && mine) {
         hit = any_in_range(sorted_pos, j + 1u, __ldg(tab + (r + x1e)), p, thr);
         if (!hit && cy + 1 < grid.ncy) hit = any_in_range(sorted_pos, __ldg(tab + (r + ncx + x0)), __ldg(tab + (r + ncx + x1e)), p, thr);
     }
-    if (mine) flag_sorted[j] = hit ? 1 : 0;
+    if (in_range) flag_sorted[j] = hit ? 1 : 0;
 
     // ---- totals: one reduction (no return value, nothing waits) per counter and warp into a striped counter; a one-CTA kernel folds the stripes
     const uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit && mine));
@@ -176,15 +214,19 @@ __global__ void __launch_bounds__(COUNTER_STRIPES) fold_stripes_kernel(unsigned 
 
 }  // namespace
 
-int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, Counters* counters,
-                       unsigned long long* stripes, Profiler* prof) {
+int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs,
+                       Counters* counters, unsigned long long* stripes, Profiler* prof, const uint32_t* n_dev, bool ghosts, uint32_t row_lo, uint32_t row_hi) {
     if (n == 0) return 0;
-    static const int threads = [] { const char* e = getenv("MSIM_TILES_THREADS"); const int v = e ? atoi(e) : 128; return v == 64 || v == 256 ? v : 128; }();
-    const uint32_t blocks = (n + threads - 1) / threads;
+    const uint32_t blocks = (n + TILES_THREADS - 1) / TILES_THREADS;
+    const int lo = static_cast<int>(row_lo), hi = static_cast<int>(row_hi);
     prof->begin(s, K_QUERY);
-    if (threads == 64) query_tiles_kernel<64><<<blocks, 64, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
-    else if (threads == 256) query_tiles_kernel<256><<<blocks, 256, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
-    else query_tiles_kernel<128><<<blocks, 128, 0, s>>>(n, sorted_pos, tab, flag_sorted, grid, stripes);
+    if (ghosts) {
+        if (count_pairs) query_tiles_kernel<true, true><<<blocks, TILES_THREADS, 0, s>>>(n, n_dev, sorted_pos, tab, flag_sorted, grid, stripes, lo, hi);
+        else query_tiles_kernel<false, true><<<blocks, TILES_THREADS, 0, s>>>(n, n_dev, sorted_pos, tab, flag_sorted, grid, stripes, lo, hi);
+    } else {
+        if (count_pairs) query_tiles_kernel<true, false><<<blocks, TILES_THREADS, 0, s>>>(n, nullptr, sorted_pos, tab, flag_sorted, grid, stripes, 0, 0);
+        else query_tiles_kernel<false, false><<<blocks, TILES_THREADS, 0, s>>>(n, nullptr, sorted_pos, tab, flag_sorted, grid, stripes, 0, 0);
+    }
     fold_stripes_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
     prof->end(s);
     return 2;

@@ -1,23 +1,22 @@
-// csort.cu — single-digit radix sort of the cell keys (a counting sort over the whole key): the
-// opt-in (MSIM_FLAG_SORT_COUNTING) per-tick rebuild of the neighbour structure for populations whose
-// storage order is spatially coherent; the per-cell counter table must fit the L2
+// csort.cu — single-digit radix sort of the cell keys (a counting sort over the whole key): the per-tick rebuild of the
+// neighbour structure for populations whose storage order is spatially coherent; the per-cell counter table must fit the L2
 // (Munich: 4.77 M cells x 4 B = 19 MB of B200's 126 MB).
 //
-// An LSD radix sort needs one pass per digit; with a table as large as the key space the digit IS the
-// key and one pass suffices:
-//   count    rank[e] = atomicAdd(&cell_count[key[e]], 1)   — fused into the move kernel (move.cu), or
-//            cell_count_kernel below when the keys did not come from a move pass (sharded / keygen)
+// An LSD radix sort needs one pass per digit; with a table as large as the key space the digit IS the key and one pass suffices:
+//   count    cell_count[key] += 1 per entity, as one RED per run of equal keys in adjacent lanes - fused into the move kernel
+//            (move.cu), or cell_count_kernel below when the dispatch was not preceded by a counting move pass
 //   scan     cell_start = exclusive prefix sum of cell_count (one kernel, one pass over the table)
-//   scatter  slot = cell_start[key] + rank: sorted_pos[slot] = pos[e], sorted_idx[slot] = e
-// Per entity that is key W4 + rank W4 in the move pass and key R4 + rank R4 + pos R8 + pos W8 + idx W4
-// in the scatter = 36 B, against 44 B + 24 B for three onesweep passes plus the gather — and far fewer
-// instructions (no ranking by warp votes).  The prefix table doubles as the cell directory: the run
-// of cells x0..x1 of a row is [cell_start[row*ncx+x0], cell_start[row*ncx+x1+1]).
-// The order of entities inside one cell is the arrival order of the atomics (not deterministic);
-// nothing observable depends on it: flags and the unique-pair count are order-independent.
-// Measured (profiles/r1_sort_paths.md): with entities in random index order the 20 M scattered 4/8-byte
-// stores cost 484 us at 10 M entities against 3 x 90 us for the staged onesweep scatter, so onesweep
-// (sort.cu) stays the default; with cell-ordered storage the scatter drops to 92 us and this path wins.
+//   scatter  slot = atomicAdd(&cell_start[key], run length): sorted_pos[slot] = pos[e], slot_of_entity[e] = slot
+// When the scatter is done cell_start[c] = start(c) + count(c) = start(c + 1): the same table read one word earlier (the scan
+// leaves a 0 in front of its first word) is the prefix table the query walks, tab[c] = first slot of cell c, and the cell
+// directory: the run of cells x0..x1 of a row is [tab[row*ncx+x0], tab[row*ncx+x1+1]).
+// Per entity: position R8 (+ key R4 on sharded handles; otherwise the key is recomputed: 6 instructions instead of 8 bytes),
+// sorted position W8, slot W4 (coalesced, entity order: the flag readback and the periodic re-sort find an entity's slot there).
+// The order of entities inside one cell is the arrival order of the atomics (not deterministic); nothing observable depends
+// on it: flags and the unique-pair count are order-independent.
+// Measured (profiles/r1_sort_paths.md): with entities in random index order the scattered stores cost 4-5 times as much, so
+// the storage is kept in cell order (periodic re-sort, pack.cu); upload-ordered storage (MSIM_FLAG_NO_REORDER) takes the
+// staged onesweep radix sort (sort.cu) unless MSIM_FLAG_SORT_COUNTING asks for this path.
 #include <cstdlib>
 
 #include "msim_internal.h"
@@ -29,14 +28,15 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096 cells per CTA
 
+// count pass for keys that did not come from a counting move pass (sharded handles after a host-side exchange)
 __global__ void __launch_bounds__(256)
-cell_count_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
-                  uint32_t* __restrict__ rank, uint32_t c0, uint32_t c1) {
+cell_count_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count, uint32_t c0,
+                  uint32_t c1) {
     const uint32_t n = n_dev ? *n_dev : n_host;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint32_t k = __ldcs(keys + e);
         // keys outside the counted cell range [c0, c1) (sharded handles only) stay out of the order
-        rank[e] = (k - c0 < c1 - c0) ? atomicAdd(&cell_count[k], 1u) : CSORT_SKIP;
+        if (k - c0 < c1 - c0) atomicAdd(&cell_count[k], 1u);
     }
 }
 
@@ -136,6 +136,7 @@ scan_cells_kernel(uint32_t* __restrict__ counts, uint32_t cells, uint32_t* __res
     const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
     const uint32_t g = tile / st.group, in_group = tile - g * st.group;
     if (threadIdx.x == 0) {
+        if (tile == 0u) starts[-1] = 0u;  // the word in front of the table: tab[first cell] = 0 for the readers of the shifted table
         st_relaxed_u64(st.tile_total + tile, tag | total);
         const uint32_t members = min(st.group, gridDim.x - g * st.group);
         const unsigned long long old = atomicAdd(st.group_acc + g, (1ull << 32) | total);
@@ -187,91 +188,72 @@ scan_cells_kernel(uint32_t* __restrict__ counts, uint32_t cells, uint32_t* __res
     }
 }
 
-// two entities per thread: 128-bit position loads, 64-bit key / rank loads.  Measured and rejected (profiles/r1_final.md):
-// four entities per thread (+20 %: a warp's stores spread over 128 slots and coalesce less) and a software pipeline that
-// issues the next pair's streaming loads before the dependent cell-start gathers (+3 %).
-__global__ void __launch_bounds__(256)
-cell_scatter_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint2* __restrict__ keys, const uint2* __restrict__ rank,
-                    const float4* __restrict__ pos, const uint32_t* __restrict__ starts, float2* __restrict__ sorted_pos, uint32_t* __restrict__ sorted_idx) {
-    const uint32_t n = n_dev ? *n_dev : n_host;
-    const uint32_t pairs = (n + 1u) >> 1;
-    for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < pairs; pi += gridDim.x * blockDim.x) {
-        const uint2 k = __ldcs(keys + pi), r = __ldcs(rank + pi);
-        const float4 p = __ldcs(pos + pi);
-        const uint32_t e0 = pi * 2u, e1 = e0 + 1u;
-        if (r.x != CSORT_SKIP) {
-            const uint32_t s0 = __ldg(starts + k.x) + r.x;
-            sorted_pos[s0] = make_float2(p.x, p.y);
-            sorted_idx[s0] = e0;
-        }
-        if (e1 < n && r.y != CSORT_SKIP) {
-            const uint32_t s1 = __ldg(starts + k.y) + r.y;
-            sorted_pos[s1] = make_float2(p.z, p.w);
-            sorted_idx[s1] = e1;
-        }
-    }
-}
-
-
-// ---- slot-returning scatter (single-GPU default) ------------------------------------------------------------------
-// The move pass only COUNTED the cells (one RED per run, move.cu); here the run heads take their slots from the scanned
-// table itself: base = atomicAdd(&cursor[key], run length), where cursor[c] starts out as start(c).  When the kernel is
-// done cursor[c] = start(c) + count(c) = start(c + 1), so the same table, read one word earlier (the word in front of it is
-// a permanent 0), is the prefix table the query needs: tab[c] = start(c), tab[ncells] = n.
-// Per entity: position R8 (the key is recomputed: 6 instructions instead of 8 bytes), sorted position W8, slot W4
-// (coalesced, entity order: the flag readback and the periodic re-sort find an entity's slot there; nothing scattered but
-// the positions themselves).  One entity per lane per load: a warp's 32 consecutive entities form a few runs whose slots are
-// consecutive, so the 8-byte stores of a run coalesce into whole sectors; eight independent chunks per warp iteration keep
-// eight atomic round trips in flight per lane (the kernel is bound by those round trips: 79 % long-scoreboard stalls).
-
+// ---- slot-returning scatter -----------------------------------------------------------------------------------------------------
+// The count pass only COUNTED the cells; here the run heads take their slots from the scanned table itself:
+// base = atomicAdd(&cursor[key], run length), where cursor[c] starts out as start(c).  One entity per lane per load: a warp's 32
+// consecutive entities form a few runs whose slots are consecutive, so the 8-byte stores of a run coalesce into whole sectors;
+// eight independent chunks per warp iteration keep eight atomic round trips in flight per lane (the kernel is bound by those
+// round trips: 79 % long-scoreboard stalls; 2 / 4 / 8 chunks = 85 / 82.6 / 76.3 us at 10 M entities).
+// BAND (sharded handles): the element count lives in device memory, the keys are read (the exchange kernels maintain them), and
+// keys outside the band's cell range [c0, c1) stay out of the order (slot CSORT_SKIP).
 struct RunSlot {
     uint32_t base;     // head lanes: first slot of the run
     uint32_t my_head;  // lane of the head of this lane's run
 };
 __device__ __forceinline__ RunSlot run_slot_issue(uint32_t* __restrict__ cursor, uint32_t key, bool valid, uint32_t lane) {
+    if (!valid) key = 0xffffffffu - lane;  // a key nobody shares: its own run, never issued
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool head = lane == 0 || key != prev;
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
     RunSlot r;
     r.my_head = 31u - __clz(heads & ((2u << lane) - 1u));
     r.base = 0;
-    if (head && valid) {  // valid lanes precede invalid ones (tail of the array), so a run with a valid member has a valid head
+    if (head && valid) {
         const uint32_t above = (heads >> lane) >> 1;  // heads behind this lane, shifted down to bit 0
         const uint32_t len = above ? static_cast<uint32_t>(__ffs(above)) : 32u - lane;  // lanes up to the next head
-        const uint32_t run = (len == 32u ? 0xffffffffu : ((1u << len) - 1u)) << lane;
-        r.base = atomicAdd(&cursor[key], static_cast<uint32_t>(__popc(run & valid_mask)));
+        r.base = atomicAdd(&cursor[key], len);
     }
     return r;
 }
 
-template <int SCATTER_CHUNKS>
+template <int SCATTER_CHUNKS, bool BAND>
 __global__ void __launch_bounds__(256)
-cell_scatter_slots_kernel(uint32_t n, const float2* __restrict__ pos, uint32_t* __restrict__ cursor, float2* __restrict__ sorted_pos,
-                          uint32_t* __restrict__ slot_of_entity, GridParams grid) {
+cell_scatter_slots_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float2* __restrict__ pos, const uint32_t* __restrict__ keys,
+                          uint32_t* __restrict__ cursor, float2* __restrict__ sorted_pos, uint32_t* __restrict__ slot_of_entity, GridParams grid, uint32_t c0,
+                          uint32_t c1) {
+    const uint32_t n = BAND && n_dev ? *n_dev : n_host;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps_total = (gridDim.x * blockDim.x) >> 5;
     constexpr uint32_t PER_WARP = 32u * SCATTER_CHUNKS;
     for (uint32_t base = warp_global * PER_WARP; base < n; base += warps_total * PER_WARP) {
         float2 p[SCATTER_CHUNKS];
+        uint32_t key[SCATTER_CHUNKS];
         RunSlot r[SCATTER_CHUNKS];
 #pragma unroll
         for (int k = 0; k < SCATTER_CHUNKS; k++) {
             const uint32_t e = base + k * 32u + lane;
             p[k] = e < n ? __ldcs(pos + e) : make_float2(0.f, 0.f);
+            if (BAND) key[k] = e < n ? __ldcs(keys + e) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < SCATTER_CHUNKS; k++) {
             const uint32_t e = base + k * 32u + lane;
-            r[k] = run_slot_issue(cursor, cell_key_of(p[k], grid), e < n, lane);
+            if (!BAND) key[k] = cell_key_of(p[k], grid);
+            const bool valid = e < n && (!BAND || key[k] - c0 < c1 - c0);
+            r[k] = run_slot_issue(cursor, key[k], valid, lane);
+            if (!valid) r[k].my_head = 32u;  // marks the lane: nothing to store
         }
 #pragma unroll
         for (int k = 0; k < SCATTER_CHUNKS; k++) {
             const uint32_t e = base + k * 32u + lane;
-            const uint32_t slot = __shfl_sync(0xffffffffu, r[k].base, r[k].my_head) + (lane - r[k].my_head);
-            if (e < n) {
+            const bool valid = r[k].my_head != 32u;
+            const uint32_t head = valid ? r[k].my_head : lane;
+            const uint32_t slot = __shfl_sync(0xffffffffu, r[k].base, head) + (lane - head);
+            if (valid) {
                 sorted_pos[slot] = p[k];
                 __stcs(slot_of_entity + e, slot);
+            } else if (BAND && e < n) {
+                __stcs(slot_of_entity + e, CSORT_SKIP);
             }
         }
     }
@@ -285,16 +267,22 @@ cell_count_pos_kernel(uint32_t n, const float2* __restrict__ pos, uint32_t* __re
 }
 
 // sorted slot -> entity, from the entity -> slot map the scatter wrote (only the periodic re-sort wants this direction)
-__global__ void __launch_bounds__(256) invert_slots_kernel(uint32_t n, const uint32_t* __restrict__ slot_of_entity, uint32_t* __restrict__ sorted_idx) {
+__global__ void __launch_bounds__(256)
+invert_slots_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ slot_of_entity, uint32_t* __restrict__ sorted_idx) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) sorted_idx[__ldcs(slot_of_entity + e)] = e;
+    if (e >= n) return;
+    const uint32_t slot = __ldcs(slot_of_entity + e);
+    if (slot != CSORT_SKIP) sorted_idx[slot] = e;
 }
 
 // collision flag per entity = flag of its sorted slot (+1: 1 = green, 2 = blue, 0 = "no collision pass yet")
 __global__ void __launch_bounds__(256)
 gather_flags_kernel(uint32_t n, const uint32_t* __restrict__ slot_of_entity, const uint8_t* __restrict__ flag_sorted, uint8_t* __restrict__ flag_entity) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) flag_entity[e] = flag_sorted[__ldcs(slot_of_entity + e)] + 1;
+    if (e >= n) return;
+    const uint32_t slot = __ldcs(slot_of_entity + e);
+    flag_entity[e] = slot != CSORT_SKIP ? flag_sorted[slot] + 1 : 1;  // out of everybody's reach: green
 }
 
 }  // namespace
@@ -320,13 +308,12 @@ void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int n
     if (*c1 > cells) *c1 = cells;
 }
 
-int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
-                      const uint32_t* n_dev) {
+int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
     uint32_t blocks = (n + 255u) / 256u;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
     prof->begin(s, K_CELL_COUNT);
-    cell_count_kernel<<<blocks, 256, 0, s>>>(n, n_dev, keys, cell_count, rank, c0, c1);
+    cell_count_kernel<<<blocks, 256, 0, s>>>(n, n_dev, keys, cell_count, c0, c1);
     prof->end(s);
     return 1;
 }
@@ -352,32 +339,18 @@ int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint3
     return 1;
 }
 
-int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
-                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev) {
+int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, const uint32_t* keys, uint32_t* cursor, float2* sorted_pos,
+                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
-    const uint32_t pairs = (n + 1u) >> 1;
-    uint32_t blocks = (pairs + 255u) / 256u;
-    if (blocks > 148u * 8u) blocks = 148u * 8u;
-    prof->begin(s, K_CELL_SCATTER);
-    cell_scatter_kernel<<<blocks, 256, 0, s>>>(n, n_dev, reinterpret_cast<const uint2*>(keys), reinterpret_cast<const uint2*>(rank),
-                                               reinterpret_cast<const float4*>(pos), cell_start, sorted_pos, sorted_idx);
-    prof->end(s);
-    return 1;
-}
-
-}  // namespace msim
-
-namespace msim {
-
-int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cursor, float2* sorted_pos, uint32_t* slot_of_entity,
-                              const GridParams& grid, Profiler* prof) {
-    if (n == 0) return 0;
-    constexpr uint32_t chunks = 8u;  // measured: 2 / 4 / 8 chunks in flight per warp = 85 / 82.6 / 76.3 us at 10 M entities
+    constexpr uint32_t chunks = 8u;
     uint32_t blocks = (n + 256u * chunks - 1u) / (256u * chunks);
     const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
     if (blocks > resident) blocks = resident;
     prof->begin(s, K_CELL_SCATTER);
-    cell_scatter_slots_kernel<chunks><<<blocks, 256, 0, s>>>(n, pos, cursor, sorted_pos, slot_of_entity, grid);
+    if (keys)
+        cell_scatter_slots_kernel<chunks, true><<<blocks, 256, 0, s>>>(n, n_dev, pos, keys, cursor, sorted_pos, slot_of_entity, grid, c0, c1);
+    else
+        cell_scatter_slots_kernel<chunks, false><<<blocks, 256, 0, s>>>(n, nullptr, pos, nullptr, cursor, sorted_pos, slot_of_entity, grid, 0u, grid.ncells);
     prof->end(s);
     return 1;
 }
@@ -393,10 +366,10 @@ int launch_cell_count_pos(cudaStream_t s, int sm_count, uint32_t n, const float2
     return 1;
 }
 
-int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof) {
+int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev) {
     if (n == 0) return 0;
     prof->begin(s, K_MISC);
-    invert_slots_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, slot_of_entity, sorted_idx);
+    invert_slots_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(n, n_dev, slot_of_entity, sorted_idx);
     prof->end(s);
     return 1;
 }

@@ -99,48 +99,21 @@ __device__ __forceinline__ float2 walk(float2 p, float2 t, bool& arrived) {
     return make_float2(__fadd_rn(p.x, dirx), __fadd_rn(p.y, diry));
 }
 
-// Rank of one entity per lane inside its cell = old value of the cell's counter.  Storage is kept in
-// cell order, so neighbouring lanes mostly hold the same key: each run of equal keys in adjacent lanes
-// issues ONE atomic (by its first lane) and shares the result — a few times fewer L2 atomics than one per
-// entity.  Ranks inside a cell are a permutation either way; nothing observable depends on their order.
-struct RunRank {
-    uint32_t base;     // the run head's atomic result (valid in the head lane only, until finished)
-    uint32_t my_head;  // lane of the head of this lane's run
-};
-// phase 1: find the runs and issue the heads' atomics; the result is not consumed here, so several of these can be
-// in flight per thread before anybody waits (the atomics' L2 round trips dominated the kernel: profiles/r1m)
-__device__ __forceinline__ RunRank run_rank_issue(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, uint32_t lane) {
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool prev_valid = __shfl_up_sync(0xffffffffu, valid ? 1u : 0u, 1) != 0u;
-    const bool head = lane == 0 || key != prev || !valid || !prev_valid;
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    RunRank r;
-    r.my_head = 31u - __clz(heads & ((2u << lane) - 1u));        // nearest head at or below this lane (lane 0 is one)
-    const uint32_t above = r.my_head == 31u ? 0u : (heads >> (r.my_head + 1u)) << (r.my_head + 1u);
-    const uint32_t next_head = above ? static_cast<uint32_t>(__ffs(above) - 1) : 32u;
-    r.base = 0;
-    if (lane == r.my_head && valid) r.base = atomicAdd(&cell_count[key], next_head - r.my_head);
-    return r;
-}
-// phase 2: every lane of a run takes the head's result plus its distance from the head
-__device__ __forceinline__ uint32_t run_rank_finish(const RunRank& r, uint32_t lane) {
-    return __shfl_sync(0xffffffffu, r.base, r.my_head) + (lane - r.my_head);
-}
-
-// Count-only variant (single-GPU counting sort, csort.cu): the run heads add their run length to the cell's counter with a
-// reduction that returns nothing (RED): no L2 round trip to wait for, the streaming loop never stalls on it.  The rank
-// inside the cell is taken later by the scatter kernel, whose atomics return the slot directly.
-// `full`: every lane of the warp holds a live entity (warp-uniform; true everywhere but in the last warp of the array).
+// Per-cell population for the counting sort (csort.cu).  Storage is kept in cell order, so neighbouring lanes mostly hold the
+// same key: each run of equal keys in adjacent lanes issues ONE reduction (by its first lane) - a few times fewer L2 operations
+// than one per entity - and the reduction returns nothing (RED): no L2 round trip to wait for, the streaming loop never stalls
+// on it.  The slot inside the cell is taken later by the scatter kernel, whose atomics return it directly.
+// `full`: every lane of the warp holds an entity that counts (warp-uniform; true everywhere but in the last warp of the array and,
+// on sharded handles, in warps that hold a leaver).  Otherwise the lanes that do not count break the runs.
 __device__ __forceinline__ void run_count(uint32_t* __restrict__ cell_count, uint32_t key, bool valid, bool full, uint32_t lane) {
+    if (!full) key = valid ? key : 0xffffffffu - lane;  // a key nobody shares: its own run, never issued
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || key != prev;  // dead lanes only exist in the padded tail: they may extend a run, never start a counted one
+    const bool head = lane == 0 || key != prev;
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t valid_mask = full ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
     if (head && (full || valid)) {
         const uint32_t above = (heads >> lane) >> 1;  // heads behind this lane, shifted down to bit 0
         const uint32_t len = above ? static_cast<uint32_t>(__ffs(above)) : 32u - lane;  // lanes up to the next head
-        const uint32_t run = (len == 32u ? 0xffffffffu : ((1u << len) - 1u)) << lane;
-        atomicAdd(&cell_count[key], full ? len : static_cast<uint32_t>(__popc(run & valid_mask)));
+        atomicAdd(&cell_count[key], len);
     }
 }
 
@@ -176,15 +149,15 @@ __device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t
 //   MOVE_COUNT  the per-cell population (csort.cu, single-GPU default): cell key of the new position -> one RED per run of
 //               equal keys in adjacent lanes.  No key or rank is written: the scatter kernel recomputes the key from the
 //               position it has to read anyway and takes the slot from an atomic on the scanned table
-//   MOVE_KEYS   cell key (4 B) + rank inside the cell (4 B, counting sort with ranks: sharded handles) and / or the radix
-//               sort's digit histograms for all passes, accumulated in shared memory and flushed once per CTA (onesweep)
+//   MOVE_KEYS   cell key (4 B) plus either the per-cell population as above (sharded handles: the exchange kernels work on keys) or
+//               the radix sort's digit histograms for all passes, accumulated in shared memory and flushed once per CTA (onesweep)
 // SHARD (multi-GPU bands, MOVE_KEYS only) additionally does the shard pack for the entities it has just moved (see above).
 enum { MOVE_PLAIN = 0, MOVE_COUNT = 1, MOVE_KEYS = 2 };
 template <int MODE, bool SHARD>
 __global__ void __launch_bounds__(MOVE_THREADS)
 move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* __restrict__ pos_in, float4* __restrict__ pos_out, const float4* __restrict__ target,
             uint32_t* __restrict__ arrived_mask, uint2* __restrict__ keys, GridParams grid, uint32_t* __restrict__ ghist, int hist_passes,
-            uint32_t* __restrict__ cell_count, uint2* __restrict__ rank, ShardMoveArgs sh) {
+            uint32_t* __restrict__ cell_count, ShardMoveArgs sh) {
     static_assert(!SHARD || MODE == MOVE_KEYS, "the shard pack classifies by key");
     constexpr bool EMIT_KEYS = MODE == MOVE_KEYS;
     __shared__ uint32_t s_hist[EMIT_KEYS ? MAX_SORT_PASSES * RADIX : 1];
@@ -210,7 +183,6 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                 T[k] = __ldcs(target + pi);
             }
         }
-        RunRank R0[MOVE_ITEMS], R1[MOVE_ITEMS];
 #pragma unroll
         for (int k = 0; k < MOVE_ITEMS; k++) {
             if (!live[k]) continue;  // warp-uniform
@@ -235,14 +207,15 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
             if (EMIT_KEYS) {
                 const uint32_t k0 = cell_key_of(q0, grid), k1 = cell_key_of(q1, grid);
                 keys[pi] = make_uint2(k0, k1);
-                if (cell_count) {  // counting sort: the atomic's return value is the entity's rank inside its cell
+                if (cell_count) {  // counting sort: per-cell population of the entities that stay
                     bool v0 = e0 < n, v1 = e1 < n;
-                    if (SHARD) {  // leavers are not part of this band's order any more; arrivals take their rank in the integrate kernel
+                    if (SHARD) {  // leavers are not part of this band's order any more; arrivals are counted by the integrate kernel
                         v0 = v0 && !((sh.buf_down && k0 < sh.lo_key) || (sh.buf_up && k0 >= sh.hi_key));
                         v1 = v1 && !((sh.buf_down && k1 < sh.lo_key) || (sh.buf_up && k1 >= sh.hi_key));
                     }
-                    R0[k] = run_rank_issue(cell_count, k0, v0, lane);
-                    R1[k] = run_rank_issue(cell_count, k1, v1, lane);
+                    const bool full = __all_sync(0xffffffffu, v0 && v1);
+                    run_count(cell_count, k0, v0, full, lane);
+                    run_count(cell_count, k1, v1, full, lane);
                 }
                 for (int p = 0; p < hist_passes; p++) {
                     if (e0 < n) atomicAdd(&s_hist[p * RADIX + ((k0 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
@@ -252,14 +225,6 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                     shard_classify(sh, e0, e0 < n, k0, q0);
                     shard_classify(sh, e1, e1 < n, k1, q1);
                 }
-            }
-        }
-        if (EMIT_KEYS && cell_count) {  // all of this thread's rank atomics are in flight by now
-#pragma unroll
-            for (int k = 0; k < MOVE_ITEMS; k++) {
-                if (!live[k]) continue;
-                const uint32_t pi = base + k * MOVE_THREADS + threadIdx.x;
-                rank[pi] = make_uint2(run_rank_finish(R0[k], lane), run_rank_finish(R1[k], lane));
             }
         }
     }
@@ -335,10 +300,10 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 
 }  // namespace
 
-// `keys` non-NULL: MOVE_KEYS (key + rank / digit histograms, optionally the shard pack); `keys` NULL and `cell_count` non-NULL:
+// `keys` non-NULL: MOVE_KEYS (key + per-cell population or digit histograms, optionally the shard pack); `keys` NULL and `cell_count` non-NULL:
 // MOVE_COUNT; neither: MOVE_PLAIN.  The grid is 8 CTAs per SM (2048 threads) with a grid-stride loop inside.
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
-                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, uint32_t* rank, Profiler* prof,
+                uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, Profiler* prof,
                 const uint32_t* n_dev, const ShardMoveArgs* shard) {
     if (n == 0) return 0;
     const uint32_t pairs = (n + 1u) >> 1;
@@ -350,18 +315,17 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     float4* pout = reinterpret_cast<float4*>(pos_out);
     const float4* tgt = reinterpret_cast<const float4*>(target);
     uint2* keys2 = reinterpret_cast<uint2*>(keys);
-    uint2* rank2 = reinterpret_cast<uint2*>(rank);
     const int passes = hist ? hist_passes : 0;
     const ShardMoveArgs none{};
     prof->begin(s, K_MOVE);
     if (keys && shard)
-        move_kernel<MOVE_KEYS, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, *shard);
+        move_kernel<MOVE_KEYS, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, *shard);
     else if (keys)
-        move_kernel<MOVE_KEYS, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, rank2, none);
+        move_kernel<MOVE_KEYS, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, none);
     else if (cell_count)
-        move_kernel<MOVE_COUNT, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, cell_count, nullptr, none);
+        move_kernel<MOVE_COUNT, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, cell_count, none);
     else
-        move_kernel<MOVE_PLAIN, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, nullptr, none);
+        move_kernel<MOVE_PLAIN, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, nullptr, none);
     prof->end(s);
     return 1;
 }

@@ -136,7 +136,7 @@ const Tuning& tuning();
 // bound used to size the grid.
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
-                int hist_passes, uint32_t* cell_count /* nullable: fused counting-sort rank */, uint32_t* rank, Profiler* prof,
+                int hist_passes, uint32_t* cell_count /* nullable: fused per-cell population */, Profiler* prof,
                 const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr);
 // `beside`: the pass runs on the side stream next to the issue-bound query (see Tuning::arrive_beside_ctas_per_sm)
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
@@ -156,32 +156,33 @@ void sort_prepare(cudaStream_t s, uint32_t n, int key_bits, const SortWorkspace&
 uint32_t csort_tiles(uint32_t cells);
 void csort_clear(cudaStream_t s, uint32_t* cell_count, uint32_t cells, Profiler* prof);
 void csort_band(uint32_t cells, int ncx, uint32_t row_lo, uint32_t row_hi, int ncy, uint32_t* c0, uint32_t* c1);
-int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t* rank, uint32_t c0, uint32_t c1, Profiler* prof,
+int launch_cell_count(cudaStream_t s, uint32_t n, const uint32_t* keys, uint32_t* cell_count, uint32_t c0, uint32_t c1, Profiler* prof,
                       const uint32_t* n_dev = nullptr);
+int launch_cell_count_pos(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cell_count, const GridParams& grid, Profiler* prof);
 size_t csort_scan_scratch_words(uint32_t cells);
 int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint32_t* scratch, uint32_t scratch_tiles, uint32_t epoch, uint32_t* cell_start,
                      uint32_t* error_flag, Profiler* prof);
-int launch_cell_scatter(cudaStream_t s, uint32_t n, const uint32_t* keys, const uint32_t* rank, const float2* pos, const uint32_t* cell_start,
-                        float2* sorted_pos, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
-// single-GPU default (count-only move pass): slots come from atomics on the scanned table `cursor`, which ends up shifted by one cell
-int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cursor, float2* sorted_pos, uint32_t* slot_of_entity,
-                              const GridParams& grid, Profiler* prof);
-int launch_cell_count_pos(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, uint32_t* cell_count, const GridParams& grid, Profiler* prof);
-int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof);
+// slots come from atomics on the scanned table `cursor`, which ends up shifted by one cell.  `keys` non-NULL (sharded handles):
+// keys are read instead of recomputed, entities whose key is outside [c0, c1) get the slot CSORT_SKIP, the count may live in n_dev
+int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, const uint32_t* keys, uint32_t* cursor, float2* sorted_pos,
+                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev = nullptr);
+int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
 int launch_gather_flags(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // collide.cu
 int launch_build_cells(cudaStream_t s, uint32_t n, const uint64_t* sorted, const float2* pos, float2* sorted_pos, uint32_t* sorted_idx,
                        uint2* cell_range, const GridParams& grid, Counters* counters, Profiler* prof, const uint32_t* n_dev = nullptr);
 // n_owned < n: slots whose entity index (sorted_idx) is >= n_owned are ghosts (neighbours only).
-// Cell directory: either cell_range ({first, ~end} per cell, onesweep path) or cell_start (prefix table, csort path).
+// Cell directory: cell_range ({first, ~end} per cell) built from the onesweep order; the counting sort has its own query (collide_tiles.cu).
 int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const float2* sorted_pos, const uint2* cell_range,
-                 const uint32_t* cell_start, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
+                 uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
                  const uint32_t* n_dev = nullptr, const uint32_t* n_owned_dev = nullptr);
 size_t query_stripe_bytes();
-// collide_tiles.cu — single-GPU default query: aligned candidate groups, striped counters folded by a one-CTA kernel behind it
-int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, Counters* counters,
-                       unsigned long long* stripes, Profiler* prof);
+// collide_tiles.cu — the query over the counting sort's prefix table: aligned candidate groups, striped counters folded by a one-CTA
+// kernel behind it.  ghosts (sharded handles): slots whose cell row is outside [row_lo, row_hi) are neighbours only; n_dev: slot count
+int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs,
+                       Counters* counters, unsigned long long* stripes, Profiler* prof, const uint32_t* n_dev = nullptr, bool ghosts = false,
+                       uint32_t row_lo = 0, uint32_t row_hi = 0);
 int launch_scatter_flags(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* sorted_idx, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
 // pack.cu
@@ -257,14 +258,13 @@ struct ShardArrays {
     uint32_t* gid;
     uint32_t* keys;
     uint32_t* arrived;
-    // counting-sort ranks maintained through the exchange (NULL cell_count: a count kernel runs later instead): the fused
-    // move + pack kernel has ranked the entities that stay, so whoever is placed, relocated or appended as a ghost
-    // afterwards takes / keeps its own rank and the per-cell counters are complete when the integrate is done
+    // per-cell population maintained through the exchange (NULL cell_count: a count kernel runs later instead): the fused
+    // move + pack kernel has counted the entities that stay, so whoever is placed or appended as a ghost afterwards is
+    // counted on arrival and the per-cell counters are complete when the integrate is done
     uint32_t* cell_count;
-    uint32_t* rank;
-    uint32_t c0, c1;  // counted cell range; keys outside it get CSORT_SKIP
+    uint32_t c0, c1;  // counted cell range; keys outside it stay out of the order
 };
-constexpr uint32_t CSORT_SKIP = 0xffffffffu;  // rank of an entity that is left out of the cell order
+constexpr uint32_t CSORT_SKIP = 0xffffffffu;  // slot of an entity that is left out of the cell order
 
 int launch_shard_reset(cudaStream_t s, void* buf_down, void* buf_up, uint32_t* ctr);
 int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx, uint32_t row_lo, uint32_t row_hi, void* buf_down, void* buf_up,

@@ -28,9 +28,9 @@ __device__ __forceinline__ void set_arrived_bit(uint32_t* mask, uint32_t e, bool
     else atomicAnd(w, ~bit);
 }
 
-// rank of an entity that joins the cell order after the move kernel has ranked the ones that stayed
-__device__ __forceinline__ void take_rank(const ShardArrays& a, uint32_t e, uint32_t key) {
-    if (a.cell_count) a.rank[e] = (key - a.c0 < a.c1 - a.c0) ? atomicAdd(&a.cell_count[key], 1u) : CSORT_SKIP;
+// an entity that joins the cell order after the move kernel has counted the ones that stayed
+__device__ __forceinline__ void count_cell(const ShardArrays& a, uint32_t key) {
+    if (a.cell_count && key - a.c0 < a.c1 - a.c0) atomicAdd(&a.cell_count[key], 1u);
 }
 
 // one tiny launch instead of three memsets: clears the two headers and the hole / ghost counters
@@ -123,7 +123,7 @@ shard_place_kernel(ShardArrays a, const void* recv_down, uint32_t n_down, const 
     a.gid[e] = r7.y;
     const uint32_t key = cell_key_of(p, grid);
     a.keys[e] = key;
-    take_rank(a, e, key);
+    count_cell(a, key);
     set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
 }
 
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(128) shard_relocate_kernel(ShardArrays a, cons
     a.road[dst] = a.road[src];
     a.gid[dst] = a.gid[src];
     a.keys[dst] = a.keys[src];
-    if (a.cell_count) a.rank[dst] = a.rank[src];
     set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
 }
 
@@ -157,7 +156,7 @@ shard_append_ghosts_kernel(ShardArrays a, uint32_t first, const void* recv_down,
     a.pos_cur[first + i] = p;
     const uint32_t key = cell_key_of(p, grid);
     a.keys[first + i] = key;
-    take_rank(a, first + i, key);
+    count_cell(a, key);
 }
 
 // ---- second half of the fused move + pack ---------------------------------------------------------
@@ -245,7 +244,6 @@ __device__ __forceinline__ void copy_entity(const ShardArrays& a, uint32_t src, 
     a.road[dst] = a.road[src];
     a.gid[dst] = a.gid[src];
     a.keys[dst] = a.keys[src];
-    if (a.cell_count) a.rank[dst] = a.rank[src];
     set_arrived_bit(a.arrived, dst, ((a.arrived[arrived_word(src)] >> arrived_bit(src)) & 1u) != 0u);
 }
 
@@ -264,7 +262,7 @@ __device__ __forceinline__ void place_record(const ShardArrays& a, const void* b
     a.gid[e] = r7.y;
     const uint32_t key = cell_key_of(p, grid);
     a.keys[e] = key;
-    take_rank(a, e, key);
+    count_cell(a, key);
     set_arrived_bit(a.arrived, e, (r8.x & 1u) != 0u);
 }
 
@@ -410,7 +408,7 @@ __device__ __forceinline__ void ghosts_body(const ShardArrays& a, const uint32_t
         a.pos_cur[first + i] = p;
         const uint32_t key = cell_key_of(p, grid);
         a.keys[first + i] = key;
-        take_rank(a, first + i, key);
+        count_cell(a, key);
     }
 }
 

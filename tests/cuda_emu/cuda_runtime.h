@@ -132,6 +132,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     return cuda_emu::collective(pred ? 1ull : 0ull, [](const unsigned long long* s) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= (s[i] ? 1u : 0u) << i; return r; });
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::warp_sync(); }
 inline unsigned __shfl_sync(unsigned, unsigned v, unsigned src) {
     return cuda_emu::collective(v, [src](const unsigned long long* s) { return static_cast<unsigned>(s[src & 31u]); });
