@@ -171,10 +171,58 @@ def build_workload(M, name: str, entities_override: int | None, seed: int = 42):
     return w, m
 
 
+def build_population(M, m, total: int, box=None, seed: int = 42):
+    """The seeded global population every arm runs (1, 2, 4, 8 GPUs and the CPU reference): 1 Mi-entity chunks with seeds seed + 1000 * chunk
+    (movement-sim_b200/sharding.py generate_population), so that pair and flag counts can be compared across arms."""
+    from movement_sim_b200 import sharding
+
+    threads = max(1, min(8, os.cpu_count() or 1))
+    parts = sharding._map_chunks(lambda c: m.init_entities(c[2], seed=seed + 1000 * c[0], box=box), total, threads)
+    return np.concatenate(parts) if parts else m.init_entities(0, seed=seed, box=box)
+
+
+COUNTS_PATH = os.path.join(ROOT, "tests", "golden", "bench_counts.json")
+
+
+def check_counts(workload: str, entities: int, move_passes: int, pairs, flagged) -> dict:
+    """Self-check of a bench line: unique pairs and flagged entities of the last timed tick against the values stored for the same
+    population after the same number of move passes (tests/golden/bench_counts.json: measured at N = 1 and reproduced by the CPU
+    oracle, tests/golden/make_bench_counts.py).  Every N must report the same numbers; a mismatch fails the run."""
+    if pairs is None:
+        return {"status": "not applicable (collisions off)"}
+    try:
+        with open(COUNTS_PATH) as f:
+            stored = json.load(f).get(workload, {}).get(str(entities), {}).get(str(move_passes))
+    except (OSError, ValueError):
+        stored = None
+    if not stored:
+        return {"status": "no stored value", "key": [workload, entities, move_passes]}
+    ok = int(stored["pairs"]) == int(pairs) and int(stored["flagged"]) == int(flagged)
+    return {"status": "ok" if ok else "mismatch", "expected": stored, "key": [workload, entities, move_passes]}
+
+
+RESORT_EVERY = 32  # collision passes between two re-sorts of the resident state into cell order (api.cu reorder_every)
+
+
+def align_resort_phase(stats, step, limit: int = 2 * RESORT_EVERY):
+    """Ticks (untimed) until the NEXT collision pass is one that re-sorts the storage: the timed K steps that follow then hold
+    1 + (K - 1) // RESORT_EVERY re-sorts, never fewer than their share K / RESORT_EVERY.  Returns the ticks spent."""
+    start = stats()["reorders"]
+    spent = 0
+    while stats()["reorders"] == start and spent < limit:
+        step()
+        spent += 1
+    if stats()["reorders"] == start:
+        return spent  # re-sorting is off (MSIM_FLAG_NO_REORDER, onesweep): nothing to align
+    for _ in range(RESORT_EVERY - 1):
+        step()
+    return spent + RESORT_EVERY - 1
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU: the reference's own CPU path (oracle/_ref quadtree) + the oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree):
+def cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree, large=False):
     """One sim tick on the host with as much of the reference's OWN code as compiles here (oracle/_ref):
     movement = the shader's update_direction / move / new_target / next compiled for the CPU (random_move.comp:725-852,
     libref_shader_move.so) on all host threads by static entity ranges, else the oracle port;
@@ -189,23 +237,30 @@ def cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree):
     if not collisions:
         return
     if ref_tree:
-        q = O.RefQuadTree(omap.world_w, omap.world_h, radius, 10)
+        q = O.RefQuadTree(omap.world_w, omap.world_h, radius, 10, large=large)
         q.insert(e["pos"], 1)
-        q.collide(threads)
+        flags, _ = q.collide(threads)
+        return int(flags.sum())
     else:
         O.collide_pass(e, omap.world_w, omap.world_h, radius, threads=threads)
 
 
-def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, ref_move, ref_tree, threads):
+def time_cpu(O, ents_aos, omap, radius, collisions, steps, warmup, ref_move, ref_tree, threads, large=False, budget_s=None):
+    """Returns (entity-updates/s, seconds per step, steps done, flagged entities of the last step or None).  budget_s: stop after the
+    step that crosses it (at least one step is always timed)."""
     e = np.ascontiguousarray(ents_aos).view(O.ENTITY_DTYPE).copy()
     e["initialized"] = 1
     for _ in range(warmup):
-        cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree)
+        cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree, large)
     t0 = time.perf_counter()
+    done, flagged = 0, None
     for _ in range(steps):
-        cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree)
+        flagged = cpu_step(O, e, omap, radius, threads, collisions, ref_move, ref_tree, large)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return e.shape[0] * steps / dt, dt / steps
+    return e.shape[0] * done / dt, dt / done, done, flagged
 
 
 def time_whole_shader(O, ents_aos, m, radius, collisions, sample=100_000, ticks=2, limit_s=90.0):
@@ -279,37 +334,63 @@ def cpu_arm_description(ref_move, ref_tree, collisions):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, on the GPU arm's configuration:
+    the same seeded population at its full size, the same pre-roll.  The reference's collision walk is quadratic in the leaf
+    population (depth-8 quadtree, shader_validation/src/main.cpp), so one full-size sim tick costs minutes of CPU time at 10 M
+    entities: the run times as many of the K steps as fit --ref-budget-s (at least one) and says how many it did."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import movement_sim_b200 as M
+    import movement_sim_b200 as M  # host-only helpers (libmsim_host.so): this arm never loads the CUDA library
     from oracle import oracle as O
 
     w, m = build_workload(M, args.workload, args.entities)
     threads = os.cpu_count() or 1
+    collisions = w["collisions"]
+    total = w["entities"] * (args.gpus if args.scaling == "weak" else 1)
     ref_move = O.ref_shader_available()
-    ref_tree = O.ref_available() and w["collisions"]
-    sample = min(w["entities"], args.ref_sample, int(O.ref().ref_capacity()) if ref_tree else 1 << 62)
+    sample = min(total, args.ref_sample) if args.ref_sample else total
+    large = collisions and sample > (int(O.ref().ref_capacity()) if O.ref_available() else 0) and O.ref_large_available()
+    if large:
+        sample = min(sample, int(O.ref(large=True).ref_capacity()))
+    ref_tree = collisions and (large or (O.ref_available() and sample <= int(O.ref().ref_capacity())))
+    if collisions and not ref_tree and O.ref_available():  # no large build on this box: the largest sample the harness holds
+        sample = min(sample, int(O.ref().ref_capacity()))
+        ref_tree = True
     omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
-    ents = m.init_entities(sample, seed=42, box=w["box"])
+    ents = build_population(M, m, total, w["box"])[:sample]
     e = np.ascontiguousarray(ents).view(O.ENTITY_DTYPE).copy()
+    del ents
     O.move_pass(e, omap, threads=threads)  # init dispatch
-    for _ in range(args.preroll):
+    for _ in range(args.preroll + 1):  # the GPU arm's pre-roll and its one untimed collision tick's move pass
         O.move_pass(e, omap, threads=threads)
-    steps = max(1, min(args.steps, args.ref_max_steps))
-    warmup = max(1, min(args.warmup, 2))
-    value, sec = time_cpu(O, e, omap, 10.0, w["collisions"], steps, warmup, ref_move, ref_tree, threads)
-    kind, how = cpu_arm_description(ref_move, ref_tree, w["collisions"])
-    sample_desc = f"{sample} of {w['entities']} entities of the same workload, {steps} sim ticks after {args.preroll} pre-roll move passes; {how}"
-    try:
-        whole = time_whole_shader(O, e, m, 10.0, w["collisions"])
-    except Exception as ex:  # an extra beside the baseline: never allowed to cost the line
-        whole = {"error": repr(ex)}
+    # warm-up: the GPU arm's W warm-up ticks as move passes (same population state when timing starts); the reference rebuilds its
+    # tree from nothing every tick, so a warm-up collision pass would only warm caches - at minutes per pass it is left out and says so
+    warm_moves = max(3, args.warmup)
+    for _ in range(warm_moves):
+        O.move_pass(e, omap, threads=threads)
+    steps_asked = max(1, args.steps)
+    value, sec, steps, flagged = time_cpu(O, e, omap, 10.0, collisions, steps_asked, 0, ref_move, ref_tree, threads, large=large,
+                                          budget_s=args.ref_budget_s)
+    kind, how = cpu_arm_description(ref_move, ref_tree, collisions)
+    if large:
+        how = how.replace("libref_quadtree.so", "libref_quadtree_large.so")
+    sample_desc = (f"{sample} of {total} entities of the same seeded population, {steps} of {steps_asked} sim ticks timed (budget {args.ref_budget_s:.0f} s, "
+                   f"{sec:.1f} s per tick) after {args.preroll} pre-roll + {warm_moves + 1} warm-up move passes; {how}")
+    whole = None
+    if not args.no_whole_shader:
+        try:
+            whole = time_whole_shader(O, e, m, 10.0, collisions, limit_s=45.0)
+        except Exception as ex:  # an extra beside the baseline: never allowed to cost the line
+            whole = {"error": repr(ex)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32",
-        "data": "synthetic", "config": {"workload": args.workload, "entities_sampled": sample, "collisions": w["collisions"], "map": w["map_desc"]},
+        "warmup": max(3, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "entities": total, "entities_sampled": sample, "same_config": sample == total, "collisions": collisions,
+                   "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll,
+                   "steps_asked": steps_asked, "steps_timed": steps, "warmup_as_move_passes": warm_moves,
+                   "flagged_last_tick": flagged, "move_passes_done": args.preroll + 1 + warm_moves + steps},
         "cpu_baseline": {"value": value, "unit": "entity-updates/s", "cores": threads, "kind": kind, "sample": sample_desc, "whole_shader_1_thread": whole},
         "e2e": {"value": value, "unit": "entity-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -347,7 +428,7 @@ def run_b200(args):
     collisions = w["collisions"]
     peak, peak_src = load_peaks()
     stream = torch.cuda.Stream()
-    ents = m.init_entities(n, seed=42, box=w["box"])
+    ents = build_population(M, m, n, w["box"])  # the same seeded population at every N (sharding.generate_population)
     if args.presort:  # experiment: spatially coherent storage order (sort the host array by cell row, then x)
         rows, _, _ = M.grid_rows(m.width, m.height, 10.0, ents["pos"])
         order = np.lexsort((ents["pos"][:, 0], rows))
@@ -390,14 +471,18 @@ def run_b200(args):
         return total
 
     timed_steps(max(3, args.warmup))
+    aligned = align_resort_phase(sim.stats, lambda: sim.enqueue_ticks(1, collisions)) if collisions else 0
     sim.sync()
-    launches0 = sim.stats()["kernel_launches"]
+    st0 = sim.stats()
+    launches0 = st0["kernel_launches"]
     torch.cuda.synchronize()
     ms = timed_steps(args.steps)
     torch.cuda.synchronize()
     sim.sync()
-    launches = sim.stats()["kernel_launches"] - launches0
+    st1 = sim.stats()  # state at the END of the timed region: what the line's self-check fields describe
+    launches = st1["kernel_launches"] - launches0
     value = n * args.steps / (ms * 1e-3)
+    check = check_counts(args.workload, n, st1["move_passes"], st1["last_pair_count"] if collisions else None, st1["last_flagged_count"] if collisions else None)
 
     # per-kernel device time over the same K steps (events around every launch; separate pass so the
     # event records do not sit inside the throughput measurement)
@@ -499,9 +584,10 @@ def run_b200(args):
     e2e = {"value": n * e2e_steps / (e2e_ms * 1e-3), "unit": "entity-updates/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 64,
            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
            "what": "msim_upload_entities(pinned AoS) + msim_dispatch(move)" + (" + msim_dispatch(collide)" if collisions else "") + " + msim_read_entities(pinned AoS), blocking calls"}
-    if args.e2e_pipelined:
-        # experiment (msim_snapshot_* has not run on hardware yet): the readback of step i leaves through the copy stream while
-        # step i+1 uploads and computes - PCIe is full duplex, so the two 64 B x N transfers overlap instead of adding up
+    variants = {"blocking_full_aos": dict(e2e)}
+    if not args.no_e2e_variants:
+        # (1) the same bytes, pipelined: the readback of step i leaves through the copy stream (msim_snapshot_begin/end, library-owned pinned
+        # buffers) while step i+1 uploads and computes - PCIe is full duplex, so the two 64 B x N transfers overlap instead of adding up
         def piped_step(first):
             nonlocal tick
             sim.upload_ptr(ptr, n)
@@ -510,7 +596,7 @@ def run_b200(args):
                 sim.dispatch(tick + 1)
             tick += 2
             if not first:
-                sim.snapshot_end(copy=False)  # result of the previous step (library-owned pinned memory)
+                sim.snapshot_end(copy=False)  # result of the previous step
             sim.snapshot_begin()
 
         piped_step(True)
@@ -519,8 +605,40 @@ def run_b200(args):
             piped_step(False)
         sim.snapshot_end(copy=False)
         wall = time.perf_counter() - t0
-        e2e["pipelined"] = {"value": n * e2e_steps / wall, "ms_per_step": wall * 1e3 / e2e_steps,
-                            "what": "same bytes per step; msim_snapshot_begin/end instead of msim_read_entities (D2H of step i overlaps H2D + compute of step i+1), wall clock"}
+        variants["pipelined_full_aos"] = {
+            "value": n * e2e_steps / wall, "unit": "entity-updates/s", "ms_per_step": wall * 1e3 / e2e_steps, "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 64,
+            "steps": e2e_steps, "what": "same bytes per step; msim_snapshot_begin/end instead of msim_read_entities (D2H of step i overlaps H2D + compute of step i+1), wall clock"}
+        # (2) what the renderer consumes per frame (EntityGlObject.cpp:9-12: position + colour): 8 B position + 1 B collision flag per entity
+        pos_host = torch.empty(n * 2, dtype=torch.float32, pin_memory=True)
+        flag_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+
+        def render_step():
+            nonlocal tick
+            sim.upload_ptr(ptr, n)
+            sim.dispatch(tick)
+            if collisions:
+                sim.dispatch(tick + 1)
+            tick += 2
+            sim.read_positions_ptr(pos_host.data_ptr(), n)
+            if collisions:
+                sim.read_collision_flags_ptr(flag_host.data_ptr(), n)
+
+        render_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            render_step()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        variants["full_aos_up_render_state_down"] = {
+            "value": n * e2e_steps / wall, "unit": "entity-updates/s", "ms_per_step": wall * 1e3 / e2e_steps, "h2d_bytes_per_step": n * 64,
+            "d2h_bytes_per_step": n * (9 if collisions else 8), "steps": e2e_steps,
+            "what": "msim_upload_entities(pinned AoS) + sim tick + msim_read_positions" + (" + msim_read_collision_flags" if collisions else "") + " (pinned), blocking calls"}
+        # the headline keeps the FULL 64-byte AoS in both directions (what sim::Simulator::get_entities hands the UI): the faster of the two
+        best = min(("blocking_full_aos", "pipelined_full_aos"), key=lambda k: variants[k]["ms_per_step"])
+        e2e = dict(variants[best])
+        e2e["variant"] = best
+    e2e["variants"] = variants
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
     cpu = None
@@ -533,10 +651,10 @@ def run_b200(args):
         sample = min(n, args.cpu_sample, int(O.ref().ref_capacity()) if ref_tree else 1 << 62)
         host = np.frombuffer(pinned.numpy(), dtype=M.ENTITY_DTYPE)[:sample]
         omap = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
-        v, sec = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, ref_move, ref_tree, threads)
-        v_port, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, False, False, threads)
+        v, sec, _, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, ref_move, ref_tree, threads)
+        v_port, _, _, _ = time_cpu(O, host, omap, 10.0, collisions, args.cpu_steps, 1, False, False, threads)
         kind, how = cpu_arm_description(ref_move, ref_tree, collisions)
-        cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": kind,
+        cpu = {"value": v, "unit": "entity-updates/s", "cores": threads, "kind": kind, "entities_sampled": int(sample), "same_config": int(sample) == n,
                "sample": f"first {sample} entities of the resident population, {args.cpu_steps} sim ticks, {sec:.3f} s per tick; {how}",
                "port_value": v_port}
         try:  # an extra beside the baseline: never allowed to cost the line
@@ -549,6 +667,11 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
         "config": {"workload": args.workload, "entities": n, "collisions": collisions, "collision_radius_m": 10.0, "map": w["map_desc"],
                    "entity_seed": 42, "preroll_move_passes": args.preroll, "pair_count": collisions,
+                   "move_passes_done": st1["move_passes"], "pairs_last_tick": st1["last_pair_count"] if collisions else None,
+                   "flagged_last_tick": st1["last_flagged_count"] if collisions else None, "counts_check": check,
+                   "resort": {"every_collision_passes": RESORT_EVERY, "in_timed_region": st1["reorders"] - st0["reorders"],
+                              "alignment_ticks_untimed": aligned,
+                              "note": "the timed region starts on a re-sorting tick: it holds 1 + (K - 1) // 32 re-sorts, never fewer than its share"},
                    "l2": ("flushed between timed steps (512 MiB fill)" if small else "inputs larger than L2 (no flush)"),
                    "experiments": {k: v for k, v in os.environ.items() if k.startswith("MSIM_") and k != "MSIM_BENCH_RESULT_FD"},
                    "grid": sim.stats()},
@@ -565,7 +688,7 @@ def run_b200(args):
     }
     sim.close()
     emit(line)
-    return 0
+    return 3 if check.get("status") == "mismatch" else 0
 
 
 def main():
@@ -580,8 +703,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--ref-sample", type=int, default=1_000_000)
-    ap.add_argument("--ref-max-steps", type=int, default=20)
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: entities of the population to run (0 = all of them, the GPU arm's configuration)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after the step that crosses this many seconds")
+    ap.add_argument("--no-whole-shader", action="store_true", help="skip the single-thread whole-shader extra of the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flags-only", action="store_true", help="skip the extra colours-only measurement")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
@@ -592,7 +716,7 @@ def main():
     ap.add_argument("--counting-sort", action="store_true", help="force the single-digit counting sort")
     ap.add_argument("--onesweep", action="store_true", help="force the multi-pass onesweep radix sort")
     ap.add_argument("--no-reorder", action="store_true", help="keep the state in upload order (onesweep rebuild)")
-    ap.add_argument("--e2e-pipelined", action="store_true", help="experiment (not yet run on hardware): adds e2e.pipelined, readback through msim_snapshot_*")
+    ap.add_argument("--no-e2e-variants", action="store_true", help="only the blocking full-AoS round trip (skips the pipelined and render-state variants)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

@@ -181,21 +181,15 @@ class KernelTime(C.Structure):
 
 
 _lib = None
+_host = None
+HOST_LIB_PATH = os.path.join(HERE, "libmsim_host.so")
+# the C-ABI entry points that never touch a GPU (csrc/host_map.cpp, csrc/host_mapgen.cpp): map loading / generation and entity initialisation
+HOST_SYMBOLS = ["msim_map_load_json", "msim_map_save_json", "msim_map_generate_city", "msim_map_generate_grid", "msim_map_free", "msim_map_width", "msim_map_height", "msim_map_road_count", "msim_map_connection_count", "msim_map_roads", "msim_map_connections", "msim_map_last_error", "msim_entities_init", "msim_entities_init_roads", "msim_calc_node_count", "msim_abi_version", "msim_map_from_geojson", "msim_map_save_binary", "msim_map_load_binary", "msim_map_load", "msim_map_from_arrays", "msim_haversine_m"]
 
 
-def lib():
-    """Loads libmsim_cuda.so; raises if it has not been built (no fallback exists)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()). "
-            "movement_sim_b200 has no CPU or alternative backend."
-        )
-    L = C.CDLL(LIB_PATH)
+def _signatures():
     vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
-    sigs = {
+    return {
         "msim_create": (i32, [C.POINTER(_Config), C.POINTER(vp)]),
         "msim_destroy": (None, [vp]),
         "msim_last_error": (C.c_char_p, [vp]),
@@ -259,12 +253,40 @@ def lib():
         "msim_map_from_arrays": (i32, [f32, f32, vp, u64, vp, u64, C.POINTER(vp)]),
         "msim_haversine_m": (C.c_double, [C.c_double] * 4),
     }
-    for name, (res, args) in sigs.items():
+
+
+def _bind(L, names):
+    sigs = _signatures()
+    for name in names:
         fn = getattr(L, name)
-        fn.restype = res
-        fn.argtypes = args
-    _lib = L
+        fn.restype, fn.argtypes = sigs[name]
     return L
+
+
+def lib():
+    """Loads libmsim_cuda.so; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()). "
+            "movement_sim_b200 has no CPU or alternative backend."
+        )
+    _lib = _bind(C.CDLL(LIB_PATH), list(_signatures()))
+    return _lib
+
+
+def host_lib():
+    """The host-only part of the C ABI (HOST_SYMBOLS) from libmsim_host.so: the same objects libmsim_cuda.so links, without the CUDA
+    runtime, so that a process that only prepares inputs (bench.py --impl reference) never maps the CUDA library."""
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_LIB_PATH):
+        raise ImportError(f"{HOST_LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()).")
+    _host = _bind(C.CDLL(HOST_LIB_PATH), HOST_SYMBOLS)
+    return _host
 
 
 # ---- map -------------------------------------------------------------------------------------
@@ -280,7 +302,7 @@ class Map:
 
     @classmethod
     def _take(cls, handle) -> "Map":
-        L = lib()
+        L = host_lib()
         try:
             nr, nc = L.msim_map_road_count(handle), L.msim_map_connection_count(handle)
             roads = np.empty(nr, dtype=ROAD_DTYPE)
@@ -296,7 +318,7 @@ class Map:
     @classmethod
     def load_json(cls, path: str) -> "Map":
         """Map::load_from_file (/root/reference/src/sim/Map.cpp:28-150)."""
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         rc = L.msim_map_load_json(os.fsencode(path), C.byref(h))
         if rc != MSIM_OK:
@@ -306,7 +328,7 @@ class Map:
     @classmethod
     def load(cls, path: str) -> "Map":
         """Any supported map file: binary cache, GeoJSON export, or the reference's map JSON (msim_map_load)."""
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         rc = L.msim_map_load(os.fsencode(path), C.byref(h))
         if rc != MSIM_OK:
@@ -316,7 +338,7 @@ class Map:
     @classmethod
     def from_geojson(cls, path: str, flags: int = 0, with_stats: bool = False):
         """/root/reference/map/generate_map.py as a native pipeline (include/msim_mapgen.h)."""
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         st = MapgenStats()
         rc = L.msim_map_from_geojson(os.fsencode(path), flags, C.byref(h), C.byref(st))
@@ -327,7 +349,7 @@ class Map:
 
     def save_binary(self, path: str) -> None:
         """Binary map cache (msim_map_save_binary)."""
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         rc = L.msim_map_from_arrays(self.width, self.height, self.roads.ctypes.data, self.roads.shape[0], self.connections.ctypes.data,
                                     self.connections.shape[0], C.byref(h))
@@ -345,7 +367,7 @@ class Map:
              drop_prob: float = 0.12, seed: int = 2022) -> "Map":
         """Seeded stand-in for the missing munich.json (world size from
         /root/reference/shader_validation/src/main.cpp:155)."""
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         rc = L.msim_map_generate_city(world_w, world_h, spacing, jitter, drop_prob, seed, C.byref(h))
         if rc != MSIM_OK:
@@ -354,7 +376,7 @@ class Map:
 
     @classmethod
     def grid(cls, nx: int, ny: int, spacing: float = 20.0) -> "Map":
-        L = lib()
+        L = host_lib()
         h = C.c_void_p()
         rc = L.msim_map_generate_grid(nx, ny, spacing, C.byref(h))
         if rc != MSIM_OK:
@@ -363,7 +385,7 @@ class Map:
 
     def init_entities(self, count: int, seed: int = 42, box=None) -> np.ndarray:
         """Simulator::add_entities (/root/reference/src/sim/Simulator.cpp:114-129), seeded."""
-        L = lib()
+        L = host_lib()
         out = np.zeros(count, dtype=ENTITY_DTYPE)
         boxp = None
         if box is not None:
@@ -384,9 +406,9 @@ def _init_road_indices(self, count: int, seed: int = 42, box=None) -> np.ndarray
         box = np.ascontiguousarray(box, dtype=np.float32)
         assert box.shape == (4,)
         boxp = box.ctypes.data
-    rc = lib().msim_entities_init_roads(self.roads.ctypes.data, self.roads.shape[0], count, seed, boxp, out.ctypes.data)
+    rc = host_lib().msim_entities_init_roads(self.roads.ctypes.data, self.roads.shape[0], count, seed, boxp, out.ctypes.data)
     if rc != MSIM_OK:
-        raise MsimError(rc, lib().msim_map_last_error().decode())
+        raise MsimError(rc, host_lib().msim_map_last_error().decode())
     return out
 
 
@@ -430,7 +452,7 @@ def shard_buffer_bytes(migrant_capacity: int, halo_capacity: int) -> int:
 
 
 def calc_node_count(depth: int) -> int:
-    return int(lib().msim_calc_node_count(depth))
+    return int(host_lib().msim_calc_node_count(depth))
 
 
 # ---- simulation handle -----------------------------------------------------------------------
@@ -548,6 +570,12 @@ class Simulation:
         out = np.empty((self.count, 2), dtype=np.float32)
         self._check(lib().msim_read_positions(self._h, out.ctypes.data, self.count))
         return out
+
+    def read_positions_ptr(self, ptr: int, count: int):
+        self._check(lib().msim_read_positions(self._h, ptr, count))
+
+    def read_collision_flags_ptr(self, ptr: int, count: int):
+        self._check(lib().msim_read_collision_flags(self._h, ptr, count))
 
     def read_collision_flags(self) -> np.ndarray:
         out = np.empty(self.count, dtype=np.uint8)

@@ -131,6 +131,7 @@ struct msim_handle {
     uint32_t* place_dst{nullptr};
     uint2* moves{nullptr};
     uint32_t* row_hist{nullptr};
+    uint32_t row_hist_rows{0};  // rows the allocation holds (the grid can grow through push constants)
     uint32_t* host_stage{nullptr};  // pinned, two halves
     bool stage_flip{false};
     void* sent_down{nullptr};
@@ -962,15 +963,25 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
     return check_device_errors(h);
 }
 
-int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
+namespace {
+// what every readback checks first: the host's entity count is current (asynchronous sharded ticks keep it on the device), the
+// request fits it, and a sharded handle is not in the middle of an exchange
+int readback_preconditions(msim_handle* h, const char* who, const void* dst, uint64_t count, bool needs_flags) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     rc = refresh_counts(h);
     if (rc != MSIM_OK) return rc;
-    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: count exceeds the resident entity count");
-    if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: dst is null");
-    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_move_pack and msim_shard_integrate");
-    if (h->flags_stale) return fail(h, MSIM_ERR_INVALID, "msim_read_entities: sharded handle is between msim_shard_integrate and the collision pass");
+    if (count > h->n) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": count exceeds the resident entity count");
+    if (count && !dst) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": dst is null");
+    if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": sharded handle is between msim_shard_move_pack and msim_shard_integrate");
+    if (needs_flags && h->flags_stale) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": sharded handle is between msim_shard_integrate and the collision pass");
+    return MSIM_OK;
+}
+}  // namespace
+
+int msim_read_entities(msim_handle* h, msim_entity* dst, uint64_t count) {
+    int rc = readback_preconditions(h, "msim_read_entities", dst, count, true);
+    if (rc != MSIM_OK) return rc;
     const PackArgs a = pack_args(h);
     for (uint64_t off = 0; off < count; off += STAGE_ENTITIES) {
         const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(STAGE_ENTITIES, count - off));
@@ -1045,10 +1056,8 @@ int msim_snapshot_end(msim_handle* h, const msim_entity** entities, uint64_t* co
 }
 
 int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count) {
-    int rc = bind(h);
+    int rc = readback_preconditions(h, "msim_read_positions", dst_xy, count, false);
     if (rc != MSIM_OK) return rc;
-    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: count exceeds the resident entity count");
-    if (count && !dst_xy) return fail(h, MSIM_ERR_INVALID, "msim_read_positions: dst is null");
     const float2* src = h->pos[h->cur];
     if (count && h->perm_active) {  // storage is in cell order: gather into external order first
         float2* tmp = reinterpret_cast<float2*>(h->sort_a);
@@ -1060,25 +1069,20 @@ int msim_read_positions(msim_handle* h, float* dst_xy, uint64_t count) {
 }
 
 int msim_read_collision_flags(msim_handle* h, uint8_t* dst, uint64_t count) {
-    int rc = bind(h);
+    int rc = readback_preconditions(h, "msim_read_collision_flags", dst, count, true);
     if (rc != MSIM_OK) return rc;
-    if (count > h->n) return fail(h, MSIM_ERR_INVALID, "msim_read_collision_flags: count exceeds the resident entity count");
-    if (count && !dst) return fail(h, MSIM_ERR_INVALID, "msim_read_collision_flags: dst is null");
     if (!h->collided) {
-        std::memset(dst, 0, count);
+        if (count) std::memset(dst, 0, count);
         return MSIM_OK;
     }
-    materialise_flags(h);
-    const uint8_t* fsrc = h->flag_entity;
-    if (count && h->perm_active) {
+    rc = materialise_flags(h);
+    if (rc != MSIM_OK) return rc;
+    if (count) {  // external order, 0 / 1: one gather on the device instead of a pass over the result on the host
         uint8_t* tmp = reinterpret_cast<uint8_t*>(h->sort_b);
-        h->launches += launch_gather_flag(h->stream, static_cast<uint32_t>(count), h->slot_of, h->flag_entity, tmp);
-        fsrc = tmp;
+        h->launches += launch_gather_flag(h->stream, static_cast<uint32_t>(count), h->perm_active ? h->slot_of : nullptr, h->flag_entity, tmp);
+        MSIM_CUDA(h, cudaMemcpyAsync(dst, tmp, count, cudaMemcpyDeviceToHost, h->stream));
     }
-    if (count) MSIM_CUDA(h, cudaMemcpyAsync(dst, fsrc, count, cudaMemcpyDeviceToHost, h->stream));
-    rc = check_device_errors(h);
-    for (uint64_t i = 0; i < count; i++) dst[i] = dst[i] == 2 ? 1 : 0;
-    return rc;
+    return check_device_errors(h);
 }
 
 namespace {
@@ -1310,6 +1314,7 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->place_dst, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    h->row_hist_rows = static_cast<uint32_t>(h->grid.ncy);
     MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_COUNT_WORDS));
     rc = write_dev_counts(h);
     if (rc != MSIM_OK) return rc;
@@ -1661,7 +1666,13 @@ int msim_shard_row_histogram(msim_handle* h, uint32_t* dst, uint32_t rows) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
     if (!dst || rows != static_cast<uint32_t>(h->grid.ncy)) return fail(h, MSIM_ERR_INVALID, "msim_shard_row_histogram: rows must equal grid_cells_y");
-    if (!h->row_hist) MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
+    if (!h->row_hist || h->row_hist_rows < rows) {  // first use, or the grid has grown since (radius / world change through push constants)
+        cudaFree(h->row_hist);
+        h->row_hist = nullptr;
+        h->row_hist_rows = 0;
+        MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(rows)));
+        h->row_hist_rows = rows;
+    }
     rc = refresh_counts(h);
     if (rc != MSIM_OK) return rc;
     rc = ensure_keys(h);

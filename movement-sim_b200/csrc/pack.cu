@@ -130,9 +130,10 @@ __global__ void __launch_bounds__(256) gather_pos_kernel(uint32_t n, const uint3
     if (i < n) out[i] = pos[slot_of[i]];
 }
 
+// readback form of the collision flag: 1 = blue (a neighbour within the radius), 0 = green or no collision pass yet (internally 2 / 1 / 0)
 __global__ void __launch_bounds__(256) gather_flag_kernel(uint32_t n, const uint32_t* __restrict__ slot_of, const uint8_t* __restrict__ flag, uint8_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = flag[slot_of ? slot_of[i] : i];
+    if (i < n) out[i] = flag[slot_of ? slot_of[i] : i] == 2 ? 1 : 0;
 }
 
 }  // namespace

@@ -356,7 +356,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     import torch
     import torch.distributed as dist
 
-    from bench import KERNEL_BYTES, METRIC, SURVEY_BYTES, ClockSampler, build_workload, emit, load_peaks, load_traffic
+    from bench import KERNEL_BYTES, METRIC, RESORT_EVERY, ClockSampler, align_resort_phase, build_workload, check_counts, emit, load_peaks
 
     w, m = build_workload(M, args.workload, args.entities)
     collisions = w["collisions"]
@@ -385,9 +385,12 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
             sim.dispatch(2)
             sim.enqueue_ticks(args.preroll, False)
             step = lambda: sim.enqueue_ticks(1, False)
+        step()  # (the single-GPU arm's one untimed tick behind the pre-roll: every N is at the same tick when timing starts)
         for _ in range(max(3, args.warmup)):
             step()
+        aligned = align_resort_phase(sim.stats, step) if collisions else 0  # same cadence on every rank: same number of ticks
         sim.sync()
+        st0 = sim.stats()
         if rank == 0:
             props = torch.cuda.get_device_properties(local_rank)
             uuid = getattr(props, "uuid", None)
@@ -407,15 +410,16 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         t = torch.tensor([ms_local], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
         ms = float(t.item())
-        launches = sim.stats()["kernel_launches"] - launches0
-        owned = torch.tensor([sim.stats()["entity_count"]], dtype=torch.int64, device=device)
+        st1 = sim.stats()  # state at the END of the timed region
+        launches = st1["kernel_launches"] - launches0
+        owned = torch.tensor([st1["entity_count"]], dtype=torch.int64, device=device)
         gathered = [torch.zeros_like(owned) for _ in range(world)]
         dist.all_gather(gathered, owned)
         per_rank = [int(g.item()) for g in gathered]
         pairs = flagged = None
         if collisions:
-            st = sim.stats()
-            pairs, flagged = sh.global_sum(st["last_pair_count"]), sh.global_sum(st["last_flagged_count"])
+            pairs, flagged = sh.global_sum(st1["last_pair_count"]), sh.global_sum(st1["last_flagged_count"])
+        check = check_counts(args.workload, total, st1["move_passes"], pairs, flagged)
         # per-kernel device time on rank 0 over a second pass of the same K steps (events around every launch)
         kernels = None
         if rank == 0:
@@ -493,7 +497,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
             "metric": METRIC, "value": value, "unit": "entity-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": args.workload, "entities_per_gpu": per_gpu, "entities_total": total, "collisions": collisions,
-                       "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll,
+                       "collision_radius_m": 10.0, "map": w["map_desc"], "entity_seed": 42, "preroll_move_passes": args.preroll, "entities": total,
                        "parallelism": (f"{world} spatial bands of cell rows; halo + migrants per tick "
                                        + ("stored by the move kernel into the neighbours' buffers over NVLink peer memory, flag-synchronised (no collective call)"
                                           if sh.exchange == "p2p" else "through one NCCL all_to_all_single")
@@ -503,7 +507,10 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
                        "owned_per_rank": per_rank, "l2": ("inputs larger than L2 (no flush)" if per_gpu * 40 > 200e6 else "per-GPU working set may sit in L2 (strong scaling of a fixed population)"),
                        "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels,
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
-                       "global_pairs_last_tick": pairs, "global_flagged_last_tick": flagged},
+                       "move_passes_done": st1["move_passes"], "pairs_last_tick": pairs, "flagged_last_tick": flagged, "counts_check": check,
+                       "resort": {"every_collision_passes": RESORT_EVERY, "in_timed_region": st1["reorders"] - st0["reorders"],
+                                  "alignment_ticks_untimed": aligned,
+                                  "note": "the timed region starts on a re-sorting tick: it holds 1 + (K - 1) // 32 re-sorts, never fewer than its share"}},
             "roofline": roofline,
             "tick": {"survey_bytes_per_entity_update": w["survey_bytes"], "achieved_gbs": tick_gbs, "frac_of_measured_peak": tick_gbs / (peak * world),
                      "frac_of_nominal_8tbs": tick_gbs / (8000.0 * world), "peak_source": peak_src},
@@ -518,4 +525,4 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
     dist.barrier()
     sim.close()
     dist.destroy_process_group()
-    return 0
+    return 3 if check.get("status") == "mismatch" else 0

@@ -7,6 +7,7 @@
 #include <array>
 #include <chrono>
 #include <cstddef>
+#include <cstdio>
 #include <string>
 
 namespace utils {
@@ -39,9 +40,19 @@ class TickDurationHistory {
         if (count_ < WINDOW) count_++;
     }
     [[nodiscard]] std::chrono::nanoseconds get_avg_time() const { return count_ ? sum_ / static_cast<int64_t>(count_) : std::chrono::nanoseconds(0); }
+    // the overlay string, as the reference prints it (utils/TickDurationHistory.cpp:36-55): two decimals in the largest unit of
+    // ns / us / ms / s that keeps the value >= 1, e.g. "12.30us"
     [[nodiscard]] std::string get_avg_time_str() const {
-        const double ms = std::chrono::duration<double, std::milli>(get_avg_time()).count();
-        return std::to_string(ms) + "ms";
+        static constexpr struct { double ns; const char* unit; } SCALES[] = {{1e9, "s"}, {1e6, "ms"}, {1e3, "us"}, {1.0, "ns"}};
+        const double t = static_cast<double>(get_avg_time().count());
+        for (const auto& sc : SCALES) {
+            if (t >= sc.ns || sc.ns == 1.0) {
+                char buf[48];
+                std::snprintf(buf, sizeof(buf), "%.2f%s", t / sc.ns, sc.unit);
+                return buf;
+            }
+        }
+        return "0.00ns";
     }
 
  private:

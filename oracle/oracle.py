@@ -185,18 +185,34 @@ def collision_flags(e: np.ndarray) -> np.ndarray:
 # oracle/_ref: the reference's own CPU quadtree (shader_validation/src/main.cpp) compiled here
 # --------------------------------------------------------------------------------------------
 REF_LIB = os.path.join(HERE, "_ref", "libref_quadtree.so")
+REF_LIB_LARGE = os.path.join(HERE, "_ref", "libref_quadtree_large.so")  # same sources, capacity for BASELINE config 3 at full size
 REF_KAT = os.path.join(HERE, "_ref", "ref_kat")
 _ref = None
+_ref_large = None
 
 
 def ref_available() -> bool:
     return os.path.exists(REF_LIB)
 
 
-def ref():
-    global _ref
+def ref_large_available() -> bool:
+    return os.path.exists(REF_LIB_LARGE)
+
+
+def ref(large: bool = False):
+    """The compiled reference harness.  large=True: the build with room for 10 M entities (bench.py's reference arm)."""
+    global _ref, _ref_large
+    if large:
+        if _ref_large is None:
+            _ref_large = _bind_ref(C.CDLL(REF_LIB_LARGE))
+        return _ref_large
     if _ref is None:
-        R = C.CDLL(REF_LIB)
+        _ref = _bind_ref(C.CDLL(REF_LIB))
+    return _ref
+
+
+def _bind_ref(R):
+    if True:
         R.ref_capacity.restype = C.c_size_t
         R.ref_node_count.restype = C.c_size_t
         R.ref_reset.restype = None
@@ -212,16 +228,15 @@ def ref():
         R.ref_count_entities_in_tree.restype = C.c_size_t
         R.ref_dump_tree.restype = C.c_size_t
         R.ref_dump_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
-        _ref = R
-    return _ref
+    return R
 
 
 class RefQuadTree:
     """Drives the compiled reference quadtree: insert -> (update)* -> collide, as the shader's
     dispatches do (random_move.comp:863-877)."""
 
-    def __init__(self, world_w: float, world_h: float, radius: float = 10.0, node_cap: int = 10):
-        self.R = ref()
+    def __init__(self, world_w: float, world_h: float, radius: float = 10.0, node_cap: int = 10, large: bool = False):
+        self.R = ref(large)
         self.R.ref_reset(world_w, world_h, node_cap, radius)
         self.n = 0
 

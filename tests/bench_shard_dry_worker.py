@@ -64,6 +64,24 @@ def run(rank, world, port, out_path, argv):
     class FakeSim:
         def __init__(self, engine):
             self.engine, self.launches, self.profiling = engine, 0, False
+            # the library's counters the bench reads: move passes, and the re-sort cadence of api.cu (first collision pass, then every 32nd)
+            self.moves, self.reorders, self.since = 0, 0, 32
+            for name in ("move", "move_pack"):
+                if hasattr(engine, name):
+                    setattr(engine, name, self._counted(getattr(engine, name), "moves"))
+            if hasattr(engine, "collide"):
+                engine.collide = self._counted(engine.collide, "collides")
+
+        def _counted(self, fn, what):
+            def wrapped(*a, **k):
+                if what == "moves":
+                    self.moves += 1
+                else:
+                    self.since += 1
+                    if self.since >= 32:
+                        self.reorders, self.since = self.reorders + 1, 0
+                return fn(*a, **k)
+            return wrapped
 
         def dispatch(self, tick):
             self.engine.move()  # the init-only first dispatch
@@ -73,7 +91,7 @@ def run(rank, world, port, out_path, argv):
 
         def stats(self):
             self.launches += 11
-            return dict(self.engine.stats(), kernel_launches=self.launches)
+            return dict(self.engine.stats(), kernel_launches=self.launches, move_passes=self.moves, reorders=self.reorders)
 
         def profile_begin(self):
             self.profiling = True

@@ -84,3 +84,98 @@ def test_workload_builders(msim, monkeypatch):
 
     w, m = bench.build_workload(msim, "munich_10m_collisions", None)
     assert w["entities"] == 10_000_000 and w["box"] is None and w["survey_bytes"] == 124.0
+
+
+def test_reference_arm_runs_the_gpu_arms_configuration():
+    """same population, same pre-roll, structured same_config / sampled-count fields; a budget that one step crosses stops the timing"""
+    line = run_bench("--impl", "reference", "--workload", "munich_10m_collisions", "--entities", "4000", "--steps", "5", "--warmup", "3", "--preroll", "4",
+                     "--ref-budget-s", "0", "--no-whole-shader")
+    check_reference_line(line, "munich_10m_collisions")
+    c = line["config"]
+    assert c["entities"] == 4000 and c["entities_sampled"] == 4000 and c["same_config"] is True
+    assert c["steps_asked"] == 5 and c["steps_timed"] == 1 and line["steps"] == 1
+    assert c["move_passes_done"] == 4 + 1 + 3 + 1 and c["entity_seed"] == 42 and c["preroll_move_passes"] == 4
+    assert isinstance(c["flagged_last_tick"], int) or c["flagged_last_tick"] is None
+
+
+def test_input_preparation_never_maps_the_cuda_library():
+    """bench.py --impl reference prepares its inputs through libmsim_host.so (the reference arm loaded libmsim_cuda.so)"""
+    code = ("import sys; sys.path.insert(0, %r); import bench, movement_sim_b200 as M; w, m = bench.build_workload(M, 'munich_10m_collisions', 2000); "
+            "e = bench.build_population(M, m, 2000, w['box']); maps = open('/proc/self/maps').read(); "
+            "assert 'libmsim_host.so' in maps and 'libmsim_cuda.so' not in maps, maps; print(e.shape[0])") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == "2000"
+
+
+def test_population_is_the_sharded_generators(msim):
+    """N = 1 and N > 1 bench the same draws: bench.build_population == concatenated sharding.generate_population chunks"""
+    import bench
+    from movement_sim_b200 import sharding
+
+    m = msim.Map.load_json(os.path.join(ROOT, "tests", "golden", "test_map.json"))
+    old = sharding.CHUNK
+    sharding.CHUNK = 700
+    try:
+        a = bench.build_population(msim, m, 2000)
+        b = np.concatenate([e for _, e in sharding.generate_population(msim, m, 2000, 42)])
+    finally:
+        sharding.CHUNK = old
+    assert a.shape[0] == 2000 and a.tobytes() == b.tobytes()
+
+
+def test_resort_alignment_matches_the_golden_generators_formula():
+    """align_resort_phase leaves the NEXT collision pass a re-sorting one, and tests/golden/make_bench_counts.py predicts the tick index"""
+    import importlib.util
+
+    import bench
+
+    spec = importlib.util.spec_from_file_location("make_bench_counts", os.path.join(ROOT, "tests", "golden", "make_bench_counts.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    class Fake:  # api.cu's cadence: since_reorder = every at upload; a collision pass re-sorts when since_reorder reaches `every`
+        def __init__(self):
+            self.since, self.reorders, self.moves = bench.RESORT_EVERY, 0, 0
+
+        def tick(self):
+            self.moves += 1
+            self.since += 1
+            if self.since >= bench.RESORT_EVERY:
+                self.reorders += 1
+                self.since = 0
+
+        def stats(self):
+            return {"reorders": self.reorders}
+
+    for warmup in (0, 3, 5, 10, 31, 40):
+        for steps in (1, 20, 33, 200):
+            f = Fake()
+            f.since = bench.RESORT_EVERY - 1  # (the first collision pass behind an upload re-sorts)
+            preroll = 7
+            f.moves = preroll
+            f.tick()
+            for _ in range(max(3, warmup)):
+                f.tick()
+            bench.align_resort_phase(f.stats, f.tick)
+            before = f.reorders
+            f.tick()
+            assert f.reorders == before + 1, "the first timed tick must re-sort"
+            for _ in range(steps - 1):
+                f.tick()
+            assert f.reorders - before == 1 + (steps - 1) // bench.RESORT_EVERY
+            assert f.moves == gen.passes_done(preroll, warmup, steps)
+
+
+def test_check_counts(tmp_path, monkeypatch):
+    import bench
+
+    p = tmp_path / "counts.json"
+    p.write_text(json.dumps({"w": {"100": {"340": {"pairs": 7, "flagged": 5}}}}))
+    monkeypatch.setattr(bench, "COUNTS_PATH", str(p))
+    assert bench.check_counts("w", 100, 340, 7, 5)["status"] == "ok"
+    assert bench.check_counts("w", 100, 340, 8, 5)["status"] == "mismatch"
+    assert bench.check_counts("w", 100, 341, 7, 5)["status"] == "no stored value"
+    assert bench.check_counts("w", 100, 340, None, None)["status"].startswith("not applicable")
+    stored = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_counts.json")))
+    assert "340" in stored["munich_10m_collisions"]["10000000"]  # the driver's --steps 20 --warmup 5

@@ -34,8 +34,8 @@ class FakeEvent:
 
 
 class FakeTensor:
-    def __init__(self, n):
-        self.a = np.zeros(n, dtype=np.uint8)
+    def __init__(self, n, itemsize=1):
+        self.a = np.zeros(n * itemsize, dtype=np.uint8)
 
     def data_ptr(self):
         return self.a.ctypes.data
@@ -49,8 +49,8 @@ class FakeTensor:
 
 def fake_torch():
     t = types.ModuleType("torch")
-    t.uint8 = "uint8"
-    t.empty = lambda n, dtype=None, pin_memory=False, device=None: FakeTensor(n)
+    t.uint8, t.float32 = "uint8", "float32"
+    t.empty = lambda n, dtype=None, pin_memory=False, device=None: FakeTensor(n, 4 if dtype == "float32" else 1)
     cuda = types.SimpleNamespace()
     cuda.set_device = lambda d: None
     cuda.Stream = lambda: types.SimpleNamespace(cuda_stream=0)
@@ -81,10 +81,18 @@ def make_fake_simulation(M, O):
             self.radius, self.flags, self.count = float(radius), flags, self.e.shape[0]
             self.launches, self.pairs, self.profile = 0, 0, None
             self.snap = None
+            self.moves = self.collides = self.reorders = 0
+            self.since = 32  # api.cu: the first collision pass behind an upload re-sorts, then every 32nd
 
         def _tick(self, collide):
             O.move_pass(self.e, self.om, threads=4)
+            self.moves += 1
             self.launches += 2
+            if collide:
+                self.collides += 1
+                self.since += 1
+                if self.since >= 32:
+                    self.reorders, self.since = self.reorders + 1, 0
             if self.profile is not None:
                 for k in ("move", "arrive"):
                     c, ms = self.profile.get(k, (0, 0.0))
@@ -112,7 +120,8 @@ def make_fake_simulation(M, O):
 
         def stats(self):
             return {"kernel_launches": self.launches, "last_pair_count": self.pairs, "last_flagged_count": int(O.collision_flags(self.e).sum()),
-                    "entity_count": self.count, "grid_cells_x": 1, "grid_cells_y": 1}
+                    "entity_count": self.count, "grid_cells_x": 1, "grid_cells_y": 1, "move_passes": self.moves, "collide_passes": self.collides,
+                    "reorders": self.reorders}
 
         def profile_begin(self):
             self.profile = {}
@@ -126,6 +135,12 @@ def make_fake_simulation(M, O):
 
         def upload_ptr(self, ptr, n):
             ctypes.memmove(self.e.ctypes.data, ptr, n * 64)
+
+        def read_positions_ptr(self, ptr, n):
+            ctypes.memmove(ptr, np.ascontiguousarray(self.e["pos"][:n]).ctypes.data, n * 8)
+
+        def read_collision_flags_ptr(self, ptr, n):
+            ctypes.memmove(ptr, np.ascontiguousarray(O.collision_flags(self.e)[:n]).ctypes.data, n)
 
         def snapshot_begin(self):
             self.snap = self.e.copy()
@@ -143,10 +158,10 @@ def make_fake_simulation(M, O):
 @pytest.mark.parametrize("backend,argv", [
     ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "6000"]),
     ("stand-in", ["--workload", "munich_1m_nocollisions", "--entities", "5000"]),
-    ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "4000", "--e2e-pipelined", "--no-flags-only"]),
+    ("stand-in", ["--workload", "munich_10m_collisions", "--entities", "4000", "--no-e2e-variants", "--no-flags-only"]),
     # against the real api.cu + kernels under the emulator: the bench's map has 4.8 M grid cells, i.e. 2 x 1165 scan CTAs per tick, which costs
     # the emulator minutes - all three configurations passed that way by hand; in the suite only with MSIM_TEST_SLOW=1
-    pytest.param("emulated library", ["--workload", "munich_10m_collisions", "--entities", "1200", "--e2e-pipelined"],
+    pytest.param("emulated library", ["--workload", "munich_10m_collisions", "--entities", "1200"],
                  marks=pytest.mark.skipif(os.environ.get("MSIM_TEST_SLOW") != "1", reason="minutes under the emulator: set MSIM_TEST_SLOW=1")),
 ])
 def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv, backend):
@@ -184,7 +199,15 @@ def test_gpu_arm_assembles_its_json_line(msim, orc, monkeypatch, capfd, argv, ba
         assert "move" in names and (("query" in names and "cell_scatter" in names) if collisions else "query" not in names)
         assert line["gpu_launches"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == line["config"]["entities"] * 64 == line["e2e"]["d2h_bytes_per_step"]
-    assert ("pipelined" in line["e2e"]) == ("--e2e-pipelined" in argv)
+    variants = line["e2e"]["variants"]
+    assert ("pipelined_full_aos" in variants) == ("--no-e2e-variants" not in argv)
+    if "--no-e2e-variants" not in argv:
+        assert variants["full_aos_up_render_state_down"]["d2h_bytes_per_step"] == line["config"]["entities"] * (9 if collisions else 8)
+        assert line["e2e"]["variant"] in ("blocking_full_aos", "pipelined_full_aos")
+    c = line["config"]
+    assert c["move_passes_done"] > 0 and c["counts_check"]["status"] in ("no stored value", "not applicable (collisions off)")
+    if collisions:
+        assert c["pairs_last_tick"] is not None and c["flagged_last_tick"] is not None and c["resort"]["in_timed_region"] == 1
     assert (line["move_only"] is not None) == collisions
     if collisions and "--no-flags-only" not in argv:
         assert line["flags_only"]["ms_per_step"] > 0
@@ -230,7 +253,9 @@ def test_multi_gpu_arm_assembles_its_json_line(tmp_path, argv):
     assert line["tick"]["survey_bytes_per_entity_update"] == (124.0 if collisions else 24.0)
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     if collisions:
-        assert line["config"]["exchange"] == "collective" and line["config"]["global_pairs_last_tick"] is not None
+        assert line["config"]["exchange"] == "collective" and line["config"]["pairs_last_tick"] is not None
+        assert line["config"]["flagged_last_tick"] is not None and line["config"]["move_passes_done"] > 0
+        assert line["config"]["counts_check"]["status"] == "no stored value"
         assert line["roofline"]["kernel"] == "query"
     if "dense" in argv[1]:
         assert "central box" in line["config"]["map"]
