@@ -704,7 +704,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: entities of the population to run (0 = all of them, the GPU arm's configuration)")
-    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after the step that crosses this many seconds")
+    ap.add_argument("--ref-budget-s", type=float, default=100.0, help="--impl reference: stop timing after the step that crosses this many seconds")
     ap.add_argument("--no-whole-shader", action="store_true", help="skip the single-thread whole-shader extra of the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flags-only", action="store_true", help="skip the extra colours-only measurement")

@@ -28,7 +28,7 @@ thread_local std::string g_create_error;
 constexpr uint64_t MAX_ENTITIES_PER_HANDLE = 1ull << 30;  // look-back words carry 30-bit counts
 constexpr uint32_t MAX_GRID_CELLS = 1u << 27;
 constexpr uint32_t STAGE_ENTITIES = 1u << 20;  // 64 MiB AoS staging chunk
-// counting sort: counter + prefix tables of 2 x 128 MiB at most by default (2^25 cells); beyond that: onesweep
+// counting sort: counter + prefix tables of 2 x 512 MiB at most (2^27 cells, the largest grid the library accepts) unless the limit is lowered
 inline uint32_t csort_max_cells() { return 1u << msim::tuning().csort_max_cells_log2; }
 }  // namespace
 
@@ -142,19 +142,23 @@ struct msim_handle {
     size_t p2p_buf_bytes{0};
     char* p2p_peer_down{nullptr};
     char* p2p_peer_up{nullptr};
+    char* p2p_send{nullptr};             // local send buffers, index 2 * parity + side: the move kernel fills them, the push kernel copies them out
+    uint32_t* p2p_push_ticket{nullptr};
+    cudaStream_t push_stream{nullptr};   // the push kernel's own stream: its remote stores complete off the tick's critical path
+    cudaEvent_t ev_packed_move{nullptr}, ev_pushed{nullptr};
+    bool push_pending{false};
     bool p2p_down_ipc{false}, p2p_up_ipc{false};
     bool p2p_connected{false};
     uint32_t p2p_tick{0};
     unsigned long long p2p_timeout_ns{10000000000ull};
     uint32_t band_lo{0}, band_hi{0};  // cell rows that can hold this handle's keys after the last pack + integrate (ghost rows excluded)
     bool packed{false};
-    bool p2p_merged{true};            // emit rides in the exchange kernel (false: separate launch right behind the move kernel)
-    bool emit_pending{false};         // peer-memory exchange: the emit step rides in the exchange kernel of msim_shard_p2p_integrate
-    ShardMoveArgs pending_emit{};
     bool count_fused{false};          // the last move + pack ranked the stayers: place / relocate / ghost kernels complete the per-cell counters
     bool awaiting_integrate{false};   // a fused move + pack has run: pass B stays deferred until the exchange has been integrated
     bool band_valid{false};           // false between a move pass and the integrate that follows it
-    uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, error bits}: what asynchronous sharded ticks run on
+    unsigned long long* shard_trace{nullptr};  // MSIM_SHARD_TRACE=1: phase times of the exchange kernel, printed at msim_destroy
+    uint32_t* dev_counts{nullptr};  // device-resident {owned, ghosts, total, ...} in two alternating sets + sticky error bits: what asynchronous sharded ticks run on
+    uint32_t counts_set{0};         // the set that holds the current counts (msim_internal.h ShardCounts)
     bool async_counts{false};       // host-side n / n_ghost are stale (upper bound = capacity) until the next refresh
 
     // asynchronous readback (msim_snapshot_*): device image of the AoS state, two pinned host buffers used alternately
@@ -267,7 +271,10 @@ void free_all(msim_handle* h) {
     cudaFree(h->dev_counts); cudaFree(h->gid_alt);
     if (h->p2p_peer_down && h->p2p_down_ipc) cudaIpcCloseMemHandle(h->p2p_peer_down);
     if (h->p2p_peer_up && h->p2p_up_ipc) cudaIpcCloseMemHandle(h->p2p_peer_up);
-    cudaFree(h->p2p_arena);
+    cudaFree(h->p2p_arena); cudaFree(h->p2p_send); cudaFree(h->p2p_push_ticket);
+    if (h->push_stream) cudaStreamDestroy(h->push_stream);
+    if (h->ev_packed_move) cudaEventDestroy(h->ev_packed_move);
+    if (h->ev_pushed) cudaEventDestroy(h->ev_pushed);
     cudaFree(h->gid); cudaFree(h->holes); cudaFree(h->local_ghosts); cudaFree(h->shard_ctr); cudaFree(h->place_dst);
     cudaFree(h->moves); cudaFree(h->row_hist);
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -292,8 +299,17 @@ void free_all(msim_handle* h) {
 // bound for grid sizing plus device pointers the kernels read the exact counts from
 inline uint32_t launch_owned(const msim_handle* h) { return h->async_counts ? h->cap : h->n; }
 inline uint32_t launch_total(const msim_handle* h) { return h->async_counts ? h->cap : h->n + h->n_ghost; }
-inline const uint32_t* dev_owned(const msim_handle* h) { return h->async_counts ? h->dev_counts + DEV_N_OWNED : nullptr; }
-inline const uint32_t* dev_total(const msim_handle* h) { return h->async_counts ? h->dev_counts + DEV_N_TOTAL : nullptr; }
+inline uint32_t* cur_counts(const msim_handle* h) { return h->dev_counts + h->counts_set * DEV_COUNT_WORDS; }
+inline const uint32_t* dev_owned(const msim_handle* h) { return h->async_counts ? cur_counts(h) + DEV_N_OWNED : nullptr; }
+inline const uint32_t* dev_total(const msim_handle* h) { return h->async_counts ? cur_counts(h) + DEV_N_TOTAL : nullptr; }
+inline uint32_t* dev_error(const msim_handle* h) { return h->dev_counts + DEV_SHARD_ERROR; }
+// counts for an integrate: reads the current set, writes the other one, which becomes current for everything enqueued behind it
+inline ShardCounts flip_counts(msim_handle* h) {
+    ShardCounts c{cur_counts(h), nullptr, dev_error(h)};
+    h->counts_set ^= 1u;
+    c.out = cur_counts(h);
+    return c;
+}
 
 void launch_deferred_arrive(msim_handle* h, bool beside) {
     if (!h->arrive_deferred) return;
@@ -351,7 +367,11 @@ void join_side(msim_handle* h) {
 
 int write_dev_counts(msim_handle* h) {
     if (!h->dev_counts) return MSIM_OK;
-    const uint32_t v[DEV_COUNT_WORDS] = {h->n, h->n_ghost, h->n + h->n_ghost, 0, 0, 0, 0, 0};
+    uint32_t v[DEV_ALLOC_WORDS] = {0};  // (the sticky error word is cleared as well: the population is new)
+    h->counts_set = 0;
+    v[DEV_N_OWNED] = h->n;
+    v[DEV_N_GHOST] = h->n_ghost;
+    v[DEV_N_TOTAL] = h->n + h->n_ghost;
     MSIM_CUDA(h, cudaMemcpyAsync(h->dev_counts, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged before return
     return MSIM_OK;
 }
@@ -359,9 +379,11 @@ int write_dev_counts(msim_handle* h) {
 // asynchronous sharded ticks: bring the host-side counts up to date (one small D2H + stream sync)
 int refresh_counts(msim_handle* h) {
     if (!h->async_counts) return MSIM_OK;
-    uint32_t v[DEV_COUNT_WORDS] = {0};
-    MSIM_CUDA(h, cudaMemcpyAsync(v, h->dev_counts, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    uint32_t all[DEV_ALLOC_WORDS] = {0};
+    MSIM_CUDA(h, cudaMemcpyAsync(all, h->dev_counts, sizeof(all), cudaMemcpyDeviceToHost, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    const uint32_t* v = all + h->counts_set * DEV_COUNT_WORDS;
+    const uint32_t errors = all[DEV_SHARD_ERROR];
     h->n = v[DEV_N_OWNED];
     h->n_ghost = v[DEV_N_GHOST];
     h->async_counts = false;
@@ -369,9 +391,9 @@ int refresh_counts(msim_handle* h) {
         h->collide_owned = h->n;
         h->collide_total = h->n + h->n_ghost;
     }
-    if (v[DEV_SHARD_ERROR] & 32u) return fail(h, MSIM_ERR_INTERNAL, "peer-memory exchange: a neighbour never signalled its tick (timeout)");
-    if (v[DEV_SHARD_ERROR] & 7u) return fail(h, MSIM_ERR_CAPACITY, "shard exchange overflow (migrant / halo / entity capacity) during asynchronous ticks");
-    if (v[DEV_SHARD_ERROR]) return fail(h, MSIM_ERR_INTERNAL, "shard compaction bookkeeping mismatch");
+    if (errors & 32u) return fail(h, MSIM_ERR_INTERNAL, "peer-memory exchange: a neighbour never signalled its tick (timeout)");
+    if (errors & 7u) return fail(h, MSIM_ERR_CAPACITY, "shard exchange overflow (migrant / halo / entity capacity) during asynchronous ticks");
+    if (errors) return fail(h, MSIM_ERR_INTERNAL, "shard compaction bookkeeping mismatch");
     return MSIM_OK;
 }
 
@@ -466,7 +488,6 @@ int upload(msim_handle* h, const msim_entity* src, uint64_t count) {
     h->flags_stale = false;
     h->async_counts = false;
     h->awaiting_integrate = false;          // a pending exchange refers to the population that has just been replaced
-    h->emit_pending = false;
     h->packed = false;
     h->band_valid = false;
     h->count_fused = false;
@@ -584,10 +605,10 @@ int reorder_storage(msim_handle* h) {
         a.arrived = h->arrived;    a.arrived_new = h->arrived_alt;
         a.flag_entity = h->flag_entity;
         a.first_owned = h->cell_start - 1 + static_cast<size_t>(h->band_lo) * static_cast<size_t>(h->grid.ncx);  // the shifted table: run starts
-        a.n_owned_dev = h->dev_counts + DEV_N_OWNED;
+        a.n_owned_dev = cur_counts(h) + DEV_N_OWNED;
         a.sorted_pos = h->sorted_pos;
         a.pos_cur_new = h->pos[h->cur];  // not read by the kernel: sorted_pos holds the same positions in the new order
-        a.error_word = h->dev_counts + DEV_SHARD_ERROR;
+        a.error_word = dev_error(h);
         h->launches += launch_invert_slots(h->stream, launch_total(h), h->rank, h->sorted_idx, &h->prof, dev_total(h));  // slot -> entity on demand
         h->launches += launch_reorder_sharded(h->stream, launch_owned(h), h->cap / 32 + 2, h->sorted_idx, h->flag_sorted, a, &h->prof);
         h->slots_valid = false;
@@ -876,7 +897,17 @@ void msim_destroy(msim_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->side) cudaStreamSynchronize(h->side);
+    if (h->push_stream) cudaStreamSynchronize(h->push_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->shard_trace) {  // MSIM_SHARD_TRACE=1
+        unsigned long long t[16] = {};
+        if (cudaMemcpyAsync(t, h->shard_trace, sizeof(t), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess && t[4]) {
+            const double k = 1e-3 / static_cast<double>(t[4]);
+            std::fprintf(stderr, "msim shard trace (device %d, %llu exchanges, CTA 0): gap behind the move kernel's stamp %.1f us, flag wait %.1f us, integrate %.1f us, ghosts %.1f us; start to last CTA done %.1f us, from there to a stamp kernel behind it %.1f us\n",
+                         h->device, t[4], t[0] * k, t[1] * k, t[2] * k, t[3] * k, t[10] * k, t[11] * k);
+        }
+        cudaFree(h->shard_trace);
+    }
     free_all(h);
     delete h;
 }
@@ -1315,7 +1346,7 @@ int msim_shard_enable(msim_handle* h, const uint32_t* gids, uint64_t count, uint
     MSIM_CUDA(h, dev_alloc(&h->moves, h->holes_cap));
     MSIM_CUDA(h, dev_alloc(&h->row_hist, static_cast<size_t>(h->grid.ncy)));
     h->row_hist_rows = static_cast<uint32_t>(h->grid.ncy);
-    MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_COUNT_WORDS));
+    MSIM_CUDA(h, dev_alloc(&h->dev_counts, DEV_ALLOC_WORDS));
     rc = write_dev_counts(h);
     if (rc != MSIM_OK) return rc;
     MSIM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->host_stage), 2 * (static_cast<size_t>(h->holes_cap) * 4 + 64) * sizeof(uint32_t)));
@@ -1358,7 +1389,20 @@ struct P2PSignal {
     uint32_t* flag_down;
     uint32_t* flag_up;
     uint32_t value;
+    void* peer_down;  // the neighbours' receive buffers of this tick (the send buffers handed to move_pack_common are local)
+    void* peer_up;
 };
+
+// sender side of the peer-memory exchange, on its own stream behind the pack that has just been enqueued on the main one
+int enqueue_push(msim_handle* h, const void* send_down, const void* send_up, const P2PSignal& sig, bool counts_in_headers) {
+    MSIM_CUDA(h, cudaEventRecord(h->ev_packed_move, h->stream));
+    MSIM_CUDA(h, cudaStreamWaitEvent(h->push_stream, h->ev_packed_move, 0));
+    h->launches += launch_shard_push(h->push_stream, send_down, send_up, sig.peer_down, sig.peer_up, sig.flag_down, sig.flag_up, sig.value, h->mig_cap, h->halo_cap,
+                                     h->holes_cap, h->shard_ctr, dev_error(h), h->p2p_push_ticket, counts_in_headers);
+    MSIM_CUDA(h, cudaEventRecord(h->ev_pushed, h->push_stream));
+    h->push_pending = true;
+    return MSIM_OK;
+}
 
 int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t row_hi, void* send_down, void* send_up, const P2PSignal* sig) {
     if (!h->sharded) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": call msim_shard_enable first");
@@ -1368,9 +1412,13 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     const bool init_only = h->uninitialised;  // the reference's first dispatch moves nobody (random_move.comp:863-867)
     if (init_only) consume_init_dispatch(h);
     join_side(h);  // pass B of the previous tick: the records read target / road / rng
-    // the fused kernel counts in h->shard_ctr and writes the buffer headers itself (last CTA); the stand-alone pack kernel
-    // (init-only dispatch below) counts in the headers of the buffers, which the reset clears when they are local
-    h->launches += launch_shard_reset(h->stream, (sig || !init_only) ? nullptr : send_down, (sig || !init_only) ? nullptr : send_up, h->shard_ctr);
+    if (h->push_pending) {  // the previous tick's push reads the counters that are about to be cleared (it finished long ago)
+        MSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_pushed, 0));
+        h->push_pending = false;
+    }
+    // the fused kernel counts in h->shard_ctr (a one-thread kernel behind it, or the push kernel, writes the buffer headers); the
+    // stand-alone pack kernel (init-only dispatch below) counts in the headers of the (local) buffers, which the reset clears
+    h->launches += launch_shard_reset(h->stream, init_only ? send_down : nullptr, init_only ? send_up : nullptr, h->shard_ctr);
     ShardMoveArgs sh{};
     sh.lo_key = row_lo * static_cast<uint32_t>(h->grid.ncx);
     sh.hi_key = row_hi * static_cast<uint32_t>(h->grid.ncx);
@@ -1387,12 +1435,8 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     sh.color0 = h->color0;
     sh.road = h->road;
     sh.gid = h->gid;
-    sh.error_word = h->dev_counts + DEV_SHARD_ERROR;
-    if (sig) {
-        sh.peer_flag_down = sig->flag_down;
-        sh.peer_flag_up = sig->flag_up;
-        sh.signal_value = sig->value;
-    }
+    sh.error_word = dev_error(h);
+    sh.publish = sig ? 0u : 1u;  // peer-memory exchange: the push kernel writes the headers where they are read
     // rows that can hold owned entities once the leavers are gone: without a neighbour nobody leaves on that side
     h->band_lo = send_down ? row_lo : 0u;
     h->band_hi = send_up ? row_hi : static_cast<uint32_t>(h->grid.ncy);
@@ -1403,15 +1447,17 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
         if (rc != MSIM_OK) return rc;
         h->launches += launch_shard_pack(h->stream, shard_arrays(h), launch_owned(h), h->grid.ncx, row_lo, row_hi, send_down, send_up, h->mig_cap, h->halo_cap,
                                          h->holes, h->holes_cap, h->local_ghosts, h->shard_ctr, &h->prof, dev_owned(h), /*reset=*/false);
-        if (sig) h->launches += launch_shard_signal(h->stream, sig->flag_down, sig->flag_up, sig->value);
+        if (sig) {
+            rc = enqueue_push(h, send_down, send_up, *sig, /*counts_in_headers=*/true);
+            if (rc != MSIM_OK) return rc;
+        }
     } else {
         rc = enqueue_move(h, true, &sh);
         if (rc != MSIM_OK) return rc;
-        if (sig && h->p2p_merged) {  // peer-memory exchange: emit, wait, integrate and ghosts are ONE kernel, launched by msim_shard_p2p_integrate
-            h->pending_emit = sh;
-            h->emit_pending = true;
-        } else {
-            h->launches += launch_shard_emit(h->stream, shard_arrays(h), sh, &h->prof);  // leavers -> records, headers
+        if (h->shard_trace) launch_shard_stamp(h->stream, h->shard_trace, 5);
+        if (sig) {
+            rc = enqueue_push(h, send_down, send_up, *sig, /*counts_in_headers=*/false);
+            if (rc != MSIM_OK) return rc;
         }
         h->awaiting_integrate = true;  // pass B is deferred until the exchange has been integrated
     }
@@ -1424,7 +1470,7 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
 
 int integrate_device_common(msim_handle* h, const void* recv_down, const void* recv_up, const ShardWait* wait, bool launch = true) {
     if (launch)
-        h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), h->dev_counts, h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
+        h->launches += launch_shard_integrate_device(h->stream, shard_arrays(h), flip_counts(h), h->sent_down, h->sent_up, recv_down, recv_up, h->holes,
                                                      h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves,
                                                      h->grid, &h->prof, wait);
     h->async_counts = true;  // from here on kernels take their counts from device memory; the host values are refreshed on demand
@@ -1455,10 +1501,23 @@ int msim_shard_p2p_create(msim_handle* h, void* ipc_handle_out, void** arena_out
         const size_t bytes = P2P_FLAG_BYTES + 4 * h->p2p_buf_bytes;
         MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->p2p_arena), bytes));
         MSIM_CUDA(h, cudaMemsetAsync(h->p2p_arena, 0, bytes, h->stream));
+        MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->p2p_send), 4 * h->p2p_buf_bytes));
+        MSIM_CUDA(h, cudaMemsetAsync(h->p2p_send, 0, 4 * h->p2p_buf_bytes, h->stream));
+        MSIM_CUDA(h, dev_alloc(&h->p2p_push_ticket, 1));
+        MSIM_CUDA(h, cudaMemsetAsync(h->p2p_push_ticket, 0, sizeof(uint32_t), h->stream));
+        MSIM_CUDA(h, cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_packed_move, cudaEventDisableTiming));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_pushed, cudaEventDisableTiming));
         MSIM_CUDA(h, cudaStreamSynchronize(h->stream));  // neighbours may write as soon as they hold the pointer
         if (const char* env = std::getenv("MSIM_P2P_TIMEOUT_MS")) {
             const long v = std::atol(env);
             if (v > 0) h->p2p_timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
+        }
+        if (const char* env = std::getenv("MSIM_SHARD_TRACE")) {
+            if (std::atoi(env) == 1 && !h->shard_trace) {
+                MSIM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->shard_trace), 16 * sizeof(unsigned long long)));
+                MSIM_CUDA(h, cudaMemsetAsync(h->shard_trace, 0, 16 * sizeof(unsigned long long), h->stream));
+            }
         }
     }
     if (ipc_handle_out) {
@@ -1506,12 +1565,8 @@ int msim_shard_p2p_connect_local(msim_handle* h, void* down_arena, void* up_aren
     h->p2p_peer_down = static_cast<char*>(down_arena);
     h->p2p_peer_up = static_cast<char*>(up_arena);
     h->p2p_connected = true;
-    // Neighbours driven by ONE process are usually enqueued on one stream, band after band.  The merged exchange kernel
-    // raises its flags and then waits for the neighbours' in the same launch, which on a single stream would wait for a
-    // kernel queued behind itself; so here the emit step stays a separate launch right behind the move kernel.
-    // MSIM_P2P_MERGED=1 (handles on separate streams) selects the merged kernel anyway.
-    const char* env = std::getenv("MSIM_P2P_MERGED");
-    h->p2p_merged = env && std::atoi(env) != 0;
+    // (Neighbours driven by ONE process may share a stream: the move kernels raise the flags themselves, so as long as every band's
+    // move + pack is enqueued before any band's integrate, no kernel waits for one queued behind it.)
     return MSIM_OK;
 }
 
@@ -1525,8 +1580,11 @@ int msim_shard_p2p_move_pack(msim_handle* h, uint32_t row_lo, uint32_t row_hi) {
     sig.flag_down = h->p2p_peer_down ? p2p_flag(h->p2p_peer_down, 1) : nullptr;
     sig.flag_up = h->p2p_peer_up ? p2p_flag(h->p2p_peer_up, 0) : nullptr;
     sig.value = h->p2p_tick + 1u;
-    return move_pack_common(h, "msim_shard_p2p_move_pack", row_lo, row_hi, h->p2p_peer_down ? p2p_recv(h, h->p2p_peer_down, parity, 1) : nullptr,
-                            h->p2p_peer_up ? p2p_recv(h, h->p2p_peer_up, parity, 0) : nullptr, &sig);
+    sig.peer_down = h->p2p_peer_down ? p2p_recv(h, h->p2p_peer_down, parity, 1) : nullptr;
+    sig.peer_up = h->p2p_peer_up ? p2p_recv(h, h->p2p_peer_up, parity, 0) : nullptr;
+    // the pack fills local send buffers (two sets, by tick parity); the push kernel copies them into the neighbours' arenas
+    return move_pack_common(h, "msim_shard_p2p_move_pack", row_lo, row_hi, h->p2p_peer_down ? h->p2p_send + (2u * parity) * h->p2p_buf_bytes : nullptr,
+                            h->p2p_peer_up ? h->p2p_send + (2u * parity + 1u) * h->p2p_buf_bytes : nullptr, &sig);
 }
 
 int msim_shard_p2p_integrate(msim_handle* h) {
@@ -1543,10 +1601,10 @@ int msim_shard_p2p_integrate(msim_handle* h) {
     w.expected = h->p2p_tick + 1u;
     w.timeout_ns = h->p2p_timeout_ns;
     h->p2p_tick++;
-    h->launches += launch_shard_exchange(h->stream, shard_arrays(h), h->emit_pending ? &h->pending_emit : nullptr, h->dev_counts, recv_down, recv_up, h->holes,
+    h->launches += launch_shard_exchange(h->stream, shard_arrays(h), flip_counts(h), recv_down, recv_up, h->holes,
                                          h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves, h->grid,
-                                         &h->prof, w);
-    h->emit_pending = false;
+                                         &h->prof, w, h->shard_trace);
+    if (h->shard_trace) launch_shard_stamp(h->stream, h->shard_trace, 9);
     return integrate_device_common(h, recv_down, recv_up, nullptr, /*launch=*/false);
 }
 

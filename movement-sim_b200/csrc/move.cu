@@ -120,24 +120,55 @@ __device__ __forceinline__ void run_count(uint32_t* __restrict__ cell_count, uin
 // ---- fused shard pack (multi-GPU bands, shard.cu) ------------------------------------------------
 // Whole warp calls this once per entity slot.  Storage is in cell order, so only the warps at either end of
 // the slot range ever see a boundary row: everybody else leaves after one vote.
-//   leaver (new cell row outside the band)  -> its slot goes on the hole list; shard_emit_kernel (shard.cu), a
-//                                              one-CTA kernel right behind this one, writes the migrant records
+//   leaver (new cell row outside the band)  -> its slot goes on the hole list, its position on the local ghost list, its 72-byte
+//                                              record into that side's exchange buffer
 //   stays in the band's first / last row    -> its position is appended to the halo list of that side's exchange
 //                                              buffer (local send buffer, or the neighbour's receive buffer over
 //                                              NVLink peer memory: plain stores, the slot comes from a LOCAL counter)
-__device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new) {
+// a leaver's 72-byte migrant record, written by the thread that moved it (rare: a few hundred entities per boundary per tick; kept out
+// of line so that the streaming loop does not carry its registers).  The record holds the state BEFORE pass B (target = the waypoint
+// just reached, arrival bit set): pass B runs on whichever GPU owns the entity after the exchange and yields the same result there,
+// because new_target() reads nothing but the entity and the replicated road graph.
+// Everything but the new position is re-read from memory: nothing of it has to stay in the streaming loop's registers.
+__device__ __noinline__ void shard_write_record(void* buf, uint32_t slot, uint32_t e, float2 p_new, bool arrived, const float2* pos_old, const float2* target,
+                                                const uint4* rng, const float4* color0, const uint32_t* road, const uint32_t* gid) {
+    uint2* rec = records_of(buf) + static_cast<size_t>(slot) * (MIGRANT_BYTES / 8);
+    const float2 p_old = pos_old[e], t = target[e];
+    const uint4 r = rng[e];
+    const float4 c = color0[e];
+    rec[0] = make_uint2(__float_as_uint(p_new.x), __float_as_uint(p_new.y));
+    rec[1] = make_uint2(__float_as_uint(p_old.x), __float_as_uint(p_old.y));
+    rec[2] = make_uint2(__float_as_uint(t.x), __float_as_uint(t.y));
+    rec[3] = make_uint2(r.x, r.y);
+    rec[4] = make_uint2(r.z, r.w);
+    rec[5] = make_uint2(__float_as_uint(c.x), __float_as_uint(c.y));
+    rec[6] = make_uint2(__float_as_uint(c.z), __float_as_uint(c.w));
+    rec[7] = make_uint2(road[e], gid[e]);
+    rec[8] = make_uint2(arrived ? 1u : 0u, 0u);
+}
+
+__device__ __forceinline__ void shard_classify(const ShardMoveArgs& sh, uint32_t e, bool valid, uint32_t key, float2 p_new, bool arrived, const float2* pos_old,
+                                               const float2* target) {
     const bool low = valid && sh.buf_down && key < sh.lo_key + sh.ncx;   // leaves downwards or sits in the first row
     const bool high = valid && sh.buf_up && key >= sh.hi_key - sh.ncx;   // leaves upwards or sits in the last row
     if (!__any_sync(0xffffffffu, low || high)) return;
-    const bool leaves = (low && key < sh.lo_key) || (high && key >= sh.hi_key);
+    const bool leaves_down = low && key < sh.lo_key, leaves_up = high && key >= sh.hi_key;
+    const bool leaves = leaves_down || leaves_up;
     const uint32_t hslot = warp_append(leaves, &sh.ctr[SHARD_CTR_HOLES]);
-    if (leaves && hslot < sh.holes_cap) sh.holes[hslot] = e;
+    if (leaves && hslot < sh.holes_cap) {
+        sh.holes[hslot] = e;
+        sh.local_ghosts[hslot] = p_new;  // it lands in the neighbour's boundary row: still within reach of ours
+    }
     if (sh.buf_down) {
+        const uint32_t mslot = warp_append(leaves_down, &sh.ctr[SHARD_CTR_MIG_DOWN]);
+        if (leaves_down && mslot < sh.mig_cap) shard_write_record(sh.buf_down, mslot, e, p_new, arrived, pos_old, target, sh.rng, sh.color0, sh.road, sh.gid);  // beyond the capacity the count alone reports the overflow
         const bool halo = low && !leaves;
         const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_DOWN]);
         if (halo && slot < sh.halo_cap) halo_of(sh.buf_down, sh.mig_cap)[slot] = p_new;
     }
     if (sh.buf_up) {
+        const uint32_t mslot = warp_append(leaves_up, &sh.ctr[SHARD_CTR_MIG_UP]);
+        if (leaves_up && mslot < sh.mig_cap) shard_write_record(sh.buf_up, mslot, e, p_new, arrived, pos_old, target, sh.rng, sh.color0, sh.road, sh.gid);
         const bool halo = high && !leaves;
         const uint32_t slot = warp_append(halo, &sh.ctr[SHARD_CTR_HALO_UP]);
         if (halo && slot < sh.halo_cap) halo_of(sh.buf_up, sh.mig_cap)[slot] = p_new;
@@ -222,8 +253,8 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
                     if (e1 < n) atomicAdd(&s_hist[p * RADIX + ((k1 >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
                 }
                 if (SHARD) {
-                    shard_classify(sh, e0, e0 < n, k0, q0);
-                    shard_classify(sh, e1, e1 < n, k1, q1);
+                    shard_classify(sh, e0, e0 < n, k0, q0, arr0, reinterpret_cast<const float2*>(pos_in), reinterpret_cast<const float2*>(target));
+                    shard_classify(sh, e1, e1 < n, k1, q1, arr1, reinterpret_cast<const float2*>(pos_in), reinterpret_cast<const float2*>(target));
                 }
             }
         }
@@ -289,6 +320,11 @@ arrive_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint32_
     } while (w - threadIdx.x < words);  // CTA-uniform: whole warps stay together for the shuffles
 }
 
+// One thread right behind the fused move + pack kernel (collective exchange): writes the list lengths into the send buffers' headers.
+// (Doing this at the end of the move kernel itself - last CTA to take a ticket, one system-scope fence per CTA - was measured: the pass
+// grew from 41 to 64 us at 5 M entities, far more than this launch costs.)
+__global__ void shard_publish_kernel(ShardMoveArgs sh) { shard_publish(sh); }
+
 __global__ void __launch_bounds__(256)
 keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ keys, GridParams grid) {
     const uint32_t pairs_pad = (((n + 1u) >> 1) + 31u) & ~31u;
@@ -305,7 +341,11 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, Profiler* prof,
                 const uint32_t* n_dev, const ShardMoveArgs* shard) {
-    if (n == 0) return 0;
+    if (n == 0) {  // (a band without entities still has to publish its empty lists)
+        if (!shard || !shard->publish) return 0;
+        shard_publish_kernel<<<1, 1, 0, s>>>(*shard);
+        return 1;
+    }
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
     uint32_t blocks = (pairs + per_block - 1) / per_block;
@@ -318,9 +358,10 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     const int passes = hist ? hist_passes : 0;
     const ShardMoveArgs none{};
     prof->begin(s, K_MOVE);
-    if (keys && shard)
+    if (keys && shard) {
         move_kernel<MOVE_KEYS, true><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, *shard);
-    else if (keys)
+        if (shard->publish) shard_publish_kernel<<<1, 1, 0, s>>>(*shard);
+    } else if (keys)
         move_kernel<MOVE_KEYS, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, keys2, grid, hist, passes, cell_count, none);
     else if (cell_count)
         move_kernel<MOVE_COUNT, false><<<blocks, MOVE_THREADS, 0, s>>>(n, n_dev, pin, pout, tgt, arrived, nullptr, grid, nullptr, 0, cell_count, none);

@@ -80,12 +80,11 @@ struct ShardMoveArgs {
     const float4* color0;
     const uint32_t* road;
     const uint32_t* gid;
-    // peer-memory exchange: buf_down / buf_up are the NEIGHBOURS' receive buffers (NVLink peer pointers); the emit
-    // kernel behind the move kernel publishes `signal_value` into their flag words after a system-scope fence
     uint32_t* error_word;      // |= 2 when the hole list overflows
-    uint32_t* peer_flag_down;  // raised by shard_emit_kernel once everything of this tick is in the buffers
+    uint32_t* peer_flag_down;  // (stand-alone use of shard_publish on remote buffers) raised once everything of this tick is in the buffers
     uint32_t* peer_flag_up;
     uint32_t signal_value;
+    uint32_t publish;  // 1: a one-thread kernel behind the move kernel writes the headers of buf_down / buf_up (local send buffers of the collective exchange)
 };
 
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
@@ -122,8 +121,9 @@ struct Tuning {
     int arrive_beside_ctas_per_sm{1};  // MSIM_ARRIVE_BESIDE_CTAS=0..8: when pass B rides beside the query it is launched as a strided grid of that many
                                   // CTAs per SM, so that it trickles through the whole query on a fraction of the warp slots (it is latency-bound and
                                   // only has to finish before the next move); 0 = full grid.  Measured at 10 M entities: tick 361 / 334 / 339 us for 0 / 1 / 2
-    int csort_max_cells_log2{25};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 (default) .. 27; grids with more cells take the onesweep rebuild.  BASELINE
-                                  // config 4 (8182 x 8182 cells = 2^26.0) needs 27 to keep the counting sort (two 268 MB tables per GPU)
+    int csort_max_cells_log2{27};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 .. 27 (default: every grid the library accepts); grids with more cells take the onesweep
+                                  // rebuild.  BASELINE config 4 (8159 x 8159 cells = 2^25.99) keeps the counting sort: two 266 MB tables per GPU, of
+                                  // which a band-sharded handle scans and touches only its own rows
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
 };
 const Tuning& tuning();
@@ -246,6 +246,7 @@ constexpr uint32_t MIGRANT_BYTES = 72;  // pos, pos_prev, target, rng, color0, r
 // memory, and publish the totals into the (possibly remote) buffer headers once: the exchange buffers only ever see plain
 // stores, never an atomic round trip over NVLink
 enum { SHARD_CTR_HOLES = 0, SHARD_CTR_LOCAL_GHOSTS = 1, SHARD_CTR_MIG_DOWN = 2, SHARD_CTR_MIG_UP = 3, SHARD_CTR_HALO_DOWN = 4, SHARD_CTR_HALO_UP = 5,
+       SHARD_CTR_COMPACTED = 7,  // merged exchange kernel: CTA 0 has emptied the tail the ghosts are about to overwrite
        SHARD_CTR_COUNT = 8 };
 
 struct ShardArrays {
@@ -271,9 +272,20 @@ int launch_shard_pack(cudaStream_t s, const ShardArrays& a, uint32_t n, int ncx,
                       uint32_t mig_cap, uint32_t halo_cap, uint32_t* holes, uint32_t holes_cap, float2* local_ghosts, uint32_t* ctr, Profiler* prof,
                       const uint32_t* n_dev = nullptr, bool reset = true);
 int launch_shard_signal(cudaStream_t s, uint32_t* flag_down, uint32_t* flag_up, uint32_t value);
-int launch_shard_emit(cudaStream_t s, const ShardArrays& a, const struct ShardMoveArgs& sh, Profiler* prof);
+void launch_shard_stamp(cudaStream_t s, unsigned long long* trace, int slot);  // MSIM_SHARD_TRACE=1: %globaltimer into trace[slot]
+// peer-memory exchange, sender side: local send buffers -> the neighbours' receive buffers, headers, flags (on a stream of its own)
+int launch_shard_push(cudaStream_t s, const void* send_down, const void* send_up, void* peer_down, void* peer_up, uint32_t* flag_down, uint32_t* flag_up,
+                      uint32_t signal_value, uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t* ctr, uint32_t* error_word, uint32_t* ticket,
+                      bool counts_in_headers);
 // device-side integrate (asynchronous sharded tick): placement, tail compaction and the new counts without a host round trip
-enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_SHARD_ERROR = 3, DEV_HALO_DOWN = 4, DEV_HALO_UP = 5, DEV_COUNT_WORDS = 8 };
+// Two sets of DEV_COUNT_WORDS words that alternate from one integrate to the next (shard.cu IntegrateArgs), then the sticky error word.
+enum { DEV_N_OWNED = 0, DEV_N_GHOST = 1, DEV_N_TOTAL = 2, DEV_HALO_DOWN = 4, DEV_HALO_UP = 5, DEV_COUNT_WORDS = 8, DEV_SHARD_ERROR = 2 * DEV_COUNT_WORDS,
+       DEV_ALLOC_WORDS = 3 * DEV_COUNT_WORDS };
+struct ShardCounts {
+    const uint32_t* in;    // set the previous integrate (or the host) wrote
+    uint32_t* out;         // the other set
+    uint32_t* error_word;  // sticky error bits
+};
 // device-side wait of the peer-memory exchange: the integrate kernel spins until both flag words reach `expected`
 struct ShardWait {
     const uint32_t* flag_down;  // NULL: nothing to wait for on that side
@@ -281,13 +293,14 @@ struct ShardWait {
     uint32_t expected;
     unsigned long long timeout_ns;
 };
-int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, uint32_t* dev_counts, const void* sent_down, const void* sent_up,
+int launch_shard_integrate_device(cudaStream_t s, const ShardArrays& a, const ShardCounts& counts, const void* sent_down, const void* sent_up,
                                   const void* recv_down, const void* recv_up, const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts,
                                   uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap, uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves,
                                   const GridParams& grid, Profiler* prof, const ShardWait* wait = nullptr);
-int launch_shard_exchange(cudaStream_t s, const ShardArrays& a, const struct ShardMoveArgs* emit, uint32_t* dev_counts, const void* recv_down, const void* recv_up,
+int launch_shard_exchange(cudaStream_t s, const ShardArrays& a, const ShardCounts& counts, const void* recv_down, const void* recv_up,
                           const uint32_t* holes, const uint32_t* ctr, const float2* local_ghosts, uint32_t mig_cap, uint32_t halo_cap, uint32_t holes_cap,
-                          uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves, const GridParams& grid, Profiler* prof, const ShardWait& wait);
+                          uint32_t entity_cap, uint32_t* scratch_bits, uint2* scratch_moves, const GridParams& grid, Profiler* prof, const ShardWait& wait,
+                          unsigned long long* trace = nullptr);
 int launch_shard_place(cudaStream_t s, const ShardArrays& a, const void* recv_down, uint32_t n_down, const void* recv_up, uint32_t n_up,
                        const uint32_t* dst, const GridParams& grid, Profiler* prof);
 int launch_shard_relocate(cudaStream_t s, const ShardArrays& a, const uint2* moves, uint32_t count, Profiler* prof);
@@ -334,6 +347,35 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 #endif
+
+// ---- behind the fused move + pack kernel (move.cu shard_publish_kernel): one thread -----------------------------------------------
+// Collective exchange: writes the list lengths into the headers of the send buffers the move kernel has filled (every counter is local).
+// (The peer-memory exchange has its own sender, shard.cu shard_push_kernel, which writes the headers where they are read.)
+#ifndef MSIM_HOST_EMU
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#endif
+__device__ __forceinline__ void shard_publish(const ShardMoveArgs& sh) {
+    const uint32_t holes_total = __ldcg(sh.ctr + SHARD_CTR_HOLES);
+    sh.ctr[SHARD_CTR_LOCAL_GHOSTS] = min(holes_total, sh.holes_cap);
+    if (holes_total > sh.holes_cap) atomicOr(sh.error_word, 2u);
+    if (sh.buf_down) {
+        const uint32_t m = __ldcg(sh.ctr + SHARD_CTR_MIG_DOWN), hl = __ldcg(sh.ctr + SHARD_CTR_HALO_DOWN);
+        ShardHeader* hd = header_of(sh.buf_down);
+        hd->n_migrants = m;
+        hd->n_halo = hl;
+        hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+    }
+    if (sh.buf_up) {
+        const uint32_t m = __ldcg(sh.ctr + SHARD_CTR_MIG_UP), hl = __ldcg(sh.ctr + SHARD_CTR_HALO_UP);
+        ShardHeader* hd = header_of(sh.buf_up);
+        hd->n_migrants = m;
+        hd->n_halo = hl;
+        hd->overflow = (m > sh.mig_cap || hl > sh.halo_cap) ? 1u : 0u;
+    }
+    __threadfence_system();  // headers (and everything the finished move kernel stored) before the flags
+    if (sh.peer_flag_down) st_relaxed_sys(sh.peer_flag_down, sh.signal_value);
+    if (sh.peer_flag_up) st_relaxed_sys(sh.peer_flag_up, sh.signal_value);
+}
 
 // bit position of entity e inside the `arrived` mask written by the move kernel: entities are
 // processed as float4 pairs (2*lane, 2*lane+1) of a 64-entity warp chunk; each parity has its own word.

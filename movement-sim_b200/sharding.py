@@ -420,20 +420,19 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         if collisions:
             pairs, flagged = sh.global_sum(st1["last_pair_count"]), sh.global_sum(st1["last_flagged_count"])
         check = check_counts(args.workload, total, st1["move_passes"], pairs, flagged)
-        # per-kernel device time on rank 0 over a second pass of the same K steps (events around every launch)
-        kernels = None
-        if rank == 0:
-            sim.profile_begin()
+        # per-kernel device time on every rank over a second pass of the same K steps (events around every launch); rank 0's feed the roofline
+        sim.profile_begin()
         ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ep0.record(stream)
         for _ in range(args.steps):
             step()
         ep1.record(stream)
         ep1.synchronize()
-        if rank == 0:
-            kt = sim.profile_end()
-            kernels = {name: round(t / args.steps * 1e3, 1) for name, (cnt, t) in sorted(kt.items(), key=lambda kv: -kv[1][1])}
-            kernels["_step_us_with_events"] = round(ep0.elapsed_time(ep1) / args.steps * 1e3, 1)
+        kt = sim.profile_end()
+        kernels = {name: round(t / args.steps * 1e3, 1) for name, (cnt, t) in sorted(kt.items(), key=lambda kv: -kv[1][1])}
+        kernels["_step_us_with_events"] = round(ep0.elapsed_time(ep1) / args.steps * 1e3, 1)
+        kernels_by_rank = [None] * world
+        dist.all_gather_object(kernels_by_rank, kernels)
         # keep the load up for the clock sampler (untimed).  A FIXED number of steps derived from the all-reduced
         # time: every rank must enqueue the same number of exchanges (a wall-clock loop would not)
         for _ in range(max(10, min(5000, int(1000.0 / max(ms / args.steps, 0.01))))):
@@ -505,7 +504,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
                                        if collisions else f"{world} entity ranges, no collective"),
                        "exchange": (sh.exchange if sh else None), "p2p_fallback_reason": getattr(sh, "p2p_error", None),
                        "owned_per_rank": per_rank, "l2": ("inputs larger than L2 (no flush)" if per_gpu * 40 > 200e6 else "per-GPU working set may sit in L2 (strong scaling of a fixed population)"),
-                       "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels,
+                       "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels, "kernel_us_per_step_by_rank": kernels_by_rank,
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
                        "move_passes_done": st1["move_passes"], "pairs_last_tick": pairs, "flagged_last_tick": flagged, "counts_check": check,
                        "resort": {"every_collision_passes": RESORT_EVERY, "in_timed_region": st1["reorders"] - st0["reorders"],

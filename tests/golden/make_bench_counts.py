@@ -40,10 +40,14 @@ def main():
     ap.add_argument("--preroll", type=int, default=256)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--combos", default="5:20,3:20,10:200,5:32,5:64,10:20,5:10,3:10,5:50,5:100,5:200,10:100,10:50")
+    ap.add_argument("--passes", default=None, help="explicit move-pass counts instead of --combos (tests/test_gpu_configs45.py), e.g. 40,72")
     args = ap.parse_args()
     w, m = bench.build_workload(M, args.workload, args.entities)
     n = w["entities"]
-    want = sorted({passes_done(args.preroll, int(c.split(":")[0]), int(c.split(":")[1])) for c in args.combos.split(",")})
+    if args.passes:
+        want = sorted({int(p) for p in args.passes.split(",")})
+    else:
+        want = sorted({passes_done(args.preroll, int(c.split(":")[0]), int(c.split(":")[1])) for c in args.combos.split(",")})
     e = np.ascontiguousarray(bench.build_population(M, m, n, w["box"])).view(O.ENTITY_DTYPE).copy()
     om = O.OracleMap(m.width, m.height, m.roads.view(O.ROAD_DTYPE), m.connections)
     O.move_pass(e, om, threads=args.threads)  # the init-only first dispatch
