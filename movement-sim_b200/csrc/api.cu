@@ -39,8 +39,12 @@ struct msim_handle {
     bool own_stream{false};
     cudaStream_t side{nullptr};  // pass B of a move runs here while the collision pass uses `stream`
     cudaEvent_t ev_moved{nullptr}, ev_arrived{nullptr};
-    bool side_pending{false};
+    bool side_pending{false};     // the side stream holds work the main stream has not been ordered behind yet (ev_arrived marks its end)
     bool arrive_deferred{false};  // pass B of the last move has not been launched yet (it will ride beside the query)
+    // Overlapped ticks: the move phase of tick t+1 (pass B of tick t, move + pack, shard exchange) runs on the side stream while the
+    // query of tick t runs on the main one - movement never reads collision results, and the query only reads what the scatter copied.
+    cudaStream_t ms{nullptr};     // stream of the move phase in flight (side or main)
+    bool main_touched{true};      // the main stream has touched entity state since the side stream was last ordered behind it
     uint32_t flags{0};
 
     uint32_t n{0};
@@ -184,6 +188,11 @@ const Tuning& tuning() {
             const int k = std::atoi(e);
             if (k >= 0 && k <= 8) v.arrive_beside_ctas_per_sm = k;
         }
+        if (const char* e = std::getenv("MSIM_OVERLAP_TICKS")) v.overlap_ticks = std::atoi(e) != 0;
+        if (const char* e = std::getenv("MSIM_MOVE_BESIDE_CTAS")) {
+            const int k = std::atoi(e);
+            if (k >= 1 && k <= 8) v.move_beside_ctas_per_sm = k;
+        }
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
             const int k = std::atoi(e);
             if (k >= 25 && k <= 27) v.csort_max_cells_log2 = k;
@@ -320,6 +329,7 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
         // called right before the query, which is issue-bound and leaves the memory system idle
         cudaEventRecord(h->ev_moved, h->stream);
         cudaStreamWaitEvent(h->side, h->ev_moved, 0);
+        h->main_touched = false;  // the side stream is now ordered behind everything the main stream has done to the state (up to the scatter)
         h->launches += launch_arrive(h->side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
                                      dev_owned(h), /*beside=*/true);
         cudaEventRecord(h->ev_arrived, h->side);
@@ -357,11 +367,46 @@ void apply_l2_window(msim_handle* h) {
     cudaGetLastError();
 }
 
-void join_side(msim_handle* h) {
-    launch_deferred_arrive(h, false);
+// main stream behind the side stream (pass B, an overlapped move phase), without launching anything
+void join_side_work(msim_handle* h) {
     if (h->side_pending) {
         cudaStreamWaitEvent(h->stream, h->ev_arrived, 0);
         h->side_pending = false;
+    }
+}
+
+// everything of the resident state is current and owned by the main stream: what readbacks, uploads and re-sorts start with
+void join_side(msim_handle* h) {
+    join_side_work(h);
+    launch_deferred_arrive(h, false);  // (on the main stream, behind the move it belongs to)
+    h->main_touched = true;
+}
+
+// Stream of the move phase that is about to be enqueued.  Overlapped (side stream): ordered behind the main stream only as far as
+// needed - the collision pass recorded ev_moved right behind its scatter, so the query that follows it keeps running beside us.
+cudaStream_t begin_move_phase(msim_handle* h, bool overlap) {
+    if (!overlap) {
+        join_side(h);  // the previous pass B must have rewritten the targets before they are read again
+        h->ms = h->stream;
+        return h->ms;
+    }
+    if (h->main_touched) {  // a readback, an upload, a re-sort ... since the side stream last waited for the main one
+        cudaEventRecord(h->ev_moved, h->stream);
+        cudaStreamWaitEvent(h->side, h->ev_moved, 0);
+        h->main_touched = false;
+    }
+    if (h->arrive_deferred && !h->awaiting_integrate) {  // two moves in a row: pass B of the first one, in front of the second
+        h->arrive_deferred = false;
+        h->launches += launch_arrive(h->side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof, dev_owned(h));
+    }
+    h->ms = h->side;
+    return h->ms;
+}
+
+void end_move_phase(msim_handle* h) {
+    if (h->ms == h->side && h->side) {
+        cudaEventRecord(h->ev_arrived, h->side);
+        h->side_pending = true;
     }
 }
 
@@ -379,6 +424,7 @@ int write_dev_counts(msim_handle* h) {
 // asynchronous sharded ticks: bring the host-side counts up to date (one small D2H + stream sync)
 int refresh_counts(msim_handle* h) {
     if (!h->async_counts) return MSIM_OK;
+    join_side_work(h);  // the exchange that wrote the counts may have run beside the last query
     uint32_t all[DEV_ALLOC_WORDS] = {0};
     MSIM_CUDA(h, cudaMemcpyAsync(all, h->dev_counts, sizeof(all), cudaMemcpyDeviceToHost, h->stream));
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -400,8 +446,8 @@ int refresh_counts(msim_handle* h) {
 // The scan that consumes the per-cell counters also zeroes them (csort.cu), so between two collision passes the table is
 // all zero and the next count needs no memset.  Only a count that was never scanned (a move pass that fused the count and
 // was not followed by a collision pass, an upload in between, ...) leaves it dirty: then the whole table is cleared.
-void prepare_counts(msim_handle* h) {
-    if (h->counts_dirty) csort_clear(h->stream, h->cell_count, h->cell_capacity, &h->prof);  // the whole allocation: an earlier, larger grid may have counted beyond ncells
+void prepare_counts(msim_handle* h, cudaStream_t s = nullptr) {
+    if (h->counts_dirty) csort_clear(s ? s : h->stream, h->cell_count, h->cell_capacity, &h->prof);  // the whole allocation: an earlier, larger grid may have counted beyond ncells
     h->counts_dirty = true;  // about to be counted into
 }
 
@@ -536,7 +582,8 @@ bool consume_init_dispatch(msim_handle* h) {
     return true;
 }
 
-int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nullptr) {
+// shard != NULL: called by move_pack_common, which has begun the move phase itself (`ms`)
+int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nullptr, cudaStream_t ms = nullptr) {
     if (h->awaiting_integrate) return fail(h, MSIM_ERR_INVALID, "move pass on a sharded handle whose last msim_shard_move_pack has not been integrated");
     if (consume_init_dispatch(h)) return MSIM_OK;
     const bool emit = want_keys && !(h->flags & MSIM_FLAG_NO_COLLISIONS);
@@ -552,21 +599,25 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     const bool count_only = fuse_count && !h->sharded;  // no keys written: the scatter recomputes the key and takes the slot
     h->n_ghost = 0;
     h->count_fused = fuse_count && h->sharded;
-    if (fuse_count) {
-        prepare_counts(h);
-    }
-    if (fuse_hist) sort_prepare(h->stream, h->n, h->key_bits, h->ws, &h->prof);
-    join_side(h);  // the previous pass B must have rewritten the targets before they are read again
-    h->launches += launch_move(h->stream, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
+    // a collision pass follows and needs only positions: the pass runs beside the previous tick's query (unsharded handles; sharded
+    // ones decide in move_pack_common), and its own pass B will be launched beside the next query
+    const bool defer_arrive = emit && h->side && (!h->sharded || shard);
+    const bool beside = ms ? ms == h->side : (defer_arrive && !h->sharded && tuning().overlap_ticks);
+    if (!ms) ms = begin_move_phase(h, beside);
+    if (fuse_count) prepare_counts(h, ms);
+    if (fuse_hist) sort_prepare(ms, h->n, h->key_bits, h->ws, &h->prof);
+    h->launches += launch_move(ms, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit && !count_only ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
-                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, &h->prof, dev_owned(h), shard);
+                               passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, &h->prof, dev_owned(h), shard,
+                               beside ? tuning().move_beside_ctas_per_sm : 0);
     h->counts_valid = fuse_count;
-    if (emit && h->side && (!h->sharded || shard)) {
-        h->arrive_deferred = true;  // a collision pass follows and needs only positions: pass B is launched beside its query
+    if (defer_arrive) {
+        h->arrive_deferred = true;
     } else {
-        h->launches += launch_arrive(h->stream, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
+        h->launches += launch_arrive(ms, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
                                      dev_owned(h));
     }
+    if (!shard) end_move_phase(h);
     h->cur ^= 1;
     h->has_moved = true;
     h->band_valid = false;  // entities may have crossed the band's rows until the next pack + integrate
@@ -626,6 +677,7 @@ int reorder_storage(msim_handle* h) {
         h->counts_valid = false;
         h->since_reorder = 0;
         h->reorders++;
+        h->main_touched = true;
         return MSIM_OK;
     }
     ReorderArrays a{};
@@ -661,6 +713,7 @@ int reorder_storage(msim_handle* h) {
     h->counts_valid = false;
     h->since_reorder = 0;
     h->reorders++;
+    h->main_touched = true;
     return MSIM_OK;
 }
 
@@ -669,6 +722,7 @@ int enqueue_collide(msim_handle* h) {
     if (consume_init_dispatch(h)) return MSIM_OK;
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
+    join_side_work(h);  // an overlapped move phase (and the pass B in front of it) must be complete before the rebuild reads its results
     if (!h->keys_valid && (h->sharded || !h->use_csort)) {  // (the unsharded counting sort works on positions: no keys)
         rc = refresh_counts(h);  // (asynchronous sharded ticks) keygen is sized by the exact owned count
         if (rc != MSIM_OK) return rc;
@@ -940,7 +994,9 @@ int msim_set_stream(msim_handle* h, void* cuda_stream) {
 int msim_enqueue_move(msim_handle* h) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
-    return enqueue_move(h, true);
+    rc = enqueue_move(h, true);
+    join_side_work(h);  // callers order their own work behind the handle's stream: the pass may have run beside it
+    return rc;
 }
 
 int msim_enqueue_collide(msim_handle* h) {
@@ -1000,6 +1056,7 @@ namespace {
 int readback_preconditions(msim_handle* h, const char* who, const void* dst, uint64_t count, bool needs_flags) {
     int rc = bind(h);
     if (rc != MSIM_OK) return rc;
+    join_side(h);  // a move phase that ran beside the last query, its pass B
     rc = refresh_counts(h);
     if (rc != MSIM_OK) return rc;
     if (count > h->n) return fail(h, MSIM_ERR_INVALID, std::string(who) + ": count exceeds the resident entity count");
@@ -1169,6 +1226,7 @@ int msim_read_quadtree_nodes(msim_handle* h, msim_quadtree_node* dst, uint64_t c
     if (!root_only) {
         const size_t bins = static_cast<size_t>(1) << (2 * levels);
         if (!h->leaf_hist) MSIM_CUDA(h, dev_alloc(&h->leaf_hist, static_cast<size_t>(1) << 16));
+        join_side(h);
         h->launches += launch_leaf_histogram(h->stream, h->sm_count, h->n, h->pos[h->cur], h->world_w, h->world_h, levels, h->leaf_hist);
         sums[0].resize(bins);
         MSIM_CUDA(h, cudaMemcpyAsync(sums[0].data(), h->leaf_hist, bins * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1221,7 +1279,8 @@ int msim_get_stats(msim_handle* h, msim_stats* out) {
     out->grid_cells_x = static_cast<uint32_t>(h->grid.ncx);
     out->grid_cells_y = static_cast<uint32_t>(h->grid.ncy);
     out->key_bits = static_cast<uint32_t>(h->key_bits);
-    out->sort_passes = static_cast<uint32_t>((h->key_bits + RADIX_BITS - 1) / RADIX_BITS);
+    // passes over the keys per rebuild: one for the counting sort (known once the collision buffers exist), one per 8-bit digit for onesweep
+    out->sort_passes = (h->keys && h->use_csort) ? 1u : static_cast<uint32_t>((h->key_bits + RADIX_BITS - 1) / RADIX_BITS);
     out->cell_size = h->grid.inv_cell > 0.0f ? 1.0f / h->grid.inv_cell : 0.0f;
     out->reorders = static_cast<uint32_t>(h->reorders);
     return rc;
@@ -1309,6 +1368,7 @@ ShardArrays shard_arrays(msim_handle* h) {
 int ensure_keys(msim_handle* h) {
     int rc = alloc_collision_buffers(h);
     if (rc != MSIM_OK) return rc;
+    join_side(h);
     if (!h->keys_valid) {
         rc = refresh_counts(h);
         if (rc != MSIM_OK) return rc;
@@ -1395,7 +1455,7 @@ struct P2PSignal {
 
 // sender side of the peer-memory exchange, on its own stream behind the pack that has just been enqueued on the main one
 int enqueue_push(msim_handle* h, const void* send_down, const void* send_up, const P2PSignal& sig, bool counts_in_headers) {
-    MSIM_CUDA(h, cudaEventRecord(h->ev_packed_move, h->stream));
+    MSIM_CUDA(h, cudaEventRecord(h->ev_packed_move, h->ms));
     MSIM_CUDA(h, cudaStreamWaitEvent(h->push_stream, h->ev_packed_move, 0));
     h->launches += launch_shard_push(h->push_stream, send_down, send_up, sig.peer_down, sig.peer_up, sig.flag_down, sig.flag_up, sig.value, h->mig_cap, h->halo_cap,
                                      h->holes_cap, h->shard_ctr, dev_error(h), h->p2p_push_ticket, counts_in_headers);
@@ -1411,14 +1471,17 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     int rc = MSIM_OK;
     const bool init_only = h->uninitialised;  // the reference's first dispatch moves nobody (random_move.comp:863-867)
     if (init_only) consume_init_dispatch(h);
-    join_side(h);  // pass B of the previous tick: the records read target / road / rng
+    // peer-memory exchange: the whole move phase (pass B of the previous tick, move + pack, exchange) runs beside the previous tick's
+    // query; the collective exchange stays on the main stream, where the caller enqueues its collective
+    const bool beside = sig && !init_only && h->side && tuning().overlap_ticks && !(h->flags & MSIM_FLAG_NO_COLLISIONS);
+    const cudaStream_t ms = begin_move_phase(h, beside);  // (pass B of the previous tick first: the records read target / road / rng)
     if (h->push_pending) {  // the previous tick's push reads the counters that are about to be cleared (it finished long ago)
-        MSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_pushed, 0));
+        MSIM_CUDA(h, cudaStreamWaitEvent(ms, h->ev_pushed, 0));
         h->push_pending = false;
     }
     // the fused kernel counts in h->shard_ctr (a one-thread kernel behind it, or the push kernel, writes the buffer headers); the
     // stand-alone pack kernel (init-only dispatch below) counts in the headers of the (local) buffers, which the reset clears
-    h->launches += launch_shard_reset(h->stream, init_only ? send_down : nullptr, init_only ? send_up : nullptr, h->shard_ctr);
+    h->launches += launch_shard_reset(ms, init_only ? send_down : nullptr, init_only ? send_up : nullptr, h->shard_ctr);
     ShardMoveArgs sh{};
     sh.lo_key = row_lo * static_cast<uint32_t>(h->grid.ncx);
     sh.hi_key = row_hi * static_cast<uint32_t>(h->grid.ncx);
@@ -1452,9 +1515,9 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
             if (rc != MSIM_OK) return rc;
         }
     } else {
-        rc = enqueue_move(h, true, &sh);
+        rc = enqueue_move(h, true, &sh, ms);
         if (rc != MSIM_OK) return rc;
-        if (h->shard_trace) launch_shard_stamp(h->stream, h->shard_trace, 5);
+        if (h->shard_trace) launch_shard_stamp(ms, h->shard_trace, 5);
         if (sig) {
             rc = enqueue_push(h, send_down, send_up, *sig, /*counts_in_headers=*/false);
             if (rc != MSIM_OK) return rc;
@@ -1465,6 +1528,7 @@ int move_pack_common(msim_handle* h, const char* who, uint32_t row_lo, uint32_t 
     h->sent_down = sig ? nullptr : send_down;  // peer buffers: their owner checks the overflow flag
     h->sent_up = sig ? nullptr : send_up;
     h->packed = true;
+    end_move_phase(h);
     return MSIM_OK;
 }
 
@@ -1601,10 +1665,12 @@ int msim_shard_p2p_integrate(msim_handle* h) {
     w.expected = h->p2p_tick + 1u;
     w.timeout_ns = h->p2p_timeout_ns;
     h->p2p_tick++;
-    h->launches += launch_shard_exchange(h->stream, shard_arrays(h), flip_counts(h), recv_down, recv_up, h->holes,
+    const cudaStream_t ms = h->ms ? h->ms : h->stream;  // the stream the move + pack of this tick ran on
+    h->launches += launch_shard_exchange(ms, shard_arrays(h), flip_counts(h), recv_down, recv_up, h->holes,
                                          h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves, h->grid,
                                          &h->prof, w, h->shard_trace);
-    if (h->shard_trace) launch_shard_stamp(h->stream, h->shard_trace, 9);
+    if (h->shard_trace) launch_shard_stamp(ms, h->shard_trace, 9);
+    end_move_phase(h);
     return integrate_device_common(h, recv_down, recv_up, nullptr, /*launch=*/false);
 }
 

@@ -340,7 +340,7 @@ keygen_kernel(uint32_t n, const float4* __restrict__ pos, uint2* __restrict__ ke
 // MOVE_COUNT; neither: MOVE_PLAIN.  The grid is 8 CTAs per SM (2048 threads) with a grid-stride loop inside.
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys, const GridParams& grid, uint32_t* hist, int hist_passes, uint32_t* cell_count, Profiler* prof,
-                const uint32_t* n_dev, const ShardMoveArgs* shard) {
+                const uint32_t* n_dev, const ShardMoveArgs* shard, int ctas_per_sm) {
     if (n == 0) {  // (a band without entities still has to publish its empty lists)
         if (!shard || !shard->publish) return 0;
         shard_publish_kernel<<<1, 1, 0, s>>>(*shard);
@@ -349,7 +349,7 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
     const uint32_t pairs = (n + 1u) >> 1;
     const uint32_t per_block = MOVE_THREADS * MOVE_ITEMS;
     uint32_t blocks = (pairs + per_block - 1) / per_block;
-    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(ctas_per_sm > 0 && ctas_per_sm < 8 ? ctas_per_sm : 8);
     if (blocks > resident) blocks = resident;
     const float4* pin = reinterpret_cast<const float4*>(pos_in);
     float4* pout = reinterpret_cast<float4*>(pos_out);

@@ -124,6 +124,8 @@ struct Tuning {
     int csort_max_cells_log2{27};     // MSIM_CSORT_MAX_CELLS_LOG2: 25 .. 27 (default: every grid the library accepts); grids with more cells take the onesweep
                                   // rebuild.  BASELINE config 4 (8159 x 8159 cells = 2^25.99) keeps the counting sort: two 266 MB tables per GPU, of
                                   // which a band-sharded handle scans and touches only its own rows
+    bool overlap_ticks{true};         // MSIM_OVERLAP_TICKS=0: the move phase of tick t+1 waits for the query of tick t (it runs beside it by default)
+    int move_beside_ctas_per_sm{2};   // MSIM_MOVE_BESIDE_CTAS=1..8: CTAs per SM of the move kernel while it shares the SMs with a query (8 = the stand-alone grid).  Tick at 10 M entities: 304 / 306 / 313 / 317 / 315 us for 2 / 3 / 4 / 6 / 8, 327 us without the overlap
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
 };
 const Tuning& tuning();
@@ -137,7 +139,7 @@ const Tuning& tuning();
 int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, float2* pos_out, const float2* target, uint32_t* arrived,
                 uint32_t* keys /* nullable */, const GridParams& grid, uint32_t* hist /* nullable: fused digit histograms */,
                 int hist_passes, uint32_t* cell_count /* nullable: fused per-cell population */, Profiler* prof,
-                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr);
+                const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr, int ctas_per_sm = 0 /* 0: the stand-alone grid, 8 per SM */);
 // `beside`: the pass runs on the side stream next to the issue-bound query (see Tuning::arrive_beside_ctas_per_sm)
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
                   const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr, bool beside = false);
