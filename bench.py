@@ -40,9 +40,9 @@ METRIC = "entity-updates/sec"
 SURVEY_BYTES = {True: 124.0, False: 24.0}  # B_coll (23-bit keys, 3 passes) / B_move
 # algorithmic HBM bytes per entity per launch of each kernel
 KERNEL_BYTES = {
-    "move": 32.0,  # pos R8 + target R8 + pos W8 + cell key W4 + cell rank W4 (24.0 when collisions are off)
-    "cell_count": 8.0,  # key R4 + rank W4 (only when the keys did not come from a move pass)
-    "cell_scatter": 28.0,  # key R4 + rank R4 + pos R8 + sorted pos W8 + sorted idx W4
+    "move": 24.0,  # pos R8 + target R8 + pos W8 (the per-cell population leaves as reductions into an L2-resident table; sharded handles add a 4 B key)
+    "cell_count": 8.0,  # pos R8 (only when no counting move pass preceded the collision pass)
+    "cell_scatter": 20.0,  # pos R8 + sorted pos W8 + slot W4 (the key is recomputed from the position)
     "keygen": 12.0,
     "histogram": 4.0,
     "sort_pass0": 12.0,  # key R4 + pair W8
@@ -494,8 +494,6 @@ def run_b200(args):
     kernels = []
     for name, (cnt, tms) in sorted(kt.items(), key=lambda kv: -kv[1][1]):
         bpe = KERNEL_BYTES.get(name)
-        if name == "move" and not collisions:
-            bpe = 24.0
         entry = {"name": name, "launches": cnt, "avg_us": tms / cnt * 1e3, "share": tms / total_kernel_ms if total_kernel_ms else None}
         if bpe:
             gbs = bpe * n / (tms / cnt * 1e-3) / 1e9
@@ -510,7 +508,7 @@ def run_b200(args):
     tick_gbs = w["survey_bytes"] * n * args.steps / (ms * 1e-3) / 1e9
     if roofline and traffic.get("_issue_active_pct", {}).get(roofline["kernel"]) is not None:
         roofline["issue_active_pct_ncu"] = traffic["_issue_active_pct"][roofline["kernel"]]
-        roofline["note"] = ("this kernel is instruction-issue-bound, not HBM-bound (ncu smsp__issue_active, profiles/r1_ncu_full.md); "
+        roofline["note"] = ("this kernel is instruction-issue-bound, not HBM-bound (ncu smsp__issue_active, profiles/r2_ncu_full.md); "
                             "its HBM fraction is reported because the contract asks for the dominant kernel")
     # the streaming move pass alone (collisions-off dispatch on the same resident population): the HBM-bound kernel of the path
     move_only = None

@@ -193,6 +193,14 @@ const Tuning& tuning() {
             const int k = std::atoi(e);
             if (k >= 1 && k <= 8) v.move_beside_ctas_per_sm = k;
         }
+        if (const char* e = std::getenv("MSIM_SHARD_ARRIVE_BESIDE_CTAS")) {
+            const int k = std::atoi(e);
+            if (k >= 0 && k <= 8) v.shard_arrive_beside_ctas_per_sm = k;
+        }
+        if (const char* e = std::getenv("MSIM_SHARD_MOVE_BESIDE_CTAS")) {
+            const int k = std::atoi(e);
+            if (k >= 1 && k <= 8) v.shard_move_beside_ctas_per_sm = k;
+        }
         if (const char* e = std::getenv("MSIM_CSORT_MAX_CELLS_LOG2")) {
             const int k = std::atoi(e);
             if (k >= 25 && k <= 27) v.csort_max_cells_log2 = k;
@@ -331,7 +339,7 @@ void launch_deferred_arrive(msim_handle* h, bool beside) {
         cudaStreamWaitEvent(h->side, h->ev_moved, 0);
         h->main_touched = false;  // the side stream is now ordered behind everything the main stream has done to the state (up to the scatter)
         h->launches += launch_arrive(h->side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof,
-                                     dev_owned(h), /*beside=*/true);
+                                     dev_owned(h), /*beside=*/true, h->sharded ? tuning().shard_arrive_beside_ctas_per_sm : -1);
         cudaEventRecord(h->ev_arrived, h->side);
         h->side_pending = true;
     } else {
@@ -609,7 +617,7 @@ int enqueue_move(msim_handle* h, bool want_keys, const ShardMoveArgs* shard = nu
     h->launches += launch_move(ms, h->sm_count, launch_owned(h), h->pos[h->cur], h->pos[h->cur ^ 1], h->target, h->arrived,
                                emit && !count_only ? h->keys : nullptr, h->grid, fuse_hist ? h->ws.hist : nullptr,
                                passes > MAX_SORT_PASSES ? MAX_SORT_PASSES : passes, fuse_count ? h->cell_count : nullptr, &h->prof, dev_owned(h), shard,
-                               beside ? tuning().move_beside_ctas_per_sm : 0);
+                               beside ? (h->sharded ? tuning().shard_move_beside_ctas_per_sm : tuning().move_beside_ctas_per_sm) : 0);
     h->counts_valid = fuse_count;
     if (defer_arrive) {
         h->arrive_deferred = true;

@@ -372,14 +372,15 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
 }
 
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev, bool beside) {
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev, bool beside, int beside_ctas_per_sm) {
     if (n == 0) return 0;
     const uint32_t words = ((n + 63u) >> 6) << 1;  // grid size (n is an upper bound when n_dev is given)
     uint32_t blocks = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
     // 10 M entities need 1221 CTAs where 1184 are resident (31 registers, 8 per SM): the 37 left over start when the first finish.
     // MSIM_ARRIVE_GRID=persistent: one resident wave that strides over the words instead
     uint32_t cap = 0u;
-    if (beside && tuning().arrive_beside_ctas_per_sm) cap = 148u * static_cast<uint32_t>(tuning().arrive_beside_ctas_per_sm);
+    const int per_sm = beside_ctas_per_sm >= 0 ? beside_ctas_per_sm : tuning().arrive_beside_ctas_per_sm;
+    if (beside && per_sm) cap = 148u * static_cast<uint32_t>(per_sm);
     const bool stride = cap != 0u && blocks > cap;
     prof->begin(s, K_ARRIVE);
     if (stride)

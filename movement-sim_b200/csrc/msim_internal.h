@@ -126,6 +126,10 @@ struct Tuning {
                                   // which a band-sharded handle scans and touches only its own rows
     bool overlap_ticks{true};         // MSIM_OVERLAP_TICKS=0: the move phase of tick t+1 waits for the query of tick t (it runs beside it by default)
     int move_beside_ctas_per_sm{2};   // MSIM_MOVE_BESIDE_CTAS=1..8: CTAs per SM of the move kernel while it shares the SMs with a query (8 = the stand-alone grid).  Tick at 10 M entities: 304 / 306 / 313 / 317 / 315 us for 2 / 3 / 4 / 6 / 8, 327 us without the overlap
+    // band-sharded handles have their own pair of knobs (MSIM_SHARD_ARRIVE_BESIDE_CTAS 0 = full grid .. 8, MSIM_SHARD_MOVE_BESIDE_CTAS 1 .. 8).
+    // Tick at 2 GPUs, 10 M entities in total: 209 / 210 / 218 / 226 us for (1, 2) / (2, 4) / (4, 8) / (full, 8), 233 us without the overlap
+    int shard_arrive_beside_ctas_per_sm{1};
+    int shard_move_beside_ctas_per_sm{2};
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
 };
 const Tuning& tuning();
@@ -142,7 +146,8 @@ int launch_move(cudaStream_t s, int sm_count, uint32_t n, const float2* pos_in, 
                 const uint32_t* n_dev = nullptr, const struct ShardMoveArgs* shard = nullptr, int ctas_per_sm = 0 /* 0: the stand-alone grid, 8 per SM */);
 // `beside`: the pass runs on the side stream next to the issue-bound query (see Tuning::arrive_beside_ctas_per_sm)
 int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, uint4* rng, const uint32_t* arrived, const msim_road* roads,
-                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr, bool beside = false);
+                  const uint32_t* connections, uint64_t connection_count, Profiler* prof, const uint32_t* n_dev = nullptr, bool beside = false,
+                  int beside_ctas_per_sm = -1 /* -1: Tuning::arrive_beside_ctas_per_sm */);
 int launch_keygen(cudaStream_t s, uint32_t n, const float2* pos, uint32_t* keys, const GridParams& grid, Profiler* prof);
 
 // sort.cu

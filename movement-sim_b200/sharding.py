@@ -481,8 +481,10 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
             bpe = KERNEL_BYTES.get(name)
             if name.startswith("_") or not bpe:
                 continue
-            if name == "move" and not collisions:
-                bpe = 24.0
+            if name == "move" and collisions:
+                bpe = 28.0  # sharded handles also write the 4 B cell key (the exchange kernels work on keys)
+            elif name == "cell_scatter" and collisions:
+                bpe = 24.0  # ... and the scatter reads it
             n0 = per_rank[0]
             gbs = bpe * n0 / (us * 1e-6) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
