@@ -417,6 +417,8 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         dist.all_gather(gathered, owned)
         per_rank = [int(g.item()) for g in gathered]
         pairs = flagged = None
+        counts_by_rank = [None] * world
+        dist.all_gather_object(counts_by_rank, [int(st1["last_pair_count"]), int(st1["last_flagged_count"])])
         if collisions:
             pairs, flagged = sh.global_sum(st1["last_pair_count"]), sh.global_sum(st1["last_flagged_count"])
         check = check_counts(args.workload, total, st1["move_passes"], pairs, flagged)
@@ -509,6 +511,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
                        "phase_us_rank0": getattr(sh, "phase_us", None), "kernel_us_per_step_rank0": kernels, "kernel_us_per_step_by_rank": kernels_by_rank,
                        "exchange_buffer_bytes": (M.shard_buffer_bytes(sh.migrant_capacity, sh.halo_capacity) if sh else 0),
                        "move_passes_done": st1["move_passes"], "pairs_last_tick": pairs, "flagged_last_tick": flagged, "counts_check": check,
+                       "pairs_flagged_by_rank": counts_by_rank, "splits": [int(x) for x in sh.splits] if sh else None,
                        "resort": {"every_collision_passes": RESORT_EVERY, "in_timed_region": st1["reorders"] - st0["reorders"],
                                   "alignment_ticks_untimed": aligned,
                                   "note": "the timed region starts on a re-sorting tick: it holds 1 + (K - 1) // 32 re-sorts, never fewer than its share"}},
