@@ -193,6 +193,7 @@ typedef struct msim_stats {
     uint32_t key_bits, sort_passes;
     float cell_size;
     uint32_t reorders;           /* physical re-sorts of the resident state so far */
+    uint64_t total_flagged_count; /* last_flagged_count summed over every collision pass so far */
 } msim_stats;
 int msim_get_stats(msim_handle* h, msim_stats* out);
 

@@ -165,6 +165,7 @@ class Stats(C.Structure):
         ("sort_passes", C.c_uint32),
         ("cell_size", C.c_float),
         ("reorders", C.c_uint32),
+        ("total_flagged_count", C.c_uint64),
     ]
 
     def as_dict(self):

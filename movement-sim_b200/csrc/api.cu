@@ -105,7 +105,7 @@ struct msim_handle {
     bool collided{false};
     bool flags_scattered{false};
     uint64_t move_passes{0}, collide_passes{0}, launches{0}, initialised_total{0};
-    uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0};
+    uint64_t last_pairs{0}, total_pairs{0}, last_flagged{0}, total_flagged{0};
 
     // cell-ordered storage: periodic physical re-sort of the state (pack.cu), slot <-> external id maps
     bool reorder_enabled{false};
@@ -577,6 +577,7 @@ int check_device_errors(msim_handle* h) {
     h->last_pairs = h->n ? c.pairs_last : 0;
     h->total_pairs = c.pairs_total;
     h->last_flagged = h->n ? c.flagged_last : 0;
+    h->total_flagged = c.flagged_total;
     if (c.error_flag) return fail(h, MSIM_ERR_INTERNAL, "look-back watchdog tripped (radix sort / cell scan): a tile never published its total");
     return MSIM_OK;
 }
@@ -1291,6 +1292,7 @@ int msim_get_stats(msim_handle* h, msim_stats* out) {
     out->sort_passes = (h->keys && h->use_csort) ? 1u : static_cast<uint32_t>((h->key_bits + RADIX_BITS - 1) / RADIX_BITS);
     out->cell_size = h->grid.inv_cell > 0.0f ? 1.0f / h->grid.inv_cell : 0.0f;
     out->reorders = static_cast<uint32_t>(h->reorders);
+    out->total_flagged_count = h->total_flagged;
     return rc;
 }
 
@@ -1309,7 +1311,7 @@ int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32
     if (!out || !count) return fail(h, MSIM_ERR_INVALID, "msim_profile_end: null argument");
     static const char* const names[K_COUNT] = {"move", "arrive", "keygen", "histogram", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3",
                                                "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc", "shard", "cell_count",
-                                               "cell_scan", "cell_scatter", "reorder"};
+                                               "cell_scan", "cell_scatter", "reorder", "fold_counts"};
     h->prof.enabled = false;
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     double ms[K_COUNT] = {0};

@@ -171,54 +171,81 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
     // CTA-level reduction, then ONE atomic per CTA per counter into a striped counter (64 stripes on
     // separate 128-byte lines).  The first version issued three same-address atomics per warp: ~940 k
     // atomics on one L2 line serialised to ~630 us and hid everything else (profiles/r1d).
-    uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit));
-    if (COUNT_PAIRS) pairs = __reduce_add_sync(0xffffffffu, pairs);
-    __syncthreads();  // s_red is reused
-    if (lane == 0) {
-        s_red[0][warp] = hits;
-        s_red[1][warp] = pairs;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t h = 0, pr = 0;
+    if (COUNT_PAIRS) {  // (flagged entities are counted from the stored flags by fold_counts_kernel)
+        pairs = __reduce_add_sync(0xffffffffu, pairs);
+        __syncthreads();  // s_red is reused
+        if (lane == 0) s_red[1][warp] = pairs;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t pr = 0;
 #pragma unroll
-        for (int w = 0; w < QUERY_THREADS / 32; w++) {
-            h += s_red[0][w];
-            pr += s_red[1][w];
+            for (int w = 0; w < QUERY_THREADS / 32; w++) pr += s_red[1][w];
+            unsigned long long* stripe = stripes + static_cast<size_t>(blockIdx.x % COUNTER_STRIPES) * COUNTER_STRIDE;
+            if (pr) atomicAdd(stripe + 1, static_cast<unsigned long long>(pr));
         }
-        unsigned long long* stripe = stripes + static_cast<size_t>(blockIdx.x % COUNTER_STRIPES) * COUNTER_STRIDE;
-        if (h) atomicAdd(stripe, static_cast<unsigned long long>(h));
-        if (COUNT_PAIRS && pr) atomicAdd(stripe + 1, static_cast<unsigned long long>(pr));
     }
 }
 
-
-// folds the striped counters of one query into Counters and clears them for the next pass
-__global__ void __launch_bounds__(COUNTER_STRIPES) fold_counters_kernel(unsigned long long* __restrict__ stripes, Counters* __restrict__ counters) {
-    __shared__ unsigned long long s_h[COUNTER_STRIPES / 32], s_p[COUNTER_STRIPES / 32];
-    unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
-    unsigned long long h = stripe[0], pr = stripe[1];
-    stripe[0] = 0;
-    stripe[1] = 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        h += __shfl_down_sync(0xffffffffu, h, d);
-        pr += __shfl_down_sync(0xffffffffu, pr, d);
+// ---- totals of one query -----------------------------------------------------------------------------------------------------
+// Pairs: the query kernels reduce them per warp / CTA into the striped counters (a lane that takes the divergent "look above" path
+// has found nothing below, so it carries no pairs).  Flagged entities are NOT counted by the query kernels: they are counted here,
+// from the flags the query wrote (one byte per sorted slot, 0 / 1; ghost slots hold 0).  Round 2 found the in-kernel count - a
+// ballot behind the divergent look-above scans - one short of the flags it had just stored on ~10 % of the ticks at 10 M entities
+// (profiles/r2_flag_count_race.md); the flags themselves were always right.  This kernel uses no warp-level primitive at all:
+// per-thread sums meet in shared-memory atomics behind a CTA barrier, CTAs meet in one global atomic each, and the last CTA to
+// take a ticket folds the pair stripes and writes Counters.  Words behind the stripes: [0] flagged accumulator, [1] ticket.
+constexpr int FOLD_THREADS = 256;
+__global__ void __launch_bounds__(FOLD_THREADS)
+fold_counts_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint8_t* __restrict__ flag_sorted, unsigned long long* __restrict__ stripes,
+                   Counters* __restrict__ counters) {
+    __shared__ unsigned int s_flagged;
+    __shared__ unsigned long long s_pairs;
+    __shared__ unsigned int s_last;
+    if (threadIdx.x == 0) {
+        s_flagged = 0u;
+        s_pairs = 0ull;
     }
-    if ((threadIdx.x & 31u) == 0) {
-        s_h[threadIdx.x >> 5] = h;
-        s_p[threadIdx.x >> 5] = pr;
+    __syncthreads();
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    unsigned long long* const acc = stripes + static_cast<size_t>(COUNTER_STRIPES) * COUNTER_STRIDE;
+    const uint32_t chunks = n >> 4;  // 16 flags per load; every byte is 0 or 1, so a word's flags are its set bits
+    const uint4* f4 = reinterpret_cast<const uint4*>(flag_sorted);
+    uint32_t sum = 0;
+    const uint32_t stride = gridDim.x * FOLD_THREADS;
+    for (uint32_t i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < chunks; i += 4u * stride) {  // four loads in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = i + q * stride < chunks ? __ldcs(f4 + i + q * stride) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 4; q++) sum += __popc(v[q].x) + __popc(v[q].y) + __popc(v[q].z) + __popc(v[q].w);
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t k = (chunks << 4) + threadIdx.x; k < n; k += FOLD_THREADS) sum += flag_sorted[k];
+    if (sum) atomicAdd(&s_flagged, sum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_flagged) atomicAdd(acc, static_cast<unsigned long long>(s_flagged));
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int*>(acc + 1), 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < COUNTER_STRIPES) {
+        unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
+        const unsigned long long pr = stripe[1];
+        stripe[0] = 0;
+        stripe[1] = 0;
+        if (pr) atomicAdd(&s_pairs, pr);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        h = pr = 0;
-        for (int w = 0; w < COUNTER_STRIPES / 32; w++) {
-            h += s_h[w];
-            pr += s_p[w];
-        }
+        const unsigned long long h = atomicExch(acc, 0ull);
+        *reinterpret_cast<unsigned int*>(acc + 1) = 0u;
         counters->flagged_last = h;
-        counters->pairs_last = pr;
-        counters->pairs_total += pr;
+        counters->flagged_total += h;
+        counters->pairs_last = s_pairs;
+        counters->pairs_total += s_pairs;
     }
 }
 
@@ -261,9 +288,18 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
         if (ghosts) MSIM_QUERY(false, true); else MSIM_QUERY(false, false);
     }
 #undef MSIM_QUERY
-    fold_counters_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
     prof->end(s);
-    return 2;
+    return 1 + launch_fold_counts(s, n, n_dev, flag_sorted, stripes, counters, prof);
+}
+
+int launch_fold_counts(cudaStream_t s, uint32_t n, const uint32_t* n_dev, const uint8_t* flag_sorted, unsigned long long* stripes, Counters* counters, Profiler* prof) {
+    uint32_t blocks = (n / 16u + FOLD_THREADS - 1) / FOLD_THREADS;  // n is an upper bound when n_dev is given
+    if (blocks > 148u * 4u) blocks = 148u * 4u;
+    if (blocks == 0) blocks = 1;
+    prof->begin(s, K_FOLD);
+    fold_counts_kernel<<<blocks, FOLD_THREADS, 0, s>>>(n, n_dev, flag_sorted, stripes, counters);
+    prof->end(s);
+    return 1;
 }
 
 size_t query_stripe_bytes() { return static_cast<size_t>(COUNTER_STRIPES) * COUNTER_STRIDE * sizeof(unsigned long long); }

@@ -166,49 +166,58 @@ query_tiles_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const fl
         hit = count_last_group(G + 2u * (scan_hi >> 2), scan_hi & 3u, p, thr) != 0u || any_in_groups(G, own_lo >> 2, scan_hi >> 2, p, thr) ||
               any_in_groups(G, ga0, ga1, p, thr);
     }
-    // nothing below: look at the slots above (rest of the own row, then the row below), where the first hit is enough
-    if (!hit && mine) {
-        hit = any_in_range(sorted_pos, j + 1u, __ldg(tab + (r + x1e)), p, thr);
-        if (!hit && cy + 1 < grid.ncy) hit = any_in_range(sorted_pos, __ldg(tab + (r + ncx + x0)), __ldg(tab + (r + ncx + x1e)), p, thr);
+    // nothing below: look at the slots above (rest of the own row up to the end of cell cx+1, then the three cells of the row below), where the
+    // first hit is enough.  Few lanes get here (an entity with neighbours has, as a rule, some of them below it), so the warp serves them one at
+    // a time, TOGETHER: the lane's position and its two runs are broadcast, every lane tests another candidate of the concatenated runs.
+    // Control flow stays warp-uniform on purpose.  The first version let each such lane walk its runs alone inside a divergent region, and
+    // ptxas kept different kernel parameters (row count, threshold, array base) in ONE uniform register across that region's paths: lanes of a
+    // warp on different paths overwrote it for each other and, about once per 10^10 entity-ticks, a lane compared its distance with the wrong
+    // number and missed its only neighbour (profiles/r2_flag_count_race.md).
+    {
+        const bool need = !hit && mine;
+        uint32_t up0 = 0u, up1 = 0u, dn0 = 0u, dn1 = 0u;
+        if (need) {
+            up0 = j + 1u;
+            up1 = __ldg(tab + (r + x1e));
+            if (cy + 1 < grid.ncy) {
+                dn0 = __ldg(tab + (r + ncx + x0));
+                dn1 = __ldg(tab + (r + ncx + x1e));
+            }
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, need);
+        if (todo) {  // (warp-uniform) most of these lanes have their neighbour right behind them in their own cell: two straight-line tests first
+            bool near = false;
+            if (need && up0 < up1) near = dist2(__ldg(sorted_pos + up0), p) < thr;
+            if (need && up0 + 1u < up1) near = near || dist2(__ldg(sorted_pos + up0 + 1u), p) < thr;
+            if (near) hit = true;
+            todo = __ballot_sync(0xffffffffu, need && !near);
+            up0 = min(up0 + 2u, up1);
+        }
+        while (todo) {  // warp-uniform
+            const int leader = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const float2 lp = make_float2(__shfl_sync(0xffffffffu, p.x, leader), __shfl_sync(0xffffffffu, p.y, leader));
+            const uint32_t a0 = __shfl_sync(0xffffffffu, up0, leader), a1 = __shfl_sync(0xffffffffu, up1, leader);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, dn0, leader), b1 = __shfl_sync(0xffffffffu, dn1, leader);
+            const uint32_t na = a1 - a0, total = na + (b1 - b0);
+            bool found = false;
+            for (uint32_t base = 0; base < total && !found; base += 32u) {  // warp-uniform: `found` is a vote
+                const uint32_t k = base + lane;
+                bool h = false;
+                if (k < total) h = dist2(__ldg(sorted_pos + (k < na ? a0 + k : b0 + (k - na))), lp) < thr;
+                found = __any_sync(0xffffffffu, h);
+            }
+            if (static_cast<int>(lane) == leader) hit = found;
+        }
     }
     if (in_range) flag_sorted[j] = hit ? 1 : 0;
 
-    // ---- totals: one reduction (no return value, nothing waits) per counter and warp into a striped counter; a one-CTA kernel folds the stripes
-    const uint32_t hits = __popc(__ballot_sync(0xffffffffu, hit && mine));
-    pairs = __reduce_add_sync(0xffffffffu, mine ? pairs : 0u);
-    if (lane == 0) {
-        unsigned long long* stripe = stripes + ((warp_base >> 5) % COUNTER_STRIPES) * COUNTER_STRIDE;
-        if (hits) atomicAdd(stripe, static_cast<unsigned long long>(hits));
-        if (pairs) atomicAdd(stripe + 1, static_cast<unsigned long long>(pairs));
-    }
-}
-
-// folds the striped counters of one query into Counters and clears them for the next pass
-__global__ void __launch_bounds__(COUNTER_STRIPES) fold_stripes_kernel(unsigned long long* __restrict__ stripes, Counters* __restrict__ counters) {
-    __shared__ unsigned long long s_h[COUNTER_STRIPES / 32], s_p[COUNTER_STRIPES / 32];
-    unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
-    unsigned long long h = stripe[0], pr = stripe[1];
-    stripe[0] = 0;
-    stripe[1] = 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        h += __shfl_down_sync(0xffffffffu, h, d);
-        pr += __shfl_down_sync(0xffffffffu, pr, d);
-    }
-    if ((threadIdx.x & 31u) == 0) {
-        s_h[threadIdx.x >> 5] = h;
-        s_p[threadIdx.x >> 5] = pr;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        h = pr = 0;
-        for (int w = 0; w < COUNTER_STRIPES / 32; w++) {
-            h += s_h[w];
-            pr += s_p[w];
-        }
-        counters->flagged_last = h;
-        counters->pairs_last = pr;
-        counters->pairs_total += pr;
+    // ---- totals: the pairs leave as one reduction (no return value, nothing waits) per warp into a striped counter.  A lane that took the
+    // divergent look-above path found nothing below: it carries no pairs, so this sum does not depend on where the warp reconverges.
+    // The flagged entities are counted from the flags just stored, by fold_counts_kernel (collide.cu) behind this kernel.
+    if (COUNT_PAIRS) {
+        pairs = __reduce_add_sync(0xffffffffu, mine ? pairs : 0u);
+        if (lane == 0 && pairs) atomicAdd(stripes + ((warp_base >> 5) % COUNTER_STRIPES) * COUNTER_STRIDE + 1, static_cast<unsigned long long>(pairs));
     }
 }
 
@@ -227,9 +236,8 @@ int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, con
         if (count_pairs) query_tiles_kernel<true, false><<<blocks, TILES_THREADS, 0, s>>>(n, nullptr, sorted_pos, tab, flag_sorted, grid, stripes, 0, 0);
         else query_tiles_kernel<false, false><<<blocks, TILES_THREADS, 0, s>>>(n, nullptr, sorted_pos, tab, flag_sorted, grid, stripes, 0, 0);
     }
-    fold_stripes_kernel<<<1, COUNTER_STRIPES, 0, s>>>(stripes, counters);
     prof->end(s);
-    return 2;
+    return 1 + launch_fold_counts(s, n, ghosts ? n_dev : nullptr, flag_sorted, stripes, counters, prof);
 }
 
 }  // namespace msim

@@ -59,7 +59,7 @@ struct Counters {
     unsigned long long pairs_last;
     unsigned long long pairs_total;
     unsigned long long flagged_last;
-    unsigned long long initialised_total;
+    unsigned long long flagged_total;  // summed over every collision pass (cross-checks between runs on different GPU counts)
     unsigned int error_flag;
     unsigned int pad;
 };
@@ -90,7 +90,7 @@ struct ShardMoveArgs {
 // ---- per-kernel CUDA-event timing (bench.py's live roofline; off unless msim_profile_begin) -----
 enum KernelId {
     K_MOVE = 0, K_ARRIVE, K_KEYGEN, K_HISTOGRAM, K_SORT_PASS0, K_SORT_PASS1, K_SORT_PASS2, K_SORT_PASS3, K_BUILD_CELLS, K_QUERY,
-    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_CELL_COUNT, K_CELL_SCAN, K_CELL_SCATTER, K_REORDER, K_COUNT
+    K_SCATTER_FLAGS, K_PACK, K_UNPACK, K_MEMSET, K_MISC, K_SHARD, K_CELL_COUNT, K_CELL_SCAN, K_CELL_SCATTER, K_REORDER, K_FOLD, K_COUNT
 };
 
 struct Profiler {
@@ -185,6 +185,8 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
                  uint8_t* flag_sorted, const GridParams& grid, bool count_pairs, Counters* counters, unsigned long long* stripes, Profiler* prof,
                  const uint32_t* n_dev = nullptr, const uint32_t* n_owned_dev = nullptr);
 size_t query_stripe_bytes();
+// totals of one query: flagged entities counted from the stored flags, pair stripes folded, Counters written (collide.cu)
+int launch_fold_counts(cudaStream_t s, uint32_t n, const uint32_t* n_dev, const uint8_t* flag_sorted, unsigned long long* stripes, Counters* counters, Profiler* prof);
 // collide_tiles.cu — the query over the counting sort's prefix table: aligned candidate groups, striped counters folded by a one-CTA
 // kernel behind it.  ghosts (sharded handles): slots whose cell row is outside [row_lo, row_hi) are neighbours only; n_dev: slot count
 int launch_query_tiles(cudaStream_t s, uint32_t n, const float2* sorted_pos, const uint32_t* tab, uint8_t* flag_sorted, const GridParams& grid, bool count_pairs,

@@ -138,6 +138,15 @@ inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::warp_sync(); }
 inline unsigned __shfl_sync(unsigned, unsigned v, unsigned src) {
     return cuda_emu::collective(v, [src](const unsigned long long* s) { return static_cast<unsigned>(s[src & 31u]); });
 }
+inline int __shfl_sync(unsigned m, int v, int src) { return static_cast<int>(__shfl_sync(m, static_cast<unsigned>(v), static_cast<unsigned>(src))); }
+inline unsigned __shfl_sync(unsigned m, unsigned v, int src) { return __shfl_sync(m, v, static_cast<unsigned>(src)); }
+inline float __shfl_sync(unsigned m, float v, int src) {  // binary32 travels as its bit pattern
+    unsigned b;
+    std::memcpy(&b, &v, sizeof(b));
+    b = __shfl_sync(m, b, static_cast<unsigned>(src));
+    std::memcpy(&v, &b, sizeof(v));
+    return v;
+}
 inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned delta) {
     const unsigned me = cuda_emu::lane;
     return cuda_emu::collective(v, [me, delta](const unsigned long long* s) { return static_cast<unsigned>(me >= delta ? s[me - delta] : s[me]); });
@@ -165,6 +174,7 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicMax(unsigned* p, unsigned v) {
     unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
