@@ -159,15 +159,22 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
                 if (!hit && has_above) hit = any_in_range(sorted_pos, ab_lo, ab_hi, p, thr);
             }
         }
-        // nothing below: look above (rare; straight from global memory)
-        if (!hit) hit = any_in_range(sorted_pos, max(j + 1, own_lo), own_hi, p, thr);
-        if (!hit && cy + 1 < grid.ncy) {
-            uint32_t lo, hi;
-            row_run(cell_range, grid.ncx, cy + 1, x0, x1, lo, hi);
-            hit = any_in_range(sorted_pos, lo, hi, p, thr);
-        }
-        flag_sorted[j] = hit ? 1 : 0;
     }
+    // nothing below: look above, the whole warp together (collide_common.cuh; every lane of every warp gets here)
+    {
+        const bool need = mine && !hit;
+        uint32_t up0 = 0u, up1 = 0u, dn0 = 0u, dn1 = 0u;
+        if (need) {
+            up0 = max(j + 1u, own_lo);
+            up1 = max(own_hi, up0);
+            if (cy + 1 < grid.ncy) {
+                row_run(cell_range, grid.ncx, cy + 1, x0, x1, dn0, dn1);
+                if (dn0 > dn1) dn0 = dn1;
+            }
+        }
+        look_above_cooperative(need, p, up0, up1, dn0, dn1, sorted_pos, grid.hit_threshold, lane, hit);
+    }
+    if (mine) flag_sorted[j] = hit ? 1 : 0;
     // CTA-level reduction, then ONE atomic per CTA per counter into a striped counter (64 stripes on
     // separate 128-byte lines).  The first version issued three same-address atomics per warp: ~940 k
     // atomics on one L2 line serialised to ~630 us and hid everything else (profiles/r1d).
@@ -194,7 +201,8 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
 // (profiles/r2_flag_count_race.md); the flags themselves were always right.  This kernel uses no warp-level primitive at all:
 // per-thread sums meet in shared-memory atomics behind a CTA barrier, CTAs meet in one global atomic each, and the last CTA to
 // take a ticket folds the pair stripes and writes Counters.  Words behind the stripes: [0] flagged accumulator, [1] ticket.
-constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_THREADS = 512;
+constexpr int FOLD_UNROLL = 8;  // 148 CTAs x 512 threads x 8 x 16 B = 9.7 MB in flight per sweep: one sweep at 10 M entities, two global atomics per CTA
 __global__ void __launch_bounds__(FOLD_THREADS)
 fold_counts_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint8_t* __restrict__ flag_sorted, unsigned long long* __restrict__ stripes,
                    Counters* __restrict__ counters) {
@@ -212,12 +220,12 @@ fold_counts_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const ui
     const uint4* f4 = reinterpret_cast<const uint4*>(flag_sorted);
     uint32_t sum = 0;
     const uint32_t stride = gridDim.x * FOLD_THREADS;
-    for (uint32_t i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < chunks; i += 4u * stride) {  // four loads in flight per thread
-        uint4 v[4];
+    for (uint32_t i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < chunks; i += FOLD_UNROLL * stride) {  // FOLD_UNROLL loads in flight per thread
+        uint4 v[FOLD_UNROLL];
 #pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = i + q * stride < chunks ? __ldcs(f4 + i + q * stride) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < FOLD_UNROLL; q++) v[q] = i + q * stride < chunks ? __ldcs(f4 + i + q * stride) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int q = 0; q < 4; q++) sum += __popc(v[q].x) + __popc(v[q].y) + __popc(v[q].z) + __popc(v[q].w);
+        for (int q = 0; q < FOLD_UNROLL; q++) sum += __popc(v[q].x) + __popc(v[q].y) + __popc(v[q].z) + __popc(v[q].w);
     }
     if (blockIdx.x == 0)
         for (uint32_t k = (chunks << 4) + threadIdx.x; k < n; k += FOLD_THREADS) sum += flag_sorted[k];
@@ -293,8 +301,8 @@ int launch_query(cudaStream_t s, uint32_t n, uint32_t n_owned, const uint32_t* s
 }
 
 int launch_fold_counts(cudaStream_t s, uint32_t n, const uint32_t* n_dev, const uint8_t* flag_sorted, unsigned long long* stripes, Counters* counters, Profiler* prof) {
-    uint32_t blocks = (n / 16u + FOLD_THREADS - 1) / FOLD_THREADS;  // n is an upper bound when n_dev is given
-    if (blocks > 148u * 4u) blocks = 148u * 4u;
+    uint32_t blocks = (n / 16u + FOLD_THREADS * FOLD_UNROLL - 1) / (FOLD_THREADS * FOLD_UNROLL);  // n is an upper bound when n_dev is given
+    if (blocks > 148u) blocks = 148u;
     if (blocks == 0) blocks = 1;
     prof->begin(s, K_FOLD);
     fold_counts_kernel<<<blocks, FOLD_THREADS, 0, s>>>(n, n_dev, flag_sorted, stripes, counters);

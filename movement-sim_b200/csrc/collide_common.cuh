@@ -63,6 +63,42 @@ __device__ __forceinline__ void row_run(const uint2* __restrict__ cell_range, in
     if (lo > hi) lo = hi;  // all three empty
 }
 
+// ---- the look-above scan, served by the whole warp ------------------------------------------------------------------------------
+// `need`: this lane found nothing among the slots below it and wants to know whether some slot of [up0, up1) (rest of its own row) or
+// [dn0, dn1) (row below) is in range.  Few lanes do, so they are served one at a time, TOGETHER: a ballot, the leader's position and runs
+// broadcast by shuffles, every lane tests another candidate of the concatenated runs, a vote ends the loop.  Two straight-line tests of the
+// next two slots come first (most such lanes have their neighbour right behind them in their own cell).  Control flow is warp-uniform on
+// purpose: per-lane divergent scans here were miscompiled into sharing one uniform register between paths (profiles/r2_flag_count_race.md).
+// Must be called by all 32 lanes of a converged warp.
+__device__ __forceinline__ void look_above_cooperative(bool need, float2 p, uint32_t up0, uint32_t up1, uint32_t dn0, uint32_t dn1,
+                                                       const float2* __restrict__ sorted_pos, float thr, uint32_t lane, bool& hit) {
+    uint32_t todo = __ballot_sync(0xffffffffu, need);
+    if (todo) {  // (warp-uniform)
+        bool near = false;
+        if (need && up0 < up1) near = dist2(__ldg(sorted_pos + up0), p) < thr;
+        if (need && up0 + 1u < up1) near = near || dist2(__ldg(sorted_pos + up0 + 1u), p) < thr;
+        if (near) hit = true;
+        todo = __ballot_sync(0xffffffffu, need && !near);
+        up0 = min(up0 + 2u, up1);
+    }
+    while (todo) {  // warp-uniform
+        const int leader = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float2 lp = make_float2(__shfl_sync(0xffffffffu, p.x, leader), __shfl_sync(0xffffffffu, p.y, leader));
+        const uint32_t a0 = __shfl_sync(0xffffffffu, up0, leader), a1 = __shfl_sync(0xffffffffu, up1, leader);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, dn0, leader), b1 = __shfl_sync(0xffffffffu, dn1, leader);
+        const uint32_t na = a1 - a0, total = na + (b1 - b0);
+        bool found = false;
+        for (uint32_t base = 0; base < total && !found; base += 32u) {  // warp-uniform: `found` is a vote
+            const uint32_t k = base + lane;
+            bool h = false;
+            if (k < total) h = dist2(__ldg(sorted_pos + (k < na ? a0 + k : b0 + (k - na))), lp) < thr;
+            found = __any_sync(0xffffffffu, h);
+        }
+        if (static_cast<int>(lane) == leader) hit = found;
+    }
+}
+
 // ---- shared-memory variants of the scans (same arithmetic, candidates already staged) -----------
 __device__ __forceinline__ uint32_t count_in_tile(const float2* __restrict__ tile, uint32_t a, uint32_t b, float2 p, float threshold) {
     uint32_t c = 0;

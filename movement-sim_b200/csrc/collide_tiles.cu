@@ -184,31 +184,7 @@ query_tiles_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const fl
                 dn1 = __ldg(tab + (r + ncx + x1e));
             }
         }
-        uint32_t todo = __ballot_sync(0xffffffffu, need);
-        if (todo) {  // (warp-uniform) most of these lanes have their neighbour right behind them in their own cell: two straight-line tests first
-            bool near = false;
-            if (need && up0 < up1) near = dist2(__ldg(sorted_pos + up0), p) < thr;
-            if (need && up0 + 1u < up1) near = near || dist2(__ldg(sorted_pos + up0 + 1u), p) < thr;
-            if (near) hit = true;
-            todo = __ballot_sync(0xffffffffu, need && !near);
-            up0 = min(up0 + 2u, up1);
-        }
-        while (todo) {  // warp-uniform
-            const int leader = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const float2 lp = make_float2(__shfl_sync(0xffffffffu, p.x, leader), __shfl_sync(0xffffffffu, p.y, leader));
-            const uint32_t a0 = __shfl_sync(0xffffffffu, up0, leader), a1 = __shfl_sync(0xffffffffu, up1, leader);
-            const uint32_t b0 = __shfl_sync(0xffffffffu, dn0, leader), b1 = __shfl_sync(0xffffffffu, dn1, leader);
-            const uint32_t na = a1 - a0, total = na + (b1 - b0);
-            bool found = false;
-            for (uint32_t base = 0; base < total && !found; base += 32u) {  // warp-uniform: `found` is a vote
-                const uint32_t k = base + lane;
-                bool h = false;
-                if (k < total) h = dist2(__ldg(sorted_pos + (k < na ? a0 + k : b0 + (k - na))), lp) < thr;
-                found = __any_sync(0xffffffffu, h);
-            }
-            if (static_cast<int>(lane) == leader) hit = found;
-        }
+        look_above_cooperative(need, p, up0, up1, dn0, dn1, sorted_pos, thr, lane, hit);
     }
     if (in_range) flag_sorted[j] = hit ? 1 : 0;
 
