@@ -71,6 +71,13 @@ struct msim_handle {
     uint64_t* sort_b{nullptr};
     uint64_t* sorted{nullptr};
     float2* sorted_pos{nullptr};
+    // pipelined rebuild (unsharded handles): a second {sorted positions, prefix table} set, so that scan + scatter of tick t+1 can run
+    // (side stream) while the query of tick t (main stream) still reads the first; the pointers above always name the set in use
+    float2* sorted_pos_alt{nullptr};
+    uint32_t* cell_table_alt{nullptr};
+    cudaEvent_t ev_built{nullptr}, ev_queried[2]{nullptr, nullptr};
+    bool queried_recorded[2]{false, false};
+    uint32_t build_set{0};
     uint2* cell_range{nullptr};   // onesweep path: {first, ~end} per cell
     uint32_t cell_capacity{0};
     uint32_t* cell_count{nullptr};  // counting-sort path: per-cell counters, prefix table, scan scratch, ranks
@@ -189,6 +196,7 @@ const Tuning& tuning() {
             if (k >= 0 && k <= 8) v.arrive_beside_ctas_per_sm = k;
         }
         if (const char* e = std::getenv("MSIM_OVERLAP_TICKS")) v.overlap_ticks = std::atoi(e) != 0;
+        if (const char* e = std::getenv("MSIM_PIPELINE_BUILD")) v.pipeline_build = std::atoi(e) != 0;
         if (const char* e = std::getenv("MSIM_MOVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
             if (k >= 1 && k <= 8) v.move_beside_ctas_per_sm = k;
@@ -308,6 +316,10 @@ void free_all(msim_handle* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_arrived) cudaEventDestroy(h->ev_arrived);
+    cudaFree(h->sorted_pos_alt); cudaFree(h->cell_table_alt);
+    if (h->ev_built) cudaEventDestroy(h->ev_built);
+    for (cudaEvent_t e : h->ev_queried)
+        if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -460,9 +472,9 @@ void prepare_counts(msim_handle* h, cudaStream_t s = nullptr) {
 }
 
 // exclusive prefix sum of the per-cell counters over cells [c0, c1) into cell_start (one kernel, csort.cu)
-int scan_cells(msim_handle* h, uint32_t c0, uint32_t c1) {
+int scan_cells(msim_handle* h, uint32_t c0, uint32_t c1, cudaStream_t s = nullptr) {
     if (++h->scan_epoch == 0u) ++h->scan_epoch;
-    return launch_cell_scan(h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->scan_tiles_cap, h->scan_epoch, h->cell_start + c0, &h->counters->error_flag,
+    return launch_cell_scan(s ? s : h->stream, h->cell_count + c0, c1 - c0, h->tile_sums, h->scan_tiles_cap, h->scan_epoch, h->cell_start + c0, &h->counters->error_flag,
                             &h->prof);
 }
 
@@ -471,8 +483,8 @@ int ensure_cells(msim_handle* h) {
     const bool want_counting = (h->flags & MSIM_FLAG_SORT_COUNTING) || (h->reorder_enabled && !(h->flags & MSIM_FLAG_SORT_ONESWEEP));
     h->use_csort = want_counting && h->grid.ncells <= csort_max_cells();
     if (h->grid.ncells <= h->cell_capacity && (h->use_csort ? h->cell_count != nullptr : h->cell_range != nullptr)) return MSIM_OK;
-    cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_table); cudaFree(h->tile_sums);
-    h->cell_range = nullptr; h->cell_count = nullptr; h->cell_table = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr;
+    cudaFree(h->cell_range); cudaFree(h->cell_count); cudaFree(h->cell_table); cudaFree(h->tile_sums); cudaFree(h->cell_table_alt);
+    h->cell_range = nullptr; h->cell_count = nullptr; h->cell_table = nullptr; h->cell_start = nullptr; h->tile_sums = nullptr; h->cell_table_alt = nullptr;
     h->cell_capacity = 0;
     if (h->use_csort) {
         MSIM_CUDA(h, dev_alloc(&h->cell_count, static_cast<size_t>(h->grid.ncells) + 1));
@@ -726,6 +738,77 @@ int reorder_storage(msim_handle* h) {
     return MSIM_OK;
 }
 
+int finish_collide(msim_handle* h, uint32_t total) {
+    h->collide_total = total;
+    h->collide_owned = launch_owned(h);
+    h->flags_stale = false;
+    h->collided = true;
+    h->flags_scattered = false;
+    h->collide_passes++;
+    h->since_reorder++;
+    // a sharded handle finds its owned run through the counting sort's prefix table and only while every owned entity lies in the band
+    if (h->reorder_enabled && h->has_moved && (h->n > 1 || h->async_counts) && h->since_reorder >= h->reorder_every &&
+        (!h->sharded || (h->use_csort && h->band_valid)))
+        return reorder_storage(h);
+    return MSIM_OK;
+}
+
+// Unsharded handles, counting sort (the single-GPU default).  The main stream carries nothing but the query and its fold; everything else
+// of a tick - pass B, the move pass, the scan of the per-cell counters, the scatter into cell order - lives on the side stream, so the
+// rebuild of tick t+1 runs beside the query of tick t instead of behind it (the query is issue-bound, the rest is memory-bound).  The
+// rebuild writes the other of two {sorted positions, prefix table} sets; a set is rewritten only when the query that read it is done
+// (ev_queried), and a query starts when its set is built (ev_built).  The pointers h->sorted_pos / h->cell_start name the set of the
+// collision pass enqueued last, which is what readbacks and the periodic re-sort work on (they join the streams first).
+int enqueue_collide_pipelined(msim_handle* h, uint32_t total, bool count_pairs) {
+    if (!h->sorted_pos_alt) {
+        MSIM_CUDA(h, dev_alloc(&h->sorted_pos_alt, h->cap));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_built, cudaEventDisableTiming));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_queried[0], cudaEventDisableTiming));
+        MSIM_CUDA(h, cudaEventCreateWithFlags(&h->ev_queried[1], cudaEventDisableTiming));
+    }
+    if (!h->cell_table_alt) {  // (freed with the first table when the grid outgrows it)
+        MSIM_CUDA(h, dev_alloc(&h->cell_table_alt, static_cast<size_t>(h->cell_capacity) + 8));
+        MSIM_CUDA(h, cudaMemsetAsync(h->cell_table_alt, 0, 4 * sizeof(uint32_t), h->stream));
+        h->main_touched = true;
+    }
+    const cudaStream_t side = h->side;
+    if (h->main_touched) {  // an upload, a readback, a re-sort ... since the side stream last waited for the main one
+        MSIM_CUDA(h, cudaEventRecord(h->ev_moved, h->stream));
+        MSIM_CUDA(h, cudaStreamWaitEvent(side, h->ev_moved, 0));
+        h->main_touched = false;
+    }
+    // the other set: free once the query that read it (two collision passes ago) is done
+    h->build_set ^= 1u;
+    std::swap(h->sorted_pos, h->sorted_pos_alt);
+    std::swap(h->cell_table, h->cell_table_alt);
+    h->cell_start = h->cell_table + 4;
+    if (h->queried_recorded[h->build_set]) MSIM_CUDA(h, cudaStreamWaitEvent(side, h->ev_queried[h->build_set], 0));
+    if (!h->counts_valid) {  // no counting move pass in front of this dispatch: count now
+        prepare_counts(h, side);
+        h->launches += launch_cell_count_pos(side, h->sm_count, h->n, h->pos[h->cur], h->cell_count, h->grid, &h->prof);
+    }
+    h->counts_valid = false;
+    h->launches += scan_cells(h, 0, h->grid.ncells, side);
+    h->counts_dirty = false;  // the scan zeroed every counter it read
+    h->launches += launch_cell_scatter_slots(side, h->sm_count, total, h->pos[h->cur], nullptr, h->cell_start, h->sorted_pos, h->rank, h->grid, 0, h->grid.ncells,
+                                             &h->prof, nullptr);
+    MSIM_CUDA(h, cudaEventRecord(h->ev_built, side));
+    if (h->arrive_deferred && !h->awaiting_integrate) {  // pass B of the move in front of this pass: behind the scatter, beside the query
+        h->arrive_deferred = false;
+        h->launches += launch_arrive(side, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof, nullptr,
+                                     /*beside=*/true, -1);
+    }
+    MSIM_CUDA(h, cudaEventRecord(h->ev_arrived, side));
+    h->side_pending = true;
+    MSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_built, 0));
+    h->launches += launch_query_tiles(h->stream, total, h->sorted_pos, h->cell_start - 1, h->flag_sorted, h->grid, count_pairs, h->counters, h->stripes, &h->prof,
+                                      nullptr, false, 0, 0);
+    MSIM_CUDA(h, cudaEventRecord(h->ev_queried[h->build_set], h->stream));
+    h->queried_recorded[h->build_set] = true;
+    h->slots_valid = true;
+    return finish_collide(h, total);
+}
+
 int enqueue_collide(msim_handle* h) {
     if (h->flags & MSIM_FLAG_NO_COLLISIONS) return fail(h, MSIM_ERR_INVALID, "collision dispatch on a handle created with MSIM_FLAG_NO_COLLISIONS");
     if (consume_init_dispatch(h)) return MSIM_OK;
@@ -741,6 +824,7 @@ int enqueue_collide(msim_handle* h) {
     }
     const uint32_t total = launch_total(h);  // ghosts (multi-GPU halo) sit behind the owned entities
     const bool count_pairs = !(h->flags & MSIM_FLAG_NO_PAIR_COUNT);
+    if (h->use_csort && !h->sharded && h->side && tuning().overlap_ticks && tuning().pipeline_build) return enqueue_collide_pipelined(h, total, count_pairs);
     if (h->use_csort) {
         // sharded handles: the counter table is cleared / scanned over the band's cell range only, keys outside it
         // (a leaver that jumped two rows while the boundary moved: out of everybody's reach) are left out of the
@@ -775,18 +859,7 @@ int enqueue_collide(msim_handle* h) {
                                     h->counters, h->stripes, &h->prof, dev_total(h), dev_owned(h));
         h->slots_valid = false;
     }
-    h->collide_total = total;
-    h->collide_owned = launch_owned(h);
-    h->flags_stale = false;
-    h->collided = true;
-    h->flags_scattered = false;
-    h->collide_passes++;
-    h->since_reorder++;
-    // a sharded handle finds its owned run through the counting sort's prefix table and only while every owned entity lies in the band
-    if (h->reorder_enabled && h->has_moved && (h->n > 1 || h->async_counts) && h->since_reorder >= h->reorder_every &&
-        (!h->sharded || (h->use_csort && h->band_valid)))
-        return reorder_storage(h);
-    return MSIM_OK;
+    return finish_collide(h, total);
 }
 
 int bind(msim_handle* h) {

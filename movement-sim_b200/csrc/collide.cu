@@ -198,29 +198,34 @@ query_kernel(uint32_t n_host, uint32_t n_owned_host, const uint32_t* __restrict_
 // has found nothing below, so it carries no pairs).  Flagged entities are NOT counted by the query kernels: they are counted here,
 // from the flags the query wrote (one byte per sorted slot, 0 / 1; ghost slots hold 0).  Round 2 found the in-kernel count - a
 // ballot behind the divergent look-above scans - one short of the flags it had just stored on ~10 % of the ticks at 10 M entities
-// (profiles/r2_flag_count_race.md); the flags themselves were always right.  This kernel uses no warp-level primitive at all:
-// per-thread sums meet in shared-memory atomics behind a CTA barrier, CTAs meet in one global atomic each, and the last CTA to
-// take a ticket folds the pair stripes and writes Counters.  Words behind the stripes: [0] flagged accumulator, [1] ticket.
+// (profiles/r2_flag_count_race.md); the flags themselves were almost always right.  This kernel uses no warp-level primitive at all:
+// per-thread sums meet in shared-memory atomics behind a CTA barrier and CTAs meet in ONE global atomic each, which carries the CTA's
+// count and its ticket - the CTA that completes the set finds the total in the value it gets back (no fence, no second round trip:
+// the first version's ticket chain and last-CTA fold were 8 of its 12 us).  CTA 0 folds the pair stripes while its flags are in flight.
 constexpr int FOLD_THREADS = 512;
-constexpr int FOLD_UNROLL = 8;  // 148 CTAs x 512 threads x 8 x 16 B = 9.7 MB in flight per sweep: one sweep at 10 M entities, two global atomics per CTA
+constexpr int FOLD_UNROLL = 8;  // 148 CTAs x 512 threads x 8 x 16 B = 9.7 MB per sweep: one sweep at 10 M entities
+constexpr int FOLD_TICKET_SHIFT = 40;  // word behind the stripes: {CTAs done : 24 | flagged so far : 40}
 __global__ void __launch_bounds__(FOLD_THREADS)
 fold_counts_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const uint8_t* __restrict__ flag_sorted, unsigned long long* __restrict__ stripes,
                    Counters* __restrict__ counters) {
     __shared__ unsigned int s_flagged;
     __shared__ unsigned long long s_pairs;
-    __shared__ unsigned int s_last;
     if (threadIdx.x == 0) {
         s_flagged = 0u;
         s_pairs = 0ull;
     }
     __syncthreads();
     const uint32_t n = n_dev ? *n_dev : n_host;
-    unsigned long long* const acc = stripes + static_cast<size_t>(COUNTER_STRIPES) * COUNTER_STRIDE;
+    // CTA 0 folds the pair stripes (final since the query kernel ended) while it waits for its flags
+    unsigned long long pr = 0ull;
+    const bool folds = blockIdx.x == 0 && threadIdx.x < COUNTER_STRIPES;
+    unsigned long long* const stripe = stripes + static_cast<size_t>(threadIdx.x % COUNTER_STRIPES) * COUNTER_STRIDE;
+    if (folds) pr = stripe[1];
     const uint32_t chunks = n >> 4;  // 16 flags per load; every byte is 0 or 1, so a word's flags are its set bits
     const uint4* f4 = reinterpret_cast<const uint4*>(flag_sorted);
     uint32_t sum = 0;
     const uint32_t stride = gridDim.x * FOLD_THREADS;
-    for (uint32_t i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < chunks; i += FOLD_UNROLL * stride) {  // FOLD_UNROLL loads in flight per thread
+    for (uint32_t i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < chunks; i += FOLD_UNROLL * stride) {
         uint4 v[FOLD_UNROLL];
 #pragma unroll
         for (int q = 0; q < FOLD_UNROLL; q++) v[q] = i + q * stride < chunks ? __ldcs(f4 + i + q * stride) : make_uint4(0u, 0u, 0u, 0u);
@@ -230,31 +235,25 @@ fold_counts_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const ui
     if (blockIdx.x == 0)
         for (uint32_t k = (chunks << 4) + threadIdx.x; k < n; k += FOLD_THREADS) sum += flag_sorted[k];
     if (sum) atomicAdd(&s_flagged, sum);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_flagged) atomicAdd(acc, static_cast<unsigned long long>(s_flagged));
-        __threadfence();
-        s_last = atomicAdd(reinterpret_cast<unsigned int*>(acc + 1), 1u) == gridDim.x - 1u ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x < COUNTER_STRIPES) {
-        unsigned long long* stripe = stripes + static_cast<size_t>(threadIdx.x) * COUNTER_STRIDE;
-        const unsigned long long pr = stripe[1];
+    if (folds) {
         stripe[0] = 0;
         stripe[1] = 0;
         if (pr) atomicAdd(&s_pairs, pr);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long h = atomicExch(acc, 0ull);
-        *reinterpret_cast<unsigned int*>(acc + 1) = 0u;
-        counters->flagged_last = h;
-        counters->flagged_total += h;
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x == 0) {
         counters->pairs_last = s_pairs;
         counters->pairs_total += s_pairs;
     }
+    // one atomic per CTA carries its count and its ticket; the CTA that completes the set has the total in the value it got back
+    unsigned long long* const acc = stripes + static_cast<size_t>(COUNTER_STRIPES) * COUNTER_STRIDE;
+    const unsigned long long old = atomicAdd(acc, (1ull << FOLD_TICKET_SHIFT) | static_cast<unsigned long long>(s_flagged));
+    if ((old >> FOLD_TICKET_SHIFT) != gridDim.x - 1u) return;
+    const unsigned long long h = (old & ((1ull << FOLD_TICKET_SHIFT) - 1ull)) + s_flagged;
+    *acc = 0ull;  // (the next launch is behind this one on the stream)
+    counters->flagged_last = h;
+    counters->flagged_total += h;
 }
 
 __global__ void __launch_bounds__(256)
