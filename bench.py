@@ -51,6 +51,7 @@ KERNEL_BYTES = {
     "sort_pass3": 16.0,
     "build_cells": 24.0,  # pair R8 + pos gather R8 + sorted pos W8
     "query": 9.0,  # sorted pos R8 + flag W1 (neighbour reads are cache hits)
+    "fold_counts": 1.0,  # flag R1: the flagged count is taken from the stored flags (collide.cu fold_counts_kernel)
     "reorder": 98.0,  # every 32nd tick: idx R4 + flag R1 + (prev pos 8, target 8, road 4, rng 16, id 4) gathered and written + flag W1 + slot map W4
 }
 

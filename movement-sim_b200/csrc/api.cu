@@ -39,6 +39,7 @@ struct msim_handle {
     bool own_stream{false};
     cudaStream_t side{nullptr};  // pass B of a move runs here while the collision pass uses `stream`
     cudaEvent_t ev_moved{nullptr}, ev_arrived{nullptr};
+    bool arrive_early{false};     // pass B of this tick was launched behind the exchange; the collision pass only has to order the next move behind its scatter
     bool side_pending{false};     // the side stream holds work the main stream has not been ordered behind yet (ev_arrived marks its end)
     bool arrive_deferred{false};  // pass B of the last move has not been launched yet (it will ride beside the query)
     // Overlapped ticks: the move phase of tick t+1 (pass B of tick t, move + pack, shard exchange) runs on the side stream while the
@@ -197,6 +198,7 @@ const Tuning& tuning() {
         }
         if (const char* e = std::getenv("MSIM_OVERLAP_TICKS")) v.overlap_ticks = std::atoi(e) != 0;
         if (const char* e = std::getenv("MSIM_PIPELINE_BUILD")) v.pipeline_build = std::atoi(e) != 0;
+        if (const char* e = std::getenv("MSIM_SHARD_ARRIVE_EARLY")) v.shard_arrive_early = std::atoi(e) != 0;
         if (const char* e = std::getenv("MSIM_MOVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
             if (k >= 1 && k <= 8) v.move_beside_ctas_per_sm = k;
@@ -341,6 +343,18 @@ inline ShardCounts flip_counts(msim_handle* h) {
 }
 
 void launch_deferred_arrive(msim_handle* h, bool beside) {
+    if (h->arrive_early && beside && h->side) {
+        // pass B is already on the side stream, right behind the exchange (msim_shard_p2p_integrate).  What is left to do here, behind the
+        // scatter: the next move pass (side stream) rewrites the keys the scatter has just read
+        h->arrive_early = false;
+        cudaEventRecord(h->ev_moved, h->stream);
+        cudaStreamWaitEvent(h->side, h->ev_moved, 0);
+        h->main_touched = false;
+        cudaEventRecord(h->ev_arrived, h->side);
+        h->side_pending = true;
+        return;
+    }
+    h->arrive_early = false;
     if (!h->arrive_deferred) return;
     if (h->awaiting_integrate) return;  // migrants travel with their pre-arrival state: pass B must see the integrated population
     h->arrive_deferred = false;
@@ -1753,8 +1767,17 @@ int msim_shard_p2p_integrate(msim_handle* h) {
                                          h->shard_ctr, h->local_ghosts, h->mig_cap, h->halo_cap, h->holes_cap, h->cap, h->place_dst, h->moves, h->grid,
                                          &h->prof, w, h->shard_trace);
     if (h->shard_trace) launch_shard_stamp(ms, h->shard_trace, 9);
+    rc = integrate_device_common(h, recv_down, recv_up, nullptr, /*launch=*/false);
+    // pass B needs the integrated population and nothing of the rebuild: it follows the exchange at once (side stream), beside the scan and
+    // the scatter of the collision pass on the main stream, instead of waiting for them
+    if (rc == MSIM_OK && tuning().shard_arrive_early && ms == h->side && h->side && h->arrive_deferred && !h->awaiting_integrate) {
+        h->arrive_deferred = false;
+        h->launches += launch_arrive(ms, launch_owned(h), h->target, h->road, h->rng, h->arrived, h->roads, h->conn, h->conn_count, &h->prof, dev_owned(h),
+                                     /*beside=*/true, tuning().shard_arrive_beside_ctas_per_sm);
+        h->arrive_early = true;
+    }
     end_move_phase(h);
-    return integrate_device_common(h, recv_down, recv_up, nullptr, /*launch=*/false);
+    return rc;
 }
 
 int msim_shard_integrate(msim_handle* h, const void* recv_down, const void* recv_up, uint64_t* owned, uint64_t* ghosts) {

@@ -130,6 +130,10 @@ struct Tuning {
     // Tick at 2 GPUs, 10 M entities in total: 209 / 210 / 218 / 226 us for (1, 2) / (2, 4) / (4, 8) / (full, 8), 233 us without the overlap
     int shard_arrive_beside_ctas_per_sm{1};
     int shard_move_beside_ctas_per_sm{2};
+    bool shard_arrive_early{false};   // MSIM_SHARD_ARRIVE_EARLY=1: pass B of a band-sharded tick follows the exchange on the side stream instead of waiting for the
+                                  // scatter (the tick's dependency loop move -> exchange -> scan -> scatter -> pass B -> move loses its last link).  Measured
+                                  // at 2 GPUs, 5 M entities each: 245 us per tick against 210 us - beside the memory-bound scan and scatter pass B costs more
+                                  // than the shorter loop saves; off by default
     bool pipeline_build{true};        // MSIM_PIPELINE_BUILD=0: scan + scatter of tick t+1 wait for the query of tick t on the main stream (by default they follow the
                                   // move phase on the side stream, into the other of two {sorted positions, prefix table} sets; unsharded handles)
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
