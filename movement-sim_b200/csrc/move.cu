@@ -273,7 +273,7 @@ move_kernel(uint32_t n_host, const uint32_t* __restrict__ n_dev, const float4* _
 // and hands exactly one arrival to each lane per round: the gather chains run 32-wide and balanced.
 constexpr int ARRIVE_THREADS = 256;
 
-// STRIDE = false (default): the grid covers every mask word, one pass.  STRIDE = true (MSIM_ARRIVE_GRID=persistent): the grid is capped
+// STRIDE = false (default): the grid covers every mask word, one pass.  STRIDE = true (pass B beside a query, MSIM_ARRIVE_BESIDE_CTAS): the grid is capped
 // at the resident CTAs and strides over the words (10 M entities need 1221 CTAs where 1184 are resident: no left-over wave).
 template <bool STRIDE>
 __global__ void __launch_bounds__(ARRIVE_THREADS)
@@ -377,7 +377,7 @@ int launch_arrive(cudaStream_t s, uint32_t n, float2* target, uint32_t* road, ui
     const uint32_t words = ((n + 63u) >> 6) << 1;  // grid size (n is an upper bound when n_dev is given)
     uint32_t blocks = (words + ARRIVE_THREADS - 1) / ARRIVE_THREADS;
     // 10 M entities need 1221 CTAs where 1184 are resident (31 registers, 8 per SM): the 37 left over start when the first finish.
-    // MSIM_ARRIVE_GRID=persistent: one resident wave that strides over the words instead
+    // beside a query: a strided grid of `per_sm` CTAs per SM instead (Tuning::arrive_beside_ctas_per_sm)
     uint32_t cap = 0u;
     const int per_sm = beside_ctas_per_sm >= 0 ? beside_ctas_per_sm : tuning().arrive_beside_ctas_per_sm;
     if (beside && per_sm) cap = 148u * static_cast<uint32_t>(per_sm);
