@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSIM_ABI_VERSION 1u
+#define MSIM_ABI_VERSION 2u /* 2: msim_stats grew by total_flagged_count */
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {

@@ -62,7 +62,7 @@ QUADTREE_NODE_DTYPE = np.dtype(
 )
 assert ENTITY_DTYPE.itemsize == 64 and ROAD_DTYPE.itemsize == 32 and QUADTREE_NODE_DTYPE.itemsize == 64
 
-MSIM_ABI_VERSION = 1
+MSIM_ABI_VERSION = 2
 (MSIM_OK, MSIM_ERR_INVALID, MSIM_ERR_CUDA, MSIM_ERR_OOM, MSIM_ERR_UNSUPPORTED, MSIM_ERR_IO, MSIM_ERR_PARSE,
  MSIM_ERR_CAPACITY, MSIM_ERR_INTERNAL) = range(9)
 FLAG_NO_COLLISIONS = 1 << 0
