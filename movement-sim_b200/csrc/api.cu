@@ -198,6 +198,10 @@ const Tuning& tuning() {
         }
         if (const char* e = std::getenv("MSIM_OVERLAP_TICKS")) v.overlap_ticks = std::atoi(e) != 0;
         if (const char* e = std::getenv("MSIM_PIPELINE_BUILD")) v.pipeline_build = std::atoi(e) != 0;
+        if (const char* e = std::getenv("MSIM_SCATTER_BESIDE_CTAS")) {
+            const int k = std::atoi(e);
+            if (k >= 1 && k <= 8) v.scatter_beside_ctas_per_sm = k;
+        }
         if (const char* e = std::getenv("MSIM_SHARD_ARRIVE_EARLY")) v.shard_arrive_early = std::atoi(e) != 0;
         if (const char* e = std::getenv("MSIM_MOVE_BESIDE_CTAS")) {
             const int k = std::atoi(e);
@@ -805,7 +809,7 @@ int enqueue_collide_pipelined(msim_handle* h, uint32_t total, bool count_pairs) 
     h->launches += scan_cells(h, 0, h->grid.ncells, side);
     h->counts_dirty = false;  // the scan zeroed every counter it read
     h->launches += launch_cell_scatter_slots(side, h->sm_count, total, h->pos[h->cur], nullptr, h->cell_start, h->sorted_pos, h->rank, h->grid, 0, h->grid.ncells,
-                                             &h->prof, nullptr);
+                                             &h->prof, nullptr, tuning().scatter_beside_ctas_per_sm);
     MSIM_CUDA(h, cudaEventRecord(h->ev_built, side));
     if (h->arrive_deferred && !h->awaiting_integrate) {  // pass B of the move in front of this pass: behind the scatter, beside the query
         h->arrive_deferred = false;
@@ -999,8 +1003,9 @@ int msim_create(const msim_config* cfg, msim_handle** out) {
             h->own_stream = true;
         }
         {
-            // the side stream carries pass B beside the (issue-bound, ~20 k CTA) collision query: highest priority, so that its
-            // few CTAs are placed as soon as query CTAs retire instead of queueing behind all of them
+            // the side stream carries pass B, the move pass and (unsharded handles) the rebuild beside the issue-bound, ~80 k CTA collision
+            // query: highest priority, so that its CTAs are placed as soon as query CTAs retire instead of queueing behind all of them
+            // (measured with the pipelined rebuild: 288 us per tick, 336 us with the side stream at the LOWEST priority)
             int prio_low = 0, prio_high = 0;
             MSIM_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
             MSIM_CUDA(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_high));
@@ -1126,7 +1131,9 @@ int msim_dispatch(msim_handle* h, const msim_push_consts* pc) {
     if (rc != MSIM_OK) return rc;
     if (!pc) return fail(h, MSIM_ERR_INVALID, "msim_dispatch: push constants are null");
     if (pc->world_size_x != h->world_w || pc->world_size_y != h->world_h || pc->collision_radius != h->radius) {
-        // push constants are per-dispatch state in the reference: follow them
+        // push constants are per-dispatch state in the reference: follow them.  Work enqueued asynchronously under the old grid (a move
+        // phase or a rebuild still on the side stream) is completed first
+        join_side(h);
         MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
         h->world_w = pc->world_size_x;
         h->world_h = pc->world_size_y;

@@ -340,11 +340,11 @@ int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint3
 }
 
 int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, const uint32_t* keys, uint32_t* cursor, float2* sorted_pos,
-                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev) {
+                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev, int ctas_per_sm) {
     if (n == 0) return 0;
     constexpr uint32_t chunks = 8u;
     uint32_t blocks = (n + 256u * chunks - 1u) / (256u * chunks);
-    const uint32_t resident = static_cast<uint32_t>(sm_count) * 8u;
+    const uint32_t resident = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(ctas_per_sm > 0 && ctas_per_sm < 8 ? ctas_per_sm : 8);
     if (blocks > resident) blocks = resident;
     prof->begin(s, K_CELL_SCATTER);
     if (keys)

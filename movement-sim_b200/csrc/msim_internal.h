@@ -134,6 +134,7 @@ struct Tuning {
                                   // scatter (the tick's dependency loop move -> exchange -> scan -> scatter -> pass B -> move loses its last link).  Measured
                                   // at 2 GPUs, 5 M entities each: 245 us per tick against 210 us - beside the memory-bound scan and scatter pass B costs more
                                   // than the shorter loop saves; off by default
+    int scatter_beside_ctas_per_sm{8};  // MSIM_SCATTER_BESIDE_CTAS=1..8: CTAs per SM of the scatter in the pipelined rebuild (it runs beside the previous tick's query)
     bool pipeline_build{true};        // MSIM_PIPELINE_BUILD=0: scan + scatter of tick t+1 wait for the query of tick t on the main stream (by default they follow the
                                   // move phase on the side stream, into the other of two {sorted positions, prefix table} sets; unsharded handles)
     bool l2_persist_roads{false};        // MSIM_L2_PERSIST_ROADS=1: road table as a persisting L2 access-policy window on the handle's streams (api.cu)
@@ -178,7 +179,8 @@ int launch_cell_scan(cudaStream_t s, uint32_t* cell_count, uint32_t cells, uint3
 // slots come from atomics on the scanned table `cursor`, which ends up shifted by one cell.  `keys` non-NULL (sharded handles):
 // keys are read instead of recomputed, entities whose key is outside [c0, c1) get the slot CSORT_SKIP, the count may live in n_dev
 int launch_cell_scatter_slots(cudaStream_t s, int sm_count, uint32_t n, const float2* pos, const uint32_t* keys, uint32_t* cursor, float2* sorted_pos,
-                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev = nullptr);
+                              uint32_t* slot_of_entity, const GridParams& grid, uint32_t c0, uint32_t c1, Profiler* prof, const uint32_t* n_dev = nullptr,
+                              int ctas_per_sm = 8 /* fewer while the kernel shares the SMs with a query */);
 int launch_invert_slots(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, uint32_t* sorted_idx, Profiler* prof, const uint32_t* n_dev = nullptr);
 int launch_gather_flags(cudaStream_t s, uint32_t n, const uint32_t* slot_of_entity, const uint8_t* flag_sorted, uint8_t* flag_entity, Profiler* prof);
 
