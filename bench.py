@@ -456,6 +456,7 @@ def run_b200(args):
             e0.record(stream)
             for _ in range(k):
                 sim.enqueue_ticks(1, collisions)
+            sim.join()  # the library's side stream (pass B of the last tick) is inside the timed region too
             e1.record(stream)
             e1.synchronize()
             return e0.elapsed_time(e1)
@@ -466,6 +467,7 @@ def run_b200(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             sim.enqueue_ticks(1, collisions)
+            sim.join()
             e1.record(stream)
             e1.synchronize()
             total += e0.elapsed_time(e1)
@@ -518,6 +520,7 @@ def run_b200(args):
         sim.enqueue_ticks(3, False)
         e0.record(stream)
         sim.enqueue_ticks(args.steps, False)
+        sim.join()
         e1.record(stream)
         e1.synchronize()
         mo_ms = e0.elapsed_time(e1) / args.steps
@@ -538,6 +541,7 @@ def run_b200(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             sim2.enqueue_ticks(args.steps, True)
+            sim2.join()
             e1.record(stream)
             e1.synchronize()
             fo_ms = e0.elapsed_time(e1) / args.steps

@@ -674,3 +674,8 @@ class Simulation:
         v = DeviceView()
         self._check(lib().msim_get_device_view(self._h, C.byref(v)))
         return v
+
+    def join(self):
+        """Orders the handle's stream behind everything enqueued so far, the library's internal streams included (pass B, an overlapped move
+        phase, the pipelined rebuild); no host wait.  An event recorded on the handle's stream after this call marks the end of ALL that work."""
+        self.device_view()

@@ -402,6 +402,7 @@ def bench_main(args, M, rank: int, world: int, local_rank: int) -> int:
         e0.record(stream)
         for _ in range(args.steps):
             step()
+        sim.join()  # the library's side / push streams (pass B, the exchange of the last tick) are inside the timed region too
         e1.record(stream)
         e1.synchronize()
         torch.cuda.synchronize()

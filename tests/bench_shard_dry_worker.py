@@ -86,6 +86,9 @@ def run(rank, world, port, out_path, argv):
         def dispatch(self, tick):
             self.engine.move()  # the init-only first dispatch
 
+        def join(self):
+            pass
+
         def sync(self):
             pass
 

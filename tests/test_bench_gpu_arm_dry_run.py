@@ -115,6 +115,9 @@ def make_fake_simulation(M, O):
             for _ in range(k):
                 self._tick(collide)
 
+        def join(self):
+            pass
+
         def sync(self):
             pass
 

@@ -127,7 +127,7 @@ def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
     """msim_read_quadtree_nodes (device histogram with dynamic shared memory + host builder) equals its host twin."""
     ents = emu_city.init_entities(3000, seed=3)
     with emu_msim.Simulation(emu_city, ents, radius=10.0) as sim:
-        for tick in range(2, 40):
+        for tick in range(2, 18):
             sim.dispatch(tick)
         got = sim.read_quadtree_nodes()
         pos = sim.read_positions()
@@ -150,7 +150,7 @@ def test_cpp_simulator_and_headless_runner_on_the_emulated_library(emu_msim, orc
     assert r.returncode == 0, r.stderr[-2000:]
     path = str(tmp_path / "city.msimmap")
     emu_city.save_binary(path)
-    n, ticks = 2000, 60
+    n, ticks = 1500, 16  # (emulator speed: every tick is read back in full by the blocking mode)
     dump = str(tmp_path / "entities.bin")
     cmd = [runner, "--headless", "--quiet", "--map", path, "--entities", str(n), "--seed", "7", "--ticks", str(ticks), "--consume-entities", "--dump", dump,
            "--csv", str(tmp_path / "t.csv")] + (["--async-readback"] if mode == "async" else [])
