@@ -24,7 +24,10 @@
 //     them are a few hundred contiguous bytes that stay in L1 (75 % hit rate); staging them per CTA or per warp with TMA
 //     bulk copies was measured slower (mbarrier set-up, hull exchange and waits cost more issue slots than the loads save:
 //     191 / 212 us against 156 us), so every warp is independent from its first instruction;
-//   * totals leave as one reduction per warp and counter (RED, nothing waits) into striped counters; a one-CTA kernel folds them.
+//   * the pair total leaves as one reduction per warp (RED, nothing waits) into striped counters; the flagged total is NOT taken here:
+//     fold_counts_kernel (collide.cu) counts the flag bytes this kernel stored and folds the pair stripes (profiles/r2_flag_count_race.md);
+//   * lanes that find nothing below look above warp-cooperatively (collide_common.cuh look_above_cooperative): what is left of
+//     divergence are the count loops, whose lanes differ in trip count only (one code path, one value per uniform register).
 #include <cstdlib>
 
 #include "msim_internal.h"

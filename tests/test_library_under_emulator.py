@@ -35,9 +35,15 @@ def emu_test_map(emu_msim):
     return emu_msim.Map.load_json(os.path.join(ROOT, "tests", "golden", "test_map.json"))
 
 
+# The emulator runs one OS thread per CUDA thread: the default CPU suite keeps one case per kernel family (default rebuild = counting sort with
+# re-sorts, onesweep, colours only); MSIM_TEST_SLOW=1 adds the remaining flag combinations and the C++ drop-in Simulator with its headless runner
+SLOW = os.environ.get("MSIM_TEST_SLOW") == "1"
+slow = pytest.mark.skipif(not SLOW, reason="emulator: long case, MSIM_TEST_SLOW=1 runs it")
+
+
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("flag_names", [(), ("FLAG_NO_REORDER",), ("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), ("FLAG_SORT_ONESWEEP",),
-                                        ("FLAG_NO_PAIR_COUNT",)])
+@pytest.mark.parametrize("flag_names", [(), pytest.param(("FLAG_NO_REORDER",), marks=slow), pytest.param(("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), marks=slow),
+                                        ("FLAG_SORT_ONESWEEP",), ("FLAG_NO_PAIR_COUNT",)])
 def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkeypatch):
     """Blocking dispatches, every rebuild mode of the neighbour structure, a cell re-sort every 3 collision passes, readback at several points."""
     monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
@@ -61,7 +67,7 @@ def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkey
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("mode", ["default", "counting"])
+@pytest.mark.parametrize("mode", ["default", pytest.param("counting", marks=slow)])
 def test_radius_back_and_forth(emu_msim, orc, emu_city, mode):
     """tests/test_gpu_parity.py::test_radius_back_and_forth_reuses_the_counter_table through the emulated library (the sequence the round-1
     advisor reproduced a crash with)."""
@@ -136,7 +142,7 @@ def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("mode", ["blocking", "async"])
+@pytest.mark.parametrize("mode", [pytest.param("blocking", marks=slow), "async"])
 def test_cpp_simulator_and_headless_runner_on_the_emulated_library(emu_msim, orc, emu_city, tmp_path, mode):
     """The drop-in sim::Simulator (worker thread, hand-off protocol, CSV) and the headless runner, linked against libmsim_emu.so: a consumer takes
     the entity buffer every 2 ms like the UI does per frame; blocking readback and the asynchronous snapshot path must give the same simulation."""
