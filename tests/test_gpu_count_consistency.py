@@ -11,7 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 N = 10_000_000
-TICKS = 60
+TICKS = 600        # two handles in lock step: the count was wrong on every tenth tick
+TICKS_BANDS = 1500  # bands against the unsharded handle: a wrong FLAG showed up about once per 700 ticks (both take a few seconds on a B200)
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +40,7 @@ def test_flagged_count_equals_stored_flags_every_tick(msim, munich, population, 
             b.enqueue_ticks(1, True)
             sa, sb = a.stats(), b.stats()
             assert (sa["last_flagged_count"], sa["last_pair_count"]) == (sb["last_flagged_count"], sb["last_pair_count"]), f"tick {t}: two handles, same input"
-            if t % 4 == 0 or t == ticks - 1:
+            if t % 50 == 0 or t == ticks - 1:
                 fa = a.read_collision_flags()
                 assert int(fa.sum()) == sa["last_flagged_count"], f"tick {t}: count vs stored flags"
         assert a.stats()["total_flagged_count"] == b.stats()["total_flagged_count"] > 0
@@ -72,7 +73,7 @@ def test_bands_on_one_gpu_report_the_unsharded_counts_every_tick(msim, munich, p
             s.shard_p2p_connect_local(arenas[r - 1] if r > 0 else None, arenas[r + 1] if r + 1 < world else None)
         for s in [ref] + sims:
             s.dispatch(2)
-        for t in range(100 + TICKS):
+        for t in range(100 + TICKS_BANDS):
             collide = t >= 100
             ref.enqueue_ticks(1, collide)
             for r, s in enumerate(sims):  # every band's move + pack before any band's integrate (one stream: see test_gpu_sharding)
@@ -87,7 +88,7 @@ def test_bands_on_one_gpu_report_the_unsharded_counts_every_tick(msim, munich, p
             got = [s.stats() for s in sims]
             assert sum(g["last_pair_count"] for g in got) == want["last_pair_count"], f"tick {t}"
             assert sum(g["last_flagged_count"] for g in got) == want["last_flagged_count"], f"tick {t}"
-            if t % 16 == 0:
+            if t % 250 == 0:
                 for s, g in zip(sims, got):
                     s.shard_counts()
                     assert int(s.read_collision_flags().sum()) == g["last_flagged_count"], f"tick {t}"
