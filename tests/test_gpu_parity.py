@@ -228,6 +228,52 @@ def test_upload_readback_roundtrip_and_reupload(msim, orc, small_city):
     assert_entities_equal(a, b, what="re-upload continuation")
 
 
+def test_asynchronous_ticks_interleaved_with_host_operations(msim, orc, small_city, monkeypatch, n=30_011):
+    """Ticks that are only enqueued keep two of them in flight on two streams (pipelined rebuild, overlapped move phase, pass B beside the
+    query); every host-visible call in between must see exactly the state of the ticks enqueued so far: statistics, fast readbacks, a full
+    readback, a re-upload, a radius change through the push constants, a re-sort every third collision pass."""
+    monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
+    ents = small_city.init_entities(n, seed=19)
+    omap = oracle_map(orc, small_city)
+    want = to_oracle_entities(orc, ents)
+
+    def oracle_ticks(k, radius=10.0):
+        pairs = 0
+        for _ in range(k):
+            orc.move_pass(want, omap, threads=4)
+            pairs = orc.collide_pass(want, omap.world_w, omap.world_h, radius, threads=4)
+        return pairs
+
+    with msim.Simulation(small_city, ents, radius=10.0) as sim:
+        sim.dispatch(2)  # initialise only
+        orc.move_pass(want, omap, threads=4)
+        for k in (1, 2, 5, 3):
+            sim.enqueue_ticks(k, True)
+            pairs = oracle_ticks(k)
+            st = sim.stats()  # (joins the streams)
+            assert (st["last_pair_count"], st["last_flagged_count"]) == (pairs, int(orc.collision_flags(want).sum())), f"after {k} more ticks"
+            assert (sim.read_positions() == want["pos"]).all()
+        sim.enqueue_ticks(4, True)
+        oracle_ticks(4)
+        assert (sim.read_collision_flags() == orc.collision_flags(want)).all()
+        mid = sim.read_entities()
+        assert_entities_equal(mid, want, what="full readback between enqueued ticks")
+        sim.enqueue_ticks(2, True)  # ... these two are thrown away by the re-upload
+        sim.upload(mid)
+        sim.enqueue_ticks(3, True)
+        oracle_ticks(3)
+        sim.radius = 25.0  # a different grid: work still in flight under the old one is completed first
+        sim.dispatch(40)
+        orc.move_pass(want, omap, threads=4)
+        sim.dispatch(41)
+        pairs = orc.collide_pass(want, omap.world_w, omap.world_h, 25.0, threads=4)
+        assert sim.stats()["last_pair_count"] == pairs
+        sim.enqueue_ticks(2, True)
+        pairs = oracle_ticks(2, 25.0)
+        assert sim.stats()["last_pair_count"] == pairs
+        assert_entities_equal(sim.read_entities(), want, what="after the radius change")
+
+
 def test_collide_without_prior_move_and_radius_change(msim, orc, small_city):
     ents = small_city.init_entities(20_000, seed=11)
     ents["initialized"] = 1

@@ -129,6 +129,12 @@ def test_required_parity_tests_at_emulator_size(emu_msim, orc, emu_test_map, emu
 
 
 @pytest.mark.timeout(1800)
+@slow
+def test_asynchronous_ticks_interleaved_with_host_operations(emu_msim, orc, emu_city, monkeypatch):
+    """The required GPU test as it is, at emulator size: the handle's state machine around enqueued ticks (joins, re-upload, grid change)."""
+    parity.test_asynchronous_ticks_interleaved_with_host_operations(emu_msim, orc, emu_city, monkeypatch, n=1201)
+
+
 def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
     """msim_read_quadtree_nodes (device histogram with dynamic shared memory + host builder) equals its host twin."""
     ents = emu_city.init_entities(3000, seed=3)
