@@ -36,14 +36,15 @@ def emu_test_map(emu_msim):
 
 
 # The emulator runs one OS thread per CUDA thread: the default CPU suite keeps one case per kernel family (default rebuild = counting sort with
-# re-sorts, onesweep, colours only); MSIM_TEST_SLOW=1 adds the remaining flag combinations and the C++ drop-in Simulator with its headless runner
+# re-sorts, onesweep) plus the snapshot, quadtree and grid-change cases; MSIM_TEST_SLOW=1 adds the remaining flag combinations, the enqueued-ticks
+# state-machine test and the C++ drop-in Simulator with its headless runner (all of them run on the GPU in the required suite)
 SLOW = os.environ.get("MSIM_TEST_SLOW") == "1"
 slow = pytest.mark.skipif(not SLOW, reason="emulator: long case, MSIM_TEST_SLOW=1 runs it")
 
 
 @pytest.mark.timeout(1800)
 @pytest.mark.parametrize("flag_names", [(), pytest.param(("FLAG_NO_REORDER",), marks=slow), pytest.param(("FLAG_NO_REORDER", "FLAG_SORT_COUNTING"), marks=slow),
-                                        ("FLAG_SORT_ONESWEEP",), ("FLAG_NO_PAIR_COUNT",)])
+                                        ("FLAG_SORT_ONESWEEP",), pytest.param(("FLAG_NO_PAIR_COUNT",), marks=slow)])
 def test_sim_ticks_through_the_c_abi(emu_msim, orc, emu_city, flag_names, monkeypatch):
     """Blocking dispatches, every rebuild mode of the neighbour structure, a cell re-sort every 3 collision passes, readback at several points."""
     monkeypatch.setenv("MSIM_REORDER_EVERY", "3")
@@ -148,7 +149,7 @@ def test_display_quadtree_through_the_c_abi(emu_msim, orc, emu_city):
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("mode", [pytest.param("blocking", marks=slow), "async"])
+@pytest.mark.parametrize("mode", [pytest.param("blocking", marks=slow), pytest.param("async", marks=slow)])
 def test_cpp_simulator_and_headless_runner_on_the_emulated_library(emu_msim, orc, emu_city, tmp_path, mode):
     """The drop-in sim::Simulator (worker thread, hand-off protocol, CSV) and the headless runner, linked against libmsim_emu.so: a consumer takes
     the entity buffer every 2 ms like the UI does per frame; blocking readback and the asynchronous snapshot path must give the same simulation."""
