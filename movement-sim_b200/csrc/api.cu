@@ -1407,7 +1407,9 @@ int msim_profile_end(msim_handle* h, msim_kernel_time* out, uint32_t cap, uint32
                                                "build_cells", "query", "scatter_flags", "pack", "unpack", "memset", "misc", "shard", "cell_count",
                                                "cell_scan", "cell_scatter", "reorder", "fold_counts"};
     h->prof.enabled = false;
+    join_side(h);  // events were recorded on the library's own streams too
     MSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->push_stream) MSIM_CUDA(h, cudaStreamSynchronize(h->push_stream));
     double ms[K_COUNT] = {0};
     uint64_t launches[K_COUNT] = {0};
     for (size_t i = 0; i < h->prof.ids.size(); i++) {
